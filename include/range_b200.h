@@ -1,0 +1,106 @@
+/* range_b200 - C ABI of the B200-native RANGE / RANGE+ embedding hot path.
+ *
+ * The reference (mvrl/RANGE) has no FFI: the path sits behind the Python API
+ *     load_model(model_name, pretrained_path, device, db_path=..., beta=...)   range/load_model.py:16-51
+ *     model(locs) -> np.ndarray (N, 1280) float64                              range/range.py:206-242
+ * range_b200/load_model.py keeps that API and binds this library with ctypes (INTEGRATION.md shows the
+ * stub).  Each entry point below names the reference lines it replaces.
+ *
+ * Conventions: extern "C", plain pointers and sizes only.  Every function returns 0 on success or a
+ * negative RANGE_ERR_* code; range_last_error() gives the thread-local message.  All data pointers are
+ * DEVICE pointers owned by the caller (e.g. the PyTorch allocator) unless marked "host".  `stream` is a
+ * cudaStream_t passed as void*.  The library allocates no device memory: scratch comes from the caller
+ * (range_*_workspace_bytes).  One ctx per device; calls on one ctx must be serialised by the caller.
+ */
+#ifndef RANGE_B200_H
+#define RANGE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RANGE_OK 0
+#define RANGE_ERR_INVALID (-1)     /* bad argument / state (e.g. database not set)   */
+#define RANGE_ERR_CUDA (-2)        /* a CUDA runtime / driver call failed            */
+#define RANGE_ERR_WORKSPACE (-3)   /* workspace too small                            */
+#define RANGE_ERR_UNSUPPORTED (-4) /* shape outside what the kernels are built for   */
+
+#define RANGE_MODE_RANGE 0      /* one softmax, temperature 15        range/range.py:102-105 */
+#define RANGE_MODE_RANGE_PLUS 1 /* semantic (12) + geographic (40)     range/range.py:107-112 */
+
+#define RANGE_OUT_F64 0
+#define RANGE_OUT_F32 1
+
+typedef struct range_ctx range_ctx;
+
+const char* range_last_error(void);
+int range_version(void);
+
+/* lifetime */
+int range_ctx_create(int device, range_ctx** out);
+int range_ctx_destroy(range_ctx* ctx);
+
+/* Spherical-harmonics coefficient table (range_b200/sh_table.py:build_table) - replaces the generated
+ * spherical_harmonics_ylm.py the reference imports at positional_encoding/spherical_harmonics.py:3.
+ * Borrowed device arrays; entries ordered |m|-major. */
+int range_ctx_set_sh_table(range_ctx* ctx, int L, int n_entries, const double* pref, const int32_t* off,
+                           const double* coef, const int32_t* par);
+
+/* SIREN weights - replaces SirenNet's parameters, location_encoder.py:73-112 (checkpoint keys
+ * model.location.nnet.layers.{i}.{weight,bias}, model.location.nnet.last_layer.{weight,bias}).
+ * dims: host array of n_layers+1 ints (dims[0] == L*L); W, b: host arrays of n_layers device pointers,
+ * W[i] is (dims[i+1], dims[i]) row-major fp64.  All but the last layer apply sin(w0 * x), w0 = w0_first
+ * for layer 0 and w0_hidden after (location_encoder.py:80-83,119). */
+int range_ctx_set_encoder(range_ctx* ctx, int n_layers, const int32_t* dims, const double* const* W,
+                          const double* const* b, double w0_first, double w0_hidden);
+
+/* Device-resident database (range_b200/database.py) - replaces the tensors built at range/range.py:78-100.
+ *   Kh  (Mpad, 256) fp16 row-major: row-normalised keys, rows >= M zero
+ *   Vt  (1024, Mpad) fp16: values transposed (entries contiguous) times vscale, columns >= M zero
+ *   xyz (Mpad, 4) fp32: unit vectors (x, y, z, 0)
+ * Mpad is a multiple of 128.  Borrowed; must outlive the ctx or the next set_db. */
+int range_ctx_set_db(range_ctx* ctx, int64_t M, int64_t Mpad, const void* Kh, const void* Vt, const float* xyz,
+                     float vscale);
+
+/* K1: features Yt[f * ld + n] = Y_f(lonlat[n]) for f < L*L - SphericalHarmonics.forward,
+ * positional_encoding/spherical_harmonics.py:27-42.  lonlat (N,2) fp64 (lon, lat) degrees. */
+int range_sh_features(range_ctx* ctx, int64_t N, const double* lonlat, double* Yt, int64_t ld, void* stream);
+
+/* K1 + K1b + K3: LocationEncoder.forward (location_encoder.py:273-275) then the L2 normalisation of
+ * range/range.py:212 and the query unit vector of range/range.py:225-229.
+ *   q64 (N,256) fp64, q16 (N,256) fp16, qxyz (N,4) fp32 */
+size_t range_encode_workspace_bytes(range_ctx* ctx, int64_t N);
+int range_encode(range_ctx* ctx, int64_t N, const double* lonlat, double* q64, void* q16, float* qxyz,
+                 void* workspace, size_t workspace_bytes, void* stream);
+
+/* K2: retrieval, range/range.py:213-217 (RANGE) and :213-238 (RANGE+).
+ *   stats: sums (N,2) = {sum_j exp(temp (s_j-1)), sum_j exp(geo_temp (g_j-1))}, maxs (N,2) = {max s, max g}
+ *          over THIS ctx's database shard; shards merge with SUM / MAX (M-sharding across GPUs).
+ *   apply: O (N,1024) fp32 = this shard's contribution to the retrieved feature, normalised with the given
+ *          (global) sums; shards merge with SUM.
+ *   retrieve = stats + apply for an unsharded database. */
+size_t range_retrieve_workspace_bytes(range_ctx* ctx, int64_t N);
+int range_retrieve_stats(range_ctx* ctx, int mode, int64_t N, const void* q16, const float* qxyz, float temp,
+                         float geo_temp, float* sums, float* maxs, void* workspace, size_t workspace_bytes,
+                         void* stream);
+int range_retrieve_apply(range_ctx* ctx, int mode, int64_t N, const void* q16, const float* qxyz, float temp,
+                         float geo_temp, float beta, const float* sums, const float* maxs, float* O,
+                         void* workspace, size_t workspace_bytes, void* stream);
+int range_retrieve(range_ctx* ctx, int mode, int64_t N, const void* q16, const float* qxyz, float temp,
+                   float geo_temp, float beta, float* O, void* workspace, size_t workspace_bytes, void* stream);
+
+/* K3: out (N,1280) = [O | q64] as fp64 (RANGE_OUT_F64, what the reference returns: range/range.py:222,240)
+ * or fp32. */
+int range_concat(range_ctx* ctx, int64_t N, const float* O, const double* q64, void* out, int out_dtype,
+                 void* stream);
+
+/* number of kernels this library launched since process start (bench.py's gpu_launches) */
+int64_t range_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RANGE_B200_H */

@@ -1,0 +1,344 @@
+// C-ABI layer: argument checking, workspace carving, tensor-map construction, kernel sequencing.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cudaTypedefs.h>
+
+#include "../../include/range_b200.h"
+#include "range_kernels.h"
+
+using namespace rangeb200;
+
+namespace {
+
+thread_local char g_err[512] = "";
+std::atomic<int64_t> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define CUDA_TRY(expr)                                                                           \
+  do {                                                                                           \
+    cudaError_t _e = (expr);                                                                     \
+    if (_e != cudaSuccess) return fail(RANGE_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(_e)); \
+  } while (0)
+
+constexpr int kDimK = 256, kDimV = 1024, kBlockQ = 128, kBlockKeys = 128;
+constexpr int64_t kEncodeChunk = 32768;   // queries per encoder pass (bounds the feature workspace)
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  }
+  return fn;
+}
+
+// 2-D fp16 tensor [rows][cols] row-major, box [box_rows][64 cols] (128 B inner), SWIZZLE_128B
+int make_tmap(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  auto fn = get_encode_fn();
+  if (!fn) return fail(RANGE_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstr[1] = {cols * 2};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(RANGE_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", int(r));
+  return RANGE_OK;
+}
+
+}  // namespace
+
+struct range_ctx {
+  int device = 0;
+  int sm_count = 148;
+  ShTable sh;
+  int n_layers = 0;
+  std::vector<int> dims;
+  std::vector<const double*> W, b;
+  double w0_first = 30.0, w0_hidden = 1.0;
+  int64_t M = 0, Mpad = 0;
+  const void* Kh = nullptr;
+  const void* Vt = nullptr;
+  const float* xyz = nullptr;
+  float vscale = 1.f;
+  CUtensorMap tmK, tmV;
+};
+
+namespace {
+
+struct RetrievalPlan {
+  int splits, tiles_per_split;
+  size_t off_part_sum, off_part_max, off_sums, off_maxs, off_rowc, off_part_out, total;
+};
+
+// Database splits: enough CTAs to fill the SMs when there are few query tiles.
+RetrievalPlan plan_retrieval(const range_ctx* c, int64_t N) {
+  RetrievalPlan p{};
+  const int64_t qtiles = (N + kBlockQ - 1) / kBlockQ;
+  const int64_t tiles = (c->M + kBlockKeys - 1) / kBlockKeys;
+  int64_t want = 1;
+  const int64_t ctas = qtiles * 4;
+  if (ctas < 2 * c->sm_count) want = (2 * c->sm_count + ctas - 1) / ctas;
+  int64_t max_splits = tiles / 8 > 0 ? tiles / 8 : 1;      // at least 8 tiles per split
+  if (want > max_splits) want = max_splits;
+  if (want > 64) want = 64;
+  p.tiles_per_split = int((tiles + want - 1) / want);
+  p.splits = int((tiles + p.tiles_per_split - 1) / p.tiles_per_split);
+  size_t o = 0;
+  p.off_part_sum = o; o += align_up(size_t(p.splits) * N * 8, 256);
+  p.off_part_max = o; o += align_up(size_t(p.splits) * N * 8, 256);
+  p.off_sums = o;     o += align_up(size_t(N) * 8, 256);
+  p.off_maxs = o;     o += align_up(size_t(N) * 8, 256);
+  p.off_rowc = o;     o += align_up(size_t(N) * 32, 256);
+  p.off_part_out = o; o += p.splits > 1 ? align_up(size_t(p.splits) * N * kDimV * 4, 256) : 0;
+  p.total = o;
+  return p;
+}
+
+int fill_args(range_ctx* c, int mode, int64_t N, const void* q16, const float* qxyz, float temp, float geo_temp,
+              const RetrievalPlan& p, RetrievalArgs* a) {
+  if (!c || !c->Kh) return fail(RANGE_ERR_INVALID, "database not set");
+  if (mode != RANGE_MODE_RANGE && mode != RANGE_MODE_RANGE_PLUS) return fail(RANGE_ERR_INVALID, "unknown mode %d", mode);
+  if (N <= 0 || N > (int64_t(1) << 30)) return fail(RANGE_ERR_INVALID, "N out of range");
+  int r = make_tmap(&a->tmQ, q16, uint64_t(N), kDimK, kBlockQ);
+  if (r) return r;
+  a->tmK = c->tmK;
+  a->tmV = c->tmV;
+  a->db_xyz = reinterpret_cast<const float4*>(c->xyz);
+  a->q_xyz = reinterpret_cast<const float4*>(qxyz);
+  a->N = int(N);
+  a->M = int(c->M);
+  a->geo = mode == RANGE_MODE_RANGE_PLUS;
+  a->splits = p.splits;
+  a->tiles_per_split = p.tiles_per_split;
+  const float log2e = 1.4426950408889634f;
+  a->a_sem = temp * log2e;
+  a->a_geo = geo_temp * log2e;
+  return RANGE_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* range_last_error(void) { return g_err; }
+int range_version(void) { return 100; }
+int64_t range_launch_count(void) { return g_launches.load(); }
+
+int range_ctx_create(int device, range_ctx** out) {
+  if (!out) return fail(RANGE_ERR_INVALID, "out is null");
+  int count = 0;
+  CUDA_TRY(cudaGetDeviceCount(&count));
+  if (device < 0 || device >= count) return fail(RANGE_ERR_INVALID, "device %d out of range (%d devices)", device, count);
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(RANGE_ERR_UNSUPPORTED, "range_b200 needs an sm_100 device, found sm_%d%d", prop.major, prop.minor);
+  range_ctx* c = new range_ctx();
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  *out = c;
+  return RANGE_OK;
+}
+
+int range_ctx_destroy(range_ctx* ctx) {
+  delete ctx;
+  return RANGE_OK;
+}
+
+int range_ctx_set_sh_table(range_ctx* c, int L, int n_entries, const double* pref, const int32_t* off,
+                           const double* coef, const int32_t* par) {
+  if (!c || L <= 0 || n_entries != L * (L + 1) / 2 || !pref || !off || !coef || !par)
+    return fail(RANGE_ERR_INVALID, "bad spherical-harmonics table (L=%d, entries=%d)", L, n_entries);
+  c->sh = ShTable{L, n_entries, pref, off, coef, par};
+  return RANGE_OK;
+}
+
+int range_ctx_set_encoder(range_ctx* c, int n_layers, const int32_t* dims, const double* const* W,
+                          const double* const* b, double w0_first, double w0_hidden) {
+  if (!c || n_layers < 1 || !dims || !W || !b) return fail(RANGE_ERR_INVALID, "bad encoder arguments");
+  for (int i = 0; i < n_layers; ++i) {
+    if (dims[i] % 16 || dims[i + 1] % 64)
+      return fail(RANGE_ERR_UNSUPPORTED, "layer %d: (%d -> %d) needs in %% 16 == 0 and out %% 64 == 0", i, dims[i],
+                  dims[i + 1]);
+    if (!W[i] || !b[i]) return fail(RANGE_ERR_INVALID, "layer %d has null weights", i);
+  }
+  if (dims[n_layers] != kDimK)
+    return fail(RANGE_ERR_UNSUPPORTED, "embedding dim must be %d, got %d", kDimK, dims[n_layers]);
+  c->n_layers = n_layers;
+  c->dims.assign(dims, dims + n_layers + 1);
+  c->W.assign(W, W + n_layers);
+  c->b.assign(b, b + n_layers);
+  c->w0_first = w0_first;
+  c->w0_hidden = w0_hidden;
+  return RANGE_OK;
+}
+
+int range_ctx_set_db(range_ctx* c, int64_t M, int64_t Mpad, const void* Kh, const void* Vt, const float* xyz,
+                     float vscale) {
+  if (!c || M <= 0 || Mpad < M || Mpad % kBlockKeys || !Kh || !Vt || !xyz || !(vscale > 0.f))
+    return fail(RANGE_ERR_INVALID, "bad database arguments (M=%lld, Mpad=%lld)", (long long)M, (long long)Mpad);
+  if (M > (int64_t(1) << 30)) return fail(RANGE_ERR_UNSUPPORTED, "M too large");
+  CUDA_TRY(cudaSetDevice(c->device));
+  int r = make_tmap(&c->tmK, Kh, uint64_t(Mpad), kDimK, kBlockKeys);
+  if (r) return r;
+  r = make_tmap(&c->tmV, Vt, kDimV, uint64_t(Mpad), 256);
+  if (r) return r;
+  c->M = M; c->Mpad = Mpad; c->Kh = Kh; c->Vt = Vt; c->xyz = xyz; c->vscale = vscale;
+  return RANGE_OK;
+}
+
+int range_sh_features(range_ctx* c, int64_t N, const double* lonlat, double* Yt, int64_t ld, void* stream) {
+  if (!c || !c->sh.pref) return fail(RANGE_ERR_INVALID, "spherical-harmonics table not set");
+  if (N < 0 || ld < N || !lonlat || !Yt) return fail(RANGE_ERR_INVALID, "bad arguments");
+  CUDA_TRY(launch_sh(c->sh, lonlat, int(N), Yt, size_t(ld), cudaStream_t(stream)));
+  g_launches += N > 0;
+  return RANGE_OK;
+}
+
+size_t range_encode_workspace_bytes(range_ctx* c, int64_t N) {
+  if (!c || !c->n_layers || N <= 0) return 0;
+  const int64_t chunk = N < kEncodeChunk ? N : kEncodeChunk;
+  const size_t ld = align_up(size_t(chunk), 128);
+  size_t widest = 0;
+  for (int i = 1; i < c->n_layers; ++i) widest = widest > size_t(c->dims[i]) ? widest : size_t(c->dims[i]);
+  // features + two ping-pong hidden buffers (feature-major) + row-major embedding
+  return (size_t(c->dims[0]) + 2 * widest) * ld * 8 + size_t(chunk) * kDimK * 8 + 1024;
+}
+
+int range_encode(range_ctx* c, int64_t N, const double* lonlat, double* q64, void* q16, float* qxyz,
+                 void* workspace, size_t workspace_bytes, void* stream) {
+  if (!c || !c->sh.pref || !c->n_layers) return fail(RANGE_ERR_INVALID, "encoder not set");
+  if (c->dims[0] != c->sh.L * c->sh.L)
+    return fail(RANGE_ERR_INVALID, "encoder input dim %d != L*L = %d", c->dims[0], c->sh.L * c->sh.L);
+  if (N <= 0 || !lonlat || !q64 || !q16 || !qxyz) return fail(RANGE_ERR_INVALID, "bad arguments");
+  if (workspace_bytes < range_encode_workspace_bytes(c, N) || !workspace)
+    return fail(RANGE_ERR_WORKSPACE, "encode workspace too small");
+  cudaStream_t s = cudaStream_t(stream);
+  const int64_t chunk = N < kEncodeChunk ? N : kEncodeChunk;
+  const size_t ld = align_up(size_t(chunk), 128);
+  size_t widest = 0;
+  for (int i = 1; i < c->n_layers; ++i) widest = widest > size_t(c->dims[i]) ? widest : size_t(c->dims[i]);
+  double* Yt = reinterpret_cast<double*>(align_up(reinterpret_cast<size_t>(workspace), 256));
+  double* hid[2] = {Yt + size_t(c->dims[0]) * ld, Yt + (size_t(c->dims[0]) + widest) * ld};
+  double* emb = Yt + (size_t(c->dims[0]) + 2 * widest) * ld;
+  for (int64_t n0 = 0; n0 < N; n0 += chunk) {
+    const int n = int(N - n0 < chunk ? N - n0 : chunk);
+    CUDA_TRY(launch_sh(c->sh, lonlat + 2 * n0, n, Yt, ld, s));
+    const double* in = Yt;
+    for (int i = 0; i < c->n_layers; ++i) {
+      const bool last = i == c->n_layers - 1;
+      double* out = last ? emb : hid[i & 1];
+      CUDA_TRY(launch_siren_layer(c->W[i], c->b[i], in, ld, c->dims[i + 1], c->dims[i], n,
+                                  last ? 0.0 : (i == 0 ? c->w0_first : c->w0_hidden), out,
+                                  last ? size_t(kDimK) : ld, last ? 1 : 0, s));
+      in = out;
+    }
+    CUDA_TRY(launch_normalize(emb, lonlat + 2 * n0, n, kDimK, q64 + n0 * kDimK, kDimK,
+                              reinterpret_cast<char*>(q16) + n0 * kDimK * 2, qxyz + n0 * 4, s));
+    g_launches += 2 + c->n_layers;
+  }
+  return RANGE_OK;
+}
+
+size_t range_retrieve_workspace_bytes(range_ctx* c, int64_t N) {
+  if (!c || !c->Kh || N <= 0) return 0;
+  return plan_retrieval(c, N).total + 256;
+}
+
+int range_retrieve_stats(range_ctx* c, int mode, int64_t N, const void* q16, const float* qxyz, float temp,
+                         float geo_temp, float* sums, float* maxs, void* workspace, size_t workspace_bytes,
+                         void* stream) {
+  if (!c || !c->Kh) return fail(RANGE_ERR_INVALID, "database not set");
+  if (!q16 || !qxyz || !sums || !maxs || !workspace) return fail(RANGE_ERR_INVALID, "null argument");
+  if (N <= 0) return fail(RANGE_ERR_INVALID, "N must be positive");
+  const RetrievalPlan p = plan_retrieval(c, N);
+  if (workspace_bytes < p.total + 256) return fail(RANGE_ERR_WORKSPACE, "retrieve workspace too small");
+  RetrievalArgs a;
+  int r = fill_args(c, mode, N, q16, qxyz, temp, geo_temp, p, &a);
+  if (r) return r;
+  char* ws = reinterpret_cast<char*>(align_up(reinterpret_cast<size_t>(workspace), 256));
+  cudaStream_t s = cudaStream_t(stream);
+  float* part_sum = p.splits > 1 ? reinterpret_cast<float*>(ws + p.off_part_sum) : sums;
+  float* part_max = p.splits > 1 ? reinterpret_cast<float*>(ws + p.off_part_max) : maxs;
+  CUDA_TRY(launch_stats(a, part_sum, part_max, s));
+  g_launches += 1;
+  if (p.splits > 1) {
+    CUDA_TRY(launch_reduce_stats(part_sum, part_max, int(N), p.splits, sums, maxs, s));
+    g_launches += 1;
+  }
+  return RANGE_OK;
+}
+
+int range_retrieve_apply(range_ctx* c, int mode, int64_t N, const void* q16, const float* qxyz, float temp,
+                         float geo_temp, float beta, const float* sums, const float* maxs, float* O,
+                         void* workspace, size_t workspace_bytes, void* stream) {
+  if (!c || !c->Kh) return fail(RANGE_ERR_INVALID, "database not set");
+  if (!q16 || !qxyz || !sums || !maxs || !O || !workspace) return fail(RANGE_ERR_INVALID, "null argument");
+  if (N <= 0) return fail(RANGE_ERR_INVALID, "N must be positive");
+  if (mode == RANGE_MODE_RANGE_PLUS && !(beta >= 0.f && beta <= 1.f))
+    return fail(RANGE_ERR_INVALID, "beta must be in [0,1]");
+  const RetrievalPlan p = plan_retrieval(c, N);
+  if (workspace_bytes < p.total + 256) return fail(RANGE_ERR_WORKSPACE, "retrieve workspace too small");
+  RetrievalArgs a;
+  int r = fill_args(c, mode, N, q16, qxyz, temp, geo_temp, p, &a);
+  if (r) return r;
+  char* ws = reinterpret_cast<char*>(align_up(reinterpret_cast<size_t>(workspace), 256));
+  cudaStream_t s = cudaStream_t(stream);
+  float* rowc = reinterpret_cast<float*>(ws + p.off_rowc);
+  CUDA_TRY(launch_row_constants(sums, maxs, qxyz, int(N), a.geo, beta, a.a_sem, a.a_geo, 1.f / c->vscale, rowc, s));
+  float* part_out = p.splits > 1 ? reinterpret_cast<float*>(ws + p.off_part_out) : O;
+  const size_t stride = size_t(N) * kDimV;
+  CUDA_TRY(launch_apply(a, rowc, part_out, stride, s));
+  g_launches += 2;
+  if (p.splits > 1) {
+    CUDA_TRY(launch_reduce_out(part_out, stride, p.splits, stride, O, s));
+    g_launches += 1;
+  }
+  return RANGE_OK;
+}
+
+int range_retrieve(range_ctx* c, int mode, int64_t N, const void* q16, const float* qxyz, float temp,
+                   float geo_temp, float beta, float* O, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!c || !c->Kh) return fail(RANGE_ERR_INVALID, "database not set");
+  if (!workspace) return fail(RANGE_ERR_INVALID, "null workspace");
+  if (N <= 0) return fail(RANGE_ERR_INVALID, "N must be positive");
+  const RetrievalPlan p = plan_retrieval(c, N);
+  if (workspace_bytes < p.total + 256) return fail(RANGE_ERR_WORKSPACE, "retrieve workspace too small");
+  char* ws = reinterpret_cast<char*>(align_up(reinterpret_cast<size_t>(workspace), 256));
+  float* sums = reinterpret_cast<float*>(ws + p.off_sums);
+  float* maxs = reinterpret_cast<float*>(ws + p.off_maxs);
+  int r = range_retrieve_stats(c, mode, N, q16, qxyz, temp, geo_temp, sums, maxs, workspace, workspace_bytes, stream);
+  if (r) return r;
+  return range_retrieve_apply(c, mode, N, q16, qxyz, temp, geo_temp, beta, sums, maxs, O, workspace,
+                              workspace_bytes, stream);
+}
+
+int range_concat(range_ctx* c, int64_t N, const float* O, const double* q64, void* out, int out_dtype,
+                 void* stream) {
+  if (!c || N <= 0 || !O || !q64 || !out) return fail(RANGE_ERR_INVALID, "bad arguments");
+  if (out_dtype != RANGE_OUT_F64 && out_dtype != RANGE_OUT_F32) return fail(RANGE_ERR_INVALID, "unknown out dtype");
+  CUDA_TRY(launch_concat(O, q64, int(N), kDimV, kDimK, out, out_dtype, cudaStream_t(stream)));
+  g_launches += 1;
+  return RANGE_OK;
+}
+
+}  // extern "C"

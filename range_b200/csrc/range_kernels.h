@@ -1,0 +1,58 @@
+// Internal launch interface between the C-ABI layer (capi.cu) and the kernels.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+namespace rangeb200 {
+
+// ---- K1: spherical harmonics (encoder.cu) -----------------------------------------------------
+struct ShTable {
+  int L = 0;
+  int n_entries = 0;
+  const double* pref = nullptr;   // [n_entries]           entries ordered |m|-major: for am: for l >= am
+  const int* off = nullptr;       // [n_entries + 1]
+  const double* coef = nullptr;   // Horner coefficients in c^2, highest power first
+  const int* par = nullptr;       // [n_entries] polynomial parity
+};
+// Yt[f * ld + n] for f < L*L, n < N   (feature-major so a thread per query writes coalesced)
+cudaError_t launch_sh(const ShTable& t, const double* lonlat, int N, double* Yt, size_t ld, cudaStream_t s);
+
+// ---- K1b: SIREN layer  out = act(W . Xt + b) (encoder.cu) ---------------------------------------
+// W [H][K] row-major, Xt [K][ldx] feature-major.  out_rowmajor == 0: out[h * ldo + n]; 1: out[n * ldo + h].
+// act_w0 > 0: sin(act_w0 * v); act_w0 == 0: identity.   Requires H % 64 == 0, K % 16 == 0.
+cudaError_t launch_siren_layer(const double* W, const double* b, const double* Xt, size_t ldx, int H, int K, int N,
+                               double act_w0, double* out, size_t ldo, int out_rowmajor, cudaStream_t s);
+
+// ---- K3: normalise / concat (encoder.cu) ----------------------------------------------------------
+// e [N][D] fp64 row-major -> q64 [N][D] (ld = ldq), q16 [N][D] fp16, qxyz [N][4] fp32 from lonlat
+cudaError_t launch_normalize(const double* e, const double* lonlat, int N, int D, double* q64, size_t ldq,
+                             void* q16, float* qxyz, cudaStream_t s);
+// out[n] = [O[n][0:DO] | q64[n][0:DQ]]  as fp64 (dtype 0) or fp32 (dtype 1)
+cudaError_t launch_concat(const float* O, const double* q64, int N, int DO, int DQ, void* out, int dtype,
+                          cudaStream_t s);
+
+// ---- K2: retrieval (retrieval.cu) ---------------------------------------------------------------
+struct RetrievalArgs {
+  CUtensorMap tmQ, tmK, tmV;
+  const float4* db_xyz;
+  const float4* q_xyz;
+  int N, M;
+  int geo;
+  int splits, tiles_per_split;
+  float a_sem, a_geo;   // temperature * log2(e)
+};
+int retrieval_stats_smem_bytes();
+int retrieval_apply_smem_bytes();
+cudaError_t launch_stats(const RetrievalArgs& a, float* part_sum, float* part_max, cudaStream_t s);
+cudaError_t launch_reduce_stats(const float* part_sum, const float* part_max, int N, int splits, float* sums,
+                                float* maxs, cudaStream_t s);
+cudaError_t launch_row_constants(const float* sums, const float* maxs, const float* q_xyz, int N, int geo,
+                                 float beta, float a_sem, float a_geo, float inv_vscale, float* rowc, cudaStream_t s);
+cudaError_t launch_apply(const RetrievalArgs& a, const float* rowc, float* out, size_t out_split_stride,
+                         cudaStream_t s);
+cudaError_t launch_reduce_out(const float* part, size_t split_stride, int splits, size_t total, float* out,
+                              cudaStream_t s);
+
+}  // namespace rangeb200

@@ -1,0 +1,626 @@
+// K2 - fused retrieval over the database (reference: range/range.py:213-238).
+//
+//   S = q16 . Kh^T            (tcgen05.mma kind::f16, fp32 accumulators in TMEM)
+//   G = qxyz . xyz^T          (3 FFMA per pair on CUDA cores, fp32: the x40 geo logit needs fp32)
+//   RANGE :  P = softmax(15 S)                              O = P V
+//   RANGE+:  P = beta softmax(12 S) + (1-beta) softmax(40 G) O = P V     ((1-b) Pg V + b Ps V == (..) V)
+//
+// The N x M similarity matrix never exists in memory.  Two kernels, both streaming the database once:
+//
+//   range_stats_kernel   per query row: sum_j exp(t (s_j - 1)), max_j s_j (and the same for g).  Because
+//                        |s|,|g| <= 1 the offset "-1" is a fixed, data-independent softmax max, so partial
+//                        results over database splits / ranks merge with plain SUM and MAX.
+//   range_apply_kernel   P'(row, j) = 2^(a s + cs_row) + 2^(gam g + cg_row)  in fp16, scaled per row so its
+//                        largest entry is <= 2^13 (fp16 range) using the row statistics, then
+//                        O(128 x 256 slice) += P' . Vt  on the tensor cores; epilogue rescales.
+//
+// CTA = 128 queries x (apply: one 256-wide slice of the 1024 value dims - TMEM holds 512 fp32 columns:
+// 2 x 128 for the double-buffered S tile + 256 for O).  Warp roles: warps 0-7 softmax/epilogue (two
+// groups of 4; warp w owns TMEM lanes 32 (w%4)..+31, group w/4 owns key columns 64 (w/4)..+63 of a tile),
+// warp 8 TMA producer, warp 9 MMA issuer + TMEM allocator.
+#include <cstdint>
+#include <cstdio>
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include "ptx.cuh"
+#include "range_kernels.h"
+
+namespace {
+
+constexpr int kBlockQ = 128;      // queries per CTA (UMMA M)
+constexpr int kBlockKeys = 128;   // database entries per S tile (UMMA N of Q.K^T)
+constexpr int kDimK = 256;        // key dim
+constexpr int kSliceV = 256;      // value dims per CTA (UMMA N of P.V)
+constexpr int kChunkBytes = 128 * 128;  // [128 rows x 64 fp16] SWIZZLE_128B tile
+constexpr int kStageBytes = 2 * kChunkBytes;
+constexpr int kXyzBytes = kBlockKeys * 16;
+constexpr int kNumSoftmaxWarps = 8;
+constexpr int kThreads = (kNumSoftmaxWarps + 2) * 32;
+
+template <int NS, int NP, int NX>
+struct SmemLayout {
+  static constexpr int q = 0;
+  static constexpr int stages = q + 4 * kChunkBytes;
+  static constexpr int p = stages + NS * kStageBytes;
+  static constexpr int xyz = p + NP * kChunkBytes;
+  static constexpr int bars = xyz + NX * kXyzBytes;
+  // barrier slots (8 B each)
+  static constexpr int b_q_full = 0;
+  static constexpr int b_stage_full = 1;
+  static constexpr int b_stage_empty = b_stage_full + NS;
+  static constexpr int b_s_full = b_stage_empty + NS;
+  static constexpr int b_s_empty = b_s_full + 2;
+  static constexpr int b_p_full = b_s_empty + 2;
+  static constexpr int b_p_empty = b_p_full + (NP ? NP : 1);
+  static constexpr int b_xyz_full = b_p_empty + (NP ? NP : 1);
+  static constexpr int b_xyz_empty = b_xyz_full + NX;
+  static constexpr int b_o_full = b_xyz_empty + NX;
+  static constexpr int n_bars = b_o_full + 1;
+  static constexpr int tmem_slot = bars + n_bars * 8;
+  static constexpr int red = (tmem_slot + 16 + 15) / 16 * 16;  // stats cross-group reduction scratch
+  static constexpr int total = red + 2 * kBlockQ * 16;
+  static constexpr int dynamic_bytes = total + 1024;  // slack for the manual 1024-B alignment
+};
+
+struct PipeState {
+  int idx = 0;
+  uint32_t phase = 0;
+  template <int N>
+  __device__ __forceinline__ void advance() {
+    if (++idx == N) {
+      idx = 0;
+      phase ^= 1;
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------
+// shared producer / MMA building blocks
+// ---------------------------------------------------------------------------------------------------
+template <class L, int NS>
+__device__ __forceinline__ void produce_keys(uint8_t* smem, uint64_t* bars, PipeState& st, const CUtensorMap* tmK,
+                                             int key0) {
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    ptx::mbar_wait(&bars[L::b_stage_empty + st.idx], st.phase ^ 1);
+    uint8_t* dst = smem + L::stages + st.idx * kStageBytes;
+    ptx::mbar_expect_tx(&bars[L::b_stage_full + st.idx], kStageBytes);
+    ptx::tma_load_2d(dst, tmK, &bars[L::b_stage_full + st.idx], (2 * half) * 64, key0);
+    ptx::tma_load_2d(dst + kChunkBytes, tmK, &bars[L::b_stage_full + st.idx], (2 * half + 1) * 64, key0);
+    st.template advance<NS>();
+  }
+}
+
+template <class L, int NS>
+__device__ __forceinline__ void mma_qk(uint8_t* smem, uint64_t* bars, PipeState& st, uint32_t tmem_s, int lane) {
+  constexpr uint32_t idesc = ptx::umma_idesc_f16(kBlockQ, kBlockKeys);
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    ptx::mbar_wait(&bars[L::b_stage_full + st.idx], st.phase);
+    ptx::tc_fence_after();
+    if (lane == 0) {
+      const uint32_t b_base = ptx::smem_u32(smem + L::stages + st.idx * kStageBytes);
+      const uint32_t a_base = ptx::smem_u32(smem + L::q + (2 * half) * kChunkBytes);
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const uint64_t a = ptx::umma_desc_kmajor_sw128(a_base + c * kChunkBytes + kk * 32);
+          const uint64_t b = ptx::umma_desc_kmajor_sw128(b_base + c * kChunkBytes + kk * 32);
+          ptx::umma_f16_ss(tmem_s, a, b, idesc, (half | c | kk) != 0);
+        }
+      }
+      ptx::umma_commit(&bars[L::b_stage_empty + st.idx]);
+    }
+    __syncwarp();
+    st.template advance<NS>();
+  }
+}
+
+__device__ __forceinline__ void named_bar_sync_softmax() {
+  asm volatile("bar.sync 1, %0;" ::"n"(kNumSoftmaxWarps * 32) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K2a: row statistics
+// ---------------------------------------------------------------------------------------------------
+template <bool kGeo>
+__global__ void __launch_bounds__(kThreads, 1)
+range_stats_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                   const float4* __restrict__ db_xyz, const float4* __restrict__ q_xyz, int N, int M,
+                   int tiles_per_split, float a_sem, float a_geo, float* __restrict__ part_sum,
+                   float* __restrict__ part_max) {
+  constexpr int NS = 4, NX = 4;
+  using L = SmemLayout<NS, 0, NX>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::bars);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::tmem_slot);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * kBlockQ;
+  const int split = blockIdx.y;
+  const int total_tiles = (M + kBlockKeys - 1) / kBlockKeys;
+  const int t_begin = split * tiles_per_split;
+  const int t_end = min(total_tiles, t_begin + tiles_per_split);
+  const int T = t_end - t_begin;
+
+  if (threadIdx.x == 0) {
+    ptx::mbar_init(&bars[L::b_q_full], 1);
+    for (int i = 0; i < NS; ++i) {
+      ptx::mbar_init(&bars[L::b_stage_full + i], 1);
+      ptx::mbar_init(&bars[L::b_stage_empty + i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&bars[L::b_s_full + i], 1);
+      ptx::mbar_init(&bars[L::b_s_empty + i], kNumSoftmaxWarps);
+    }
+    for (int i = 0; i < NX; ++i) {
+      ptx::mbar_init(&bars[L::b_xyz_full + i], 1);
+      ptx::mbar_init(&bars[L::b_xyz_empty + i], kNumSoftmaxWarps);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 9) ptx::tmem_alloc<256>(tmem_slot);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 8) {
+    // ===== TMA producer =====
+    if (lane == 0 && T > 0) {
+      ptx::prefetch_tmap(&tmQ);
+      ptx::prefetch_tmap(&tmK);
+      ptx::mbar_expect_tx(&bars[L::b_q_full], 4 * kChunkBytes);
+      for (int c = 0; c < 4; ++c) ptx::tma_load_2d(smem + L::q + c * kChunkBytes, &tmQ, &bars[L::b_q_full], c * 64, q0);
+      PipeState st, xs;
+      for (int j = 0; j < T; ++j) {
+        const int key0 = (t_begin + j) * kBlockKeys;
+        if (kGeo) {
+          ptx::mbar_wait(&bars[L::b_xyz_empty + xs.idx], xs.phase ^ 1);
+          ptx::mbar_expect_tx(&bars[L::b_xyz_full + xs.idx], kXyzBytes);
+          ptx::bulk_load_1d(smem + L::xyz + xs.idx * kXyzBytes, db_xyz + key0, kXyzBytes, &bars[L::b_xyz_full + xs.idx]);
+          xs.advance<NX>();
+        }
+        produce_keys<L, NS>(smem, bars, st, &tmK, key0);
+      }
+    }
+  } else if (warp == 9) {
+    // ===== MMA issuer =====
+    if (T > 0) {
+      ptx::mbar_wait(&bars[L::b_q_full], 0);
+      PipeState st;
+      for (int j = 0; j < T; ++j) {
+        const int b = j & 1;
+        ptx::mbar_wait(&bars[L::b_s_empty + b], ((j >> 1) & 1) ^ 1);
+        ptx::tc_fence_after();
+        mma_qk<L, NS>(smem, bars, st, tmem_base + b * kBlockKeys, lane);
+        if (lane == 0) ptx::umma_commit(&bars[L::b_s_full + b]);
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===== softmax statistics =====
+    const int grp = warp >> 2, quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const int n = q0 + row;
+    float4 qx = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (kGeo && n < N) qx = q_xyz[n];
+    const float gx = qx.x * a_geo, gy = qx.y * a_geo, gz = qx.z * a_geo;
+    float sum_s = 0.f, sum_g = 0.f, max_s = -2.f, max_g = -2.f;
+    PipeState xs;
+    for (int j = 0; j < T; ++j) {
+      const int b = j & 1;
+      const int key0 = (t_begin + j) * kBlockKeys + grp * 64;
+      ptx::mbar_wait(&bars[L::b_s_full + b], (j >> 1) & 1);
+      ptx::tc_fence_after();
+      uint32_t s0[32], s1[32];
+      const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + b * kBlockKeys + grp * 64;
+      ptx::tmem_ld32(taddr, s0);
+      ptx::tmem_ld32(taddr + 32, s1);
+      ptx::tmem_ld_wait();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&bars[L::b_s_empty + b]);
+      const float4* kxyz = reinterpret_cast<const float4*>(smem + L::xyz + xs.idx * kXyzBytes) + grp * 64;
+      if (kGeo) ptx::mbar_wait(&bars[L::b_xyz_full + xs.idx], xs.phase);
+      const bool tail = key0 + 64 > M;
+#pragma unroll
+      for (int i = 0; i < 64; ++i) {
+        const float s = __uint_as_float(i < 32 ? s0[i] : s1[i - 32]);
+        const bool valid = !tail || (key0 + i < M);
+        float es = ptx::ex2(fmaf(s, a_sem, -a_sem));
+        if (!valid) es = 0.f;
+        sum_s += es;
+        max_s = fmaxf(max_s, valid ? s : -2.f);
+        if (kGeo) {
+          const float4 k = kxyz[i];
+          const float g = fmaf(gx, k.x, fmaf(gy, k.y, fmaf(gz, k.z, -a_geo)));   // a_geo (g - 1)
+          float eg = ptx::ex2(g);
+          if (!valid) eg = 0.f;
+          sum_g += eg;
+          max_g = fmaxf(max_g, valid ? g : -3.0e38f);
+        }
+      }
+      if (kGeo) {
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&bars[L::b_xyz_empty + xs.idx]);
+        xs.advance<NX>();
+      }
+    }
+    // combine the two column groups, write this split's partials
+    float4* red = reinterpret_cast<float4*>(smem + L::red);
+    if (grp == 1) red[row] = make_float4(sum_s, sum_g, max_s, max_g);
+    named_bar_sync_softmax();
+    if (grp == 0 && n < N) {
+      const float4 o = red[row];
+      sum_s += o.x;
+      sum_g += o.y;
+      max_s = fmaxf(max_s, o.z);
+      max_g = fmaxf(max_g, o.w);
+      // max_g holds a_geo (g - 1); store the raw cosine
+      const float raw_g = kGeo ? (max_g / a_geo + 1.f) : 0.f;
+      float2* ps = reinterpret_cast<float2*>(part_sum) + size_t(split) * N + n;
+      float2* pm = reinterpret_cast<float2*>(part_max) + size_t(split) * N + n;
+      *ps = make_float2(sum_s, sum_g);
+      *pm = make_float2(max_s, raw_g);
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 9) ptx::tmem_dealloc<256>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K2b: apply  (O slice = P' . Vt)
+// rowc[n] = {cs, cg, qx*a_geo, qy*a_geo, qz*a_geo, out_scale, -, -}
+// ---------------------------------------------------------------------------------------------------
+template <bool kGeo>
+__global__ void __launch_bounds__(kThreads, 1)
+range_apply_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                   const __grid_constant__ CUtensorMap tmV, const float4* __restrict__ db_xyz,
+                   const float4* __restrict__ rowc, int N, int M, int tiles_per_split, float a_sem,
+                   float* __restrict__ out, size_t out_split_stride) {
+  constexpr int NS = 3, NP = 3, NX = 4;
+  using L = SmemLayout<NS, NP, NX>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::bars);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::tmem_slot);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int slice = blockIdx.x;                 // fastest: the 4 slices of a query tile run together
+  const int q0 = blockIdx.y * kBlockQ;
+  const int split = blockIdx.z;
+  const int total_tiles = (M + kBlockKeys - 1) / kBlockKeys;
+  const int t_begin = split * tiles_per_split;
+  const int t_end = min(total_tiles, t_begin + tiles_per_split);
+  const int T = t_end - t_begin;
+
+  if (threadIdx.x == 0) {
+    ptx::mbar_init(&bars[L::b_q_full], 1);
+    for (int i = 0; i < NS; ++i) {
+      ptx::mbar_init(&bars[L::b_stage_full + i], 1);
+      ptx::mbar_init(&bars[L::b_stage_empty + i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&bars[L::b_s_full + i], 1);
+      ptx::mbar_init(&bars[L::b_s_empty + i], kNumSoftmaxWarps);
+    }
+    for (int i = 0; i < NP; ++i) {
+      ptx::mbar_init(&bars[L::b_p_full + i], 4);
+      ptx::mbar_init(&bars[L::b_p_empty + i], 1);
+    }
+    for (int i = 0; i < NX; ++i) {
+      ptx::mbar_init(&bars[L::b_xyz_full + i], 1);
+      ptx::mbar_init(&bars[L::b_xyz_empty + i], kNumSoftmaxWarps);
+    }
+    ptx::mbar_init(&bars[L::b_o_full], 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 9) ptx::tmem_alloc<512>(tmem_slot);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_o = tmem_base + 2 * kBlockKeys;
+
+  if (warp == 8) {
+    // ===== TMA producer: Q, then K(0), [K(j+1), V(j)]..., V(T-1) in the order the MMA warp consumes =====
+    if (lane == 0 && T > 0) {
+      ptx::prefetch_tmap(&tmQ);
+      ptx::prefetch_tmap(&tmK);
+      ptx::prefetch_tmap(&tmV);
+      ptx::mbar_expect_tx(&bars[L::b_q_full], 4 * kChunkBytes);
+      for (int c = 0; c < 4; ++c) ptx::tma_load_2d(smem + L::q + c * kChunkBytes, &tmQ, &bars[L::b_q_full], c * 64, q0);
+      PipeState st, xs;
+      for (int j = 0; j <= T; ++j) {
+        if (j < T) {
+          const int key0 = (t_begin + j) * kBlockKeys;
+          if (kGeo) {
+            ptx::mbar_wait(&bars[L::b_xyz_empty + xs.idx], xs.phase ^ 1);
+            ptx::mbar_expect_tx(&bars[L::b_xyz_full + xs.idx], kXyzBytes);
+            ptx::bulk_load_1d(smem + L::xyz + xs.idx * kXyzBytes, db_xyz + key0, kXyzBytes,
+                              &bars[L::b_xyz_full + xs.idx]);
+            xs.advance<NX>();
+          }
+          produce_keys<L, NS>(smem, bars, st, &tmK, key0);
+        }
+        if (j >= 1) {
+          const int key0 = (t_begin + j - 1) * kBlockKeys;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            ptx::mbar_wait(&bars[L::b_stage_empty + st.idx], st.phase ^ 1);
+            ptx::mbar_expect_tx(&bars[L::b_stage_full + st.idx], kStageBytes);
+            ptx::tma_load_2d(smem + L::stages + st.idx * kStageBytes, &tmV, &bars[L::b_stage_full + st.idx],
+                             key0 + h * 64, slice * kSliceV);
+            st.advance<NS>();
+          }
+        }
+      }
+    }
+  } else if (warp == 9) {
+    // ===== MMA issuer =====
+    if (T > 0) {
+      constexpr uint32_t idesc_pv = ptx::umma_idesc_f16(kBlockQ, kSliceV);
+      ptx::mbar_wait(&bars[L::b_q_full], 0);
+      PipeState st, ps;
+      for (int j = 0; j <= T; ++j) {
+        if (j < T) {
+          const int b = j & 1;
+          ptx::mbar_wait(&bars[L::b_s_empty + b], ((j >> 1) & 1) ^ 1);
+          ptx::tc_fence_after();
+          mma_qk<L, NS>(smem, bars, st, tmem_base + b * kBlockKeys, lane);
+          if (lane == 0) ptx::umma_commit(&bars[L::b_s_full + b]);
+          __syncwarp();
+        }
+        if (j >= 1) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            ptx::mbar_wait(&bars[L::b_p_full + ps.idx], ps.phase);
+            ptx::mbar_wait(&bars[L::b_stage_full + st.idx], st.phase);
+            ptx::tc_fence_after();
+            if (lane == 0) {
+              const uint32_t a_base = ptx::smem_u32(smem + L::p + ps.idx * kChunkBytes);
+              const uint32_t b_base = ptx::smem_u32(smem + L::stages + st.idx * kStageBytes);
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk) {
+                ptx::umma_f16_ss(tmem_o, ptx::umma_desc_kmajor_sw128(a_base + kk * 32),
+                                 ptx::umma_desc_kmajor_sw128(b_base + kk * 32), idesc_pv,
+                                 (j > 1) || (h | kk) != 0);
+              }
+              ptx::umma_commit(&bars[L::b_stage_empty + st.idx]);
+              ptx::umma_commit(&bars[L::b_p_empty + ps.idx]);
+            }
+            __syncwarp();
+            st.advance<NS>();
+            ps.advance<NP>();
+          }
+        }
+      }
+      if (lane == 0) ptx::umma_commit(&bars[L::b_o_full]);
+      __syncwarp();
+    }
+  } else {
+    // ===== softmax: S (TMEM) -> P' (fp16, swizzled smem) ; then epilogue =====
+    const int grp = warp >> 2, quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const int n = q0 + row;
+    float cs = -INFINITY, cg = -INFINITY, gx = 0.f, gy = 0.f, gz = 0.f, out_scale = 0.f;
+    if (n < N) {
+      const float4 c0 = rowc[2 * n], c1 = rowc[2 * n + 1];
+      cs = c0.x; cg = c0.y; gx = c0.z; gy = c0.w; gz = c1.x; out_scale = c1.y;
+    }
+    // P chunk sequence number of (tile j, group g) is 2 j + g; ring of NP chunks
+    int pidx = grp % NP;
+    uint32_t puse = 0;     // how many times this group's current ring slot sequence wrapped
+    int pseq = grp;
+    PipeState xs;
+    for (int j = 0; j < T; ++j) {
+      const int b = j & 1;
+      const int key0 = (t_begin + j) * kBlockKeys + grp * 64;
+      ptx::mbar_wait(&bars[L::b_s_full + b], (j >> 1) & 1);
+      ptx::tc_fence_after();
+      uint32_t s0[32], s1[32];
+      const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + b * kBlockKeys + grp * 64;
+      ptx::tmem_ld32(taddr, s0);
+      ptx::tmem_ld32(taddr + 32, s1);
+      ptx::tmem_ld_wait();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&bars[L::b_s_empty + b]);
+
+      pidx = pseq % NP;
+      puse = pseq / NP;
+      ptx::mbar_wait(&bars[L::b_p_empty + pidx], (puse & 1) ^ 1);
+      const float4* kxyz = reinterpret_cast<const float4*>(smem + L::xyz + xs.idx * kXyzBytes) + grp * 64;
+      if (kGeo) ptx::mbar_wait(&bars[L::b_xyz_full + xs.idx], xs.phase);
+      const bool tail = key0 + 64 > M;
+      uint8_t* prow = smem + L::p + pidx * kChunkBytes + row * 128;
+#pragma unroll
+      for (int c16 = 0; c16 < 8; ++c16) {
+        uint32_t packed[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float pv[2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int i = c16 * 8 + e * 2 + u;
+            const float s = __uint_as_float(i < 32 ? s0[i] : s1[i - 32]);
+            float p = ptx::ex2(fmaf(s, a_sem, cs));
+            if (kGeo) {
+              const float4 k = kxyz[i];
+              p += ptx::ex2(fmaf(gx, k.x, fmaf(gy, k.y, fmaf(gz, k.z, cg))));
+            }
+            if (tail && key0 + i >= M) p = 0.f;
+            pv[u] = p;
+          }
+          packed[e] = ptx::pack_half2(pv[0], pv[1]);
+        }
+        *reinterpret_cast<uint4*>(prow + ((c16 ^ (row & 7)) << 4)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+      }
+      ptx::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        ptx::mbar_arrive(&bars[L::b_p_full + pidx]);
+        if (kGeo) ptx::mbar_arrive(&bars[L::b_xyz_empty + xs.idx]);
+      }
+      if (kGeo) xs.advance<NX>();
+      pseq += 2;
+    }
+    // ----- epilogue: O (TMEM, 128 lanes x 256 cols) -> global fp32, scaled -----
+    if (T > 0) {
+      ptx::mbar_wait(&bars[L::b_o_full], 0);
+      ptx::tc_fence_after();
+      float* orow = out + size_t(split) * out_split_stride + size_t(n) * 1024 + slice * kSliceV + grp * 128;
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        uint32_t v[32];
+        ptx::tmem_ld32(tmem_o + (uint32_t(quarter * 32) << 16) + grp * 128 + cc * 32, v);
+        ptx::tmem_ld_wait();
+        if (n < N) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            float4 o;
+            o.x = __uint_as_float(v[i]) * out_scale;
+            o.y = __uint_as_float(v[i + 1]) * out_scale;
+            o.z = __uint_as_float(v[i + 2]) * out_scale;
+            o.w = __uint_as_float(v[i + 3]) * out_scale;
+            *reinterpret_cast<float4*>(orow + cc * 32 + i) = o;
+          }
+        }
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 9) ptx::tmem_dealloc<512>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// small helper kernels
+// ---------------------------------------------------------------------------------------------------
+// partials [splits][N][2] -> [N][2]
+__global__ void reduce_stats_kernel(const float2* __restrict__ part_sum, const float2* __restrict__ part_max,
+                                    int N, int splits, float2* __restrict__ sums, float2* __restrict__ maxs) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float2 s = part_sum[n], m = part_max[n];
+  for (int k = 1; k < splits; ++k) {
+    const float2 a = part_sum[size_t(k) * N + n], b = part_max[size_t(k) * N + n];
+    s.x += a.x; s.y += a.y;
+    m.x = fmaxf(m.x, b.x); m.y = fmaxf(m.y, b.y);
+  }
+  sums[n] = s;
+  maxs[n] = m;
+}
+
+// row constants of the apply kernel from the (global) row statistics
+//   sem weight of entry j:  ws 2^(a_s (s_j - 1)) / l_s ,  geo: wg 2^(a_g (g_j - 1)) / l_g   (ws = beta, wg = 1 - beta)
+//   B = upper bound of the largest blended weight; P' = weight * 2^13 / B; out = acc * B / 2^13 / vscale
+__global__ void row_constants_kernel(const float2* __restrict__ sums, const float2* __restrict__ maxs,
+                                     const float4* __restrict__ q_xyz, int N, int geo, float beta, float a_sem,
+                                     float a_geo, float inv_vscale, float4* __restrict__ rowc) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const float2 l = sums[n], m = maxs[n];
+  const float ws = geo ? beta : 1.f, wg = geo ? 1.f - beta : 0.f;
+  const float top_s = ws * exp2f(a_sem * (m.x - 1.f)) / l.x;
+  const float top_g = geo ? wg * exp2f(a_geo * (m.y - 1.f)) / l.y : 0.f;
+  const float B = top_s + top_g;
+  const float C = 8192.f;
+  const float cs = (ws > 0.f) ? -a_sem + log2f(ws * C / (B * l.x)) : -INFINITY;
+  const float cg = (wg > 0.f) ? -a_geo + log2f(wg * C / (B * l.y)) : -INFINITY;
+  float4 q = geo ? q_xyz[n] : make_float4(0.f, 0.f, 0.f, 0.f);
+  rowc[2 * n] = make_float4(cs, cg, q.x * a_geo, q.y * a_geo);
+  rowc[2 * n + 1] = make_float4(q.z * a_geo, B / C * inv_vscale, 0.f, 0.f);
+}
+
+// out[n][:] = sum over splits of part[split][n][:]
+__global__ void reduce_out_kernel(const float4* __restrict__ part, size_t split_stride4, int splits, size_t total4,
+                                  float4* __restrict__ out) {
+  const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total4) return;
+  float4 a = part[i];
+  for (int k = 1; k < splits; ++k) {
+    const float4 b = part[size_t(k) * split_stride4 + i];
+    a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+  }
+  out[i] = a;
+}
+
+int g_smem_configured = 0;
+
+template <class K>
+cudaError_t set_smem(K kernel, int bytes) {
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+}
+
+}  // namespace
+
+namespace rangeb200 {
+
+int retrieval_stats_smem_bytes() { return SmemLayout<4, 0, 4>::dynamic_bytes; }
+int retrieval_apply_smem_bytes() { return SmemLayout<3, 3, 4>::dynamic_bytes; }
+
+cudaError_t launch_stats(const RetrievalArgs& a, float* part_sum, float* part_max, cudaStream_t stream) {
+  const int bytes = retrieval_stats_smem_bytes();
+  cudaError_t e;
+  if ((e = set_smem(range_stats_kernel<true>, bytes)) != cudaSuccess) return e;
+  if ((e = set_smem(range_stats_kernel<false>, bytes)) != cudaSuccess) return e;
+  dim3 grid((a.N + kBlockQ - 1) / kBlockQ, a.splits, 1);
+  if (a.geo)
+    range_stats_kernel<true><<<grid, kThreads, bytes, stream>>>(a.tmQ, a.tmK, a.db_xyz, a.q_xyz, a.N, a.M,
+                                                               a.tiles_per_split, a.a_sem, a.a_geo, part_sum, part_max);
+  else
+    range_stats_kernel<false><<<grid, kThreads, bytes, stream>>>(a.tmQ, a.tmK, a.db_xyz, a.q_xyz, a.N, a.M,
+                                                                a.tiles_per_split, a.a_sem, a.a_geo, part_sum, part_max);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_reduce_stats(const float* part_sum, const float* part_max, int N, int splits, float* sums,
+                                float* maxs, cudaStream_t stream) {
+  reduce_stats_kernel<<<(N + 255) / 256, 256, 0, stream>>>(
+      reinterpret_cast<const float2*>(part_sum), reinterpret_cast<const float2*>(part_max), N, splits,
+      reinterpret_cast<float2*>(sums), reinterpret_cast<float2*>(maxs));
+  return cudaGetLastError();
+}
+
+cudaError_t launch_row_constants(const float* sums, const float* maxs, const float* q_xyz, int N, int geo,
+                                 float beta, float a_sem, float a_geo, float inv_vscale, float* rowc,
+                                 cudaStream_t stream) {
+  row_constants_kernel<<<(N + 255) / 256, 256, 0, stream>>>(
+      reinterpret_cast<const float2*>(sums), reinterpret_cast<const float2*>(maxs),
+      reinterpret_cast<const float4*>(q_xyz), N, geo, beta, a_sem, a_geo, inv_vscale, reinterpret_cast<float4*>(rowc));
+  return cudaGetLastError();
+}
+
+cudaError_t launch_apply(const RetrievalArgs& a, const float* rowc, float* out, size_t out_split_stride,
+                         cudaStream_t stream) {
+  const int bytes = retrieval_apply_smem_bytes();
+  cudaError_t e;
+  if ((e = set_smem(range_apply_kernel<true>, bytes)) != cudaSuccess) return e;
+  if ((e = set_smem(range_apply_kernel<false>, bytes)) != cudaSuccess) return e;
+  dim3 grid(1024 / kSliceV, (a.N + kBlockQ - 1) / kBlockQ, a.splits);
+  if (a.geo)
+    range_apply_kernel<true><<<grid, kThreads, bytes, stream>>>(a.tmQ, a.tmK, a.tmV, a.db_xyz,
+                                                               reinterpret_cast<const float4*>(rowc), a.N, a.M,
+                                                               a.tiles_per_split, a.a_sem, out, out_split_stride);
+  else
+    range_apply_kernel<false><<<grid, kThreads, bytes, stream>>>(a.tmQ, a.tmK, a.tmV, a.db_xyz,
+                                                                reinterpret_cast<const float4*>(rowc), a.N, a.M,
+                                                                a.tiles_per_split, a.a_sem, out, out_split_stride);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_reduce_out(const float* part, size_t split_stride, int splits, size_t total, float* out,
+                              cudaStream_t stream) {
+  const size_t total4 = total / 4;
+  reduce_out_kernel<<<unsigned((total4 + 255) / 256), 256, 0, stream>>>(
+      reinterpret_cast<const float4*>(part), split_stride / 4, splits, total4, reinterpret_cast<float4*>(out));
+  return cudaGetLastError();
+}
+
+}  // namespace rangeb200

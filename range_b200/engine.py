@@ -1,0 +1,154 @@
+"""Device-side engine: owns a range_ctx (C ABI) and the torch tensors it borrows.
+
+PyTorch is plumbing here (device memory, streams); every computation is a kernel of librange_b200.so.
+"""
+import ctypes
+from ctypes import c_int32, c_void_p
+
+import numpy as np
+import torch
+
+from . import _lib
+from .sh_table import build_table
+
+MODE = {"RANGE": _lib.RANGE_MODE_RANGE, "RANGE+": _lib.RANGE_MODE_RANGE_PLUS}
+
+
+def _ptr(t):
+    return c_void_p(t.data_ptr())
+
+
+def _stream():
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class RangeEngine:
+    def __init__(self, device, encoder=None, database=None, L=None):
+        """encoder: dict from checkpoint.load_satclip_location_encoder (or None: SH only with `L`);
+        database: database.DeviceDatabase or None."""
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.RangeError(f"range_b200 runs on CUDA (sm_100a) devices only, got device={device!r}; "
+                                  "there is no CPU path")
+        if not torch.cuda.is_available():
+            raise _lib.RangeError("no CUDA device is available; range_b200 has no CPU path")
+        self.lib = _lib.load()
+        self.index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.device = torch.device("cuda", self.index)
+        ctx = c_void_p()
+        with torch.cuda.device(self.index):
+            _lib.check(self.lib.range_ctx_create(self.index, ctypes.byref(ctx)))
+        self.ctx = ctx
+        self._ws = {}
+        self.db = None
+        self.L = int(encoder["L"]) if encoder is not None else int(L)
+        # spherical-harmonics table
+        t = build_table(self.L)
+        self._tab = dict(pref=torch.from_numpy(t["pref"]).to(self.device),
+                         off=torch.from_numpy(t["off"]).to(self.device),
+                         coef=torch.from_numpy(t["coef"]).to(self.device),
+                         par=torch.from_numpy(t["par"]).to(self.device))
+        _lib.check(self.lib.range_ctx_set_sh_table(self.ctx, self.L, len(t["pref"]), _ptr(self._tab["pref"]),
+                                                   _ptr(self._tab["off"]), _ptr(self._tab["coef"]),
+                                                   _ptr(self._tab["par"])))
+        self.dims = None
+        if encoder is not None:
+            self.set_encoder(encoder)
+        if database is not None:
+            self.set_database(database)
+
+    def __del__(self):
+        try:
+            if getattr(self, "ctx", None):
+                self.lib.range_ctx_destroy(self.ctx)
+                self.ctx = None
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ setup
+    def set_encoder(self, enc, w0_first=30.0, w0_hidden=1.0):
+        self._weights = [(w.to(self.device, torch.float64).contiguous(), b.to(self.device, torch.float64).contiguous())
+                         for w, b in enc["weights"]]
+        n = len(self._weights)
+        dims = (c_int32 * (n + 1))(*[int(d) for d in enc["dims"]])
+        W = (c_void_p * n)(*[w.data_ptr() for w, _ in self._weights])
+        B = (c_void_p * n)(*[b.data_ptr() for _, b in self._weights])
+        _lib.check(self.lib.range_ctx_set_encoder(self.ctx, n, dims, W, B, w0_first, w0_hidden))
+        self.dims = list(enc["dims"])
+
+    def set_database(self, db):
+        _lib.check(self.lib.range_ctx_set_db(self.ctx, db.M, db.Mpad, _ptr(db.Kh), _ptr(db.Vt), _ptr(db.xyz),
+                                             float(db.vscale)))
+        self.db = db
+
+    def _workspace(self, key, nbytes):
+        buf = self._ws.get(key)
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+            self._ws[key] = buf
+        return buf
+
+    # ------------------------------------------------------------------ kernels
+    def sh_features(self, lonlat):
+        """(N,2) fp64 device tensor -> (N, L*L) fp64 (a transposed view of the feature-major buffer)"""
+        lonlat = lonlat.to(self.device, torch.float64).contiguous()
+        N = lonlat.shape[0]
+        ld = (N + 127) // 128 * 128
+        Yt = torch.empty(self.L * self.L, ld, dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.index):
+            _lib.check(self.lib.range_sh_features(self.ctx, N, _ptr(lonlat), _ptr(Yt), ld, _stream()))
+        return Yt[:, :N].t()
+
+    def encode(self, lonlat, q64=None, q16=None, qxyz=None):
+        lonlat = lonlat.to(self.device, torch.float64).contiguous()
+        N = lonlat.shape[0]
+        q64 = torch.empty(N, 256, dtype=torch.float64, device=self.device) if q64 is None else q64
+        q16 = torch.empty(N, 256, dtype=torch.float16, device=self.device) if q16 is None else q16
+        qxyz = torch.empty(N, 4, dtype=torch.float32, device=self.device) if qxyz is None else qxyz
+        with torch.cuda.device(self.index):
+            nbytes = self.lib.range_encode_workspace_bytes(self.ctx, N)
+            ws = self._workspace("enc", nbytes)
+            _lib.check(self.lib.range_encode(self.ctx, N, _ptr(lonlat), _ptr(q64), _ptr(q16), _ptr(qxyz), _ptr(ws),
+                                             ws.numel(), _stream()))
+        return q64, q16, qxyz
+
+    def _ret_ws(self, N):
+        return self._workspace("ret", self.lib.range_retrieve_workspace_bytes(self.ctx, N))
+
+    def retrieve(self, mode, q16, qxyz, temp, geo_temp, beta, O=None):
+        N = q16.shape[0]
+        O = torch.empty(N, 1024, dtype=torch.float32, device=self.device) if O is None else O
+        with torch.cuda.device(self.index):
+            ws = self._ret_ws(N)
+            _lib.check(self.lib.range_retrieve(self.ctx, MODE[mode], N, _ptr(q16), _ptr(qxyz), temp, geo_temp,
+                                               0.0 if beta is None else float(beta), _ptr(O), _ptr(ws), ws.numel(),
+                                               _stream()))
+        return O
+
+    def retrieve_stats(self, mode, q16, qxyz, temp, geo_temp):
+        N = q16.shape[0]
+        sums = torch.empty(N, 2, dtype=torch.float32, device=self.device)
+        maxs = torch.empty(N, 2, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.index):
+            ws = self._ret_ws(N)
+            _lib.check(self.lib.range_retrieve_stats(self.ctx, MODE[mode], N, _ptr(q16), _ptr(qxyz), temp, geo_temp,
+                                                     _ptr(sums), _ptr(maxs), _ptr(ws), ws.numel(), _stream()))
+        return sums, maxs
+
+    def retrieve_apply(self, mode, q16, qxyz, temp, geo_temp, beta, sums, maxs, O=None):
+        N = q16.shape[0]
+        O = torch.empty(N, 1024, dtype=torch.float32, device=self.device) if O is None else O
+        with torch.cuda.device(self.index):
+            ws = self._ret_ws(N)
+            _lib.check(self.lib.range_retrieve_apply(self.ctx, MODE[mode], N, _ptr(q16), _ptr(qxyz), temp, geo_temp,
+                                                     0.0 if beta is None else float(beta), _ptr(sums), _ptr(maxs),
+                                                     _ptr(O), _ptr(ws), ws.numel(), _stream()))
+        return O
+
+    def concat(self, O, q64, out=None, dtype=torch.float64):
+        N = O.shape[0]
+        out = torch.empty(N, 1280, dtype=dtype, device=self.device) if out is None else out
+        code = _lib.RANGE_OUT_F64 if out.dtype == torch.float64 else _lib.RANGE_OUT_F32
+        with torch.cuda.device(self.index):
+            _lib.check(self.lib.range_concat(self.ctx, N, _ptr(O), _ptr(q64), _ptr(out), code, _stream()))
+        return out

@@ -1,0 +1,103 @@
+"""`LocationEncoder` for 'RANGE' / 'RANGE+' - the B200-native counterpart of range/range.py:69-278.
+
+Same constructor contract (an argparse-style namespace with location_model_name, pretrained_path, device,
+range_db, beta), same attributes other code reads (location_feature_dim, args.temp, args.geo_temp,
+args.beta), same forward contract: `model(locs)` with locs (N,2) float64 (lon, lat) degrees returns a
+numpy float64 (N, 1280) array = [retrieved visual feature (1024) | L2-normalised SatCLIP embedding (256)].
+Only the RANGE branches exist here; every other encoder name raises like the reference's final `else`.
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .checkpoint import load_satclip_location_encoder
+from .database import DeviceDatabase
+from .engine import RangeEngine
+
+# one wave of the stats kernel / four of the apply kernel on 148 SMs: 148 query tiles of 128
+DEFAULT_CHUNK = 148 * 128
+
+
+class LocationEncoder(nn.Module):
+    def __init__(self, args):
+        super().__init__()
+        self.args = args
+        self.location_model_name = args.location_model_name
+        if 'RANGE' not in self.location_model_name:
+            raise NotImplementedError(f'{self.location_model_name} not implemented')      # range.py:200
+        if self.location_model_name == 'RANGE':
+            self.args.temp = 15.0                                                          # range.py:103
+            print(f'Using RANGE with temperature {self.args.temp}')
+        elif self.location_model_name == 'RANGE+':
+            self.args.geo_temp = 40.0                                                      # range.py:109
+            self.args.temp = 12.0                                                          # range.py:108
+            print(f'Using RANGE+ with temperatures {self.args.temp} and {self.args.geo_temp}')
+        else:
+            raise ValueError('Unimplemented RANGE model')                                  # range.py:114
+        shard = getattr(args, 'db_shard', None)
+        db = np.load(args.range_db, allow_pickle=True) if isinstance(args.range_db, str) else args.range_db
+        enc = load_satclip_location_encoder(args.pretrained_path) if isinstance(args.pretrained_path, str) \
+            else args.pretrained_path
+        self.location_feature_dim = 1024 + 256                                             # range.py:86
+        self.engine = RangeEngine(args.device, encoder=enc, database=DeviceDatabase(db, args.device, shard=shard))
+        self.chunk = int(getattr(args, 'chunk', DEFAULT_CHUNK))
+        self.group = getattr(args, 'db_group', None)       # torch.distributed group when the DB is M-sharded
+        self._copy_stream = None
+        self.eval()
+
+    # the reference calls model.to(device) after construction (load_model.py:50); tensors live in the engine
+    def _apply(self, fn, recurse=True):
+        return self
+
+    @torch.no_grad()
+    def embed(self, coords, out=None, out_dtype=torch.float32):
+        """Device-resident path: coords (N,2) fp64 on the device -> (N,1280) device tensor."""
+        eng, a = self.engine, self.args
+        q64, q16, qxyz = eng.encode(coords)
+        beta = getattr(a, 'beta', None)
+        geo_temp = float(getattr(a, 'geo_temp', 0.0))
+        if self.group is None:
+            O = eng.retrieve(self.location_model_name, q16, qxyz, a.temp, geo_temp, beta)
+        else:
+            from .distributed import sharded_retrieve
+            O = sharded_retrieve(eng, self.location_model_name, q16, qxyz, a.temp, geo_temp, beta, self.group)
+        return eng.concat(O, q64, out=out, dtype=out_dtype)
+
+    @torch.no_grad()
+    def forward(self, coords):
+        """range.py:206-242.  Returns numpy float64 (N, 1280); chunks are computed on the current stream while
+        the previous chunk's result travels to pinned host memory on a copy stream."""
+        if 'RANGE' not in self.location_model_name:
+            raise NotImplementedError(f'{self.location_model_name} not implemented')
+        eng = self.engine
+        coords = torch.as_tensor(coords)
+        if coords.dim() != 2 or coords.shape[1] != 2:
+            raise ValueError(f'coords must be (N, 2) (lon, lat) degrees, got {tuple(coords.shape)}')
+        N = coords.shape[0]
+        host = torch.empty((N, 1280), dtype=torch.float64, pin_memory=True)
+        if N == 0:
+            return host.numpy()
+        with torch.cuda.device(eng.index):
+            dev_coords = coords.to(eng.device, torch.float64, non_blocking=True)
+            if self._copy_stream is None:
+                self._copy_stream = torch.cuda.Stream(device=eng.device)
+            chunk = min(self.chunk, N)
+            bufs = [torch.empty(chunk, 1280, dtype=torch.float64, device=eng.device) for _ in range(2 if N > chunk else 1)]
+            freed = [None] * len(bufs)
+            cur = torch.cuda.current_stream()
+            for i, lo in enumerate(range(0, N, chunk)):
+                hi = min(N, lo + chunk)
+                k = i % len(bufs)
+                if freed[k] is not None:
+                    cur.wait_event(freed[k])
+                buf = bufs[k][: hi - lo]
+                self.embed(dev_coords[lo:hi], out=buf)
+                ready = torch.cuda.Event()
+                ready.record(cur)
+                self._copy_stream.wait_event(ready)
+                with torch.cuda.stream(self._copy_stream):
+                    host[lo:hi].copy_(buf, non_blocking=True)
+                    freed[k] = torch.cuda.Event()
+                    freed[k].record(self._copy_stream)
+            self._copy_stream.synchronize()
+        return host.numpy()                                                               # range.py:222,240
