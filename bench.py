@@ -1,0 +1,258 @@
+"""Headline benchmark: RANGE+ (beta = 0.5) embeddings/s on a range_db_large-shaped synthetic database.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One "step" = the whole hot path (SH + SIREN encoder -> fused retrieval -> concat) over one batch of
+100 000 queries against a 100 000-entry database (BASELINE.json configs[1]).  `value` times it with the
+queries already in HBM and the (N,1280) result left in HBM; `e2e` times `model(locs)` - the reference's
+public API - from a pinned host tensor to the numpy float64 array it returns.  N > 1: queries are sharded
+(every rank embeds its own 100 000 queries against a replicated database, no data-path collective): weak
+scaling.  --impl reference times the CPU oracle (the reference's algorithm, torch CPU ops, all host
+threads) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_QUERIES = 100_000
+M_DB = 100_000
+H = 512
+BETA = 0.5
+FLOP_PER_PAIR = 2566.0          # 2*256 + 2*3 + 2*1024 (blended-P form)
+METRIC = "RANGE+ embeddings/sec"
+UNIT = "queries/s"
+CPU_SAMPLE_QUERIES = 4000
+
+
+def synthetic_inputs(rank=0):
+    from oracle import range_oracle as O      # synthetic-input generators only (seeded distributions)
+    rng = np.random.default_rng(0)
+    db = dict(locs=O.area_uniform(M_DB, rng),
+              satclip_embeddings=rng.standard_normal((M_DB, 256), dtype=np.float32),
+              image_embeddings=rng.standard_normal((M_DB, 1024), dtype=np.float32))
+    weights = O.siren_init(40, H, 2, 256, seed=0)
+    coords = O.area_uniform(N_QUERIES, np.random.default_rng(1 + rank))
+    return db, weights, coords
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["bf16_tflops_sustained"]), float(d["hbm_gbs"]), "measured"
+    return 1400.0, 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region"""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.t.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = max(mx, float(r[1]))
+                for nm, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_baseline(db, weights, coords, steps=1, warmup=0):
+    """the oracle (= the reference's algorithm, torch CPU ops) on a bounded sample, all host threads"""
+    from oracle import range_oracle as O
+    from range_b200.sh_table import load_entries
+    orc = O.RangeOracle("RANGE+", weights, load_entries(40), db, beta=BETA)
+    c = coords[:CPU_SAMPLE_QUERIES]
+    for _ in range(warmup):
+        orc(c[:500])
+    ts = []
+    for _ in range(steps):
+        t = time.perf_counter()
+        orc(c)
+        ts.append(time.perf_counter() - t)
+    return len(c) / float(np.mean(ts)), float(np.mean(ts))
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    db, weights, coords = synthetic_inputs()
+    torch.set_num_threads(os.cpu_count() or 1)
+    qps, sec = cpu_baseline(db, weights, coords, steps=max(1, args.steps), warmup=min(1, args.warmup))
+    cores = torch.get_num_threads()
+    sample = f"{CPU_SAMPLE_QUERIES} of {N_QUERIES} queries x full {M_DB}-entry DB per step"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"RANGE+ beta={BETA}, M={M_DB} (range_db_large shape), SatCLIP-L40 H={H} random-init",
+                   "sample": sample},
+        "cpu_baseline": {"value": qps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": qps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="range_b200", choices=["range_b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch.distributed as dist
+    from argparse import Namespace
+    from range_b200 import _lib
+    from range_b200.range import LocationEncoder
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    warmup = max(3, args.warmup)
+
+    db, weights, coords = synthetic_inputs(rank)
+    enc = dict(L=40, dims=[1600, H, H, 256], weights=weights)
+    model = LocationEncoder(Namespace(location_model_name="RANGE+", pretrained_path=enc, device=dev, range_db=db,
+                                      beta=BETA))
+    eng = model.engine
+    d_coords = torch.tensor(coords, device=dev)
+    h_coords = torch.tensor(coords).pin_memory()
+    out = torch.empty(N_QUERIES, 1280, dtype=torch.float32, device=dev)
+    q64 = torch.empty(N_QUERIES, 256, dtype=torch.float64, device=dev)
+    q16 = torch.empty(N_QUERIES, 256, dtype=torch.float16, device=dev)
+    qxyz = torch.empty(N_QUERIES, 4, dtype=torch.float32, device=dev)
+    O = torch.empty(N_QUERIES, 1024, dtype=torch.float32, device=dev)
+
+    marks = []
+
+    def step(record=False):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)] if record else None
+        if record: ev[0].record()
+        eng.encode(d_coords, q64, q16, qxyz)
+        if record: ev[1].record()
+        sums, maxs = eng.retrieve_stats("RANGE+", q16, qxyz, 12.0, 40.0)
+        if record: ev[2].record()
+        eng.retrieve_apply("RANGE+", q16, qxyz, 12.0, 40.0, BETA, sums, maxs, O)
+        if record: ev[3].record()
+        eng.concat(O, q64, out=out)
+        if record:
+            ev[4].record()
+            marks.append(ev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        step()
+    barrier()
+    launches0 = _lib.launch_count()
+    with ClockSampler(local) as clocks:
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(args.steps):
+            step(record=True)
+        t1.record()
+        barrier()
+    launches = _lib.launch_count() - launches0
+    ms = t0.elapsed_time(t1)
+    seg = np.array([[e[i].elapsed_time(e[i + 1]) for i in range(4)] for e in marks]).mean(0)   # enc, stats, apply, cat
+
+    # e2e through the public API: pinned host coords -> numpy float64 (N,1280)
+    for _ in range(2):
+        model(h_coords)
+    barrier()
+    w0 = time.perf_counter()
+    for _ in range(args.steps):
+        res = model(h_coords)
+    barrier()
+    e2e_s = (time.perf_counter() - w0)
+    assert res.shape == (N_QUERIES, 1280) and res.dtype == np.float64
+
+    t = torch.tensor([ms, e2e_s * 1e3], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, e2e_ms = float(t[0]), float(t[1])
+    if rank == 0:
+        peak_tf, _, peak_src = peaks()
+        t_k2 = (seg[1] + seg[2]) * 1e-3
+        achieved = FLOP_PER_PAIR * N_QUERIES * M_DB / t_k2 / 1e12
+        line = {
+            "metric": METRIC, "value": world * N_QUERIES * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f16 operands / f32 accumulate (retrieval), f64 (encoder)",
+            "data": "synthetic",
+            "config": {"workload": f"RANGE+ beta={BETA}, {N_QUERIES} queries/GPU x M={M_DB} (range_db_large shape), "
+                                   f"SatCLIP-L40 H={H} random-init", "parallelism": f"query-sharded x{world}, DB replicated",
+                       "l2": "inputs larger than L2 (DB 257 MB fp16 streamed every step; 512 MB output)",
+                       "segments_ms": {"encode": seg[0], "retrieve_stats": seg[1], "retrieve_apply": seg[2], "concat": seg[3]}},
+            "roofline": {"bound": "tensor", "kernel": "range_stats_kernel + range_apply_kernel (fused retrieval, K2)",
+                         "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+                         "peak_source": f"{peak_src} bf16 dense sustained", "traffic": None,
+                         "algorithmic_flop_per_launch_pair": FLOP_PER_PAIR * N_QUERIES * M_DB},
+            "e2e": {"value": world * N_QUERIES * args.steps / (e2e_ms * 1e-3), "unit": UNIT,
+                    "h2d_bytes_per_step": N_QUERIES * 16, "d2h_bytes_per_step": N_QUERIES * 1280 * 8,
+                    "api": "range_b200.load_model(...)(locs) -> numpy float64 (N,1280)"},
+            "gpu_launches": int(launches), "clocks": clocks.summary()}
+        if world == 1 and not args.no_cpu_baseline:
+            torch.set_num_threads(os.cpu_count() or 1)
+            qps, _ = cpu_baseline(db, weights, coords)
+            line["cpu_baseline"] = {"value": qps, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                                    "sample": f"{CPU_SAMPLE_QUERIES} of {N_QUERIES} queries x full {M_DB}-entry DB, 1 pass"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,92 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads and exports every symbol
+include/range_b200.h declares; the host-side API mirrors the reference's argument handling.
+No compute calls (no GPU here)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "range_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(range_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from range_b200 import _lib
+    lib = _lib.load()
+    names = declared_symbols()
+    assert len(names) >= 16
+    for n in names:
+        assert hasattr(lib, n), n
+    assert sorted(_lib.PROTOTYPES) == names       # the ctypes table covers the header exactly
+    assert lib.range_version() == 100
+    assert lib.range_launch_count() == 0
+
+
+def test_errors_without_gpu_are_loud():
+    import torch
+    from range_b200 import _lib
+    from range_b200.engine import RangeEngine
+    with pytest.raises(_lib.RangeError):
+        RangeEngine("cpu", L=40)
+    if not torch.cuda.is_available():
+        with pytest.raises(_lib.RangeError):
+            RangeEngine("cuda", L=40)
+    lib = _lib.load()
+    assert lib.range_ctx_set_db(None, 10, 128, None, None, None, ctypes.c_float(1.0)) == -1
+    assert b"bad database" in lib.range_last_error()
+    assert lib.range_retrieve_workspace_bytes(None, 100) == 0
+
+
+def test_load_model_argument_contract():
+    from range_b200.load_model import load_model
+    with pytest.raises(ValueError, match="pretrained model path"):
+        load_model("RANGE+", None)
+    with pytest.raises(AssertionError, match="db_path is required"):
+        load_model("RANGE", "x.ckpt")
+    with pytest.raises(NotImplementedError):
+        load_model("SatCLIP", "x.ckpt")
+
+
+def test_checkpoint_reader(tmp_path, golden):
+    import torch
+    from range_b200.checkpoint import load_satclip_location_encoder
+    g = golden
+    sd = {"model.visual.junk": torch.zeros(3), "model.logit_scale": torch.ones(())}
+    for i, nm in enumerate(["layers.0", "layers.1", "last_layer"]):
+        sd[f"model.location.nnet.{nm}.weight"] = torch.tensor(g[f"W{i}"])
+        sd[f"model.location.nnet.{nm}.bias"] = torch.tensor(g[f"b{i}"])
+    hp = dict(embed_dim=256, legendre_polys=40, le_type="sphericalharmonics", pe_type="siren",
+              harmonics_calculation="analytic", num_hidden_layers=2, capacity=64, eval_downstream=False,
+              air_temp_data_path=None, election_data_path=None)
+    p = tmp_path / "c.ckpt"
+    torch.save({"hyper_parameters": hp, "state_dict": sd}, p)
+    enc = load_satclip_location_encoder(str(p))
+    assert enc["L"] == 40 and enc["dims"] == [1600, 64, 64, 256]
+    assert all(w.dtype == torch.float64 for w, _ in enc["weights"])
+    hp2 = dict(hp)
+    hp2.pop("eval_downstream")                 # the reference pops these keys unconditionally (load.py:5-7)
+    torch.save({"hyper_parameters": hp2, "state_dict": sd}, p)
+    with pytest.raises(KeyError):
+        load_satclip_location_encoder(str(p))
+    hp3 = dict(hp, harmonics_calculation="closed-form")
+    torch.save({"hyper_parameters": hp3, "state_dict": sd}, p)
+    with pytest.raises(NotImplementedError):
+        load_satclip_location_encoder(str(p))
+
+
+def test_database_preparation_matches_reference_rules():
+    import numpy as np
+    from oracle import range_oracle as O
+    from range_b200.database import prepare_reference_arrays
+    db = O.synthetic_db(300, seed=9)
+    K, V, xyz = prepare_reference_arrays(db)
+    Kr, Vr, xr = O.prepare_db(db["locs"], db["satclip_embeddings"], db["image_embeddings"])
+    assert K.dtype == np.float32 and xyz.dtype == np.float32
+    assert np.array_equal(K, Kr) and np.array_equal(V, Vr) and np.array_equal(xyz, xr)
+    assert np.allclose(np.linalg.norm(K, axis=1), 1, atol=1e-6)
