@@ -20,6 +20,8 @@
 // warp 8 TMA producer, warp 9 MMA issuer + TMEM allocator.
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
+#include <type_traits>
 #include <cuda.h>
 #include <cuda_runtime.h>
 
@@ -224,26 +226,29 @@ range_stats_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&bars[L::b_s_empty + b]);
-      const float4* kxyz = reinterpret_cast<const float4*>(smem + L::xyz + xs.idx * kXyzBytes) + grp * 64;
+      const uint32_t kxyz = ptx::smem_u32(smem + L::xyz + xs.idx * kXyzBytes) + grp * 64 * 16;
       if (kGeo) ptx::mbar_wait(&bars[L::b_xyz_full + xs.idx], xs.phase);
-      const bool tail = key0 + 64 > M;
+      const int nvalid = M - key0;            // >= 64 except in the last tile
+      auto body = [&](auto masked) {
 #pragma unroll
-      for (int i = 0; i < 64; ++i) {
-        const float s = __uint_as_float(i < 32 ? s0[i] : s1[i - 32]);
-        const bool valid = !tail || (key0 + i < M);
-        float es = ptx::ex2(fmaf(s, a_sem, -a_sem));
-        if (!valid) es = 0.f;
-        sum_s += es;
-        max_s = fmaxf(max_s, valid ? s : -2.f);
-        if (kGeo) {
-          const float4 k = kxyz[i];
-          const float g = fmaf(gx, k.x, fmaf(gy, k.y, fmaf(gz, k.z, -a_geo)));   // a_geo (g - 1)
-          float eg = ptx::ex2(g);
-          if (!valid) eg = 0.f;
-          sum_g += eg;
-          max_g = fmaxf(max_g, valid ? g : -3.0e38f);
+        for (int i = 0; i < 64; ++i) {
+          const float s = __uint_as_float(i < 32 ? s0[i] : s1[i - 32]);
+          const bool valid = !decltype(masked)::value || (i < nvalid);
+          float es = ptx::ex2(fmaf(s, a_sem, -a_sem));
+          if (!valid) es = 0.f;
+          sum_s += es;
+          max_s = fmaxf(max_s, valid ? s : -2.f);
+          if (kGeo) {
+            const float4 k = ptx::lds_f4(kxyz + i * 16);
+            const float g = fmaf(gx, k.x, fmaf(gy, k.y, fmaf(gz, k.z, -a_geo)));   // a_geo (g - 1)
+            float eg = ptx::ex2(g);
+            if (!valid) eg = 0.f;
+            sum_g += eg;
+            max_g = fmaxf(max_g, valid ? g : -3.0e38f);
+          }
         }
-      }
+      };
+      if (nvalid >= 64) body(std::false_type{}); else body(std::true_type{});
       if (kGeo) {
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&bars[L::b_xyz_empty + xs.idx]);
@@ -282,7 +287,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 range_apply_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const float4* __restrict__ db_xyz,
                    const float4* __restrict__ rowc, int N, int M, int tiles_per_split, float a_sem,
-                   float* __restrict__ out, size_t out_split_stride) {
+                   float* __restrict__ out, size_t out_split_stride, int dbg) {
   constexpr int NS = 3, NP = 3, NX = 4;
   using L = SmemLayout<NS, NP, NX>;
   extern __shared__ uint8_t smem_raw[];
@@ -348,7 +353,7 @@ range_apply_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           }
           produce_keys<L, NS>(smem, bars, st, &tmK, key0);
         }
-        if (j >= 1) {
+        if (j >= 1 && !(dbg & 2)) {
           const int key0 = (t_begin + j - 1) * kBlockKeys;
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
@@ -370,7 +375,7 @@ range_apply_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       for (int j = 0; j <= T; ++j) {
         if (j < T) {
           const int b = j & 1;
-          ptx::mbar_wait(&bars[L::b_s_empty + b], ((j >> 1) & 1) ^ 1);
+          if (!(dbg & 1)) ptx::mbar_wait(&bars[L::b_s_empty + b], ((j >> 1) & 1) ^ 1);
           ptx::tc_fence_after();
           mma_qk<L, NS>(smem, bars, st, tmem_base + b * kBlockKeys, lane);
           if (lane == 0) ptx::umma_commit(&bars[L::b_s_full + b]);
@@ -379,23 +384,23 @@ range_apply_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         if (j >= 1) {
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
-            ptx::mbar_wait(&bars[L::b_p_full + ps.idx], ps.phase);
-            ptx::mbar_wait(&bars[L::b_stage_full + st.idx], st.phase);
+            if (!(dbg & 1)) ptx::mbar_wait(&bars[L::b_p_full + ps.idx], ps.phase);
+            if (!(dbg & 2)) ptx::mbar_wait(&bars[L::b_stage_full + st.idx], st.phase);
             ptx::tc_fence_after();
             if (lane == 0) {
               const uint32_t a_base = ptx::smem_u32(smem + L::p + ps.idx * kChunkBytes);
-              const uint32_t b_base = ptx::smem_u32(smem + L::stages + st.idx * kStageBytes);
+              const uint32_t b_base = ptx::smem_u32(smem + L::stages + (dbg & 2 ? 0 : st.idx) * kStageBytes);
 #pragma unroll
               for (int kk = 0; kk < 4; ++kk) {
                 ptx::umma_f16_ss(tmem_o, ptx::umma_desc_kmajor_sw128(a_base + kk * 32),
                                  ptx::umma_desc_kmajor_sw128(b_base + kk * 32), idesc_pv,
                                  (j > 1) || (h | kk) != 0);
               }
-              ptx::umma_commit(&bars[L::b_stage_empty + st.idx]);
+              if (!(dbg & 2)) ptx::umma_commit(&bars[L::b_stage_empty + st.idx]);
               ptx::umma_commit(&bars[L::b_p_empty + ps.idx]);
             }
             __syncwarp();
-            st.advance<NS>();
+            if (!(dbg & 2)) st.advance<NS>();
             ps.advance<NP>();
           }
         }
@@ -403,7 +408,7 @@ range_apply_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       if (lane == 0) ptx::umma_commit(&bars[L::b_o_full]);
       __syncwarp();
     }
-  } else {
+  } else if (!(dbg & 1)) {
     // ===== softmax: S (TMEM) -> P' (fp16, swizzled smem) ; then epilogue =====
     const int grp = warp >> 2, quarter = warp & 3;
     const int row = quarter * 32 + lane;
@@ -435,32 +440,35 @@ range_apply_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       pidx = pseq % NP;
       puse = pseq / NP;
       ptx::mbar_wait(&bars[L::b_p_empty + pidx], (puse & 1) ^ 1);
-      const float4* kxyz = reinterpret_cast<const float4*>(smem + L::xyz + xs.idx * kXyzBytes) + grp * 64;
+      const uint32_t kxyz = ptx::smem_u32(smem + L::xyz + xs.idx * kXyzBytes) + grp * 64 * 16;
       if (kGeo) ptx::mbar_wait(&bars[L::b_xyz_full + xs.idx], xs.phase);
-      const bool tail = key0 + 64 > M;
-      uint8_t* prow = smem + L::p + pidx * kChunkBytes + row * 128;
+      const int nvalid = M - key0;            // >= 64 except in the last tile
+      const uint32_t prow = ptx::smem_u32(smem + L::p + pidx * kChunkBytes + row * 128);
+      auto body = [&](auto masked) {
 #pragma unroll
-      for (int c16 = 0; c16 < 8; ++c16) {
-        uint32_t packed[4];
+        for (int c16 = 0; c16 < 8; ++c16) {
+          uint32_t packed[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          float pv[2];
+          for (int e = 0; e < 4; ++e) {
+            float pv[2];
 #pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const int i = c16 * 8 + e * 2 + u;
-            const float s = __uint_as_float(i < 32 ? s0[i] : s1[i - 32]);
-            float p = ptx::ex2(fmaf(s, a_sem, cs));
-            if (kGeo) {
-              const float4 k = kxyz[i];
-              p += ptx::ex2(fmaf(gx, k.x, fmaf(gy, k.y, fmaf(gz, k.z, cg))));
+            for (int u = 0; u < 2; ++u) {
+              const int i = c16 * 8 + e * 2 + u;
+              const float s = __uint_as_float(i < 32 ? s0[i] : s1[i - 32]);
+              float p = ptx::ex2(fmaf(s, a_sem, cs));
+              if (kGeo) {
+                const float4 k = ptx::lds_f4(kxyz + i * 16);
+                p += ptx::ex2(fmaf(gx, k.x, fmaf(gy, k.y, fmaf(gz, k.z, cg))));
+              }
+              if (decltype(masked)::value && i >= nvalid) p = 0.f;
+              pv[u] = p;
             }
-            if (tail && key0 + i >= M) p = 0.f;
-            pv[u] = p;
+            packed[e] = ptx::pack_half2(pv[0], pv[1]);
           }
-          packed[e] = ptx::pack_half2(pv[0], pv[1]);
+          ptx::sts_u4(prow + ((c16 ^ (row & 7)) << 4), packed[0], packed[1], packed[2], packed[3]);
         }
-        *reinterpret_cast<uint4*>(prow + ((c16 ^ (row & 7)) << 4)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-      }
+      };
+      if (nvalid >= 64) body(std::false_type{}); else body(std::true_type{});
       ptx::fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
@@ -604,14 +612,15 @@ cudaError_t launch_apply(const RetrievalArgs& a, const float* rowc, float* out, 
   if ((e = set_smem(range_apply_kernel<true>, bytes)) != cudaSuccess) return e;
   if ((e = set_smem(range_apply_kernel<false>, bytes)) != cudaSuccess) return e;
   dim3 grid(1024 / kSliceV, (a.N + kBlockQ - 1) / kBlockQ, a.splits);
+  static const int dbg = getenv("RANGE_DBG") ? atoi(getenv("RANGE_DBG")) : 0;   // timing experiments only
   if (a.geo)
     range_apply_kernel<true><<<grid, kThreads, bytes, stream>>>(a.tmQ, a.tmK, a.tmV, a.db_xyz,
                                                                reinterpret_cast<const float4*>(rowc), a.N, a.M,
-                                                               a.tiles_per_split, a.a_sem, out, out_split_stride);
+                                                               a.tiles_per_split, a.a_sem, out, out_split_stride, dbg);
   else
     range_apply_kernel<false><<<grid, kThreads, bytes, stream>>>(a.tmQ, a.tmK, a.tmV, a.db_xyz,
                                                                 reinterpret_cast<const float4*>(rowc), a.N, a.M,
-                                                                a.tiles_per_split, a.a_sem, out, out_split_stride);
+                                                                a.tiles_per_split, a.a_sem, out, out_split_stride, dbg);
   return cudaGetLastError();
 }
 

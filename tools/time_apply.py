@@ -1,0 +1,30 @@
+"""time the retrieval kernels at the bench workload (optionally under RANGE_DBG experiments)"""
+import os, sys
+import numpy as np, torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
+from oracle import range_oracle as O
+from range_b200.engine import RangeEngine
+from range_b200.database import DeviceDatabase
+dev = "cuda:0"
+M = int(os.environ.get("M", 100_000)); N = int(os.environ.get("N", 100_000))
+rng = np.random.default_rng(0)
+db = dict(locs=O.area_uniform(M, rng), satclip_embeddings=rng.standard_normal((M, 256), dtype=np.float32),
+          image_embeddings=rng.standard_normal((M, 1024), dtype=np.float32))
+eng = RangeEngine(dev, L=40, database=DeviceDatabase(db, dev))
+q = torch.randn(N, 256, device=dev); q = (q / q.norm(dim=1, keepdim=True)).half()
+c = torch.tensor(O.area_uniform(N, np.random.default_rng(1)))
+xyz = torch.zeros(N, 4); xyz[:, :3] = torch.tensor(O.rad_to_cart(c.numpy() * np.pi / 180)).float(); xyz = xyz.to(dev)
+def timeit(fn, reps=3):
+    fn(); torch.cuda.synchronize(); ts = []
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record(); torch.cuda.synchronize(); ts.append(a.elapsed_time(b))
+    return min(ts)
+sums, maxs = eng.retrieve_stats("RANGE+", q, xyz, 12.0, 40.0)
+t_st = timeit(lambda: eng.retrieve_stats("RANGE+", q, xyz, 12.0, 40.0))
+t_ap = timeit(lambda: eng.retrieve_apply("RANGE+", q, xyz, 12.0, 40.0, 0.5, sums, maxs))
+s2, m2 = eng.retrieve_stats("RANGE", q, xyz, 15.0, 0.0)
+t_st_r = timeit(lambda: eng.retrieve_stats("RANGE", q, xyz, 15.0, 0.0))
+t_ap_r = timeit(lambda: eng.retrieve_apply("RANGE", q, xyz, 15.0, 0.0, None, s2, m2))
+fl = 2566.0 * N * M
+print(f"DBG={os.environ.get('RANGE_DBG','0')} N={N} M={M}: RANGE+ stats {t_st:.2f} apply {t_ap:.2f} ms ({fl/((t_st+t_ap)*1e-3)/1364.5e12:.3f} of peak) | RANGE stats {t_st_r:.2f} apply {t_ap_r:.2f} ms")
