@@ -6,6 +6,7 @@
 #include <vector>
 
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <cudaTypedefs.h>
 
@@ -79,7 +80,7 @@ struct range_ctx {
   const void* Vt = nullptr;
   const float* xyz = nullptr;
   float vscale = 1.f;
-  CUtensorMap tmK, tmV;
+  CUtensorMap tmK128, tmV;
 };
 
 namespace {
@@ -120,15 +121,17 @@ int fill_args(range_ctx* c, int mode, int64_t N, const void* q16, const float* q
   if (N <= 0 || N > (int64_t(1) << 30)) return fail(RANGE_ERR_INVALID, "N out of range");
   int r = make_tmap(&a->tmQ, q16, uint64_t(N), kDimK, kBlockQ);
   if (r) return r;
-  a->tmK = c->tmK;
+  a->tmK128 = c->tmK128;
   a->tmV = c->tmV;
+  a->q16 = reinterpret_cast<const __half*>(q16);
   a->db_xyz = reinterpret_cast<const float4*>(c->xyz);
   a->q_xyz = reinterpret_cast<const float4*>(qxyz);
   a->N = int(N);
   a->M = int(c->M);
   a->geo = mode == RANGE_MODE_RANGE_PLUS;
-  a->splits = p.splits;
-  a->tiles_per_split = p.tiles_per_split;
+  a->stats_splits = a->apply_splits = p.splits;
+  a->stats_tiles_per_split = p.tiles_per_split;
+  a->apply_tiles_per_split = p.tiles_per_split;
   const float log2e = 1.4426950408889634f;
   a->a_sem = temp * log2e;
   a->a_geo = geo_temp * log2e;
@@ -142,6 +145,8 @@ extern "C" {
 const char* range_last_error(void) { return g_err; }
 int range_version(void) { return 100; }
 int64_t range_launch_count(void) { return g_launches.load(); }
+// not in the public header: developer hook used by tools/time_apply.py
+void range_debug_set_profile_buffer(void* device_buffer) { set_profile_buffer(reinterpret_cast<long long*>(device_buffer)); }
 
 int range_ctx_create(int device, range_ctx** out) {
   if (!out) return fail(RANGE_ERR_INVALID, "out is null");
@@ -198,7 +203,7 @@ int range_ctx_set_db(range_ctx* c, int64_t M, int64_t Mpad, const void* Kh, cons
     return fail(RANGE_ERR_INVALID, "bad database arguments (M=%lld, Mpad=%lld)", (long long)M, (long long)Mpad);
   if (M > (int64_t(1) << 30)) return fail(RANGE_ERR_UNSUPPORTED, "M too large");
   CUDA_TRY(cudaSetDevice(c->device));
-  int r = make_tmap(&c->tmK, Kh, uint64_t(Mpad), kDimK, kBlockKeys);
+  int r = make_tmap(&c->tmK128, Kh, uint64_t(Mpad), kDimK, 128);
   if (r) return r;
   r = make_tmap(&c->tmV, Vt, kDimV, uint64_t(Mpad), 256);
   if (r) return r;

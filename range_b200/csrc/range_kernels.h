@@ -3,6 +3,7 @@
 #include <cstddef>
 #include <cstdint>
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 namespace rangeb200 {
@@ -35,14 +36,19 @@ cudaError_t launch_concat(const float* O, const double* q64, int N, int DO, int 
 
 // ---- K2: retrieval (retrieval.cu) ---------------------------------------------------------------
 struct RetrievalArgs {
-  CUtensorMap tmQ, tmK, tmV;
+  CUtensorMap tmQ;      // queries, box [128 rows x 64 dims]
+  CUtensorMap tmK128;   // keys, box [128 entries x 64 dims]
+  CUtensorMap tmV;      // values^T, box [256 dims x 64 entries]
+  const __half* q16;
   const float4* db_xyz;
   const float4* q_xyz;
   int N, M;
   int geo;
-  int splits, tiles_per_split;
+  int stats_splits, stats_tiles_per_split;   // 128-entry tiles
+  int apply_splits, apply_tiles_per_split;   // 128-entry tiles
   float a_sem, a_geo;   // temperature * log2(e)
 };
+void set_profile_buffer(long long* device_buffer_of_64);   // debug: wait-cycle accounting of the apply kernel
 int retrieval_stats_smem_bytes();
 int retrieval_apply_smem_bytes();
 cudaError_t launch_stats(const RetrievalArgs& a, float* part_sum, float* part_max, cudaStream_t s);

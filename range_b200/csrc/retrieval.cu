@@ -14,9 +14,15 @@
 //                        largest entry is <= 2^13 (fp16 range) using the row statistics, then
 //                        O(128 x 256 slice) += P' . Vt  on the tensor cores; epilogue rescales.
 //
-// CTA = 128 queries x (apply: one 256-wide slice of the 1024 value dims - TMEM holds 512 fp32 columns:
-// 2 x 128 for the double-buffered S tile + 256 for O).  Warp roles: warps 0-7 softmax/epilogue (two
-// groups of 4; warp w owns TMEM lanes 32 (w%4)..+31, group w/4 owns key columns 64 (w/4)..+63 of a tile),
+// Shared-memory bandwidth (128 B/clk/SM, shared by TMA writes, UMMA operand reads and LDS/STS) is scarce
+// (profiles/r1a_summary.md), so P' never touches it: the softmax warps write it with tcgen05.st over the S
+// columns it was computed from (S fp32 -> P' fp16 in place) and P.V runs in TS mode (A operand from TMEM).
+// The stats kernel keeps Q in TMEM as well (TS-mode Q.K^T).
+//
+// TMEM (512 columns): apply  [0,128) S/P buf 0 | [128,256) S/P buf 1 | [256,512) O slice    (Q in smem)
+//                     stats  [0,128) Q | [128,256) S buf 0 | [256,384) S buf 1
+// CTA = 128 queries (x one 256-wide slice of the 1024 value dims for apply).  Warp roles: warps 0-7
+// softmax/epilogue (warp w owns TMEM lanes 32 (w%4)..+31, group w/4 owns half of a tile's key columns),
 // warp 8 TMA producer, warp 9 MMA issuer + TMEM allocator.
 #include <cstdint>
 #include <cstdio>
@@ -30,38 +36,31 @@
 
 namespace {
 
-constexpr int kBlockQ = 128;      // queries per CTA (UMMA M)
-constexpr int kBlockKeys = 128;   // database entries per S tile (UMMA N of Q.K^T)
-constexpr int kDimK = 256;        // key dim
-constexpr int kSliceV = 256;      // value dims per CTA (UMMA N of P.V)
-constexpr int kChunkBytes = 128 * 128;  // [128 rows x 64 fp16] SWIZZLE_128B tile
-constexpr int kStageBytes = 2 * kChunkBytes;
-constexpr int kXyzBytes = kBlockKeys * 16;
+constexpr int kBlockQ = 128;        // queries per CTA (UMMA M)
+constexpr int kSliceV = 256;        // value dims per CTA (UMMA N of P.V)
+constexpr int kStageBytes = 32768;  // one pipeline stage: a [.. x 64 fp16] SWIZZLE_128B tile set
 constexpr int kNumSoftmaxWarps = 8;
 constexpr int kThreads = (kNumSoftmaxWarps + 2) * 32;
+constexpr uint32_t kTmemQ = 0;      // column offsets
+constexpr uint32_t kTmemS = 128;
 
-template <int NS, int NP, int NX>
+template <int NS, int NX, int kXyzBytes>
 struct SmemLayout {
-  static constexpr int q = 0;
-  static constexpr int stages = q + 4 * kChunkBytes;
-  static constexpr int p = stages + NS * kStageBytes;
-  static constexpr int xyz = p + NP * kChunkBytes;
+  static constexpr int stages = 0;
+  static constexpr int xyz = stages + NS * kStageBytes;
   static constexpr int bars = xyz + NX * kXyzBytes;
-  // barrier slots (8 B each)
-  static constexpr int b_q_full = 0;
-  static constexpr int b_stage_full = 1;
+  static constexpr int b_stage_full = 0;
   static constexpr int b_stage_empty = b_stage_full + NS;
   static constexpr int b_s_full = b_stage_empty + NS;
-  static constexpr int b_s_empty = b_s_full + 2;
-  static constexpr int b_p_full = b_s_empty + 2;
-  static constexpr int b_p_empty = b_p_full + (NP ? NP : 1);
-  static constexpr int b_xyz_full = b_p_empty + (NP ? NP : 1);
+  static constexpr int b_s_empty = b_s_full + 2;      // stats only
+  static constexpr int b_p_full = b_s_empty + 2;      // apply only
+  static constexpr int b_xyz_full = b_p_full + 2;
   static constexpr int b_xyz_empty = b_xyz_full + NX;
   static constexpr int b_o_full = b_xyz_empty + NX;
   static constexpr int n_bars = b_o_full + 1;
   static constexpr int tmem_slot = bars + n_bars * 8;
   static constexpr int red = (tmem_slot + 16 + 15) / 16 * 16;  // stats cross-group reduction scratch
-  static constexpr int total = red + 2 * kBlockQ * 16;
+  static constexpr int total = red + kBlockQ * 16;
   static constexpr int dynamic_bytes = total + 1024;  // slack for the manual 1024-B alignment
 };
 
@@ -77,64 +76,43 @@ struct PipeState {
   }
 };
 
-// ---------------------------------------------------------------------------------------------------
-// shared producer / MMA building blocks
-// ---------------------------------------------------------------------------------------------------
-template <class L, int NS>
-__device__ __forceinline__ void produce_keys(uint8_t* smem, uint64_t* bars, PipeState& st, const CUtensorMap* tmK,
-                                             int key0) {
-#pragma unroll
-  for (int half = 0; half < 2; ++half) {
-    ptx::mbar_wait(&bars[L::b_stage_empty + st.idx], st.phase ^ 1);
-    uint8_t* dst = smem + L::stages + st.idx * kStageBytes;
-    ptx::mbar_expect_tx(&bars[L::b_stage_full + st.idx], kStageBytes);
-    ptx::tma_load_2d(dst, tmK, &bars[L::b_stage_full + st.idx], (2 * half) * 64, key0);
-    ptx::tma_load_2d(dst + kChunkBytes, tmK, &bars[L::b_stage_full + st.idx], (2 * half + 1) * 64, key0);
-    st.template advance<NS>();
-  }
-}
-
-template <class L, int NS>
-__device__ __forceinline__ void mma_qk(uint8_t* smem, uint64_t* bars, PipeState& st, uint32_t tmem_s, int lane) {
-  constexpr uint32_t idesc = ptx::umma_idesc_f16(kBlockQ, kBlockKeys);
-#pragma unroll
-  for (int half = 0; half < 2; ++half) {
-    ptx::mbar_wait(&bars[L::b_stage_full + st.idx], st.phase);
-    ptx::tc_fence_after();
-    if (lane == 0) {
-      const uint32_t b_base = ptx::smem_u32(smem + L::stages + st.idx * kStageBytes);
-      const uint32_t a_base = ptx::smem_u32(smem + L::q + (2 * half) * kChunkBytes);
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-          const uint64_t a = ptx::umma_desc_kmajor_sw128(a_base + c * kChunkBytes + kk * 32);
-          const uint64_t b = ptx::umma_desc_kmajor_sw128(b_base + c * kChunkBytes + kk * 32);
-          ptx::umma_f16_ss(tmem_s, a, b, idesc, (half | c | kk) != 0);
-        }
-      }
-      ptx::umma_commit(&bars[L::b_stage_empty + st.idx]);
-    }
-    __syncwarp();
-    st.template advance<NS>();
-  }
-}
-
 __device__ __forceinline__ void named_bar_sync_softmax() {
   asm volatile("bar.sync 1, %0;" ::"n"(kNumSoftmaxWarps * 32) : "memory");
 }
 
+// Q tile (rows q0..q0+127 of q16, 256 halves each) -> TMEM columns [kTmemQ, kTmemQ+128): lane = row,
+// column = dim / 2 (two fp16 per 32-bit column) - the A-operand layout of kind::f16 for M = 128.
+// Warps 0-7: warp w writes lanes 32 (w%4).., group w/4 the dims [128 g, 128 g + 128).
+__device__ __forceinline__ void load_q_to_tmem(const __half* __restrict__ q16, int q0, int N, uint32_t tmem_base,
+                                               int warp, int lane) {
+  const int grp = warp >> 2, quarter = warp & 3;
+  const int n = q0 + quarter * 32 + lane;
+  const uint4* src = reinterpret_cast<const uint4*>(q16 + size_t(n < N ? n : 0) * 256 + grp * 128);
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    uint32_t v[32];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      uint4 x = make_uint4(0u, 0u, 0u, 0u);
+      if (n < N) x = __ldg(src + half * 8 + i);
+      v[4 * i] = x.x; v[4 * i + 1] = x.y; v[4 * i + 2] = x.z; v[4 * i + 3] = x.w;
+    }
+    ptx::tmem_st32(tmem_base + (uint32_t(quarter * 32) << 16) + kTmemQ + grp * 64 + half * 32, v);
+  }
+  ptx::tmem_st_wait();
+}
+
 // ---------------------------------------------------------------------------------------------------
-// K2a: row statistics
+// K2a: row statistics.  Tile = 128 entries = two 32 KB stages (dims 0-127 | 128-255).
 // ---------------------------------------------------------------------------------------------------
 template <bool kGeo>
 __global__ void __launch_bounds__(kThreads, 1)
-range_stats_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+range_stats_kernel(const __grid_constant__ CUtensorMap tmK, const __half* __restrict__ q16,
                    const float4* __restrict__ db_xyz, const float4* __restrict__ q_xyz, int N, int M,
                    int tiles_per_split, float a_sem, float a_geo, float* __restrict__ part_sum,
                    float* __restrict__ part_max) {
-  constexpr int NS = 4, NX = 4;
-  using L = SmemLayout<NS, 0, NX>;
+  constexpr int NS = 6, NX = 4, kKeys = 128, kXyzBytes = kKeys * 16;
+  using L = SmemLayout<NS, NX, kXyzBytes>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::bars);
@@ -143,13 +121,12 @@ range_stats_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * kBlockQ;
   const int split = blockIdx.y;
-  const int total_tiles = (M + kBlockKeys - 1) / kBlockKeys;
+  const int total_tiles = (M + kKeys - 1) / kKeys;
   const int t_begin = split * tiles_per_split;
   const int t_end = min(total_tiles, t_begin + tiles_per_split);
   const int T = t_end - t_begin;
 
   if (threadIdx.x == 0) {
-    ptx::mbar_init(&bars[L::b_q_full], 1);
     for (int i = 0; i < NS; ++i) {
       ptx::mbar_init(&bars[L::b_stage_full + i], 1);
       ptx::mbar_init(&bars[L::b_stage_empty + i], 1);
@@ -164,44 +141,67 @@ range_stats_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
     ptx::fence_mbar_init();
   }
-  if (warp == 9) ptx::tmem_alloc<256>(tmem_slot);
+  if (warp == 9) ptx::tmem_alloc<512>(tmem_slot);
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (warp < kNumSoftmaxWarps) load_q_to_tmem(q16, q0, N, tmem_base, warp, lane);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
 
   if (warp == 8) {
     // ===== TMA producer =====
-    if (lane == 0 && T > 0) {
-      ptx::prefetch_tmap(&tmQ);
+    if (lane == 0) {
       ptx::prefetch_tmap(&tmK);
-      ptx::mbar_expect_tx(&bars[L::b_q_full], 4 * kChunkBytes);
-      for (int c = 0; c < 4; ++c) ptx::tma_load_2d(smem + L::q + c * kChunkBytes, &tmQ, &bars[L::b_q_full], c * 64, q0);
       PipeState st, xs;
       for (int j = 0; j < T; ++j) {
-        const int key0 = (t_begin + j) * kBlockKeys;
+        const int key0 = (t_begin + j) * kKeys;
         if (kGeo) {
           ptx::mbar_wait(&bars[L::b_xyz_empty + xs.idx], xs.phase ^ 1);
           ptx::mbar_expect_tx(&bars[L::b_xyz_full + xs.idx], kXyzBytes);
           ptx::bulk_load_1d(smem + L::xyz + xs.idx * kXyzBytes, db_xyz + key0, kXyzBytes, &bars[L::b_xyz_full + xs.idx]);
           xs.advance<NX>();
         }
-        produce_keys<L, NS>(smem, bars, st, &tmK, key0);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          ptx::mbar_wait(&bars[L::b_stage_empty + st.idx], st.phase ^ 1);
+          uint8_t* dst = smem + L::stages + st.idx * kStageBytes;
+          ptx::mbar_expect_tx(&bars[L::b_stage_full + st.idx], kStageBytes);
+          ptx::tma_load_2d(dst, &tmK, &bars[L::b_stage_full + st.idx], (2 * half) * 64, key0);
+          ptx::tma_load_2d(dst + 16384, &tmK, &bars[L::b_stage_full + st.idx], (2 * half + 1) * 64, key0);
+          st.advance<NS>();
+        }
       }
     }
   } else if (warp == 9) {
-    // ===== MMA issuer =====
-    if (T > 0) {
-      ptx::mbar_wait(&bars[L::b_q_full], 0);
-      PipeState st;
-      for (int j = 0; j < T; ++j) {
-        const int b = j & 1;
-        ptx::mbar_wait(&bars[L::b_s_empty + b], ((j >> 1) & 1) ^ 1);
+    // ===== MMA issuer: S[b] = Q (TMEM) . K^T =====
+    constexpr uint32_t idesc = ptx::umma_idesc_f16(kBlockQ, kKeys);
+    PipeState st;
+    for (int j = 0; j < T; ++j) {
+      const int b = j & 1;
+      ptx::mbar_wait(&bars[L::b_s_empty + b], ((j >> 1) & 1) ^ 1);
+      ptx::tc_fence_after();
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        ptx::mbar_wait(&bars[L::b_stage_full + st.idx], st.phase);
         ptx::tc_fence_after();
-        mma_qk<L, NS>(smem, bars, st, tmem_base + b * kBlockKeys, lane);
-        if (lane == 0) ptx::umma_commit(&bars[L::b_s_full + b]);
+        if (lane == 0) {
+          const uint32_t b_base = ptx::smem_u32(smem + L::stages + st.idx * kStageBytes);
+#pragma unroll
+          for (int c = 0; c < 2; ++c)
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+              ptx::umma_f16_ts(tmem_base + kTmemS + b * kKeys, tmem_base + kTmemQ + (2 * half + c) * 32 + kk * 8,
+                               ptx::umma_desc_kmajor_sw128(b_base + c * 16384 + kk * 32), idesc, (half | c | kk) != 0);
+          ptx::umma_commit(&bars[L::b_stage_empty + st.idx]);
+        }
         __syncwarp();
+        st.advance<NS>();
       }
+      if (lane == 0) ptx::umma_commit(&bars[L::b_s_full + b]);
+      __syncwarp();
     }
   } else {
     // ===== softmax statistics =====
@@ -211,15 +211,15 @@ range_stats_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     float4 qx = make_float4(0.f, 0.f, 0.f, 0.f);
     if (kGeo && n < N) qx = q_xyz[n];
     const float gx = qx.x * a_geo, gy = qx.y * a_geo, gz = qx.z * a_geo;
-    float sum_s = 0.f, sum_g = 0.f, max_s = -2.f, max_g = -2.f;
+    float sum_s = 0.f, sum_g = 0.f, max_s = -2.f, max_g = -3.0e38f;
     PipeState xs;
     for (int j = 0; j < T; ++j) {
       const int b = j & 1;
-      const int key0 = (t_begin + j) * kBlockKeys + grp * 64;
+      const int key0 = (t_begin + j) * kKeys + grp * 64;
       ptx::mbar_wait(&bars[L::b_s_full + b], (j >> 1) & 1);
       ptx::tc_fence_after();
       uint32_t s0[32], s1[32];
-      const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + b * kBlockKeys + grp * 64;
+      const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + kTmemS + b * kKeys + grp * 64;
       ptx::tmem_ld32(taddr, s0);
       ptx::tmem_ld32(taddr + 32, s1);
       ptx::tmem_ld_wait();
@@ -275,21 +275,50 @@ range_stats_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 9) ptx::tmem_dealloc<256>(tmem_base);
+  if (warp == 9) ptx::tmem_dealloc<512>(tmem_base);
 }
 
 // ---------------------------------------------------------------------------------------------------
-// K2b: apply  (O slice = P' . Vt)
+// K2b: apply  (O slice = P' . Vt).  Tile = 128 entries: two stages of K (dims 0-127 | 128-255, SS-mode
+// Q.K^T with Q resident in shared memory) and two stages of Vt ([256 dims x 64 entries] each, TS-mode P.V).
+// A 64-entry tile with Q in TMEM was measured slower: a TS-mode MMA fetches its 128x16 A tile from TMEM in
+// ~64 clk, which dominates UMMA_N = 64 (32 clk of math).
 // rowc[n] = {cs, cg, qx*a_geo, qy*a_geo, qz*a_geo, out_scale, -, -}
 // ---------------------------------------------------------------------------------------------------
-template <bool kGeo>
+// kProf: per-role wait-cycle accounting for tools/time_apply.py (prof[role * 8 + counter], CTA (0,1,0) only)
+#define PROF_T0() long long _t0 = kProf ? clock64() : 0
+#define PROF_ADD(role, k) do { if (kProf && prof_on) { long long _t1 = clock64(); prof_acc[k] += _t1 - _t0; _t0 = _t1; } } while (0)
+struct ApplySmem {
+  static constexpr int NS = 4, NX = 4, kKeys = 128, kXyzBytes = kKeys * 16;
+  static constexpr int q = 0;                                   // 4 x [128 rows x 64 dims] SW128
+  static constexpr int stages = q + 65536;
+  static constexpr int xyz = stages + NS * kStageBytes;
+  static constexpr int bars = xyz + NX * kXyzBytes;
+  static constexpr int b_q_full = 0;
+  static constexpr int b_stage_full = 1;
+  static constexpr int b_stage_empty = b_stage_full + NS;
+  static constexpr int b_s_full = b_stage_empty + NS;
+  static constexpr int b_p_full = b_s_full + 2;
+  static constexpr int b_xyz_full = b_p_full + 2;
+  static constexpr int b_xyz_empty = b_xyz_full + NX;
+  static constexpr int b_o_full = b_xyz_empty + NX;
+  static constexpr int n_bars = b_o_full + 1;
+  static constexpr int tmem_slot = bars + n_bars * 8;
+  static constexpr int total = tmem_slot + 16;
+  static constexpr int dynamic_bytes = total + 1024;
+};
+
+template <bool kGeo, bool kProf = false>
 __global__ void __launch_bounds__(kThreads, 1)
 range_apply_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const float4* __restrict__ db_xyz,
                    const float4* __restrict__ rowc, int N, int M, int tiles_per_split, float a_sem,
-                   float* __restrict__ out, size_t out_split_stride, int dbg) {
-  constexpr int NS = 3, NP = 3, NX = 4;
-  using L = SmemLayout<NS, NP, NX>;
+                   float* __restrict__ out, size_t out_split_stride, long long* __restrict__ prof = nullptr) {
+  using L = ApplySmem;
+  constexpr int NS = L::NS, NX = L::NX, kKeys = L::kKeys, kXyzBytes = L::kXyzBytes;
+  long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const bool prof_on = kProf && prof != nullptr && blockIdx.x == 0 && blockIdx.y == 1 && blockIdx.z == 0;
+  const long long prof_start = kProf ? clock64() : 0;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::bars);
@@ -299,7 +328,7 @@ range_apply_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const int slice = blockIdx.x;                 // fastest: the 4 slices of a query tile run together
   const int q0 = blockIdx.y * kBlockQ;
   const int split = blockIdx.z;
-  const int total_tiles = (M + kBlockKeys - 1) / kBlockKeys;
+  const int total_tiles = (M + kKeys - 1) / kKeys;
   const int t_begin = split * tiles_per_split;
   const int t_end = min(total_tiles, t_begin + tiles_per_split);
   const int T = t_end - t_begin;
@@ -312,11 +341,7 @@ range_apply_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&bars[L::b_s_full + i], 1);
-      ptx::mbar_init(&bars[L::b_s_empty + i], kNumSoftmaxWarps);
-    }
-    for (int i = 0; i < NP; ++i) {
-      ptx::mbar_init(&bars[L::b_p_full + i], 4);
-      ptx::mbar_init(&bars[L::b_p_empty + i], 1);
+      ptx::mbar_init(&bars[L::b_p_full + i], kNumSoftmaxWarps);
     }
     for (int i = 0; i < NX; ++i) {
       ptx::mbar_init(&bars[L::b_xyz_full + i], 1);
@@ -329,21 +354,21 @@ range_apply_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_o = tmem_base + 2 * kBlockKeys;
+  const uint32_t tmem_base = *tmem_slot;       // [0,128) S/P buf 0 | [128,256) S/P buf 1 | [256,512) O
+  const uint32_t tmem_o = tmem_base + 256;
 
   if (warp == 8) {
-    // ===== TMA producer: Q, then K(0), [K(j+1), V(j)]..., V(T-1) in the order the MMA warp consumes =====
+    // ===== TMA producer, in the order the MMA warp consumes: Q, K(0), [K(j+1), V(j)]..., V(T-1) =====
     if (lane == 0 && T > 0) {
       ptx::prefetch_tmap(&tmQ);
       ptx::prefetch_tmap(&tmK);
       ptx::prefetch_tmap(&tmV);
-      ptx::mbar_expect_tx(&bars[L::b_q_full], 4 * kChunkBytes);
-      for (int c = 0; c < 4; ++c) ptx::tma_load_2d(smem + L::q + c * kChunkBytes, &tmQ, &bars[L::b_q_full], c * 64, q0);
+      ptx::mbar_expect_tx(&bars[L::b_q_full], 65536);
+      for (int c = 0; c < 4; ++c) ptx::tma_load_2d(smem + L::q + c * 16384, &tmQ, &bars[L::b_q_full], c * 64, q0);
       PipeState st, xs;
       for (int j = 0; j <= T; ++j) {
         if (j < T) {
-          const int key0 = (t_begin + j) * kBlockKeys;
+          const int key0 = (t_begin + j) * kKeys;
           if (kGeo) {
             ptx::mbar_wait(&bars[L::b_xyz_empty + xs.idx], xs.phase ^ 1);
             ptx::mbar_expect_tx(&bars[L::b_xyz_full + xs.idx], kXyzBytes);
@@ -351,13 +376,25 @@ range_apply_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                               &bars[L::b_xyz_full + xs.idx]);
             xs.advance<NX>();
           }
-          produce_keys<L, NS>(smem, bars, st, &tmK, key0);
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            PROF_T0();
+            ptx::mbar_wait(&bars[L::b_stage_empty + st.idx], st.phase ^ 1);
+            PROF_ADD(0, 0);
+            uint8_t* dst = smem + L::stages + st.idx * kStageBytes;
+            ptx::mbar_expect_tx(&bars[L::b_stage_full + st.idx], kStageBytes);
+            ptx::tma_load_2d(dst, &tmK, &bars[L::b_stage_full + st.idx], (2 * half) * 64, key0);
+            ptx::tma_load_2d(dst + 16384, &tmK, &bars[L::b_stage_full + st.idx], (2 * half + 1) * 64, key0);
+            st.advance<NS>();
+          }
         }
-        if (j >= 1 && !(dbg & 2)) {
-          const int key0 = (t_begin + j - 1) * kBlockKeys;
+        if (j >= 1) {
+          const int key0 = (t_begin + j - 1) * kKeys;
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
+            PROF_T0();
             ptx::mbar_wait(&bars[L::b_stage_empty + st.idx], st.phase ^ 1);
+            PROF_ADD(0, 1);
             ptx::mbar_expect_tx(&bars[L::b_stage_full + st.idx], kStageBytes);
             ptx::tma_load_2d(smem + L::stages + st.idx * kStageBytes, &tmV, &bars[L::b_stage_full + st.idx],
                              key0 + h * 64, slice * kSliceV);
@@ -365,51 +402,76 @@ range_apply_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           }
         }
       }
+      if (prof_on) { prof[0] = prof_acc[0]; prof[1] = prof_acc[1]; prof[2] = clock64() - prof_start; }
     }
   } else if (warp == 9) {
     // ===== MMA issuer =====
     if (T > 0) {
+      constexpr uint32_t idesc_qk = ptx::umma_idesc_f16(kBlockQ, kKeys);
       constexpr uint32_t idesc_pv = ptx::umma_idesc_f16(kBlockQ, kSliceV);
       ptx::mbar_wait(&bars[L::b_q_full], 0);
-      PipeState st, ps;
+      PipeState st;
+      // S buffer b is rewritten by QK(j+2) only after PV(j) (same issuing thread, executed in order) which
+      // itself waited for the softmax warps to be done with S(j) -> P'(j): no separate "S empty" barrier.
       for (int j = 0; j <= T; ++j) {
         if (j < T) {
-          const int b = j & 1;
-          if (!(dbg & 1)) ptx::mbar_wait(&bars[L::b_s_empty + b], ((j >> 1) & 1) ^ 1);
-          ptx::tc_fence_after();
-          mma_qk<L, NS>(smem, bars, st, tmem_base + b * kBlockKeys, lane);
-          if (lane == 0) ptx::umma_commit(&bars[L::b_s_full + b]);
-          __syncwarp();
-        }
-        if (j >= 1) {
+          const uint32_t tmem_s = tmem_base + (j & 1) * kKeys;
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            if (!(dbg & 1)) ptx::mbar_wait(&bars[L::b_p_full + ps.idx], ps.phase);
-            if (!(dbg & 2)) ptx::mbar_wait(&bars[L::b_stage_full + st.idx], st.phase);
+          for (int half = 0; half < 2; ++half) {
+            PROF_T0();
+            ptx::mbar_wait(&bars[L::b_stage_full + st.idx], st.phase);
+            PROF_ADD(1, 0);
             ptx::tc_fence_after();
             if (lane == 0) {
-              const uint32_t a_base = ptx::smem_u32(smem + L::p + ps.idx * kChunkBytes);
-              const uint32_t b_base = ptx::smem_u32(smem + L::stages + (dbg & 2 ? 0 : st.idx) * kStageBytes);
+              const uint32_t b_base = ptx::smem_u32(smem + L::stages + st.idx * kStageBytes);
+              const uint32_t a_base = ptx::smem_u32(smem + L::q + (2 * half) * 16384);
 #pragma unroll
-              for (int kk = 0; kk < 4; ++kk) {
-                ptx::umma_f16_ss(tmem_o, ptx::umma_desc_kmajor_sw128(a_base + kk * 32),
-                                 ptx::umma_desc_kmajor_sw128(b_base + kk * 32), idesc_pv,
-                                 (j > 1) || (h | kk) != 0);
-              }
-              if (!(dbg & 2)) ptx::umma_commit(&bars[L::b_stage_empty + st.idx]);
-              ptx::umma_commit(&bars[L::b_p_empty + ps.idx]);
+              for (int c = 0; c < 2; ++c)
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+                  ptx::umma_f16_ss(tmem_s, ptx::umma_desc_kmajor_sw128(a_base + c * 16384 + kk * 32),
+                                   ptx::umma_desc_kmajor_sw128(b_base + c * 16384 + kk * 32), idesc_qk,
+                                   (half | c | kk) != 0);
+              ptx::umma_commit(&bars[L::b_stage_empty + st.idx]);
+              if (half == 1) ptx::umma_commit(&bars[L::b_s_full + (j & 1)]);
             }
             __syncwarp();
-            if (!(dbg & 2)) st.advance<NS>();
-            ps.advance<NP>();
+            PROF_ADD(1, 1);
+            st.advance<NS>();
+          }
+        }
+        if (j >= 1) {
+          const int jj = j - 1, b = jj & 1;
+          PROF_T0();
+          ptx::mbar_wait(&bars[L::b_p_full + b], (jj >> 1) & 1);
+          PROF_ADD(1, 2);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            ptx::mbar_wait(&bars[L::b_stage_full + st.idx], st.phase);
+            PROF_ADD(1, 3);
+            ptx::tc_fence_after();
+            if (lane == 0) {
+              const uint32_t b_base = ptx::smem_u32(smem + L::stages + st.idx * kStageBytes);
+              // P'(jj): group h wrote keys 64 h .. +63 as 32 packed columns at S-buffer column 64 h
+              const uint32_t p_base = tmem_base + b * kKeys + h * 64;
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk)
+                ptx::umma_f16_ts(tmem_o, p_base + kk * 8, ptx::umma_desc_kmajor_sw128(b_base + kk * 32), idesc_pv,
+                                 (jj > 0) || (h | kk) != 0);
+              ptx::umma_commit(&bars[L::b_stage_empty + st.idx]);
+            }
+            __syncwarp();
+            PROF_ADD(1, 4);
+            st.advance<NS>();
           }
         }
       }
       if (lane == 0) ptx::umma_commit(&bars[L::b_o_full]);
       __syncwarp();
+      if (prof_on && lane == 0) { for (int k = 0; k < 5; ++k) prof[8 + k] = prof_acc[k]; prof[8 + 5] = clock64() - prof_start; }
     }
-  } else if (!(dbg & 1)) {
-    // ===== softmax: S (TMEM) -> P' (fp16, swizzled smem) ; then epilogue =====
+  } else {
+    // ===== softmax: S (TMEM fp32) -> P' (TMEM fp16, in place) ; then epilogue =====
     const int grp = warp >> 2, quarter = warp & 3;
     const int row = quarter * 32 + lane;
     const int n = q0 + row;
@@ -418,66 +480,59 @@ range_apply_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const float4 c0 = rowc[2 * n], c1 = rowc[2 * n + 1];
       cs = c0.x; cg = c0.y; gx = c0.z; gy = c0.w; gz = c1.x; out_scale = c1.y;
     }
-    // P chunk sequence number of (tile j, group g) is 2 j + g; ring of NP chunks
-    int pidx = grp % NP;
-    uint32_t puse = 0;     // how many times this group's current ring slot sequence wrapped
-    int pseq = grp;
     PipeState xs;
     for (int j = 0; j < T; ++j) {
       const int b = j & 1;
-      const int key0 = (t_begin + j) * kBlockKeys + grp * 64;
+      const int key0 = (t_begin + j) * kKeys + grp * 64;
+      const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + b * kKeys + grp * 64;
+      PROF_T0();
       ptx::mbar_wait(&bars[L::b_s_full + b], (j >> 1) & 1);
+      PROF_ADD(2, 0);
       ptx::tc_fence_after();
       uint32_t s0[32], s1[32];
-      const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + b * kBlockKeys + grp * 64;
       ptx::tmem_ld32(taddr, s0);
       ptx::tmem_ld32(taddr + 32, s1);
       ptx::tmem_ld_wait();
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&bars[L::b_s_empty + b]);
-
-      pidx = pseq % NP;
-      puse = pseq / NP;
-      ptx::mbar_wait(&bars[L::b_p_empty + pidx], (puse & 1) ^ 1);
+      PROF_ADD(2, 1);
       const uint32_t kxyz = ptx::smem_u32(smem + L::xyz + xs.idx * kXyzBytes) + grp * 64 * 16;
       if (kGeo) ptx::mbar_wait(&bars[L::b_xyz_full + xs.idx], xs.phase);
+      PROF_ADD(2, 2);
       const int nvalid = M - key0;            // >= 64 except in the last tile
-      const uint32_t prow = ptx::smem_u32(smem + L::p + pidx * kChunkBytes + row * 128);
+      uint32_t packed[32];
       auto body = [&](auto masked) {
 #pragma unroll
-        for (int c16 = 0; c16 < 8; ++c16) {
-          uint32_t packed[4];
+        for (int w = 0; w < 32; ++w) {
+          float pv[2];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            float pv[2];
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-              const int i = c16 * 8 + e * 2 + u;
-              const float s = __uint_as_float(i < 32 ? s0[i] : s1[i - 32]);
-              float p = ptx::ex2(fmaf(s, a_sem, cs));
-              if (kGeo) {
-                const float4 k = ptx::lds_f4(kxyz + i * 16);
-                p += ptx::ex2(fmaf(gx, k.x, fmaf(gy, k.y, fmaf(gz, k.z, cg))));
-              }
-              if (decltype(masked)::value && i >= nvalid) p = 0.f;
-              pv[u] = p;
+          for (int u = 0; u < 2; ++u) {
+            const int i = 2 * w + u;
+            const float sv = __uint_as_float(i < 32 ? s0[i] : s1[i - 32]);
+            float p = ptx::ex2(fmaf(sv, a_sem, cs));
+            if (kGeo) {
+              const float4 k = ptx::lds_f4(kxyz + i * 16);
+              p += ptx::ex2(fmaf(gx, k.x, fmaf(gy, k.y, fmaf(gz, k.z, cg))));
             }
-            packed[e] = ptx::pack_half2(pv[0], pv[1]);
+            if (decltype(masked)::value && i >= nvalid) p = 0.f;
+            pv[u] = p;
           }
-          ptx::sts_u4(prow + ((c16 ^ (row & 7)) << 4), packed[0], packed[1], packed[2], packed[3]);
+          packed[w] = ptx::pack_half2(pv[0], pv[1]);
         }
       };
       if (nvalid >= 64) body(std::false_type{}); else body(std::true_type{});
-      ptx::fence_proxy_async_smem();
+      PROF_ADD(2, 3);
+      // P'(row, keys 64 g .. +63) over the first 32 of this group's 64 S columns
+      ptx::tmem_st32(taddr, packed);
+      ptx::tmem_st_wait();
+      ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        ptx::mbar_arrive(&bars[L::b_p_full + pidx]);
+        ptx::mbar_arrive(&bars[L::b_p_full + b]);
         if (kGeo) ptx::mbar_arrive(&bars[L::b_xyz_empty + xs.idx]);
       }
+      PROF_ADD(2, 4);
       if (kGeo) xs.advance<NX>();
-      pseq += 2;
     }
+    if (prof_on && threadIdx.x == 0) { for (int k = 0; k < 5; ++k) prof[16 + k] = prof_acc[k]; prof[16 + 5] = clock64() - prof_start; prof[16 + 6] = T; }
     // ----- epilogue: O (TMEM, 128 lanes x 256 cols) -> global fp32, scaled -----
     if (T > 0) {
       ptx::mbar_wait(&bars[L::b_o_full], 0);
@@ -559,8 +614,6 @@ __global__ void reduce_out_kernel(const float4* __restrict__ part, size_t split_
   out[i] = a;
 }
 
-int g_smem_configured = 0;
-
 template <class K>
 cudaError_t set_smem(K kernel, int bytes) {
   return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
@@ -570,21 +623,26 @@ cudaError_t set_smem(K kernel, int bytes) {
 
 namespace rangeb200 {
 
-int retrieval_stats_smem_bytes() { return SmemLayout<4, 0, 4>::dynamic_bytes; }
-int retrieval_apply_smem_bytes() { return SmemLayout<3, 3, 4>::dynamic_bytes; }
+long long* g_prof_buffer = nullptr;
+void set_profile_buffer(long long* p) { g_prof_buffer = p; }
+
+int retrieval_stats_smem_bytes() { return SmemLayout<6, 4, 2048>::dynamic_bytes; }
+int retrieval_apply_smem_bytes() { return ApplySmem::dynamic_bytes; }
 
 cudaError_t launch_stats(const RetrievalArgs& a, float* part_sum, float* part_max, cudaStream_t stream) {
   const int bytes = retrieval_stats_smem_bytes();
   cudaError_t e;
   if ((e = set_smem(range_stats_kernel<true>, bytes)) != cudaSuccess) return e;
   if ((e = set_smem(range_stats_kernel<false>, bytes)) != cudaSuccess) return e;
-  dim3 grid((a.N + kBlockQ - 1) / kBlockQ, a.splits, 1);
+  dim3 grid((a.N + kBlockQ - 1) / kBlockQ, a.stats_splits, 1);
   if (a.geo)
-    range_stats_kernel<true><<<grid, kThreads, bytes, stream>>>(a.tmQ, a.tmK, a.db_xyz, a.q_xyz, a.N, a.M,
-                                                               a.tiles_per_split, a.a_sem, a.a_geo, part_sum, part_max);
+    range_stats_kernel<true><<<grid, kThreads, bytes, stream>>>(a.tmK128, a.q16, a.db_xyz, a.q_xyz, a.N, a.M,
+                                                               a.stats_tiles_per_split, a.a_sem, a.a_geo, part_sum,
+                                                               part_max);
   else
-    range_stats_kernel<false><<<grid, kThreads, bytes, stream>>>(a.tmQ, a.tmK, a.db_xyz, a.q_xyz, a.N, a.M,
-                                                                a.tiles_per_split, a.a_sem, a.a_geo, part_sum, part_max);
+    range_stats_kernel<false><<<grid, kThreads, bytes, stream>>>(a.tmK128, a.q16, a.db_xyz, a.q_xyz, a.N, a.M,
+                                                                a.stats_tiles_per_split, a.a_sem, a.a_geo, part_sum,
+                                                                part_max);
   return cudaGetLastError();
 }
 
@@ -611,16 +669,21 @@ cudaError_t launch_apply(const RetrievalArgs& a, const float* rowc, float* out, 
   cudaError_t e;
   if ((e = set_smem(range_apply_kernel<true>, bytes)) != cudaSuccess) return e;
   if ((e = set_smem(range_apply_kernel<false>, bytes)) != cudaSuccess) return e;
-  dim3 grid(1024 / kSliceV, (a.N + kBlockQ - 1) / kBlockQ, a.splits);
-  static const int dbg = getenv("RANGE_DBG") ? atoi(getenv("RANGE_DBG")) : 0;   // timing experiments only
+  dim3 grid(1024 / kSliceV, (a.N + kBlockQ - 1) / kBlockQ, a.apply_splits);
+  const float4* rc = reinterpret_cast<const float4*>(rowc);
+  if (g_prof_buffer) {   // instrumented build of the same kernel (tools/time_apply.py)
+    if ((e = set_smem(range_apply_kernel<true, true>, bytes)) != cudaSuccess) return e;
+    range_apply_kernel<true, true><<<grid, kThreads, bytes, stream>>>(
+        a.tmQ, a.tmK128, a.tmV, a.db_xyz, rc, a.N, a.M, a.apply_tiles_per_split, a.a_sem, out, out_split_stride,
+        g_prof_buffer);
+    return cudaGetLastError();
+  }
   if (a.geo)
-    range_apply_kernel<true><<<grid, kThreads, bytes, stream>>>(a.tmQ, a.tmK, a.tmV, a.db_xyz,
-                                                               reinterpret_cast<const float4*>(rowc), a.N, a.M,
-                                                               a.tiles_per_split, a.a_sem, out, out_split_stride, dbg);
+    range_apply_kernel<true><<<grid, kThreads, bytes, stream>>>(a.tmQ, a.tmK128, a.tmV, a.db_xyz, rc, a.N, a.M,
+                                                               a.apply_tiles_per_split, a.a_sem, out, out_split_stride);
   else
-    range_apply_kernel<false><<<grid, kThreads, bytes, stream>>>(a.tmQ, a.tmK, a.tmV, a.db_xyz,
-                                                                reinterpret_cast<const float4*>(rowc), a.N, a.M,
-                                                                a.tiles_per_split, a.a_sem, out, out_split_stride, dbg);
+    range_apply_kernel<false><<<grid, kThreads, bytes, stream>>>(a.tmQ, a.tmK128, a.tmV, a.db_xyz, rc, a.N, a.M,
+                                                                a.apply_tiles_per_split, a.a_sem, out, out_split_stride);
   return cudaGetLastError();
 }
 

@@ -28,3 +28,14 @@ t_st_r = timeit(lambda: eng.retrieve_stats("RANGE", q, xyz, 15.0, 0.0))
 t_ap_r = timeit(lambda: eng.retrieve_apply("RANGE", q, xyz, 15.0, 0.0, None, s2, m2))
 fl = 2566.0 * N * M
 print(f"DBG={os.environ.get('RANGE_DBG','0')} N={N} M={M}: RANGE+ stats {t_st:.2f} apply {t_ap:.2f} ms ({fl/((t_st+t_ap)*1e-3)/1364.5e12:.3f} of peak) | RANGE stats {t_st_r:.2f} apply {t_ap_r:.2f} ms")
+if os.environ.get("PROF"):
+    import ctypes
+    buf = torch.zeros(64, dtype=torch.int64, device=dev)
+    eng.lib.range_debug_set_profile_buffer(ctypes.c_void_p(buf.data_ptr()))
+    eng.retrieve_apply("RANGE+", q, xyz, 12.0, 40.0, 0.5, sums, maxs); torch.cuda.synchronize()
+    eng.lib.range_debug_set_profile_buffer(None)
+    b = buf.cpu().numpy(); T = max(1, b[22])
+    print(f"tiles {T}; per-tile cycles:")
+    print(f" producer: wait_empty(K) {b[0]/T:.0f} wait_empty(V) {b[1]/T:.0f} total {b[2]/T:.0f}")
+    print(f" mma: wait_stage_qk {b[8]/T:.0f} issue_qk {b[9]/T:.0f} wait_p {b[10]/T:.0f} wait_stage_pv {b[11]/T:.0f} issue_pv {b[12]/T:.0f} total {b[13]/T:.0f}")
+    print(f" (128-entry tiles)\n softmax w0: wait_s {b[16]/T:.0f} tmem_ld {b[17]/T:.0f} wait_xyz {b[18]/T:.0f} compute {b[19]/T:.0f} st+arrive {b[20]/T:.0f} total {b[21]/T:.0f}")
