@@ -80,7 +80,7 @@ struct range_ctx {
   const void* Vt = nullptr;
   const float* xyz = nullptr;
   float vscale = 1.f;
-  CUtensorMap tmK128, tmV;
+  CUtensorMap tmK128, tmV, tmK64, tmV128;
 };
 
 namespace {
@@ -123,6 +123,8 @@ int fill_args(range_ctx* c, int mode, int64_t N, const void* q16, const float* q
   if (r) return r;
   a->tmK128 = c->tmK128;
   a->tmV = c->tmV;
+  a->tmK64 = c->tmK64;
+  a->tmV128 = c->tmV128;
   a->q16 = reinterpret_cast<const __half*>(q16);
   a->db_xyz = reinterpret_cast<const float4*>(c->xyz);
   a->q_xyz = reinterpret_cast<const float4*>(qxyz);
@@ -206,6 +208,10 @@ int range_ctx_set_db(range_ctx* c, int64_t M, int64_t Mpad, const void* Kh, cons
   int r = make_tmap(&c->tmK128, Kh, uint64_t(Mpad), kDimK, 128);
   if (r) return r;
   r = make_tmap(&c->tmV, Vt, kDimV, uint64_t(Mpad), 256);
+  if (r) return r;
+  r = make_tmap(&c->tmK64, Kh, uint64_t(Mpad), kDimK, 64);
+  if (r) return r;
+  r = make_tmap(&c->tmV128, Vt, kDimV, uint64_t(Mpad), 128);
   if (r) return r;
   c->M = M; c->Mpad = Mpad; c->Kh = Kh; c->Vt = Vt; c->xyz = xyz; c->vscale = vscale;
   return RANGE_OK;

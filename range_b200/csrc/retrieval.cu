@@ -27,6 +27,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <type_traits>
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -41,6 +42,10 @@ constexpr int kSliceV = 256;        // value dims per CTA (UMMA N of P.V)
 constexpr int kStageBytes = 32768;  // one pipeline stage: a [.. x 64 fp16] SWIZZLE_128B tile set
 constexpr int kNumSoftmaxWarps = 8;
 constexpr int kThreads = (kNumSoftmaxWarps + 2) * 32;
+// exponentials evaluated on the FMA pipe instead of MUFU (ptx::ex2_poly): every k-th element, 0 = none.
+// Measured on B200: any offload is slower (the softmax warps are issue-bound, not MUFU-bound).
+constexpr int kPolyModApply = 0;
+constexpr int kPolyModStats = 0;
 constexpr uint32_t kTmemQ = 0;      // column offsets
 constexpr uint32_t kTmemS = 128;
 
@@ -145,7 +150,10 @@ range_stats_kernel(const __grid_constant__ CUtensorMap tmK, const __half* __rest
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  // warp-uniform copies (see ptx::umma_commit_u32) for the MMA-issuing warp
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  const uint32_t smem_u = __shfl_sync(0xffffffffu, ptx::smem_u32(smem), 0);
+  const uint32_t bars_u = smem_u + L::bars;
   if (warp < kNumSoftmaxWarps) load_q_to_tmem(q16, q0, N, tmem_base, warp, lane);
   ptx::tc_fence_before();
   __syncthreads();
@@ -187,20 +195,20 @@ range_stats_kernel(const __grid_constant__ CUtensorMap tmK, const __half* __rest
       for (int half = 0; half < 2; ++half) {
         ptx::mbar_wait(&bars[L::b_stage_full + st.idx], st.phase);
         ptx::tc_fence_after();
-        if (lane == 0) {
-          const uint32_t b_base = ptx::smem_u32(smem + L::stages + st.idx * kStageBytes);
+        if (ptx::elect_one()) {
+          const uint32_t b_base = smem_u + L::stages + st.idx * kStageBytes;
 #pragma unroll
           for (int c = 0; c < 2; ++c)
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk)
               ptx::umma_f16_ts(tmem_base + kTmemS + b * kKeys, tmem_base + kTmemQ + (2 * half + c) * 32 + kk * 8,
                                ptx::umma_desc_kmajor_sw128(b_base + c * 16384 + kk * 32), idesc, (half | c | kk) != 0);
-          ptx::umma_commit(&bars[L::b_stage_empty + st.idx]);
+          ptx::umma_commit_u32(bars_u + 8 * (L::b_stage_empty + st.idx));
         }
         __syncwarp();
         st.advance<NS>();
       }
-      if (lane == 0) ptx::umma_commit(&bars[L::b_s_full + b]);
+      if (ptx::elect_one()) ptx::umma_commit_u32(bars_u + 8 * (L::b_s_full + b));
       __syncwarp();
     }
   } else {
@@ -234,14 +242,15 @@ range_stats_kernel(const __grid_constant__ CUtensorMap tmK, const __half* __rest
         for (int i = 0; i < 64; ++i) {
           const float s = __uint_as_float(i < 32 ? s0[i] : s1[i - 32]);
           const bool valid = !decltype(masked)::value || (i < nvalid);
-          float es = ptx::ex2(fmaf(s, a_sem, -a_sem));
+          const bool poly = kPolyModStats > 0 && (i % (kPolyModStats > 0 ? kPolyModStats : 1)) == 0;
+          float es = poly ? ptx::ex2_poly(fmaf(s, a_sem, -a_sem)) : ptx::ex2(fmaf(s, a_sem, -a_sem));
           if (!valid) es = 0.f;
           sum_s += es;
           max_s = fmaxf(max_s, valid ? s : -2.f);
           if (kGeo) {
             const float4 k = ptx::lds_f4(kxyz + i * 16);
             const float g = fmaf(gx, k.x, fmaf(gy, k.y, fmaf(gz, k.z, -a_geo)));   // a_geo (g - 1)
-            float eg = ptx::ex2(g);
+            float eg = poly ? ptx::ex2_poly(g) : ptx::ex2(g);
             if (!valid) eg = 0.f;
             sum_g += eg;
             max_g = fmaxf(max_g, valid ? g : -3.0e38f);
@@ -354,7 +363,10 @@ range_apply_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;       // [0,128) S/P buf 0 | [128,256) S/P buf 1 | [256,512) O
+  // warp-uniform copies (see ptx::umma_commit_u32) for the MMA-issuing warp
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  const uint32_t smem_u = __shfl_sync(0xffffffffu, ptx::smem_u32(smem), 0);
+  const uint32_t bars_u = smem_u + L::bars;       // [0,128) S/P buf 0 | [128,256) S/P buf 1 | [256,512) O
   const uint32_t tmem_o = tmem_base + 256;
 
   if (warp == 8) {
@@ -422,9 +434,9 @@ range_apply_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             ptx::mbar_wait(&bars[L::b_stage_full + st.idx], st.phase);
             PROF_ADD(1, 0);
             ptx::tc_fence_after();
-            if (lane == 0) {
-              const uint32_t b_base = ptx::smem_u32(smem + L::stages + st.idx * kStageBytes);
-              const uint32_t a_base = ptx::smem_u32(smem + L::q + (2 * half) * 16384);
+            if (ptx::elect_one()) {
+              const uint32_t b_base = smem_u + L::stages + st.idx * kStageBytes;
+              const uint32_t a_base = smem_u + L::q + (2 * half) * 16384;
 #pragma unroll
               for (int c = 0; c < 2; ++c)
 #pragma unroll
@@ -432,8 +444,8 @@ range_apply_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                   ptx::umma_f16_ss(tmem_s, ptx::umma_desc_kmajor_sw128(a_base + c * 16384 + kk * 32),
                                    ptx::umma_desc_kmajor_sw128(b_base + c * 16384 + kk * 32), idesc_qk,
                                    (half | c | kk) != 0);
-              ptx::umma_commit(&bars[L::b_stage_empty + st.idx]);
-              if (half == 1) ptx::umma_commit(&bars[L::b_s_full + (j & 1)]);
+              ptx::umma_commit_u32(bars_u + 8 * (L::b_stage_empty + st.idx));
+              if (half == 1) ptx::umma_commit_u32(bars_u + 8 * (L::b_s_full + (j & 1)));
             }
             __syncwarp();
             PROF_ADD(1, 1);
@@ -450,15 +462,15 @@ range_apply_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             ptx::mbar_wait(&bars[L::b_stage_full + st.idx], st.phase);
             PROF_ADD(1, 3);
             ptx::tc_fence_after();
-            if (lane == 0) {
-              const uint32_t b_base = ptx::smem_u32(smem + L::stages + st.idx * kStageBytes);
+            if (ptx::elect_one()) {
+              const uint32_t b_base = smem_u + L::stages + st.idx * kStageBytes;
               // P'(jj): group h wrote keys 64 h .. +63 as 32 packed columns at S-buffer column 64 h
               const uint32_t p_base = tmem_base + b * kKeys + h * 64;
 #pragma unroll
               for (int kk = 0; kk < 4; ++kk)
                 ptx::umma_f16_ts(tmem_o, p_base + kk * 8, ptx::umma_desc_kmajor_sw128(b_base + kk * 32), idesc_pv,
                                  (jj > 0) || (h | kk) != 0);
-              ptx::umma_commit(&bars[L::b_stage_empty + st.idx]);
+              ptx::umma_commit_u32(bars_u + 8 * (L::b_stage_empty + st.idx));
             }
             __syncwarp();
             PROF_ADD(1, 4);
@@ -466,7 +478,7 @@ range_apply_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           }
         }
       }
-      if (lane == 0) ptx::umma_commit(&bars[L::b_o_full]);
+      if (ptx::elect_one()) ptx::umma_commit_u32(bars_u + 8 * (L::b_o_full));
       __syncwarp();
       if (prof_on && lane == 0) { for (int k = 0; k < 5; ++k) prof[8 + k] = prof_acc[k]; prof[8 + 5] = clock64() - prof_start; }
     }
@@ -507,10 +519,12 @@ range_apply_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           for (int u = 0; u < 2; ++u) {
             const int i = 2 * w + u;
             const float sv = __uint_as_float(i < 32 ? s0[i] : s1[i - 32]);
-            float p = ptx::ex2(fmaf(sv, a_sem, cs));
+            const bool poly = kPolyModApply > 0 && (i % (kPolyModApply > 0 ? kPolyModApply : 1)) == 0;
+            float p = poly ? ptx::ex2_poly(fmaf(sv, a_sem, cs)) : ptx::ex2(fmaf(sv, a_sem, cs));
             if (kGeo) {
               const float4 k = ptx::lds_f4(kxyz + i * 16);
-              p += ptx::ex2(fmaf(gx, k.x, fmaf(gy, k.y, fmaf(gz, k.z, cg))));
+              const float tg = fmaf(gx, k.x, fmaf(gy, k.y, fmaf(gz, k.z, cg)));
+              p += poly ? ptx::ex2_poly(tg) : ptx::ex2(tg);
             }
             if (decltype(masked)::value && i >= nvalid) p = 0.f;
             pv[u] = p;
@@ -560,6 +574,282 @@ range_apply_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 9) ptx::tmem_dealloc<512>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K2b, CTA-pair variant (cta_group::2): two CTAs of a cluster = two adjacent query tiles x the same value
+// slice run ONE 256-row UMMA.  Each CTA loads only half of every B tile (64 of the 128 entries of a K tile,
+// 128 of the 256 value dims of a Vt tile), which halves TMA writes and UMMA B-operand reads per SM - the
+// shared-memory bandwidth that bounds the single-CTA kernel - and doubles the pipeline depth in tiles.
+// Leader (cluster rank 0) issues every MMA; completions are multicast to both CTAs' barriers; the peer's
+// softmax warps signal "P' ready" on the leader's barrier through DSMEM.
+// ---------------------------------------------------------------------------------------------------
+struct PairSmem : ApplySmem {
+  static constexpr int b_q_pair = ApplySmem::n_bars;
+  static constexpr int n_bars2 = b_q_pair + 1;
+  static constexpr int tmem_slot = ApplySmem::bars + n_bars2 * 8;
+  static constexpr int total = tmem_slot + 16;
+  static constexpr int dynamic_bytes = total + 1024;
+};
+
+template <bool kGeo, bool kProf = false>
+__global__ void __launch_bounds__(kThreads, 1)
+range_apply_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK64,
+                        const __grid_constant__ CUtensorMap tmV128, const float4* __restrict__ db_xyz,
+                        const float4* __restrict__ rowc, int N, int M, int tiles_per_split, float a_sem,
+                        float* __restrict__ out, size_t out_split_stride, long long* __restrict__ prof = nullptr) {
+  using L = PairSmem;
+  constexpr int NS = L::NS, NX = L::NX, kKeys = L::kKeys, kXyzBytes = L::kXyzBytes;
+  long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const bool prof_on = kProf && prof != nullptr && blockIdx.x == 2 && blockIdx.y == 0 && blockIdx.z == 0;
+  const long long prof_start = kProf ? clock64() : 0;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::bars);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::tmem_slot);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const bool leader = rank == 0;
+  const int slice = blockIdx.y;
+  const int q0 = blockIdx.x * kBlockQ;          // cluster = (2,1,1): blockIdx.x = 2 * pair + rank
+  const int split = blockIdx.z;
+  const int total_tiles = (M + kKeys - 1) / kKeys;
+  const int t_begin = split * tiles_per_split;
+  const int t_end = min(total_tiles, t_begin + tiles_per_split);
+  const int T = t_end - t_begin;
+
+  if (threadIdx.x == 0) {
+    ptx::mbar_init(&bars[L::b_q_full], 1);
+    ptx::mbar_init(&bars[L::b_q_pair], 2);
+    for (int i = 0; i < NS; ++i) {
+      ptx::mbar_init(&bars[L::b_stage_full + i], 1);
+      ptx::mbar_init(&bars[L::b_stage_empty + i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&bars[L::b_s_full + i], 1);
+      ptx::mbar_init(&bars[L::b_p_full + i], 2 * kNumSoftmaxWarps);
+    }
+    for (int i = 0; i < NX; ++i) {
+      ptx::mbar_init(&bars[L::b_xyz_full + i], 1);
+      ptx::mbar_init(&bars[L::b_xyz_empty + i], kNumSoftmaxWarps);
+    }
+    ptx::mbar_init(&bars[L::b_o_full], 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 9) ptx::tmem_alloc_2sm<512>(tmem_slot);
+  ptx::tc_fence_before();
+  ptx::cluster_sync();                           // barriers of BOTH CTAs initialised before any remote arrive
+  ptx::tc_fence_after();
+  // warp-uniform copies (see ptx::umma_commit_u32) for the MMA-issuing warp
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  const uint32_t smem_u = __shfl_sync(0xffffffffu, ptx::smem_u32(smem), 0);
+  const uint32_t bars_u = smem_u + L::bars;         // [0,128) S/P buf 0 | [128,256) S/P buf 1 | [256,512) O
+  const uint32_t tmem_o = tmem_base + 256;
+
+  if (warp == 8) {
+    // ===== TMA producer (both CTAs): own Q; own half of K(j) / Vt(j); bytes credited to the leader =====
+    if (lane == 0 && T > 0) {
+      ptx::prefetch_tmap(&tmQ);
+      ptx::prefetch_tmap(&tmK64);
+      ptx::prefetch_tmap(&tmV128);
+      ptx::mbar_expect_tx(&bars[L::b_q_full], 65536);
+      for (int c = 0; c < 4; ++c) ptx::tma_load_2d(smem + L::q + c * 16384, &tmQ, &bars[L::b_q_full], c * 64, q0);
+      PipeState st, xs;
+      for (int j = 0; j <= T; ++j) {
+        if (j < T) {
+          const int key0 = (t_begin + j) * kKeys;
+          if (kGeo) {
+            ptx::mbar_wait(&bars[L::b_xyz_empty + xs.idx], xs.phase ^ 1);
+            ptx::mbar_expect_tx(&bars[L::b_xyz_full + xs.idx], kXyzBytes);
+            ptx::bulk_load_1d(smem + L::xyz + xs.idx * kXyzBytes, db_xyz + key0, kXyzBytes,
+                              &bars[L::b_xyz_full + xs.idx]);
+            xs.advance<NX>();
+          }
+          PROF_T0();
+          ptx::mbar_wait(&bars[L::b_stage_empty + st.idx], st.phase ^ 1);
+          PROF_ADD(0, 0);
+          uint8_t* dst = smem + L::stages + st.idx * kStageBytes;
+          if (leader) ptx::mbar_expect_tx(&bars[L::b_stage_full + st.idx], 2 * kStageBytes);
+#pragma unroll
+          for (int c = 0; c < 4; ++c)     // this CTA's 64 entries x 256 dims, as 4 [64 x 64] boxes
+            ptx::tma_load_2d_2sm(dst + c * 8192, &tmK64, &bars[L::b_stage_full + st.idx], c * 64, key0 + int(rank) * 64);
+          st.advance<NS>();
+        }
+        if (j >= 1) {
+          const int key0 = (t_begin + j - 1) * kKeys;
+          PROF_T0();
+          ptx::mbar_wait(&bars[L::b_stage_empty + st.idx], st.phase ^ 1);
+          PROF_ADD(0, 1);
+          uint8_t* dst = smem + L::stages + st.idx * kStageBytes;
+          if (leader) ptx::mbar_expect_tx(&bars[L::b_stage_full + st.idx], 2 * kStageBytes);
+#pragma unroll
+          for (int h = 0; h < 2; ++h)     // this CTA's 128 value dims x 128 entries, as 2 [128 x 64] boxes
+            ptx::tma_load_2d_2sm(dst + h * 16384, &tmV128, &bars[L::b_stage_full + st.idx], key0 + h * 64,
+                                 slice * kSliceV + int(rank) * 128);
+          st.advance<NS>();
+        }
+      }
+      if (prof_on) { prof[0] = prof_acc[0]; prof[1] = prof_acc[1]; prof[2] = clock64() - prof_start; }
+    }
+  } else if (warp == 9) {
+    if (T > 0) {
+      // both CTAs: tell the leader when this CTA's Q tile has landed
+      ptx::mbar_wait(&bars[L::b_q_full], 0);
+      if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&bars[L::b_q_pair]), 0));
+      __syncwarp();
+    }
+    if (leader && T > 0) {
+      // ===== MMA issuer (leader only) =====
+      constexpr uint32_t idesc_qk = ptx::umma_idesc_f16(2 * kBlockQ, kKeys);
+      constexpr uint32_t idesc_pv = ptx::umma_idesc_f16(2 * kBlockQ, kSliceV);
+      ptx::mbar_wait_cluster(&bars[L::b_q_pair], 0);
+      PipeState st;
+      for (int j = 0; j <= T; ++j) {
+        if (j < T) {
+          const uint32_t tmem_s = tmem_base + (j & 1) * kKeys;
+          PROF_T0();
+          ptx::mbar_wait(&bars[L::b_stage_full + st.idx], st.phase);
+          PROF_ADD(1, 0);
+          ptx::tc_fence_after();
+          if (ptx::elect_one()) {
+            const uint32_t b_base = smem_u + L::stages + st.idx * kStageBytes;
+            const uint32_t a_base = smem_u + L::q;
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk)
+                ptx::umma_f16_ss_2sm(tmem_s, ptx::umma_desc_kmajor_sw128(a_base + c * 16384 + kk * 32),
+                                     ptx::umma_desc_kmajor_sw128(b_base + c * 8192 + kk * 32), idesc_qk, (c | kk) != 0);
+            ptx::umma_commit_2sm_u32(bars_u + 8 * (L::b_stage_empty + st.idx));
+            ptx::umma_commit_2sm_u32(bars_u + 8 * (L::b_s_full + (j & 1)));
+          }
+          __syncwarp();
+          PROF_ADD(1, 1);
+          st.advance<NS>();
+        }
+        if (j >= 1) {
+          const int jj = j - 1, b = jj & 1;
+          PROF_T0();
+          ptx::mbar_wait_cluster(&bars[L::b_p_full + b], (jj >> 1) & 1);
+          PROF_ADD(1, 2);
+          ptx::mbar_wait(&bars[L::b_stage_full + st.idx], st.phase);
+          PROF_ADD(1, 3);
+          ptx::tc_fence_after();
+          if (ptx::elect_one()) {
+            const uint32_t b_base = smem_u + L::stages + st.idx * kStageBytes;
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk)
+                ptx::umma_f16_ts_2sm(tmem_o, tmem_base + b * kKeys + h * 64 + kk * 8,
+                                     ptx::umma_desc_kmajor_sw128(b_base + h * 16384 + kk * 32), idesc_pv,
+                                     (jj > 0) || (h | kk) != 0);
+            ptx::umma_commit_2sm_u32(bars_u + 8 * (L::b_stage_empty + st.idx));
+          }
+          __syncwarp();
+          PROF_ADD(1, 4);
+          st.advance<NS>();
+        }
+      }
+      if (ptx::elect_one()) ptx::umma_commit_2sm_u32(bars_u + 8 * (L::b_o_full));
+      __syncwarp();
+      if (prof_on && lane == 0) { for (int k = 0; k < 5; ++k) prof[8 + k] = prof_acc[k]; prof[8 + 5] = clock64() - prof_start; }
+    }
+  } else {
+    // ===== softmax: S (TMEM fp32) -> P' (TMEM fp16, in place) ; then epilogue =====
+    const int grp = warp >> 2, quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const int n = q0 + row;
+    float cs = -INFINITY, cg = -INFINITY, gx = 0.f, gy = 0.f, gz = 0.f, out_scale = 0.f;
+    if (n < N) {
+      const float4 c0 = rowc[2 * n], c1 = rowc[2 * n + 1];
+      cs = c0.x; cg = c0.y; gx = c0.z; gy = c0.w; gz = c1.x; out_scale = c1.y;
+    }
+    const uint32_t p_full_leader[2] = {ptx::mapa(ptx::smem_u32(&bars[L::b_p_full]), 0),
+                                       ptx::mapa(ptx::smem_u32(&bars[L::b_p_full + 1]), 0)};
+    PipeState xs;
+    for (int j = 0; j < T; ++j) {
+      const int b = j & 1;
+      const int key0 = (t_begin + j) * kKeys + grp * 64;
+      const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + b * kKeys + grp * 64;
+      PROF_T0();
+      ptx::mbar_wait(&bars[L::b_s_full + b], (j >> 1) & 1);
+      PROF_ADD(2, 0);
+      ptx::tc_fence_after();
+      uint32_t s0[32], s1[32];
+      ptx::tmem_ld32(taddr, s0);
+      ptx::tmem_ld32(taddr + 32, s1);
+      ptx::tmem_ld_wait();
+      PROF_ADD(2, 1);
+      const uint32_t kxyz = ptx::smem_u32(smem + L::xyz + xs.idx * kXyzBytes) + grp * 64 * 16;
+      if (kGeo) ptx::mbar_wait(&bars[L::b_xyz_full + xs.idx], xs.phase);
+      PROF_ADD(2, 2);
+      const int nvalid = M - key0;            // >= 64 except in the last tile
+      uint32_t packed[32];
+      auto body = [&](auto masked) {
+#pragma unroll
+        for (int w = 0; w < 32; ++w) {
+          float pv[2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int i = 2 * w + u;
+            const float sv = __uint_as_float(i < 32 ? s0[i] : s1[i - 32]);
+            const bool poly = kPolyModApply > 0 && (i % (kPolyModApply > 0 ? kPolyModApply : 1)) == 0;
+            float p = poly ? ptx::ex2_poly(fmaf(sv, a_sem, cs)) : ptx::ex2(fmaf(sv, a_sem, cs));
+            if (kGeo) {
+              const float4 k = ptx::lds_f4(kxyz + i * 16);
+              const float tg = fmaf(gx, k.x, fmaf(gy, k.y, fmaf(gz, k.z, cg)));
+              p += poly ? ptx::ex2_poly(tg) : ptx::ex2(tg);
+            }
+            if (decltype(masked)::value && i >= nvalid) p = 0.f;
+            pv[u] = p;
+          }
+          packed[w] = ptx::pack_half2(pv[0], pv[1]);
+        }
+      };
+      if (nvalid >= 64) body(std::false_type{}); else body(std::true_type{});
+      PROF_ADD(2, 3);
+      ptx::tmem_st32(taddr, packed);
+      ptx::tmem_st_wait();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        // the leader's MMA warp waits for both CTAs; the payload is in TMEM, so no memory release is needed
+        if (leader) ptx::mbar_arrive(&bars[L::b_p_full + b]);
+        else ptx::mbar_arrive_cluster_relaxed(p_full_leader[b]);
+        if (kGeo) ptx::mbar_arrive(&bars[L::b_xyz_empty + xs.idx]);
+      }
+      PROF_ADD(2, 4);
+      if (kGeo) xs.advance<NX>();
+    }
+    if (prof_on && threadIdx.x == 0) { for (int k = 0; k < 5; ++k) prof[16 + k] = prof_acc[k]; prof[16 + 5] = clock64() - prof_start; prof[16 + 6] = T; }
+    if (T > 0) {
+      ptx::mbar_wait(&bars[L::b_o_full], 0);
+      ptx::tc_fence_after();
+      float* orow = out + size_t(split) * out_split_stride + size_t(n) * 1024 + slice * kSliceV + grp * 128;
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        uint32_t v[32];
+        ptx::tmem_ld32(tmem_o + (uint32_t(quarter * 32) << 16) + grp * 128 + cc * 32, v);
+        ptx::tmem_ld_wait();
+        if (n < N) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            float4 o;
+            o.x = __uint_as_float(v[i]) * out_scale;
+            o.y = __uint_as_float(v[i + 1]) * out_scale;
+            o.z = __uint_as_float(v[i + 2]) * out_scale;
+            o.w = __uint_as_float(v[i + 3]) * out_scale;
+            *reinterpret_cast<float4*>(orow + cc * 32 + i) = o;
+          }
+        }
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  ptx::cluster_sync();                           // neither CTA may free TMEM / exit while the pair is in flight
+  if (warp == 9) ptx::tmem_dealloc_2sm<512>(tmem_base);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -663,14 +953,58 @@ cudaError_t launch_row_constants(const float* sums, const float* maxs, const flo
   return cudaGetLastError();
 }
 
+template <class Kern, class... Args>
+cudaError_t launch_pair(Kern kern, dim3 grid, int bytes, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = size_t(bytes);
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, args...);
+  if (e != cudaSuccess) {
+    int nclusters = -1;
+    cudaError_t e2 = cudaOccupancyMaxActiveClusters(&nclusters, kern, &cfg);
+    fprintf(stderr, "range_b200: cluster launch failed (%s); grid (%u,%u,%u) smem %d; max active clusters %d (%s)\n",
+            cudaGetErrorString(e), grid.x, grid.y, grid.z, bytes, nclusters, cudaGetErrorString(e2));
+  }
+  return e;
+}
+
 cudaError_t launch_apply(const RetrievalArgs& a, const float* rowc, float* out, size_t out_split_stride,
                          cudaStream_t stream) {
-  const int bytes = retrieval_apply_smem_bytes();
   cudaError_t e;
+  const float4* rc = reinterpret_cast<const float4*>(rowc);
+  const int qtiles = (a.N + kBlockQ - 1) / kBlockQ;
+  long long* no_prof = nullptr;
+  static const bool single = getenv("RANGE_APPLY") && !strcmp(getenv("RANGE_APPLY"), "single");   // A/B timing only
+  if (!single) {
+    // CTA pairs: cluster (2,1,1) over the query-tile axis (an odd tile count gets one all-padding CTA)
+    const int bytes = PairSmem::dynamic_bytes;
+    dim3 grid((qtiles + 1) / 2 * 2, 1024 / kSliceV, a.apply_splits);
+    if (g_prof_buffer) {
+      if ((e = set_smem(range_apply_pair_kernel<true, true>, bytes)) != cudaSuccess) return e;
+      return launch_pair(range_apply_pair_kernel<true, true>, grid, bytes, stream, a.tmQ, a.tmK64, a.tmV128, a.db_xyz,
+                         rc, a.N, a.M, a.apply_tiles_per_split, a.a_sem, out, out_split_stride, g_prof_buffer);
+    }
+    if ((e = set_smem(range_apply_pair_kernel<true>, bytes)) != cudaSuccess) return e;
+    if ((e = set_smem(range_apply_pair_kernel<false>, bytes)) != cudaSuccess) return e;
+    if (a.geo)
+      return launch_pair(range_apply_pair_kernel<true>, grid, bytes, stream, a.tmQ, a.tmK64, a.tmV128, a.db_xyz, rc,
+                         a.N, a.M, a.apply_tiles_per_split, a.a_sem, out, out_split_stride, no_prof);
+    return launch_pair(range_apply_pair_kernel<false>, grid, bytes, stream, a.tmQ, a.tmK64, a.tmV128, a.db_xyz, rc,
+                       a.N, a.M, a.apply_tiles_per_split, a.a_sem, out, out_split_stride, no_prof);
+  }
+  const int bytes = retrieval_apply_smem_bytes();
   if ((e = set_smem(range_apply_kernel<true>, bytes)) != cudaSuccess) return e;
   if ((e = set_smem(range_apply_kernel<false>, bytes)) != cudaSuccess) return e;
-  dim3 grid(1024 / kSliceV, (a.N + kBlockQ - 1) / kBlockQ, a.apply_splits);
-  const float4* rc = reinterpret_cast<const float4*>(rowc);
+  dim3 grid(1024 / kSliceV, qtiles, a.apply_splits);
   if (g_prof_buffer) {   // instrumented build of the same kernel (tools/time_apply.py)
     if ((e = set_smem(range_apply_kernel<true, true>, bytes)) != cudaSuccess) return e;
     range_apply_kernel<true, true><<<grid, kThreads, bytes, stream>>>(
