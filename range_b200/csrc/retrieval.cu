@@ -592,8 +592,15 @@ struct PairSmem : ApplySmem {
   static constexpr int dynamic_bytes = total + 1024;
 };
 
+// 16 softmax warps = two sets of 8 that PING-PONG over tiles (set j&1 owns S/P buffer j&1): while one set
+// waits for its S tile / hands P' over, the other keeps the MUFU pipe (the RANGE+ bottleneck: 2 ex2 per pair,
+// 16/clk/SM) busy.  Within a set warp w owns TMEM lanes 32 (w%4).. and the 64-entry column half (w/4)%2,
+// processed as two 32-column chunks to stay under 112 registers.
+constexpr int kPairSoftmaxWarps = 16;
+constexpr int kPairThreads = (kPairSoftmaxWarps + 2) * 32;
+
 template <bool kGeo, bool kProf = false>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kPairThreads, 1)
 range_apply_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK64,
                         const __grid_constant__ CUtensorMap tmV128, const float4* __restrict__ db_xyz,
                         const float4* __restrict__ rowc, int N, int M, int tiles_per_split, float a_sem,
@@ -628,16 +635,16 @@ range_apply_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&bars[L::b_s_full + i], 1);
-      ptx::mbar_init(&bars[L::b_p_full + i], 2 * kNumSoftmaxWarps);
+      ptx::mbar_init(&bars[L::b_p_full + i], kPairSoftmaxWarps);       // 8 warps x 2 CTAs
     }
     for (int i = 0; i < NX; ++i) {
       ptx::mbar_init(&bars[L::b_xyz_full + i], 1);
-      ptx::mbar_init(&bars[L::b_xyz_empty + i], kNumSoftmaxWarps);
+      ptx::mbar_init(&bars[L::b_xyz_empty + i], kPairSoftmaxWarps / 2);
     }
     ptx::mbar_init(&bars[L::b_o_full], 1);
     ptx::fence_mbar_init();
   }
-  if (warp == 9) ptx::tmem_alloc_2sm<512>(tmem_slot);
+  if (warp == kPairSoftmaxWarps + 1) ptx::tmem_alloc_2sm<512>(tmem_slot);
   ptx::tc_fence_before();
   ptx::cluster_sync();                           // barriers of BOTH CTAs initialised before any remote arrive
   ptx::tc_fence_after();
@@ -647,7 +654,7 @@ range_apply_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   const uint32_t bars_u = smem_u + L::bars;         // [0,128) S/P buf 0 | [128,256) S/P buf 1 | [256,512) O
   const uint32_t tmem_o = tmem_base + 256;
 
-  if (warp == 8) {
+  if (warp == kPairSoftmaxWarps) {
     // ===== TMA producer (both CTAs): own Q; own half of K(j) / Vt(j); bytes credited to the leader =====
     if (lane == 0 && T > 0) {
       ptx::prefetch_tmap(&tmQ);
@@ -692,7 +699,7 @@ range_apply_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       }
       if (prof_on) { prof[0] = prof_acc[0]; prof[1] = prof_acc[1]; prof[2] = clock64() - prof_start; }
     }
-  } else if (warp == 9) {
+  } else if (warp == kPairSoftmaxWarps + 1) {
     if (T > 0) {
       // both CTAs: tell the leader when this CTA's Q tile has landed
       ptx::mbar_wait(&bars[L::b_q_full], 0);
@@ -742,7 +749,8 @@ range_apply_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
             for (int h = 0; h < 2; ++h)
 #pragma unroll
               for (int kk = 0; kk < 4; ++kk)
-                ptx::umma_f16_ts_2sm(tmem_o, tmem_base + b * kKeys + h * 64 + kk * 8,
+                // P'(jj): column group g = 32 entries, written as 16 packed columns at S-buffer column 32 g
+                ptx::umma_f16_ts_2sm(tmem_o, tmem_base + b * kKeys + (2 * h + (kk >> 1)) * 32 + (kk & 1) * 8,
                                      ptx::umma_desc_kmajor_sw128(b_base + h * 16384 + kk * 32), idesc_pv,
                                      (jj > 0) || (h | kk) != 0);
             ptx::umma_commit_2sm_u32(bars_u + 8 * (L::b_stage_empty + st.idx));
@@ -758,7 +766,8 @@ range_apply_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     }
   } else {
     // ===== softmax: S (TMEM fp32) -> P' (TMEM fp16, in place) ; then epilogue =====
-    const int grp = warp >> 2, quarter = warp & 3;
+    const int set = warp >> 3, half = (warp >> 2) & 1, quarter = warp & 3;
+    const int grp = warp >> 2;                 // epilogue column group (0..3)
     const int row = quarter * 32 + lane;
     const int n = q0 + row;
     float cs = -INFINITY, cg = -INFINITY, gx = 0.f, gy = 0.f, gz = 0.f, out_scale = 0.f;
@@ -766,72 +775,72 @@ range_apply_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       const float4 c0 = rowc[2 * n], c1 = rowc[2 * n + 1];
       cs = c0.x; cg = c0.y; gx = c0.z; gy = c0.w; gz = c1.x; out_scale = c1.y;
     }
-    const uint32_t p_full_leader[2] = {ptx::mapa(ptx::smem_u32(&bars[L::b_p_full]), 0),
-                                       ptx::mapa(ptx::smem_u32(&bars[L::b_p_full + 1]), 0)};
-    PipeState xs;
-    for (int j = 0; j < T; ++j) {
-      const int b = j & 1;
-      const int key0 = (t_begin + j) * kKeys + grp * 64;
-      const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + b * kKeys + grp * 64;
+    const uint32_t p_full_leader = ptx::mapa(ptx::smem_u32(&bars[L::b_p_full + set]), 0);
+    for (int j = set; j < T; j += 2) {
+      const int xi = j % NX;
+      const uint32_t xph = (j / NX) & 1;
       PROF_T0();
-      ptx::mbar_wait(&bars[L::b_s_full + b], (j >> 1) & 1);
+      ptx::mbar_wait(&bars[L::b_s_full + set], (j >> 1) & 1);
       PROF_ADD(2, 0);
       ptx::tc_fence_after();
-      uint32_t s0[32], s1[32];
-      ptx::tmem_ld32(taddr, s0);
-      ptx::tmem_ld32(taddr + 32, s1);
-      ptx::tmem_ld_wait();
-      PROF_ADD(2, 1);
-      const uint32_t kxyz = ptx::smem_u32(smem + L::xyz + xs.idx * kXyzBytes) + grp * 64 * 16;
-      if (kGeo) ptx::mbar_wait(&bars[L::b_xyz_full + xs.idx], xs.phase);
+      if (kGeo) ptx::mbar_wait(&bars[L::b_xyz_full + xi], xph);
       PROF_ADD(2, 2);
-      const int nvalid = M - key0;            // >= 64 except in the last tile
-      uint32_t packed[32];
-      auto body = [&](auto masked) {
 #pragma unroll
-        for (int w = 0; w < 32; ++w) {
-          float pv[2];
+      for (int ch = 0; ch < 2; ++ch) {
+        const int col = half * 64 + ch * 32;
+        const int key0 = (t_begin + j) * kKeys + col;
+        const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + set * kKeys + col;
+        uint32_t s0[32];
+        ptx::tmem_ld32(taddr, s0);
+        ptx::tmem_ld_wait();
+        PROF_ADD(2, 1);
+        const uint32_t kxyz = ptx::smem_u32(smem + L::xyz + xi * kXyzBytes) + col * 16;
+        const int nvalid = M - key0;            // >= 32 except in the last tile
+        uint32_t packed[16];
+        auto body = [&](auto masked) {
 #pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const int i = 2 * w + u;
-            const float sv = __uint_as_float(i < 32 ? s0[i] : s1[i - 32]);
-            const bool poly = kPolyModApply > 0 && (i % (kPolyModApply > 0 ? kPolyModApply : 1)) == 0;
-            float p = poly ? ptx::ex2_poly(fmaf(sv, a_sem, cs)) : ptx::ex2(fmaf(sv, a_sem, cs));
-            if (kGeo) {
-              const float4 k = ptx::lds_f4(kxyz + i * 16);
-              const float tg = fmaf(gx, k.x, fmaf(gy, k.y, fmaf(gz, k.z, cg)));
-              p += poly ? ptx::ex2_poly(tg) : ptx::ex2(tg);
+          for (int w = 0; w < 16; ++w) {
+            float pv[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const int i = 2 * w + u;
+              const float sv = __uint_as_float(s0[i]);
+              float p = ptx::ex2(fmaf(sv, a_sem, cs));
+              if (kGeo) {
+                const float4 k = ptx::lds_f4(kxyz + i * 16);
+                p += ptx::ex2(fmaf(gx, k.x, fmaf(gy, k.y, fmaf(gz, k.z, cg))));
+              }
+              if (decltype(masked)::value && i >= nvalid) p = 0.f;
+              pv[u] = p;
             }
-            if (decltype(masked)::value && i >= nvalid) p = 0.f;
-            pv[u] = p;
+            packed[w] = ptx::pack_half2(pv[0], pv[1]);
           }
-          packed[w] = ptx::pack_half2(pv[0], pv[1]);
-        }
-      };
-      if (nvalid >= 64) body(std::false_type{}); else body(std::true_type{});
-      PROF_ADD(2, 3);
-      ptx::tmem_st32(taddr, packed);
+        };
+        if (nvalid >= 32) body(std::false_type{}); else body(std::true_type{});
+        PROF_ADD(2, 3);
+        // P'(row, 32 entries) as 16 packed columns over the first half of the 32 S columns it came from
+        ptx::tmem_st16(taddr, packed);
+      }
       ptx::tmem_st_wait();
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) {
         // the leader's MMA warp waits for both CTAs; the payload is in TMEM, so no memory release is needed
-        if (leader) ptx::mbar_arrive(&bars[L::b_p_full + b]);
-        else ptx::mbar_arrive_cluster_relaxed(p_full_leader[b]);
-        if (kGeo) ptx::mbar_arrive(&bars[L::b_xyz_empty + xs.idx]);
+        if (leader) ptx::mbar_arrive(&bars[L::b_p_full + set]);
+        else ptx::mbar_arrive_cluster_relaxed(p_full_leader);
+        if (kGeo) ptx::mbar_arrive(&bars[L::b_xyz_empty + xi]);
       }
       PROF_ADD(2, 4);
-      if (kGeo) xs.advance<NX>();
     }
-    if (prof_on && threadIdx.x == 0) { for (int k = 0; k < 5; ++k) prof[16 + k] = prof_acc[k]; prof[16 + 5] = clock64() - prof_start; prof[16 + 6] = T; }
+    if (prof_on && threadIdx.x == 0) { for (int k = 0; k < 5; ++k) prof[16 + k] = prof_acc[k]; prof[16 + 5] = clock64() - prof_start; prof[16 + 6] = (T + 1) / 2; }
     if (T > 0) {
       ptx::mbar_wait(&bars[L::b_o_full], 0);
       ptx::tc_fence_after();
-      float* orow = out + size_t(split) * out_split_stride + size_t(n) * 1024 + slice * kSliceV + grp * 128;
+      float* orow = out + size_t(split) * out_split_stride + size_t(n) * 1024 + slice * kSliceV + grp * 64;
 #pragma unroll
-      for (int cc = 0; cc < 4; ++cc) {
+      for (int cc = 0; cc < 2; ++cc) {
         uint32_t v[32];
-        ptx::tmem_ld32(tmem_o + (uint32_t(quarter * 32) << 16) + grp * 128 + cc * 32, v);
+        ptx::tmem_ld32(tmem_o + (uint32_t(quarter * 32) << 16) + grp * 64 + cc * 32, v);
         ptx::tmem_ld_wait();
         if (n < N) {
 #pragma unroll
@@ -849,7 +858,7 @@ range_apply_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   }
   ptx::tc_fence_before();
   ptx::cluster_sync();                           // neither CTA may free TMEM / exit while the pair is in flight
-  if (warp == 9) ptx::tmem_dealloc_2sm<512>(tmem_base);
+  if (warp == kPairSoftmaxWarps + 1) ptx::tmem_dealloc_2sm<512>(tmem_base);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -957,7 +966,7 @@ template <class Kern, class... Args>
 cudaError_t launch_pair(Kern kern, dim3 grid, int bytes, cudaStream_t stream, Args... args) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid;
-  cfg.blockDim = dim3(kThreads);
+  cfg.blockDim = dim3(kPairThreads);
   cfg.dynamicSmemBytes = size_t(bytes);
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
