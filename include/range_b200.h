@@ -57,6 +57,17 @@ int range_ctx_set_sh_table(range_ctx* ctx, int L, int n_entries, const double* p
 int range_ctx_set_encoder(range_ctx* ctx, int n_layers, const int32_t* dims, const double* const* W,
                           const double* const* b, double w0_first, double w0_hidden);
 
+/* Optional tensor-core encoder: the SIREN layers as 3xTF32 tcgen05 GEMMs (fp32-class accuracy; the
+ * reference's fp64 SIREN sits on spherical-harmonic input that carries >= 1e-3 of its own rounding noise).
+ * Needs every layer width % 256 == 0.  The prepared (split / permuted) weights live in `buf`, a device
+ * buffer of range_encoder_prepared_bytes() the caller keeps alive; after a successful prepare the ctx
+ * encodes in RANGE_ENC_TF32X3 until range_ctx_set_encoder_precision(ctx, RANGE_ENC_F64). */
+#define RANGE_ENC_F64 0
+#define RANGE_ENC_TF32X3 1
+size_t range_encoder_prepared_bytes(range_ctx* ctx);
+int range_ctx_prepare_encoder(range_ctx* ctx, void* buf, size_t bytes, void* stream);
+int range_ctx_set_encoder_precision(range_ctx* ctx, int mode);
+
 /* Device-resident database (range_b200/database.py) - replaces the tensors built at range/range.py:78-100.
  *   Kh  (Mpad, 256) fp16 row-major: row-normalised keys, rows >= M zero
  *   Vt  (1024, Mpad) fp16: values transposed (entries contiguous) times vscale, columns >= M zero

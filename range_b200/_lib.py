@@ -11,6 +11,7 @@ LIB_PATH = os.path.join(_HERE, "librange_b200.so")
 
 RANGE_MODE_RANGE, RANGE_MODE_RANGE_PLUS = 0, 1
 RANGE_OUT_F64, RANGE_OUT_F32 = 0, 1
+RANGE_ENC_F64, RANGE_ENC_TF32X3 = 0, 1
 
 # every symbol include/range_b200.h declares: name -> (restype, argtypes)
 PROTOTYPES = {
@@ -22,6 +23,9 @@ PROTOTYPES = {
     "range_ctx_set_sh_table": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "range_ctx_set_encoder": (c_int, [c_void_p, c_int, POINTER(c_int32), POINTER(c_void_p), POINTER(c_void_p),
                                       c_double, c_double]),
+    "range_encoder_prepared_bytes": (c_size_t, [c_void_p]),
+    "range_ctx_prepare_encoder": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
+    "range_ctx_set_encoder_precision": (c_int, [c_void_p, c_int]),
     "range_ctx_set_db": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_float]),
     "range_sh_features": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p]),
     "range_encode_workspace_bytes": (c_size_t, [c_void_p, c_int64]),

@@ -1,0 +1,263 @@
+// K1/K1b on the tensor cores: the SIREN layers as 3xTF32 tcgen05 GEMMs (fp32-class accuracy).
+//
+// The reference runs the SIREN in fp64 (model_old.py:326-330), but its own spherical-harmonic input carries
+// 1e-3 .. 5e-2 of fp64 rounding noise; an fp32-accurate SIREN moves the normalised
+// embedding by ~3e-7 (measured, tests/test_gpu_parity.py::test_encoder_tf32x3_vs_fp64), far below that.
+// Every operand x is split x = hi + lo with hi holding the 10 mantissa bits the TF32 datapath keeps, and
+//     A.B  ~=  A_hi.B_hi + A_hi.B_lo + A_lo.B_hi          (dropped term: 2^-22 relative)
+// accumulated in fp32 in TMEM.  Bias add and the sine's argument reduction are done in fp64 in the epilogue.
+//
+//   sh_rowmajor_kernel   features in PRODUCTION order (|m|-major; the first layer's columns are permuted to
+//                        match) as hi/lo fp32, row-major [N][L*L], through a per-warp 32x32 smem transpose
+//                        so global writes are coalesced although a thread owns a whole query.
+//   split_weights_kernel W fp64 [H][K] -> W_hi, W_lo fp32 [H][K] (optionally with the column permutation)
+//   siren_tc_kernel      CTA = 128 queries x 256 outputs, K-blocks of 32: TMA (SWIZZLE_128B) -> smem ring ->
+//                        12 x tcgen05.mma kind::tf32 (128x256x8) per block -> TMEM -> epilogue warps.
+#include <cstdint>
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+#include "ptx.cuh"
+#include "range_kernels.h"
+
+namespace {
+
+constexpr double kDeg2Rad = 0.017453292519943295769236907684886;
+
+__device__ __forceinline__ void split_tf32(double x, float& hi, float& lo) {
+  const float f = float(x);
+  hi = __uint_as_float(__float_as_uint(f) & 0xFFFFE000u);      // the 19 bits kind::tf32 reads
+  lo = float(x - double(hi));
+}
+
+// ---------------------------------------------------------------------------------------------------
+// SH features, row-major hi/lo fp32, production order:  for am: for l >= am: [cos] then [sin] (am > 0)
+// ---------------------------------------------------------------------------------------------------
+constexpr int kShWarps = 4;
+__global__ void __launch_bounds__(kShWarps * 32)
+sh_rowmajor_kernel(const double* __restrict__ lonlat, int N, int L, const double* __restrict__ pref,
+                   const int* __restrict__ off, const double* __restrict__ coef, const int* __restrict__ par,
+                   float* __restrict__ Yh, float* __restrict__ Yl) {
+  __shared__ float tile[kShWarps][2][32][33];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = (blockIdx.x * kShWarps + warp) * 32;
+  if (n0 >= N) return;
+  const int n = n0 + lane;
+  const int F = L * L;
+  double lon = 0.0, lat = 0.0;
+  if (n < N) { lon = lonlat[2 * n]; lat = lonlat[2 * n + 1]; }
+  const double phi = (lon + 180.0) * kDeg2Rad;
+  const double theta = (lat + 90.0) * kDeg2Rad;
+  const double c = cos(theta);
+  const double c2 = c * c;
+  const double s = sqrt(1.0 - c2);
+  double spow = 1.0;
+  int e = 0, cnt = 0, f0 = 0;
+  auto emit = [&](double v) {
+    float hi, lo;
+    split_tf32(v, hi, lo);
+    tile[warp][0][lane][cnt] = hi;
+    tile[warp][1][lane][cnt] = lo;
+    if (++cnt == 32) {
+      __syncwarp();
+      const int rows = min(32, N - n0);
+      for (int r = 0; r < rows; ++r) {                       // row r of the tile = query n0 + r; lanes = features
+        Yh[size_t(n0 + r) * F + f0 + lane] = tile[warp][0][r][lane];
+        Yl[size_t(n0 + r) * F + f0 + lane] = tile[warp][1][r][lane];
+      }
+      __syncwarp();
+      cnt = 0;
+      f0 += 32;
+    }
+  };
+  for (int am = 0; am < L; ++am) {
+    double cm = 1.0, sm = 0.0;
+    if (am > 0) {
+      spow *= s;
+      sincos(double(am) * phi, &sm, &cm);
+    }
+    for (int l = am; l < L; ++l, ++e) {
+      int k = __ldg(off + e);
+      const int kend = __ldg(off + e + 1);
+      double acc = __ldg(coef + k);
+      for (++k; k < kend; ++k) acc = fma(acc, c2, __ldg(coef + k));
+      if (__ldg(par + e)) acc *= c;
+      if (am == 0) {
+        emit(acc);
+      } else {
+        const double leg = (__ldg(pref + e) * spow) * acc;
+        emit(leg * cm);
+        emit(leg * sm);
+      }
+    }
+  }
+}
+
+// W fp64 [H][K] -> hi/lo fp32 [H][K]; column f of the output reads column perm[f] of the input (perm may be null)
+__global__ void split_weights_kernel(const double* __restrict__ W, int H, int K, const int* __restrict__ perm,
+                                     float* __restrict__ Wh, float* __restrict__ Wl) {
+  const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= size_t(H) * K) return;
+  const int h = int(i / K), f = int(i % K);
+  float hi, lo;
+  split_tf32(W[size_t(h) * K + (perm ? perm[f] : f)], hi, lo);
+  Wh[i] = hi;
+  Wl[i] = lo;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// out(128 x 256) = act(A(128 x K) . B(256 x K)^T + bias)
+// ---------------------------------------------------------------------------------------------------
+constexpr int kTcStages = 2;
+constexpr int kTcStageBytes = 2 * 16384 + 2 * 32768;     // A_hi | A_lo | B_hi | B_lo
+constexpr int kTcEpiWarps = 8;
+constexpr int kTcThreads = (kTcEpiWarps + 2) * 32;
+constexpr int kTcSmem = kTcStages * kTcStageBytes + 256 + 1024;
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+siren_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
+                const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
+                const double* __restrict__ bias, int N, int K, int H, double act_w0, float* __restrict__ out_hi,
+                float* __restrict__ out_lo, double* __restrict__ out_f64) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kTcStages * kTcStageBytes);   // full[S] | empty[S] | done
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kTcStages + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row0 = blockIdx.x * 128, col0 = blockIdx.y * 256;
+  const int KB = K / 32;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kTcStages; ++i) {
+      ptx::mbar_init(&bars[i], 1);
+      ptx::mbar_init(&bars[kTcStages + i], 1);
+    }
+    ptx::mbar_init(&bars[2 * kTcStages], 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == kTcEpiWarps + 1) ptx::tmem_alloc<256>(tmem_slot);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  const uint32_t smem_u = __shfl_sync(0xffffffffu, ptx::smem_u32(smem), 0);
+  const uint32_t bars_u = smem_u + kTcStages * kTcStageBytes;
+
+  if (warp == kTcEpiWarps) {
+    if (lane == 0) {
+      ptx::prefetch_tmap(&tmAh); ptx::prefetch_tmap(&tmAl); ptx::prefetch_tmap(&tmBh); ptx::prefetch_tmap(&tmBl);
+      int idx = 0; uint32_t phase = 0;
+      for (int kb = 0; kb < KB; ++kb) {
+        ptx::mbar_wait(&bars[kTcStages + idx], phase ^ 1);
+        uint8_t* st = smem + idx * kTcStageBytes;
+        ptx::mbar_expect_tx(&bars[idx], kTcStageBytes);
+        ptx::tma_load_2d(st, &tmAh, &bars[idx], kb * 32, row0);
+        ptx::tma_load_2d(st + 16384, &tmAl, &bars[idx], kb * 32, row0);
+        ptx::tma_load_2d(st + 32768, &tmBh, &bars[idx], kb * 32, col0);
+        ptx::tma_load_2d(st + 65536, &tmBl, &bars[idx], kb * 32, col0);
+        if (++idx == kTcStages) { idx = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == kTcEpiWarps + 1) {
+    constexpr uint32_t idesc = ptx::umma_idesc_tf32(128, 256);
+    int idx = 0; uint32_t phase = 0;
+    for (int kb = 0; kb < KB; ++kb) {
+      ptx::mbar_wait(&bars[idx], phase);
+      ptx::tc_fence_after();
+      if (ptx::elect_one()) {
+        const uint32_t st = smem_u + idx * kTcStageBytes;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const uint64_t ah = ptx::umma_desc_kmajor_sw128(st + kk * 32);
+          const uint64_t al = ptx::umma_desc_kmajor_sw128(st + 16384 + kk * 32);
+          const uint64_t bh = ptx::umma_desc_kmajor_sw128(st + 32768 + kk * 32);
+          const uint64_t bl = ptx::umma_desc_kmajor_sw128(st + 65536 + kk * 32);
+          ptx::umma_tf32_ss(tmem_base, al, bh, idesc, (kb | kk) != 0);   // small terms first
+          ptx::umma_tf32_ss(tmem_base, ah, bl, idesc, 1);
+          ptx::umma_tf32_ss(tmem_base, ah, bh, idesc, 1);
+        }
+        ptx::umma_commit_u32(bars_u + 8 * (kTcStages + idx));
+        if (kb == KB - 1) ptx::umma_commit_u32(bars_u + 8 * (2 * kTcStages));
+      }
+      __syncwarp();
+      if (++idx == kTcStages) { idx = 0; phase ^= 1; }
+    }
+  } else {
+    // ===== epilogue: warp w -> TMEM lanes 32 (w%4).., columns 128 (w/4) .. +127 =====
+    const int quarter = warp & 3, half = warp >> 2;
+    const int n = row0 + quarter * 32 + lane;
+    ptx::mbar_wait(&bars[2 * kTcStages], 0);
+    ptx::tc_fence_after();
+#pragma unroll 1
+    for (int cc = 0; cc < 4; ++cc) {
+      uint32_t v[32];
+      const int c0 = half * 128 + cc * 32;
+      ptx::tmem_ld32(tmem_base + (uint32_t(quarter * 32) << 16) + c0, v);
+      ptx::tmem_ld_wait();
+      if (n < N) {
+        if (out_f64) {
+          double* o = out_f64 + size_t(n) * H + col0 + c0;
+#pragma unroll
+          for (int i = 0; i < 32; i += 2)
+            *reinterpret_cast<double2*>(o + i) = make_double2(double(__uint_as_float(v[i])) + __ldg(bias + col0 + c0 + i),
+                                                              double(__uint_as_float(v[i + 1])) + __ldg(bias + col0 + c0 + i + 1));
+        } else {
+          float hi[32], lo[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            // sin(w0 (acc + b)): argument reduced in fp64 (phases reach tens of radians), sine in fp32
+            const double t = act_w0 * (double(__uint_as_float(v[i])) + __ldg(bias + col0 + c0 + i));
+            const double r = fma(-rint(t * 0.15915494309189535), 6.283185307179586, t);
+            const float sv = sinf(float(r));
+            hi[i] = __uint_as_float(__float_as_uint(sv) & 0xFFFFE000u);
+            lo[i] = sv - hi[i];
+          }
+          float4* oh = reinterpret_cast<float4*>(out_hi + size_t(n) * H + col0 + c0);
+          float4* ol = reinterpret_cast<float4*>(out_lo + size_t(n) * H + col0 + c0);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            oh[i] = make_float4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
+            ol[i] = make_float4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+          }
+        }
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == kTcEpiWarps + 1) ptx::tmem_dealloc<256>(tmem_base);
+}
+
+}  // namespace
+
+namespace rangeb200 {
+
+cudaError_t launch_sh_rowmajor(const ShTable& t, const double* lonlat, int N, float* Yh, float* Yl, cudaStream_t s) {
+  if (N <= 0) return cudaSuccess;
+  const int per_block = kShWarps * 32;
+  sh_rowmajor_kernel<<<(N + per_block - 1) / per_block, per_block, 0, s>>>(lonlat, N, t.L, t.pref, t.off, t.coef,
+                                                                           t.par, Yh, Yl);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_split_weights(const double* W, int H, int K, const int* perm, float* Wh, float* Wl, cudaStream_t s) {
+  const size_t total = size_t(H) * K;
+  split_weights_kernel<<<unsigned((total + 255) / 256), 256, 0, s>>>(W, H, K, perm, Wh, Wl);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_siren_tc(const CUtensorMap& tmAh, const CUtensorMap& tmAl, const CUtensorMap& tmBh,
+                            const CUtensorMap& tmBl, const double* bias, int N, int K, int H, double act_w0,
+                            float* out_hi, float* out_lo, double* out_f64, cudaStream_t s) {
+  if (N <= 0) return cudaSuccess;
+  if (K % 32 || H % 256) return cudaErrorInvalidValue;
+  cudaError_t e = cudaFuncSetAttribute(siren_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem);
+  if (e != cudaSuccess) return e;
+  dim3 grid((N + 127) / 128, H / 256);
+  siren_tc_kernel<<<grid, kTcThreads, kTcSmem, s>>>(tmAh, tmAl, tmBh, tmBl, bias, N, K, H, act_w0, out_hi, out_lo,
+                                                    out_f64);
+  return cudaGetLastError();
+}
+
+}  // namespace rangeb200

@@ -23,9 +23,12 @@ def _stream():
 
 
 class RangeEngine:
-    def __init__(self, device, encoder=None, database=None, L=None):
+    def __init__(self, device, encoder=None, database=None, L=None, encoder_precision="auto"):
         """encoder: dict from checkpoint.load_satclip_location_encoder (or None: SH only with `L`);
-        database: database.DeviceDatabase or None."""
+        database: database.DeviceDatabase or None;
+        encoder_precision: 'fp64' (the reference's arithmetic, DMMA), 'tf32x3' (tensor cores, fp32-class
+        accuracy) or 'auto' (= tf32x3 when the layer widths allow it, else fp64)."""
+        self.encoder_precision = encoder_precision
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise _lib.RangeError(f"range_b200 runs on CUDA (sm_100a) devices only, got device={device!r}; "
@@ -75,6 +78,17 @@ class RangeEngine:
         B = (c_void_p * n)(*[b.data_ptr() for _, b in self._weights])
         _lib.check(self.lib.range_ctx_set_encoder(self.ctx, n, dims, W, B, w0_first, w0_hidden))
         self.dims = list(enc["dims"])
+        self._prepared = None
+        self.precision = "fp64"
+        want = self.encoder_precision
+        nbytes = self.lib.range_encoder_prepared_bytes(self.ctx)
+        if want == "tf32x3" and nbytes == 0:
+            raise _lib.RangeError("encoder_precision='tf32x3' needs every SIREN width to be a multiple of 256")
+        if want in ("auto", "tf32x3") and nbytes > 0:
+            self._prepared = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+            with torch.cuda.device(self.index):
+                _lib.check(self.lib.range_ctx_prepare_encoder(self.ctx, _ptr(self._prepared), int(nbytes), _stream()))
+            self.precision = "tf32x3"
 
     def set_database(self, db):
         _lib.check(self.lib.range_ctx_set_db(self.ctx, db.M, db.Mpad, _ptr(db.Kh), _ptr(db.Vt), _ptr(db.xyz),
