@@ -44,8 +44,14 @@ constexpr int kNumSoftmaxWarps = 8;
 constexpr int kThreads = (kNumSoftmaxWarps + 2) * 32;
 // exponentials evaluated on the FMA pipe instead of MUFU (ptx::ex2_poly): every k-th element, 0 = none.
 // Measured on B200: any offload is slower (the softmax warps are issue-bound, not MUFU-bound).
-constexpr int kPolyModApply = 0;
-constexpr int kPolyModStats = 0;
+#ifndef RANGE_POLY_APPLY
+#define RANGE_POLY_APPLY 0
+#endif
+#ifndef RANGE_POLY_STATS
+#define RANGE_POLY_STATS 0
+#endif
+constexpr int kPolyModApply = RANGE_POLY_APPLY;
+constexpr int kPolyModStats = RANGE_POLY_STATS;
 constexpr uint32_t kTmemQ = 0;      // column offsets
 constexpr uint32_t kTmemS = 128;
 
@@ -592,10 +598,12 @@ struct PairSmem : ApplySmem {
   static constexpr int dynamic_bytes = total + 1024;
 };
 
-// 16 softmax warps = two sets of 8 that PING-PONG over tiles (set j&1 owns S/P buffer j&1): while one set
-// waits for its S tile / hands P' over, the other keeps the MUFU pipe (the RANGE+ bottleneck: 2 ex2 per pair,
-// 16/clk/SM) busy.  Within a set warp w owns TMEM lanes 32 (w%4).. and the 64-entry column half (w/4)%2,
-// processed as two 32-column chunks to stay under 112 registers.
+// 16 softmax warps (4 per SM sub-partition; warp w owns TMEM lanes 32 (w%4).. and the 32-entry column group
+// w/4 of every tile) keep the MUFU pipe - the RANGE+ bottleneck: 2 ex2 per pair, 16/clk/SM - fed.  Measured
+// alternatives: two 8-warp sets ping-ponging over tiles (same speed: one set alone cannot saturate MUFU) and
+// evaluating part of the exponentials on the FMA pipe (slower: register spills under the 112-register cap).
+// Per tile a warp passes ONE barrier: the entries' xyz bytes are credited to the same mbarrier the MMA
+// completion arrives on.  (Prefetching S(j+1) into a second register array was measured slower: spills.)
 constexpr int kPairSoftmaxWarps = 16;
 constexpr int kPairThreads = (kPairSoftmaxWarps + 2) * 32;
 
@@ -634,13 +642,10 @@ range_apply_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       ptx::mbar_init(&bars[L::b_stage_empty + i], 1);
     }
     for (int i = 0; i < 2; ++i) {
-      ptx::mbar_init(&bars[L::b_s_full + i], 1);
-      ptx::mbar_init(&bars[L::b_p_full + i], kPairSoftmaxWarps);       // 8 warps x 2 CTAs
+      ptx::mbar_init(&bars[L::b_s_full + i], kGeo ? 2 : 1);            // MMA commit (+ this CTA's xyz bytes)
+      ptx::mbar_init(&bars[L::b_p_full + i], 2 * kPairSoftmaxWarps);  // 16 warps x 2 CTAs
     }
-    for (int i = 0; i < NX; ++i) {
-      ptx::mbar_init(&bars[L::b_xyz_full + i], 1);
-      ptx::mbar_init(&bars[L::b_xyz_empty + i], kPairSoftmaxWarps / 2);
-    }
+    for (int i = 0; i < 2; ++i) ptx::mbar_init(&bars[L::b_xyz_empty + i], kPairSoftmaxWarps);
     ptx::mbar_init(&bars[L::b_o_full], 1);
     ptx::fence_mbar_init();
   }
@@ -662,17 +667,10 @@ range_apply_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       ptx::prefetch_tmap(&tmV128);
       ptx::mbar_expect_tx(&bars[L::b_q_full], 65536);
       for (int c = 0; c < 4; ++c) ptx::tma_load_2d(smem + L::q + c * 16384, &tmQ, &bars[L::b_q_full], c * 64, q0);
-      PipeState st, xs;
+      PipeState st;
       for (int j = 0; j <= T; ++j) {
         if (j < T) {
           const int key0 = (t_begin + j) * kKeys;
-          if (kGeo) {
-            ptx::mbar_wait(&bars[L::b_xyz_empty + xs.idx], xs.phase ^ 1);
-            ptx::mbar_expect_tx(&bars[L::b_xyz_full + xs.idx], kXyzBytes);
-            ptx::bulk_load_1d(smem + L::xyz + xs.idx * kXyzBytes, db_xyz + key0, kXyzBytes,
-                              &bars[L::b_xyz_full + xs.idx]);
-            xs.advance<NX>();
-          }
           PROF_T0();
           ptx::mbar_wait(&bars[L::b_stage_empty + st.idx], st.phase ^ 1);
           PROF_ADD(0, 0);
@@ -695,6 +693,15 @@ range_apply_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
             ptx::tma_load_2d_2sm(dst + h * 16384, &tmV128, &bars[L::b_stage_full + st.idx], key0 + h * 64,
                                  slice * kSliceV + int(rank) * 128);
           st.advance<NS>();
+        }
+        if (kGeo && j < T) {
+          // xyz(j) -> slot j&1, bytes credited to s_full[j&1] (the barrier S(j) arrives on).  Issued LAST in the
+          // iteration: the slot frees only when softmax(j-2) is done, and nothing the MMA warp is about to need
+          // may queue behind that wait.
+          ptx::mbar_wait(&bars[L::b_xyz_empty + (j & 1)], ((j >> 1) & 1) ^ 1);
+          ptx::mbar_expect_tx(&bars[L::b_s_full + (j & 1)], kXyzBytes);
+          ptx::bulk_load_1d(smem + L::xyz + (j & 1) * kXyzBytes, db_xyz + (t_begin + j) * kKeys, kXyzBytes,
+                            &bars[L::b_s_full + (j & 1)]);
         }
       }
       if (prof_on) { prof[0] = prof_acc[0]; prof[1] = prof_acc[1]; prof[2] = clock64() - prof_start; }
@@ -766,8 +773,7 @@ range_apply_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     }
   } else {
     // ===== softmax: S (TMEM fp32) -> P' (TMEM fp16, in place) ; then epilogue =====
-    const int set = warp >> 3, half = (warp >> 2) & 1, quarter = warp & 3;
-    const int grp = warp >> 2;                 // epilogue column group (0..3)
+    const int grp = warp >> 2, quarter = warp & 3;
     const int row = quarter * 32 + lane;
     const int n = q0 + row;
     float cs = -INFINITY, cg = -INFINITY, gx = 0.f, gy = 0.f, gz = 0.f, out_scale = 0.f;
@@ -775,64 +781,58 @@ range_apply_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       const float4 c0 = rowc[2 * n], c1 = rowc[2 * n + 1];
       cs = c0.x; cg = c0.y; gx = c0.z; gy = c0.w; gz = c1.x; out_scale = c1.y;
     }
-    const uint32_t p_full_leader = ptx::mapa(ptx::smem_u32(&bars[L::b_p_full + set]), 0);
-    for (int j = set; j < T; j += 2) {
-      const int xi = j % NX;
-      const uint32_t xph = (j / NX) & 1;
+    const uint32_t p_full_leader[2] = {ptx::mapa(ptx::smem_u32(&bars[L::b_p_full]), 0),
+                                       ptx::mapa(ptx::smem_u32(&bars[L::b_p_full + 1]), 0)};
+    const uint32_t lane_col = (uint32_t(quarter * 32) << 16) + grp * 32;
+    for (int j = 0; j < T; ++j) {
+      const int b = j & 1;
+      const uint32_t taddr = tmem_base + lane_col + b * kKeys;
+      uint32_t cur[32];
       PROF_T0();
-      ptx::mbar_wait(&bars[L::b_s_full + set], (j >> 1) & 1);
-      PROF_ADD(2, 0);
+      ptx::mbar_wait(&bars[L::b_s_full + b], (j >> 1) & 1);      // S(j) in TMEM and xyz(j) in smem
       ptx::tc_fence_after();
-      if (kGeo) ptx::mbar_wait(&bars[L::b_xyz_full + xi], xph);
-      PROF_ADD(2, 2);
+      ptx::tmem_ld32(taddr, cur);
+      PROF_ADD(2, 0);
+      ptx::tmem_ld_wait();
+      PROF_ADD(2, 1);
+      const int key0 = (t_begin + j) * kKeys + grp * 32;
+      const uint32_t kxyz = ptx::smem_u32(smem + L::xyz + b * kXyzBytes) + grp * 32 * 16;
+      const int nvalid = M - key0;            // >= 32 except in the last tile
+      uint32_t packed[16];
+      auto body = [&](auto masked) {
 #pragma unroll
-      for (int ch = 0; ch < 2; ++ch) {
-        const int col = half * 64 + ch * 32;
-        const int key0 = (t_begin + j) * kKeys + col;
-        const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + set * kKeys + col;
-        uint32_t s0[32];
-        ptx::tmem_ld32(taddr, s0);
-        ptx::tmem_ld_wait();
-        PROF_ADD(2, 1);
-        const uint32_t kxyz = ptx::smem_u32(smem + L::xyz + xi * kXyzBytes) + col * 16;
-        const int nvalid = M - key0;            // >= 32 except in the last tile
-        uint32_t packed[16];
-        auto body = [&](auto masked) {
+        for (int w = 0; w < 16; ++w) {
+          float pv[2];
 #pragma unroll
-          for (int w = 0; w < 16; ++w) {
-            float pv[2];
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-              const int i = 2 * w + u;
-              const float sv = __uint_as_float(s0[i]);
-              float p = ptx::ex2(fmaf(sv, a_sem, cs));
-              if (kGeo) {
-                const float4 k = ptx::lds_f4(kxyz + i * 16);
-                p += ptx::ex2(fmaf(gx, k.x, fmaf(gy, k.y, fmaf(gz, k.z, cg))));
-              }
-              if (decltype(masked)::value && i >= nvalid) p = 0.f;
-              pv[u] = p;
+          for (int u = 0; u < 2; ++u) {
+            const int i = 2 * w + u;
+            float p = ptx::ex2(fmaf(__uint_as_float(cur[i]), a_sem, cs));
+            if (kGeo) {
+              const float4 k = ptx::lds_f4(kxyz + i * 16);
+              p += ptx::ex2(fmaf(gx, k.x, fmaf(gy, k.y, fmaf(gz, k.z, cg))));
             }
-            packed[w] = ptx::pack_half2(pv[0], pv[1]);
+            if (decltype(masked)::value && i >= nvalid) p = 0.f;
+            pv[u] = p;
           }
-        };
-        if (nvalid >= 32) body(std::false_type{}); else body(std::true_type{});
-        PROF_ADD(2, 3);
-        // P'(row, 32 entries) as 16 packed columns over the first half of the 32 S columns it came from
-        ptx::tmem_st16(taddr, packed);
-      }
+          packed[w] = ptx::pack_half2(pv[0], pv[1]);
+        }
+      };
+      if (nvalid >= 32) body(std::false_type{}); else body(std::true_type{});
+      PROF_ADD(2, 3);
+      // P'(row, 32 entries) as 16 packed columns over the first half of the 32 S columns it came from
+      ptx::tmem_st16(taddr, packed);
       ptx::tmem_st_wait();
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) {
         // the leader's MMA warp waits for both CTAs; the payload is in TMEM, so no memory release is needed
-        if (leader) ptx::mbar_arrive(&bars[L::b_p_full + set]);
-        else ptx::mbar_arrive_cluster_relaxed(p_full_leader);
-        if (kGeo) ptx::mbar_arrive(&bars[L::b_xyz_empty + xi]);
+        if (leader) ptx::mbar_arrive(&bars[L::b_p_full + b]);
+        else ptx::mbar_arrive_cluster_relaxed(p_full_leader[b]);
+        if (kGeo) ptx::mbar_arrive(&bars[L::b_xyz_empty + b]);
       }
       PROF_ADD(2, 4);
     }
-    if (prof_on && threadIdx.x == 0) { for (int k = 0; k < 5; ++k) prof[16 + k] = prof_acc[k]; prof[16 + 5] = clock64() - prof_start; prof[16 + 6] = (T + 1) / 2; }
+    if (prof_on && threadIdx.x == 0) { for (int k = 0; k < 5; ++k) prof[16 + k] = prof_acc[k]; prof[16 + 5] = clock64() - prof_start; prof[16 + 6] = T; }
     if (T > 0) {
       ptx::mbar_wait(&bars[L::b_o_full], 0);
       ptx::tc_fence_after();

@@ -35,8 +35,6 @@ if os.environ.get("PROF"):
     eng.retrieve_apply("RANGE+", q, xyz, 12.0, 40.0, 0.5, sums, maxs); torch.cuda.synchronize()
     eng.lib.range_debug_set_profile_buffer(None)
     b = buf.cpu().numpy().astype(float); T = max(1, b[22])
-    if os.environ.get("RANGE_APPLY") != "single":
-        b[:16] /= 2.0      # pair kernel: softmax warp 0 sees every other tile; producer / MMA see all
     print(f"tiles {T}; per-tile cycles:")
     print(f" producer: wait_empty(K) {b[0]/T:.0f} wait_empty(V) {b[1]/T:.0f} total {b[2]/T:.0f}")
     print(f" mma: wait_stage_qk {b[8]/T:.0f} issue_qk {b[9]/T:.0f} wait_p {b[10]/T:.0f} wait_stage_pv {b[11]/T:.0f} issue_pv {b[12]/T:.0f} total {b[13]/T:.0f}")
