@@ -93,7 +93,8 @@ struct range_ctx {
 namespace {
 
 struct RetrievalPlan {
-  int splits, tiles_per_split;
+  int splits, tiles_per_split;              // apply kernel
+  int stats_splits, stats_tiles_per_split;  // stats kernel
   size_t off_part_sum, off_part_max, off_sums, off_maxs, off_rowc, off_part_out, total;
 };
 
@@ -110,9 +111,20 @@ RetrievalPlan plan_retrieval(const range_ctx* c, int64_t N) {
   if (want > 64) want = 64;
   p.tiles_per_split = int((tiles + want - 1) / want);
   p.splits = int((tiles + p.tiles_per_split - 1) / p.tiles_per_split);
+  // stats kernel: one CTA per (query tile, split).  Its partials are tiny, so choose the split count that
+  // minimises wave quantisation: waves(s) / s with waves(s) = ceil(qtiles * s / SMs), keeping >= 32 tiles per split.
+  int64_t best = want;
+  double best_cost = 1e30;
+  for (int64_t sp = want; sp <= 16 && sp <= (tiles / 32 > 0 ? tiles / 32 : 1); ++sp) {
+    const double waves = double((qtiles * sp + c->sm_count - 1) / c->sm_count);
+    const double cost = waves / double(sp) * (1.0 + 0.004 * double(sp));      // small per-CTA fixed cost
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = sp; }
+  }
+  p.stats_tiles_per_split = int((tiles + best - 1) / best);
+  p.stats_splits = int((tiles + p.stats_tiles_per_split - 1) / p.stats_tiles_per_split);
   size_t o = 0;
-  p.off_part_sum = o; o += align_up(size_t(p.splits) * N * 8, 256);
-  p.off_part_max = o; o += align_up(size_t(p.splits) * N * 8, 256);
+  p.off_part_sum = o; o += align_up(size_t(p.stats_splits) * N * 8, 256);
+  p.off_part_max = o; o += align_up(size_t(p.stats_splits) * N * 8, 256);
   p.off_sums = o;     o += align_up(size_t(N) * 8, 256);
   p.off_maxs = o;     o += align_up(size_t(N) * 8, 256);
   p.off_rowc = o;     o += align_up(size_t(N) * 32, 256);
@@ -138,9 +150,10 @@ int fill_args(range_ctx* c, int mode, int64_t N, const void* q16, const float* q
   a->N = int(N);
   a->M = int(c->M);
   a->geo = mode == RANGE_MODE_RANGE_PLUS;
-  a->stats_splits = a->apply_splits = p.splits;
-  a->stats_tiles_per_split = p.tiles_per_split;
+  a->apply_splits = p.splits;
   a->apply_tiles_per_split = p.tiles_per_split;
+  a->stats_splits = p.stats_splits;
+  a->stats_tiles_per_split = p.stats_tiles_per_split;
   const float log2e = 1.4426950408889634f;
   a->a_sem = temp * log2e;
   a->a_geo = geo_temp * log2e;
@@ -400,12 +413,12 @@ int range_retrieve_stats(range_ctx* c, int mode, int64_t N, const void* q16, con
   if (r) return r;
   char* ws = reinterpret_cast<char*>(align_up(reinterpret_cast<size_t>(workspace), 256));
   cudaStream_t s = cudaStream_t(stream);
-  float* part_sum = p.splits > 1 ? reinterpret_cast<float*>(ws + p.off_part_sum) : sums;
-  float* part_max = p.splits > 1 ? reinterpret_cast<float*>(ws + p.off_part_max) : maxs;
+  float* part_sum = p.stats_splits > 1 ? reinterpret_cast<float*>(ws + p.off_part_sum) : sums;
+  float* part_max = p.stats_splits > 1 ? reinterpret_cast<float*>(ws + p.off_part_max) : maxs;
   CUDA_TRY(launch_stats(a, part_sum, part_max, s));
   g_launches += 1;
-  if (p.splits > 1) {
-    CUDA_TRY(launch_reduce_stats(part_sum, part_max, int(N), p.splits, sums, maxs, s));
+  if (p.stats_splits > 1) {
+    CUDA_TRY(launch_reduce_stats(part_sum, part_max, int(N), p.stats_splits, sums, maxs, s));
     g_launches += 1;
   }
   return RANGE_OK;

@@ -93,37 +93,55 @@ __device__ __forceinline__ void named_bar_sync_softmax() {
 
 // Q tile (rows q0..q0+127 of q16, 256 halves each) -> TMEM columns [kTmemQ, kTmemQ+128): lane = row,
 // column = dim / 2 (two fp16 per 32-bit column) - the A-operand layout of kind::f16 for M = 128.
-// Warps 0-7: warp w writes lanes 32 (w%4).., group w/4 the dims [128 g, 128 g + 128).
-__device__ __forceinline__ void load_q_to_tmem(const __half* __restrict__ q16, int q0, int N, uint32_t tmem_base,
-                                               int warp, int lane) {
+// 16 warps: warp w writes lanes 32 (w%4).., column group w/4 = dims [64 g, 64 g + 64).
+__device__ __forceinline__ void load_q_to_tmem16(const __half* __restrict__ q16, int q0, int N, uint32_t tmem_base,
+                                                 int warp, int lane) {
   const int grp = warp >> 2, quarter = warp & 3;
   const int n = q0 + quarter * 32 + lane;
-  const uint4* src = reinterpret_cast<const uint4*>(q16 + size_t(n < N ? n : 0) * 256 + grp * 128);
+  const uint4* src = reinterpret_cast<const uint4*>(q16 + size_t(n < N ? n : 0) * 256 + grp * 64);
+  uint32_t v[32];
 #pragma unroll
-  for (int half = 0; half < 2; ++half) {
-    uint32_t v[32];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      uint4 x = make_uint4(0u, 0u, 0u, 0u);
-      if (n < N) x = __ldg(src + half * 8 + i);
-      v[4 * i] = x.x; v[4 * i + 1] = x.y; v[4 * i + 2] = x.z; v[4 * i + 3] = x.w;
-    }
-    ptx::tmem_st32(tmem_base + (uint32_t(quarter * 32) << 16) + kTmemQ + grp * 64 + half * 32, v);
+  for (int i = 0; i < 8; ++i) {
+    uint4 x = make_uint4(0u, 0u, 0u, 0u);
+    if (n < N) x = __ldg(src + i);
+    v[4 * i] = x.x; v[4 * i + 1] = x.y; v[4 * i + 2] = x.z; v[4 * i + 3] = x.w;
   }
+  ptx::tmem_st32(tmem_base + (uint32_t(quarter * 32) << 16) + kTmemQ + grp * 32, v);
   ptx::tmem_st_wait();
 }
 
 // ---------------------------------------------------------------------------------------------------
-// K2a: row statistics.  Tile = 128 entries = two 32 KB stages (dims 0-127 | 128-255).
+// K2a: row statistics.  Tile = 128 entries = two 32 KB stages (dims 0-127 | 128-255); Q in TMEM (TS-mode).
+// 16 softmax warps (warp w: TMEM lanes 32 (w%4).., 32-entry column group w/4) + producer + MMA issuer.
+// The xyz bytes of a tile are credited to the barrier its S tile arrives on (one wait per tile).
 // ---------------------------------------------------------------------------------------------------
+constexpr int kStatsWarps = 16;
+constexpr int kStatsThreads = (kStatsWarps + 2) * 32;
+struct StatsSmem {
+  static constexpr int NS = 6, kKeys = 128, kXyzBytes = kKeys * 16;
+  static constexpr int stages = 0;
+  static constexpr int xyz = stages + NS * kStageBytes;            // 2 slots
+  static constexpr int bars = xyz + 2 * kXyzBytes;
+  static constexpr int b_stage_full = 0;
+  static constexpr int b_stage_empty = b_stage_full + NS;
+  static constexpr int b_s_full = b_stage_empty + NS;
+  static constexpr int b_s_empty = b_s_full + 2;
+  static constexpr int b_xyz_empty = b_s_empty + 2;
+  static constexpr int n_bars = b_xyz_empty + 2;
+  static constexpr int tmem_slot = bars + n_bars * 8;
+  static constexpr int red = (tmem_slot + 16 + 15) / 16 * 16;      // cross-group reduction scratch [3][128] float4
+  static constexpr int total = red + 3 * kBlockQ * 16;
+  static constexpr int dynamic_bytes = total + 1024;
+};
+
 template <bool kGeo>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kStatsThreads, 1)
 range_stats_kernel(const __grid_constant__ CUtensorMap tmK, const __half* __restrict__ q16,
                    const float4* __restrict__ db_xyz, const float4* __restrict__ q_xyz, int N, int M,
                    int tiles_per_split, float a_sem, float a_geo, float* __restrict__ part_sum,
                    float* __restrict__ part_max) {
-  constexpr int NS = 6, NX = 4, kKeys = 128, kXyzBytes = kKeys * 16;
-  using L = SmemLayout<NS, NX, kXyzBytes>;
+  using L = StatsSmem;
+  constexpr int NS = L::NS, kKeys = L::kKeys, kXyzBytes = L::kXyzBytes;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::bars);
@@ -143,16 +161,13 @@ range_stats_kernel(const __grid_constant__ CUtensorMap tmK, const __half* __rest
       ptx::mbar_init(&bars[L::b_stage_empty + i], 1);
     }
     for (int i = 0; i < 2; ++i) {
-      ptx::mbar_init(&bars[L::b_s_full + i], 1);
-      ptx::mbar_init(&bars[L::b_s_empty + i], kNumSoftmaxWarps);
-    }
-    for (int i = 0; i < NX; ++i) {
-      ptx::mbar_init(&bars[L::b_xyz_full + i], 1);
-      ptx::mbar_init(&bars[L::b_xyz_empty + i], kNumSoftmaxWarps);
+      ptx::mbar_init(&bars[L::b_s_full + i], kGeo ? 2 : 1);     // MMA commit (+ the tile's xyz bytes)
+      ptx::mbar_init(&bars[L::b_s_empty + i], kStatsWarps);
+      ptx::mbar_init(&bars[L::b_xyz_empty + i], kStatsWarps);
     }
     ptx::fence_mbar_init();
   }
-  if (warp == 9) ptx::tmem_alloc<512>(tmem_slot);
+  if (warp == kStatsWarps + 1) ptx::tmem_alloc<512>(tmem_slot);
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -160,24 +175,18 @@ range_stats_kernel(const __grid_constant__ CUtensorMap tmK, const __half* __rest
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
   const uint32_t smem_u = __shfl_sync(0xffffffffu, ptx::smem_u32(smem), 0);
   const uint32_t bars_u = smem_u + L::bars;
-  if (warp < kNumSoftmaxWarps) load_q_to_tmem(q16, q0, N, tmem_base, warp, lane);
+  if (warp < kStatsWarps) load_q_to_tmem16(q16, q0, N, tmem_base, warp, lane);
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
 
-  if (warp == 8) {
+  if (warp == kStatsWarps) {
     // ===== TMA producer =====
     if (lane == 0) {
       ptx::prefetch_tmap(&tmK);
-      PipeState st, xs;
+      PipeState st;
       for (int j = 0; j < T; ++j) {
         const int key0 = (t_begin + j) * kKeys;
-        if (kGeo) {
-          ptx::mbar_wait(&bars[L::b_xyz_empty + xs.idx], xs.phase ^ 1);
-          ptx::mbar_expect_tx(&bars[L::b_xyz_full + xs.idx], kXyzBytes);
-          ptx::bulk_load_1d(smem + L::xyz + xs.idx * kXyzBytes, db_xyz + key0, kXyzBytes, &bars[L::b_xyz_full + xs.idx]);
-          xs.advance<NX>();
-        }
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           ptx::mbar_wait(&bars[L::b_stage_empty + st.idx], st.phase ^ 1);
@@ -187,9 +196,14 @@ range_stats_kernel(const __grid_constant__ CUtensorMap tmK, const __half* __rest
           ptx::tma_load_2d(dst + 16384, &tmK, &bars[L::b_stage_full + st.idx], (2 * half + 1) * 64, key0);
           st.advance<NS>();
         }
+        if (kGeo) {      // xyz(j) -> slot j&1 (free once the softmax warps are done with tile j-2), last in the iteration
+          ptx::mbar_wait(&bars[L::b_xyz_empty + (j & 1)], ((j >> 1) & 1) ^ 1);
+          ptx::mbar_expect_tx(&bars[L::b_s_full + (j & 1)], kXyzBytes);
+          ptx::bulk_load_1d(smem + L::xyz + (j & 1) * kXyzBytes, db_xyz + key0, kXyzBytes, &bars[L::b_s_full + (j & 1)]);
+        }
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == kStatsWarps + 1) {
     // ===== MMA issuer: S[b] = Q (TMEM) . K^T =====
     constexpr uint32_t idesc = ptx::umma_idesc_f16(kBlockQ, kKeys);
     PipeState st;
@@ -226,60 +240,57 @@ range_stats_kernel(const __grid_constant__ CUtensorMap tmK, const __half* __rest
     if (kGeo && n < N) qx = q_xyz[n];
     const float gx = qx.x * a_geo, gy = qx.y * a_geo, gz = qx.z * a_geo;
     float sum_s = 0.f, sum_g = 0.f, max_s = -2.f, max_g = -3.0e38f;
-    PipeState xs;
     for (int j = 0; j < T; ++j) {
       const int b = j & 1;
-      const int key0 = (t_begin + j) * kKeys + grp * 64;
-      ptx::mbar_wait(&bars[L::b_s_full + b], (j >> 1) & 1);
+      const int key0 = (t_begin + j) * kKeys + grp * 32;
+      ptx::mbar_wait(&bars[L::b_s_full + b], (j >> 1) & 1);      // S(j) in TMEM and xyz(j) in smem
       ptx::tc_fence_after();
-      uint32_t s0[32], s1[32];
-      const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + kTmemS + b * kKeys + grp * 64;
-      ptx::tmem_ld32(taddr, s0);
-      ptx::tmem_ld32(taddr + 32, s1);
+      uint32_t s0[32];
+      ptx::tmem_ld32(tmem_base + (uint32_t(quarter * 32) << 16) + kTmemS + b * kKeys + grp * 32, s0);
       ptx::tmem_ld_wait();
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&bars[L::b_s_empty + b]);
-      const uint32_t kxyz = ptx::smem_u32(smem + L::xyz + xs.idx * kXyzBytes) + grp * 64 * 16;
-      if (kGeo) ptx::mbar_wait(&bars[L::b_xyz_full + xs.idx], xs.phase);
-      const int nvalid = M - key0;            // >= 64 except in the last tile
+      const uint32_t kxyz = ptx::smem_u32(smem + L::xyz + b * kXyzBytes) + grp * 32 * 16;
+      const int nvalid = M - key0;            // >= 32 except in the last tile
       auto body = [&](auto masked) {
 #pragma unroll
-        for (int i = 0; i < 64; ++i) {
-          const float s = __uint_as_float(i < 32 ? s0[i] : s1[i - 32]);
+        for (int i = 0; i < 32; ++i) {
+          const float s = __uint_as_float(s0[i]);
           const bool valid = !decltype(masked)::value || (i < nvalid);
-          const bool poly = kPolyModStats > 0 && (i % (kPolyModStats > 0 ? kPolyModStats : 1)) == 0;
-          float es = poly ? ptx::ex2_poly(fmaf(s, a_sem, -a_sem)) : ptx::ex2(fmaf(s, a_sem, -a_sem));
+          float es = ptx::ex2(fmaf(s, a_sem, -a_sem));
           if (!valid) es = 0.f;
           sum_s += es;
           max_s = fmaxf(max_s, valid ? s : -2.f);
           if (kGeo) {
             const float4 k = ptx::lds_f4(kxyz + i * 16);
             const float g = fmaf(gx, k.x, fmaf(gy, k.y, fmaf(gz, k.z, -a_geo)));   // a_geo (g - 1)
-            float eg = poly ? ptx::ex2_poly(g) : ptx::ex2(g);
+            float eg = ptx::ex2(g);
             if (!valid) eg = 0.f;
             sum_g += eg;
             max_g = fmaxf(max_g, valid ? g : -3.0e38f);
           }
         }
       };
-      if (nvalid >= 64) body(std::false_type{}); else body(std::true_type{});
+      if (nvalid >= 32) body(std::false_type{}); else body(std::true_type{});
       if (kGeo) {
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&bars[L::b_xyz_empty + xs.idx]);
-        xs.advance<NX>();
+        if (lane == 0) ptx::mbar_arrive(&bars[L::b_xyz_empty + b]);
       }
     }
-    // combine the two column groups, write this split's partials
+    // combine the four column groups, write this split's partials
     float4* red = reinterpret_cast<float4*>(smem + L::red);
-    if (grp == 1) red[row] = make_float4(sum_s, sum_g, max_s, max_g);
-    named_bar_sync_softmax();
+    if (grp > 0) red[(grp - 1) * kBlockQ + row] = make_float4(sum_s, sum_g, max_s, max_g);
+    asm volatile("bar.sync 1, %0;" ::"n"(kStatsWarps * 32) : "memory");
     if (grp == 0 && n < N) {
-      const float4 o = red[row];
-      sum_s += o.x;
-      sum_g += o.y;
-      max_s = fmaxf(max_s, o.z);
-      max_g = fmaxf(max_g, o.w);
+#pragma unroll
+      for (int g2 = 0; g2 < 3; ++g2) {
+        const float4 o = red[g2 * kBlockQ + row];
+        sum_s += o.x;
+        sum_g += o.y;
+        max_s = fmaxf(max_s, o.z);
+        max_g = fmaxf(max_g, o.w);
+      }
       // max_g holds a_geo (g - 1); store the raw cosine
       const float raw_g = kGeo ? (max_g / a_geo + 1.f) : 0.f;
       float2* ps = reinterpret_cast<float2*>(part_sum) + size_t(split) * N + n;
@@ -290,7 +301,7 @@ range_stats_kernel(const __grid_constant__ CUtensorMap tmK, const __half* __rest
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 9) ptx::tmem_dealloc<512>(tmem_base);
+  if (warp == kStatsWarps + 1) ptx::tmem_dealloc<512>(tmem_base);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -925,7 +936,7 @@ namespace rangeb200 {
 long long* g_prof_buffer = nullptr;
 void set_profile_buffer(long long* p) { g_prof_buffer = p; }
 
-int retrieval_stats_smem_bytes() { return SmemLayout<6, 4, 2048>::dynamic_bytes; }
+int retrieval_stats_smem_bytes() { return StatsSmem::dynamic_bytes; }
 int retrieval_apply_smem_bytes() { return ApplySmem::dynamic_bytes; }
 
 cudaError_t launch_stats(const RetrievalArgs& a, float* part_sum, float* part_max, cudaStream_t stream) {
@@ -935,11 +946,11 @@ cudaError_t launch_stats(const RetrievalArgs& a, float* part_sum, float* part_ma
   if ((e = set_smem(range_stats_kernel<false>, bytes)) != cudaSuccess) return e;
   dim3 grid((a.N + kBlockQ - 1) / kBlockQ, a.stats_splits, 1);
   if (a.geo)
-    range_stats_kernel<true><<<grid, kThreads, bytes, stream>>>(a.tmK128, a.q16, a.db_xyz, a.q_xyz, a.N, a.M,
+    range_stats_kernel<true><<<grid, kStatsThreads, bytes, stream>>>(a.tmK128, a.q16, a.db_xyz, a.q_xyz, a.N, a.M,
                                                                a.stats_tiles_per_split, a.a_sem, a.a_geo, part_sum,
                                                                part_max);
   else
-    range_stats_kernel<false><<<grid, kThreads, bytes, stream>>>(a.tmK128, a.q16, a.db_xyz, a.q_xyz, a.N, a.M,
+    range_stats_kernel<false><<<grid, kStatsThreads, bytes, stream>>>(a.tmK128, a.q16, a.db_xyz, a.q_xyz, a.N, a.M,
                                                                 a.stats_tiles_per_split, a.a_sem, a.a_geo, part_sum,
                                                                 part_max);
   return cudaGetLastError();
