@@ -157,6 +157,8 @@ int fill_args(range_ctx* c, int mode, int64_t N, const void* q16, const float* q
   const float log2e = 1.4426950408889634f;
   a->a_sem = temp * log2e;
   a->a_geo = geo_temp * log2e;
+  a->geo_mask = nullptr;
+  a->mask_words = 0;
   return RANGE_OK;
 }
 

@@ -60,11 +60,16 @@ struct RetrievalArgs {
   int stats_splits, stats_tiles_per_split;   // 128-entry tiles
   int apply_splits, apply_tiles_per_split;   // 128-entry tiles
   float a_sem, a_geo;   // temperature * log2(e)
+  const uint32_t* geo_mask;   // [query tiles][mask_words] skip bits per 128-entry database tile, or null
+  int mask_words;
 };
 void set_profile_buffer(long long* device_buffer_of_64);   // debug: wait-cycle accounting of the apply kernel
 int retrieval_stats_smem_bytes();
 int retrieval_apply_smem_bytes();
 cudaError_t launch_stats(const RetrievalArgs& a, float* part_sum, float* part_max, cudaStream_t s);
+// skip bits from the query tiles' and database tiles' bounding caps (retrieval.cu: geo_mask_kernel)
+cudaError_t launch_geo_mask(const float* q_xyz, int N, const float* caps, int n_tiles, float delta, uint32_t* mask,
+                            int words, cudaStream_t s);
 cudaError_t launch_reduce_stats(const float* part_sum, const float* part_max, int N, int splits, float* sums,
                                 float* maxs, cudaStream_t s);
 cudaError_t launch_row_constants(const float* sums, const float* maxs, const float* q_xyz, int N, int geo,

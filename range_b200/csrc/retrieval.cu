@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(kStatsThreads, 1)
 range_stats_kernel(const __grid_constant__ CUtensorMap tmK, const __half* __restrict__ q16,
                    const float4* __restrict__ db_xyz, const float4* __restrict__ q_xyz, int N, int M,
                    int tiles_per_split, float a_sem, float a_geo, float* __restrict__ part_sum,
-                   float* __restrict__ part_max) {
+                   float* __restrict__ part_max, const uint32_t* __restrict__ geo_mask, int mask_words) {
   using L = StatsSmem;
   constexpr int NS = L::NS, kKeys = L::kKeys, kXyzBytes = L::kXyzBytes;
   extern __shared__ uint8_t smem_raw[];
@@ -154,6 +154,9 @@ range_stats_kernel(const __grid_constant__ CUtensorMap tmK, const __half* __rest
   const int t_begin = split * tiles_per_split;
   const int t_end = min(total_tiles, t_begin + tiles_per_split);
   const int T = t_end - t_begin;
+  // geo-skip bit of database tile t for this query tile (see geo_mask_kernel); warp-uniform
+  const uint32_t* mask_row = (kGeo && geo_mask) ? geo_mask + size_t(blockIdx.x) * mask_words : nullptr;
+  auto skip_geo = [&](int t) { return mask_row != nullptr && ((__ldg(mask_row + (t >> 5)) >> (t & 31)) & 1u); };
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < NS; ++i) {
@@ -198,8 +201,12 @@ range_stats_kernel(const __grid_constant__ CUtensorMap tmK, const __half* __rest
         }
         if (kGeo) {      // xyz(j) -> slot j&1 (free once the softmax warps are done with tile j-2), last in the iteration
           ptx::mbar_wait(&bars[L::b_xyz_empty + (j & 1)], ((j >> 1) & 1) ^ 1);
-          ptx::mbar_expect_tx(&bars[L::b_s_full + (j & 1)], kXyzBytes);
-          ptx::bulk_load_1d(smem + L::xyz + (j & 1) * kXyzBytes, db_xyz + key0, kXyzBytes, &bars[L::b_s_full + (j & 1)]);
+          if (skip_geo(t_begin + j)) {
+            ptx::mbar_arrive(&bars[L::b_s_full + (j & 1)]);                       // nothing to load for this tile
+          } else {
+            ptx::mbar_expect_tx(&bars[L::b_s_full + (j & 1)], kXyzBytes);
+            ptx::bulk_load_1d(smem + L::xyz + (j & 1) * kXyzBytes, db_xyz + key0, kXyzBytes, &bars[L::b_s_full + (j & 1)]);
+          }
         }
       }
     }
@@ -253,6 +260,7 @@ range_stats_kernel(const __grid_constant__ CUtensorMap tmK, const __half* __rest
       if (lane == 0) ptx::mbar_arrive(&bars[L::b_s_empty + b]);
       const uint32_t kxyz = ptx::smem_u32(smem + L::xyz + b * kXyzBytes) + grp * 32 * 16;
       const int nvalid = M - key0;            // >= 32 except in the last tile
+      const bool with_geo = kGeo && !skip_geo(t_begin + j);
       auto body = [&](auto masked) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
@@ -262,7 +270,7 @@ range_stats_kernel(const __grid_constant__ CUtensorMap tmK, const __half* __rest
           if (!valid) es = 0.f;
           sum_s += es;
           max_s = fmaxf(max_s, valid ? s : -2.f);
-          if (kGeo) {
+          if (kGeo && with_geo) {
             const float4 k = ptx::lds_f4(kxyz + i * 16);
             const float g = fmaf(gx, k.x, fmaf(gy, k.y, fmaf(gz, k.z, -a_geo)));   // a_geo (g - 1)
             float eg = ptx::ex2(g);
@@ -305,10 +313,10 @@ range_stats_kernel(const __grid_constant__ CUtensorMap tmK, const __half* __rest
 }
 
 // ---------------------------------------------------------------------------------------------------
-// K2b: apply  (O slice = P' . Vt).  Tile = 128 entries: two stages of K (dims 0-127 | 128-255, SS-mode
-// Q.K^T with Q resident in shared memory) and two stages of Vt ([256 dims x 64 entries] each, TS-mode P.V).
-// A 64-entry tile with Q in TMEM was measured slower: a TS-mode MMA fetches its 128x16 A tile from TMEM in
-// ~64 clk, which dominates UMMA_N = 64 (32 clk of math).
+// K2b: apply  (O slice = P' . Vt).  Tile = 128 entries.  SS-mode Q.K^T with Q resident in shared memory,
+// TS-mode P.V with P' in TMEM.  Measured dead ends (profiles/r1b_notes.md): a 64-entry tile with Q in TMEM
+// (a TS-mode MMA fetches its 128x16 A tile from TMEM in ~64 clk, which dominates UMMA_N = 64), sharing P'
+// between the four value-slice CTAs over DSMEM (9 B/clk/SM with the whole chip active).
 // rowc[n] = {cs, cg, qx*a_geo, qy*a_geo, qz*a_geo, out_scale, -, -}
 // ---------------------------------------------------------------------------------------------------
 // kProf: per-role wait-cycle accounting for tools/time_apply.py (prof[role * 8 + counter], CTA (0,1,0) only)
@@ -334,268 +342,9 @@ struct ApplySmem {
   static constexpr int dynamic_bytes = total + 1024;
 };
 
-template <bool kGeo, bool kProf = false>
-__global__ void __launch_bounds__(kThreads, 1)
-range_apply_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                   const __grid_constant__ CUtensorMap tmV, const float4* __restrict__ db_xyz,
-                   const float4* __restrict__ rowc, int N, int M, int tiles_per_split, float a_sem,
-                   float* __restrict__ out, size_t out_split_stride, long long* __restrict__ prof = nullptr) {
-  using L = ApplySmem;
-  constexpr int NS = L::NS, NX = L::NX, kKeys = L::kKeys, kXyzBytes = L::kXyzBytes;
-  long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  const bool prof_on = kProf && prof != nullptr && blockIdx.x == 0 && blockIdx.y == 1 && blockIdx.z == 0;
-  const long long prof_start = kProf ? clock64() : 0;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::bars);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::tmem_slot);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int slice = blockIdx.x;                 // fastest: the 4 slices of a query tile run together
-  const int q0 = blockIdx.y * kBlockQ;
-  const int split = blockIdx.z;
-  const int total_tiles = (M + kKeys - 1) / kKeys;
-  const int t_begin = split * tiles_per_split;
-  const int t_end = min(total_tiles, t_begin + tiles_per_split);
-  const int T = t_end - t_begin;
-
-  if (threadIdx.x == 0) {
-    ptx::mbar_init(&bars[L::b_q_full], 1);
-    for (int i = 0; i < NS; ++i) {
-      ptx::mbar_init(&bars[L::b_stage_full + i], 1);
-      ptx::mbar_init(&bars[L::b_stage_empty + i], 1);
-    }
-    for (int i = 0; i < 2; ++i) {
-      ptx::mbar_init(&bars[L::b_s_full + i], 1);
-      ptx::mbar_init(&bars[L::b_p_full + i], kNumSoftmaxWarps);
-    }
-    for (int i = 0; i < NX; ++i) {
-      ptx::mbar_init(&bars[L::b_xyz_full + i], 1);
-      ptx::mbar_init(&bars[L::b_xyz_empty + i], kNumSoftmaxWarps);
-    }
-    ptx::mbar_init(&bars[L::b_o_full], 1);
-    ptx::fence_mbar_init();
-  }
-  if (warp == 9) ptx::tmem_alloc<512>(tmem_slot);
-  ptx::tc_fence_before();
-  __syncthreads();
-  ptx::tc_fence_after();
-  // warp-uniform copies (see ptx::umma_commit_u32) for the MMA-issuing warp
-  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
-  const uint32_t smem_u = __shfl_sync(0xffffffffu, ptx::smem_u32(smem), 0);
-  const uint32_t bars_u = smem_u + L::bars;       // [0,128) S/P buf 0 | [128,256) S/P buf 1 | [256,512) O
-  const uint32_t tmem_o = tmem_base + 256;
-
-  if (warp == 8) {
-    // ===== TMA producer, in the order the MMA warp consumes: Q, K(0), [K(j+1), V(j)]..., V(T-1) =====
-    if (lane == 0 && T > 0) {
-      ptx::prefetch_tmap(&tmQ);
-      ptx::prefetch_tmap(&tmK);
-      ptx::prefetch_tmap(&tmV);
-      ptx::mbar_expect_tx(&bars[L::b_q_full], 65536);
-      for (int c = 0; c < 4; ++c) ptx::tma_load_2d(smem + L::q + c * 16384, &tmQ, &bars[L::b_q_full], c * 64, q0);
-      PipeState st, xs;
-      for (int j = 0; j <= T; ++j) {
-        if (j < T) {
-          const int key0 = (t_begin + j) * kKeys;
-          if (kGeo) {
-            ptx::mbar_wait(&bars[L::b_xyz_empty + xs.idx], xs.phase ^ 1);
-            ptx::mbar_expect_tx(&bars[L::b_xyz_full + xs.idx], kXyzBytes);
-            ptx::bulk_load_1d(smem + L::xyz + xs.idx * kXyzBytes, db_xyz + key0, kXyzBytes,
-                              &bars[L::b_xyz_full + xs.idx]);
-            xs.advance<NX>();
-          }
-#pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            PROF_T0();
-            ptx::mbar_wait(&bars[L::b_stage_empty + st.idx], st.phase ^ 1);
-            PROF_ADD(0, 0);
-            uint8_t* dst = smem + L::stages + st.idx * kStageBytes;
-            ptx::mbar_expect_tx(&bars[L::b_stage_full + st.idx], kStageBytes);
-            ptx::tma_load_2d(dst, &tmK, &bars[L::b_stage_full + st.idx], (2 * half) * 64, key0);
-            ptx::tma_load_2d(dst + 16384, &tmK, &bars[L::b_stage_full + st.idx], (2 * half + 1) * 64, key0);
-            st.advance<NS>();
-          }
-        }
-        if (j >= 1) {
-          const int key0 = (t_begin + j - 1) * kKeys;
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            PROF_T0();
-            ptx::mbar_wait(&bars[L::b_stage_empty + st.idx], st.phase ^ 1);
-            PROF_ADD(0, 1);
-            ptx::mbar_expect_tx(&bars[L::b_stage_full + st.idx], kStageBytes);
-            ptx::tma_load_2d(smem + L::stages + st.idx * kStageBytes, &tmV, &bars[L::b_stage_full + st.idx],
-                             key0 + h * 64, slice * kSliceV);
-            st.advance<NS>();
-          }
-        }
-      }
-      if (prof_on) { prof[0] = prof_acc[0]; prof[1] = prof_acc[1]; prof[2] = clock64() - prof_start; }
-    }
-  } else if (warp == 9) {
-    // ===== MMA issuer =====
-    if (T > 0) {
-      constexpr uint32_t idesc_qk = ptx::umma_idesc_f16(kBlockQ, kKeys);
-      constexpr uint32_t idesc_pv = ptx::umma_idesc_f16(kBlockQ, kSliceV);
-      ptx::mbar_wait(&bars[L::b_q_full], 0);
-      PipeState st;
-      // S buffer b is rewritten by QK(j+2) only after PV(j) (same issuing thread, executed in order) which
-      // itself waited for the softmax warps to be done with S(j) -> P'(j): no separate "S empty" barrier.
-      for (int j = 0; j <= T; ++j) {
-        if (j < T) {
-          const uint32_t tmem_s = tmem_base + (j & 1) * kKeys;
-#pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            PROF_T0();
-            ptx::mbar_wait(&bars[L::b_stage_full + st.idx], st.phase);
-            PROF_ADD(1, 0);
-            ptx::tc_fence_after();
-            if (ptx::elect_one()) {
-              const uint32_t b_base = smem_u + L::stages + st.idx * kStageBytes;
-              const uint32_t a_base = smem_u + L::q + (2 * half) * 16384;
-#pragma unroll
-              for (int c = 0; c < 2; ++c)
-#pragma unroll
-                for (int kk = 0; kk < 4; ++kk)
-                  ptx::umma_f16_ss(tmem_s, ptx::umma_desc_kmajor_sw128(a_base + c * 16384 + kk * 32),
-                                   ptx::umma_desc_kmajor_sw128(b_base + c * 16384 + kk * 32), idesc_qk,
-                                   (half | c | kk) != 0);
-              ptx::umma_commit_u32(bars_u + 8 * (L::b_stage_empty + st.idx));
-              if (half == 1) ptx::umma_commit_u32(bars_u + 8 * (L::b_s_full + (j & 1)));
-            }
-            __syncwarp();
-            PROF_ADD(1, 1);
-            st.advance<NS>();
-          }
-        }
-        if (j >= 1) {
-          const int jj = j - 1, b = jj & 1;
-          PROF_T0();
-          ptx::mbar_wait(&bars[L::b_p_full + b], (jj >> 1) & 1);
-          PROF_ADD(1, 2);
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            ptx::mbar_wait(&bars[L::b_stage_full + st.idx], st.phase);
-            PROF_ADD(1, 3);
-            ptx::tc_fence_after();
-            if (ptx::elect_one()) {
-              const uint32_t b_base = smem_u + L::stages + st.idx * kStageBytes;
-              // P'(jj): group h wrote keys 64 h .. +63 as 32 packed columns at S-buffer column 64 h
-              const uint32_t p_base = tmem_base + b * kKeys + h * 64;
-#pragma unroll
-              for (int kk = 0; kk < 4; ++kk)
-                ptx::umma_f16_ts(tmem_o, p_base + kk * 8, ptx::umma_desc_kmajor_sw128(b_base + kk * 32), idesc_pv,
-                                 (jj > 0) || (h | kk) != 0);
-              ptx::umma_commit_u32(bars_u + 8 * (L::b_stage_empty + st.idx));
-            }
-            __syncwarp();
-            PROF_ADD(1, 4);
-            st.advance<NS>();
-          }
-        }
-      }
-      if (ptx::elect_one()) ptx::umma_commit_u32(bars_u + 8 * (L::b_o_full));
-      __syncwarp();
-      if (prof_on && lane == 0) { for (int k = 0; k < 5; ++k) prof[8 + k] = prof_acc[k]; prof[8 + 5] = clock64() - prof_start; }
-    }
-  } else {
-    // ===== softmax: S (TMEM fp32) -> P' (TMEM fp16, in place) ; then epilogue =====
-    const int grp = warp >> 2, quarter = warp & 3;
-    const int row = quarter * 32 + lane;
-    const int n = q0 + row;
-    float cs = -INFINITY, cg = -INFINITY, gx = 0.f, gy = 0.f, gz = 0.f, out_scale = 0.f;
-    if (n < N) {
-      const float4 c0 = rowc[2 * n], c1 = rowc[2 * n + 1];
-      cs = c0.x; cg = c0.y; gx = c0.z; gy = c0.w; gz = c1.x; out_scale = c1.y;
-    }
-    PipeState xs;
-    for (int j = 0; j < T; ++j) {
-      const int b = j & 1;
-      const int key0 = (t_begin + j) * kKeys + grp * 64;
-      const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + b * kKeys + grp * 64;
-      PROF_T0();
-      ptx::mbar_wait(&bars[L::b_s_full + b], (j >> 1) & 1);
-      PROF_ADD(2, 0);
-      ptx::tc_fence_after();
-      uint32_t s0[32], s1[32];
-      ptx::tmem_ld32(taddr, s0);
-      ptx::tmem_ld32(taddr + 32, s1);
-      ptx::tmem_ld_wait();
-      PROF_ADD(2, 1);
-      const uint32_t kxyz = ptx::smem_u32(smem + L::xyz + xs.idx * kXyzBytes) + grp * 64 * 16;
-      if (kGeo) ptx::mbar_wait(&bars[L::b_xyz_full + xs.idx], xs.phase);
-      PROF_ADD(2, 2);
-      const int nvalid = M - key0;            // >= 64 except in the last tile
-      uint32_t packed[32];
-      auto body = [&](auto masked) {
-#pragma unroll
-        for (int w = 0; w < 32; ++w) {
-          float pv[2];
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const int i = 2 * w + u;
-            const float sv = __uint_as_float(i < 32 ? s0[i] : s1[i - 32]);
-            const bool poly = kPolyModApply > 0 && (i % (kPolyModApply > 0 ? kPolyModApply : 1)) == 0;
-            float p = poly ? ptx::ex2_poly(fmaf(sv, a_sem, cs)) : ptx::ex2(fmaf(sv, a_sem, cs));
-            if (kGeo) {
-              const float4 k = ptx::lds_f4(kxyz + i * 16);
-              const float tg = fmaf(gx, k.x, fmaf(gy, k.y, fmaf(gz, k.z, cg)));
-              p += poly ? ptx::ex2_poly(tg) : ptx::ex2(tg);
-            }
-            if (decltype(masked)::value && i >= nvalid) p = 0.f;
-            pv[u] = p;
-          }
-          packed[w] = ptx::pack_half2(pv[0], pv[1]);
-        }
-      };
-      if (nvalid >= 64) body(std::false_type{}); else body(std::true_type{});
-      PROF_ADD(2, 3);
-      // P'(row, keys 64 g .. +63) over the first 32 of this group's 64 S columns
-      ptx::tmem_st32(taddr, packed);
-      ptx::tmem_st_wait();
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        ptx::mbar_arrive(&bars[L::b_p_full + b]);
-        if (kGeo) ptx::mbar_arrive(&bars[L::b_xyz_empty + xs.idx]);
-      }
-      PROF_ADD(2, 4);
-      if (kGeo) xs.advance<NX>();
-    }
-    if (prof_on && threadIdx.x == 0) { for (int k = 0; k < 5; ++k) prof[16 + k] = prof_acc[k]; prof[16 + 5] = clock64() - prof_start; prof[16 + 6] = T; }
-    // ----- epilogue: O (TMEM, 128 lanes x 256 cols) -> global fp32, scaled -----
-    if (T > 0) {
-      ptx::mbar_wait(&bars[L::b_o_full], 0);
-      ptx::tc_fence_after();
-      float* orow = out + size_t(split) * out_split_stride + size_t(n) * 1024 + slice * kSliceV + grp * 128;
-#pragma unroll
-      for (int cc = 0; cc < 4; ++cc) {
-        uint32_t v[32];
-        ptx::tmem_ld32(tmem_o + (uint32_t(quarter * 32) << 16) + grp * 128 + cc * 32, v);
-        ptx::tmem_ld_wait();
-        if (n < N) {
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            float4 o;
-            o.x = __uint_as_float(v[i]) * out_scale;
-            o.y = __uint_as_float(v[i + 1]) * out_scale;
-            o.z = __uint_as_float(v[i + 2]) * out_scale;
-            o.w = __uint_as_float(v[i + 3]) * out_scale;
-            *reinterpret_cast<float4*>(orow + cc * 32 + i) = o;
-          }
-        }
-      }
-    }
-  }
-  ptx::tc_fence_before();
-  __syncthreads();
-  if (warp == 9) ptx::tmem_dealloc<512>(tmem_base);
-}
-
 // ---------------------------------------------------------------------------------------------------
-// K2b, CTA-pair variant (cta_group::2): two CTAs of a cluster = two adjacent query tiles x the same value
-// slice run ONE 256-row UMMA.  Each CTA loads only half of every B tile (64 of the 128 entries of a K tile,
+// CTA pairs (cta_group::2): two CTAs of a cluster = two adjacent query tiles x the same value slice run ONE
+// 256-row UMMA.  Each CTA loads only half of every B tile (64 of the 128 entries of a K tile,
 // 128 of the 256 value dims of a Vt tile), which halves TMA writes and UMMA B-operand reads per SM - the
 // shared-memory bandwidth that bounds the single-CTA kernel - and doubles the pipeline depth in tiles.
 // Leader (cluster rank 0) issues every MMA; completions are multicast to both CTAs' barriers; the peer's
@@ -623,7 +372,8 @@ __global__ void __launch_bounds__(kPairThreads, 1)
 range_apply_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK64,
                         const __grid_constant__ CUtensorMap tmV128, const float4* __restrict__ db_xyz,
                         const float4* __restrict__ rowc, int N, int M, int tiles_per_split, float a_sem,
-                        float* __restrict__ out, size_t out_split_stride, long long* __restrict__ prof = nullptr) {
+                        float* __restrict__ out, size_t out_split_stride, const uint32_t* __restrict__ geo_mask,
+                        int mask_words, long long* __restrict__ prof = nullptr) {
   using L = PairSmem;
   constexpr int NS = L::NS, NX = L::NX, kKeys = L::kKeys, kXyzBytes = L::kXyzBytes;
   long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -644,6 +394,9 @@ range_apply_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   const int t_begin = split * tiles_per_split;
   const int t_end = min(total_tiles, t_begin + tiles_per_split);
   const int T = t_end - t_begin;
+  // geo-skip bit of database tile t for THIS CTA's query tile (see geo_mask_kernel); warp-uniform
+  const uint32_t* mask_row = (kGeo && geo_mask) ? geo_mask + size_t(blockIdx.x) * mask_words : nullptr;
+  auto skip_geo = [&](int t) { return mask_row != nullptr && ((__ldg(mask_row + (t >> 5)) >> (t & 31)) & 1u); };
 
   if (threadIdx.x == 0) {
     ptx::mbar_init(&bars[L::b_q_full], 1);
@@ -710,9 +463,13 @@ range_apply_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
           // iteration: the slot frees only when softmax(j-2) is done, and nothing the MMA warp is about to need
           // may queue behind that wait.
           ptx::mbar_wait(&bars[L::b_xyz_empty + (j & 1)], ((j >> 1) & 1) ^ 1);
-          ptx::mbar_expect_tx(&bars[L::b_s_full + (j & 1)], kXyzBytes);
-          ptx::bulk_load_1d(smem + L::xyz + (j & 1) * kXyzBytes, db_xyz + (t_begin + j) * kKeys, kXyzBytes,
-                            &bars[L::b_s_full + (j & 1)]);
+          if (skip_geo(t_begin + j)) {
+            ptx::mbar_arrive(&bars[L::b_s_full + (j & 1)]);                       // nothing to load for this tile
+          } else {
+            ptx::mbar_expect_tx(&bars[L::b_s_full + (j & 1)], kXyzBytes);
+            ptx::bulk_load_1d(smem + L::xyz + (j & 1) * kXyzBytes, db_xyz + (t_begin + j) * kKeys, kXyzBytes,
+                              &bars[L::b_s_full + (j & 1)]);
+          }
         }
       }
       if (prof_on) { prof[0] = prof_acc[0]; prof[1] = prof_acc[1]; prof[2] = clock64() - prof_start; }
@@ -809,6 +566,7 @@ range_apply_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       const int key0 = (t_begin + j) * kKeys + grp * 32;
       const uint32_t kxyz = ptx::smem_u32(smem + L::xyz + b * kXyzBytes) + grp * 32 * 16;
       const int nvalid = M - key0;            // >= 32 except in the last tile
+      const bool with_geo = kGeo && !skip_geo(t_begin + j);
       uint32_t packed[16];
       auto body = [&](auto masked) {
 #pragma unroll
@@ -818,7 +576,7 @@ range_apply_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
           for (int u = 0; u < 2; ++u) {
             const int i = 2 * w + u;
             float p = ptx::ex2(fmaf(__uint_as_float(cur[i]), a_sem, cs));
-            if (kGeo) {
+            if (kGeo && with_geo) {
               const float4 k = ptx::lds_f4(kxyz + i * 16);
               p += ptx::ex2(fmaf(gx, k.x, fmaf(gy, k.y, fmaf(gz, k.z, cg))));
             }
@@ -870,6 +628,70 @@ range_apply_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   ptx::tc_fence_before();
   ptx::cluster_sync();                           // neither CTA may free TMEM / exit while the pair is in flight
   if (warp == kPairSoftmaxWarps + 1) ptx::tmem_dealloc_2sm<512>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Geographic tile skipping.  The geo weight of an entry is exp(T (g - 1)) / l_g with l_g >= exp(T (g_max - 1)),
+// so an entry with g <= g_max - D carries at most exp(-T D) of the row's normaliser; with
+// D = (ln M_total + 24 ln 2) / T every such entry of the WHOLE database together is < 2^-24 relative - below
+// fp32 resolution.  When the database is stored in a spatially sorted order (range_b200/database.py) and the
+// queries of a tile are close to each other (rasters; range.py sorts scattered queries), whole 128-entry
+// tiles satisfy the bound for all 128 queries and skip the geo exponential, its 3 FFMA and the xyz load.
+// caps[t] = (unit centre, angular radius) of database tile t.  mask bit (qtile, t) = 1 -> skip.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float block128_reduce(float v, bool is_max, float* scratch) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float w = __shfl_xor_sync(0xffffffffu, v, o);
+    v = is_max ? fmaxf(v, w) : v + w;
+  }
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+  __syncthreads();
+  const float a = scratch[0], b = scratch[1], c = scratch[2], d = scratch[3];
+  return is_max ? fmaxf(fmaxf(a, b), fmaxf(c, d)) : (a + b) + (c + d);
+}
+
+__global__ void __launch_bounds__(128)
+geo_mask_kernel(const float4* __restrict__ q_xyz, int N, const float4* __restrict__ caps, int n_tiles, float delta,
+                uint32_t* __restrict__ mask, int words) {
+  __shared__ float scratch[4];
+  const int n = blockIdx.x * 128 + threadIdx.x;
+  const bool valid = n < N;
+  float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (valid) x = q_xyz[n];
+  const float sx = block128_reduce(x.x, false, scratch);
+  const float sy = block128_reduce(x.y, false, scratch);
+  const float sz = block128_reduce(x.z, false, scratch);
+  const float norm = sqrtf(sx * sx + sy * sy + sz * sz);
+  const float kPi = 3.14159274f, kEps = 2e-4f;       // eps covers acosf / fp32 dot rounding
+  float cx = 0.f, cy = 0.f, cz = 1.f, r_q = kPi;       // degenerate tile (antipodal points): never skip
+  if (norm > 1e-3f) {
+    cx = sx / norm; cy = sy / norm; cz = sz / norm;
+    const float d = valid ? acosf(fminf(1.f, fmaxf(-1.f, cx * x.x + cy * x.y + cz * x.z))) : 0.f;
+    r_q = block128_reduce(d, true, scratch) + kEps;
+  }
+  // lower bound of every row's g_max: the farthest point of the closest database tile
+  float glb = -1.f;
+  for (int t = threadIdx.x; t < n_tiles; t += 128) {
+    const float4 c = caps[t];
+    const float far = acosf(fminf(1.f, fmaxf(-1.f, cx * c.x + cy * c.y + cz * c.z))) + r_q + c.w + kEps;
+    if (far < kPi) glb = fmaxf(glb, cosf(far));
+  }
+  glb = block128_reduce(glb, true, scratch);
+  const float thr = glb - delta;
+  for (int w = threadIdx.x; w < words; w += 128) {
+    uint32_t bits = 0;
+    for (int b = 0; b < 32; ++b) {
+      const int t = w * 32 + b;
+      if (t < n_tiles) {
+        const float4 c = caps[t];
+        const float near = acosf(fminf(1.f, fmaxf(-1.f, cx * c.x + cy * c.y + cz * c.z))) - r_q - c.w - kEps;
+        if (near > 0.f && cosf(near) <= thr) bits |= 1u << b;
+      }
+    }
+    mask[size_t(blockIdx.x) * words + w] = bits;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -937,7 +759,7 @@ long long* g_prof_buffer = nullptr;
 void set_profile_buffer(long long* p) { g_prof_buffer = p; }
 
 int retrieval_stats_smem_bytes() { return StatsSmem::dynamic_bytes; }
-int retrieval_apply_smem_bytes() { return ApplySmem::dynamic_bytes; }
+int retrieval_apply_smem_bytes() { return PairSmem::dynamic_bytes; }
 
 cudaError_t launch_stats(const RetrievalArgs& a, float* part_sum, float* part_max, cudaStream_t stream) {
   const int bytes = retrieval_stats_smem_bytes();
@@ -948,11 +770,18 @@ cudaError_t launch_stats(const RetrievalArgs& a, float* part_sum, float* part_ma
   if (a.geo)
     range_stats_kernel<true><<<grid, kStatsThreads, bytes, stream>>>(a.tmK128, a.q16, a.db_xyz, a.q_xyz, a.N, a.M,
                                                                a.stats_tiles_per_split, a.a_sem, a.a_geo, part_sum,
-                                                               part_max);
+                                                               part_max, a.geo_mask, a.mask_words);
   else
     range_stats_kernel<false><<<grid, kStatsThreads, bytes, stream>>>(a.tmK128, a.q16, a.db_xyz, a.q_xyz, a.N, a.M,
                                                                 a.stats_tiles_per_split, a.a_sem, a.a_geo, part_sum,
-                                                                part_max);
+                                                                part_max, nullptr, 0);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_geo_mask(const float* q_xyz, int N, const float* caps, int n_tiles, float delta, uint32_t* mask,
+                            int words, cudaStream_t stream) {
+  geo_mask_kernel<<<(N + 127) / 128, 128, 0, stream>>>(reinterpret_cast<const float4*>(q_xyz), N,
+                                                       reinterpret_cast<const float4*>(caps), n_tiles, delta, mask, words);
   return cudaGetLastError();
 }
 
@@ -1003,42 +832,24 @@ cudaError_t launch_apply(const RetrievalArgs& a, const float* rowc, float* out, 
   const float4* rc = reinterpret_cast<const float4*>(rowc);
   const int qtiles = (a.N + kBlockQ - 1) / kBlockQ;
   long long* no_prof = nullptr;
-  static const bool single = getenv("RANGE_APPLY") && !strcmp(getenv("RANGE_APPLY"), "single");   // A/B timing only
-  if (!single) {
-    // CTA pairs: cluster (2,1,1) over the query-tile axis (an odd tile count gets one all-padding CTA)
-    const int bytes = PairSmem::dynamic_bytes;
-    dim3 grid((qtiles + 1) / 2 * 2, 1024 / kSliceV, a.apply_splits);
-    if (g_prof_buffer) {
-      if ((e = set_smem(range_apply_pair_kernel<true, true>, bytes)) != cudaSuccess) return e;
-      return launch_pair(range_apply_pair_kernel<true, true>, grid, bytes, stream, a.tmQ, a.tmK64, a.tmV128, a.db_xyz,
-                         rc, a.N, a.M, a.apply_tiles_per_split, a.a_sem, out, out_split_stride, g_prof_buffer);
-    }
-    if ((e = set_smem(range_apply_pair_kernel<true>, bytes)) != cudaSuccess) return e;
-    if ((e = set_smem(range_apply_pair_kernel<false>, bytes)) != cudaSuccess) return e;
-    if (a.geo)
-      return launch_pair(range_apply_pair_kernel<true>, grid, bytes, stream, a.tmQ, a.tmK64, a.tmV128, a.db_xyz, rc,
-                         a.N, a.M, a.apply_tiles_per_split, a.a_sem, out, out_split_stride, no_prof);
-    return launch_pair(range_apply_pair_kernel<false>, grid, bytes, stream, a.tmQ, a.tmK64, a.tmV128, a.db_xyz, rc,
-                       a.N, a.M, a.apply_tiles_per_split, a.a_sem, out, out_split_stride, no_prof);
-  }
-  const int bytes = retrieval_apply_smem_bytes();
-  if ((e = set_smem(range_apply_kernel<true>, bytes)) != cudaSuccess) return e;
-  if ((e = set_smem(range_apply_kernel<false>, bytes)) != cudaSuccess) return e;
-  dim3 grid(1024 / kSliceV, qtiles, a.apply_splits);
+  const uint32_t* no_mask = nullptr;
+  // CTA pairs: cluster (2,1,1) over the query-tile axis (an odd tile count gets one all-padding CTA)
+  const int bytes = PairSmem::dynamic_bytes;
+  dim3 grid((qtiles + 1) / 2 * 2, 1024 / kSliceV, a.apply_splits);
   if (g_prof_buffer) {   // instrumented build of the same kernel (tools/time_apply.py)
-    if ((e = set_smem(range_apply_kernel<true, true>, bytes)) != cudaSuccess) return e;
-    range_apply_kernel<true, true><<<grid, kThreads, bytes, stream>>>(
-        a.tmQ, a.tmK128, a.tmV, a.db_xyz, rc, a.N, a.M, a.apply_tiles_per_split, a.a_sem, out, out_split_stride,
-        g_prof_buffer);
-    return cudaGetLastError();
+    if ((e = set_smem(range_apply_pair_kernel<true, true>, bytes)) != cudaSuccess) return e;
+    return launch_pair(range_apply_pair_kernel<true, true>, grid, bytes, stream, a.tmQ, a.tmK64, a.tmV128, a.db_xyz,
+                       rc, a.N, a.M, a.apply_tiles_per_split, a.a_sem, out, out_split_stride, a.geo_mask, a.mask_words,
+                       g_prof_buffer);
   }
+  if ((e = set_smem(range_apply_pair_kernel<true>, bytes)) != cudaSuccess) return e;
+  if ((e = set_smem(range_apply_pair_kernel<false>, bytes)) != cudaSuccess) return e;
   if (a.geo)
-    range_apply_kernel<true><<<grid, kThreads, bytes, stream>>>(a.tmQ, a.tmK128, a.tmV, a.db_xyz, rc, a.N, a.M,
-                                                               a.apply_tiles_per_split, a.a_sem, out, out_split_stride);
-  else
-    range_apply_kernel<false><<<grid, kThreads, bytes, stream>>>(a.tmQ, a.tmK128, a.tmV, a.db_xyz, rc, a.N, a.M,
-                                                                a.apply_tiles_per_split, a.a_sem, out, out_split_stride);
-  return cudaGetLastError();
+    return launch_pair(range_apply_pair_kernel<true>, grid, bytes, stream, a.tmQ, a.tmK64, a.tmV128, a.db_xyz, rc,
+                       a.N, a.M, a.apply_tiles_per_split, a.a_sem, out, out_split_stride, a.geo_mask, a.mask_words,
+                       no_prof);
+  return launch_pair(range_apply_pair_kernel<false>, grid, bytes, stream, a.tmQ, a.tmK64, a.tmV128, a.db_xyz, rc,
+                     a.N, a.M, a.apply_tiles_per_split, a.a_sem, out, out_split_stride, no_mask, 0, no_prof);
 }
 
 cudaError_t launch_reduce_out(const float* part, size_t split_stride, int splits, size_t total, float* out,
