@@ -76,6 +76,28 @@ int range_ctx_set_encoder_precision(range_ctx* ctx, int mode);
 int range_ctx_set_db(range_ctx* ctx, int64_t M, int64_t Mpad, const void* Kh, const void* Vt, const float* xyz,
                      float vscale);
 
+/* Optional: bounding caps of the database's 128-entry tiles, caps (Mpad/128, 4) fp32 device = (unit centre x, y, z,
+ * angular radius in radians), borrowed.  With caps set, RANGE+ retrieval skips the geographic term of every
+ * (128-query tile, 128-entry tile) whose entries all lie so far from all the tile's queries that together they
+ * carry < 2^-24 of each row's geo normaliser (the geo softmax of range/range.py:231-234 has temperature 40:
+ * exp(40 (cos d - 1))).  Effective when the database is stored in a spatially sorted order
+ * (range_b200/database.py) and queries are batched spatially (range_sort_queries).  M_total = entries of the
+ * whole database when this ctx holds one shard of it.  caps = NULL disables.  Reset by range_ctx_set_db. */
+int range_ctx_set_db_caps(range_ctx* ctx, int64_t n_tiles, const float* caps, int64_t M_total);
+
+/* Diagnostic: the skip mask the RANGE+ kernels would use for these queries - mask [rows][words] uint32, bit t of
+ * row r set = query tile r (128 rows of qxyz) skips the geo term of database tile t.  Shape from
+ * range_geo_mask_shape (rows = query tiles rounded up to even). */
+int range_geo_mask_shape(range_ctx* ctx, int64_t N, int32_t* rows, int32_t* words);
+int range_geo_mask(range_ctx* ctx, int64_t N, const float* qxyz, float geo_temp, uint32_t* mask, void* stream);
+
+/* Spatial batching of a query batch (no reference counterpart: rows are independent, range/range.py:213-240).
+ * perm[i] = caller's row index of sorted row i, lonlat_sorted[i] = lonlat[perm[i]]; cube-map Morton cells,
+ * deterministic.  Run the encoder / retrieval on lonlat_sorted and hand perm to range_concat_scatter. */
+size_t range_sort_workspace_bytes(range_ctx* ctx, int64_t N);
+int range_sort_queries(range_ctx* ctx, int64_t N, const double* lonlat, double* lonlat_sorted, int32_t* perm,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
 /* K1: features Yt[f * ld + n] = Y_f(lonlat[n]) for f < L*L - SphericalHarmonics.forward,
  * positional_encoding/spherical_harmonics.py:27-42.  lonlat (N,2) fp64 (lon, lat) degrees. */
 int range_sh_features(range_ctx* ctx, int64_t N, const double* lonlat, double* Yt, int64_t ld, void* stream);
@@ -107,6 +129,10 @@ int range_retrieve(range_ctx* ctx, int mode, int64_t N, const void* q16, const f
  * or fp32. */
 int range_concat(range_ctx* ctx, int64_t N, const float* O, const double* q64, void* out, int out_dtype,
                  void* stream);
+
+/* as range_concat, writing row n to out row perm[n] (perm from range_sort_queries; NULL = identity) */
+int range_concat_scatter(range_ctx* ctx, int64_t N, const float* O, const double* q64, const int32_t* perm,
+                         void* out, int out_dtype, void* stream);
 
 /* number of kernels this library launched since process start (bench.py's gpu_launches) */
 int64_t range_launch_count(void);

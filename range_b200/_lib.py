@@ -27,6 +27,11 @@ PROTOTYPES = {
     "range_ctx_prepare_encoder": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
     "range_ctx_set_encoder_precision": (c_int, [c_void_p, c_int]),
     "range_ctx_set_db": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_float]),
+    "range_ctx_set_db_caps": (c_int, [c_void_p, c_int64, c_void_p, c_int64]),
+    "range_geo_mask_shape": (c_int, [c_void_p, c_int64, POINTER(c_int32), POINTER(c_int32)]),
+    "range_geo_mask": (c_int, [c_void_p, c_int64, c_void_p, c_float, c_void_p, c_void_p]),
+    "range_sort_workspace_bytes": (c_size_t, [c_void_p, c_int64]),
+    "range_sort_queries": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "range_sh_features": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p]),
     "range_encode_workspace_bytes": (c_size_t, [c_void_p, c_int64]),
     "range_encode": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
@@ -39,6 +44,7 @@ PROTOTYPES = {
     "range_retrieve": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_float, c_float, c_float, c_void_p,
                                c_void_p, c_size_t, c_void_p]),
     "range_concat": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "range_concat_scatter": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
 }
 
 _lib = None

@@ -82,6 +82,8 @@ struct range_ctx {
   const float* xyz = nullptr;
   float vscale = 1.f;
   CUtensorMap tmK128, tmV, tmK64, tmV128;
+  const float* caps = nullptr;     // (Mpad / 128, 4) bounding caps of the database tiles, or null
+  int64_t M_total = 0;             // entries of the whole (unsharded) database: sets the geo-skip threshold
   // tensor-core encoder (3xTF32): prepared weights live in a caller-provided buffer
   int enc_precision = RANGE_ENC_F64;
   bool enc_prepared = false;
@@ -95,7 +97,8 @@ namespace {
 struct RetrievalPlan {
   int splits, tiles_per_split;              // apply kernel
   int stats_splits, stats_tiles_per_split;  // stats kernel
-  size_t off_part_sum, off_part_max, off_sums, off_maxs, off_rowc, off_part_out, total;
+  int mask_rows, mask_words;                // geo-skip mask: [even-padded query tiles][ceil(tiles / 32)]
+  size_t off_part_sum, off_part_max, off_sums, off_maxs, off_rowc, off_mask, off_part_out, total;
 };
 
 // Database splits: enough CTAs to fill the SMs when there are few query tiles.
@@ -128,13 +131,17 @@ RetrievalPlan plan_retrieval(const range_ctx* c, int64_t N) {
   p.off_sums = o;     o += align_up(size_t(N) * 8, 256);
   p.off_maxs = o;     o += align_up(size_t(N) * 8, 256);
   p.off_rowc = o;     o += align_up(size_t(N) * 32, 256);
+  p.mask_rows = int((qtiles + 1) / 2 * 2);
+  p.mask_words = int((tiles + 31) / 32);
+  p.off_mask = o;     o += c->caps ? align_up(size_t(p.mask_rows) * p.mask_words * 4, 256) : 0;
   p.off_part_out = o; o += p.splits > 1 ? align_up(size_t(p.splits) * N * kDimV * 4, 256) : 0;
   p.total = o;
   return p;
 }
 
+// ws: aligned workspace base; when the database carries bounding caps the geo-skip mask is (re)computed here
 int fill_args(range_ctx* c, int mode, int64_t N, const void* q16, const float* qxyz, float temp, float geo_temp,
-              const RetrievalPlan& p, RetrievalArgs* a) {
+              const RetrievalPlan& p, char* ws, cudaStream_t stream, RetrievalArgs* a) {
   if (!c || !c->Kh) return fail(RANGE_ERR_INVALID, "database not set");
   if (mode != RANGE_MODE_RANGE && mode != RANGE_MODE_RANGE_PLUS) return fail(RANGE_ERR_INVALID, "unknown mode %d", mode);
   if (N <= 0 || N > (int64_t(1) << 30)) return fail(RANGE_ERR_INVALID, "N out of range");
@@ -159,6 +166,16 @@ int fill_args(range_ctx* c, int mode, int64_t N, const void* q16, const float* q
   a->a_geo = geo_temp * log2e;
   a->geo_mask = nullptr;
   a->mask_words = 0;
+  if (a->geo && c->caps && geo_temp > 0.f) {
+    // entries with g <= g_max - delta together carry < 2^-24 of the row's geo normaliser (retrieval.cu)
+    const float delta = (logf(float(c->M_total)) + 24.f * 0.6931471805599453f) / geo_temp;
+    uint32_t* mask = reinterpret_cast<uint32_t*>(ws + p.off_mask);
+    CUDA_TRY(launch_geo_mask(qxyz, int(N), p.mask_rows, c->caps, int(c->Mpad / kBlockKeys), delta, mask, p.mask_words,
+                             stream));
+    g_launches += 1;
+    a->geo_mask = mask;
+    a->mask_words = p.mask_words;
+  }
   return RANGE_OK;
 }
 
@@ -238,6 +255,52 @@ int range_ctx_set_db(range_ctx* c, int64_t M, int64_t Mpad, const void* Kh, cons
   r = make_tmap(&c->tmV128, Vt, kDimV, uint64_t(Mpad), 128);
   if (r) return r;
   c->M = M; c->Mpad = Mpad; c->Kh = Kh; c->Vt = Vt; c->xyz = xyz; c->vscale = vscale;
+  c->caps = nullptr; c->M_total = M;
+  return RANGE_OK;
+}
+
+int range_ctx_set_db_caps(range_ctx* c, int64_t n_tiles, const float* caps, int64_t M_total) {
+  if (!c || !c->Kh) return fail(RANGE_ERR_INVALID, "database not set");
+  if (!caps) { c->caps = nullptr; c->M_total = c->M; return RANGE_OK; }
+  if (n_tiles != c->Mpad / kBlockKeys || M_total < c->M)
+    return fail(RANGE_ERR_INVALID, "caps: %lld tiles for Mpad=%lld, M_total=%lld", (long long)n_tiles,
+                (long long)c->Mpad, (long long)M_total);
+  c->caps = caps;
+  c->M_total = M_total;
+  return RANGE_OK;
+}
+
+int range_geo_mask_shape(range_ctx* c, int64_t N, int32_t* rows, int32_t* words) {
+  if (!c || !c->Kh || N <= 0 || !rows || !words) return fail(RANGE_ERR_INVALID, "bad arguments");
+  const RetrievalPlan p = plan_retrieval(c, N);
+  *rows = p.mask_rows;
+  *words = p.mask_words;
+  return RANGE_OK;
+}
+
+int range_geo_mask(range_ctx* c, int64_t N, const float* qxyz, float geo_temp, uint32_t* mask, void* stream) {
+  if (!c || !c->Kh || !c->caps) return fail(RANGE_ERR_INVALID, "database caps not set");
+  if (N <= 0 || !qxyz || !mask || !(geo_temp > 0.f)) return fail(RANGE_ERR_INVALID, "bad arguments");
+  const RetrievalPlan p = plan_retrieval(c, N);
+  const float delta = (logf(float(c->M_total)) + 24.f * 0.6931471805599453f) / geo_temp;
+  CUDA_TRY(launch_geo_mask(qxyz, int(N), p.mask_rows, c->caps, int(c->Mpad / kBlockKeys), delta, mask, p.mask_words,
+                           cudaStream_t(stream)));
+  g_launches += 1;
+  return RANGE_OK;
+}
+
+size_t range_sort_workspace_bytes(range_ctx* c, int64_t N) {
+  if (!c || N <= 0 || N > (int64_t(1) << 30)) return 0;
+  return sort_workspace_bytes(int(N));
+}
+
+int range_sort_queries(range_ctx* c, int64_t N, const double* lonlat, double* lonlat_sorted, int32_t* perm,
+                       void* workspace, size_t workspace_bytes, void* stream) {
+  if (!c || N <= 0 || N > (int64_t(1) << 30) || !lonlat || !lonlat_sorted || !perm || !workspace)
+    return fail(RANGE_ERR_INVALID, "bad arguments");
+  if (workspace_bytes < sort_workspace_bytes(int(N))) return fail(RANGE_ERR_WORKSPACE, "sort workspace too small");
+  CUDA_TRY(launch_sort_queries(lonlat, int(N), lonlat_sorted, perm, workspace, cudaStream_t(stream)));
+  g_launches += 4;
   return RANGE_OK;
 }
 
@@ -411,10 +474,10 @@ int range_retrieve_stats(range_ctx* c, int mode, int64_t N, const void* q16, con
   const RetrievalPlan p = plan_retrieval(c, N);
   if (workspace_bytes < p.total + 256) return fail(RANGE_ERR_WORKSPACE, "retrieve workspace too small");
   RetrievalArgs a;
-  int r = fill_args(c, mode, N, q16, qxyz, temp, geo_temp, p, &a);
-  if (r) return r;
   char* ws = reinterpret_cast<char*>(align_up(reinterpret_cast<size_t>(workspace), 256));
   cudaStream_t s = cudaStream_t(stream);
+  int r = fill_args(c, mode, N, q16, qxyz, temp, geo_temp, p, ws, s, &a);
+  if (r) return r;
   float* part_sum = p.stats_splits > 1 ? reinterpret_cast<float*>(ws + p.off_part_sum) : sums;
   float* part_max = p.stats_splits > 1 ? reinterpret_cast<float*>(ws + p.off_part_max) : maxs;
   CUDA_TRY(launch_stats(a, part_sum, part_max, s));
@@ -437,10 +500,10 @@ int range_retrieve_apply(range_ctx* c, int mode, int64_t N, const void* q16, con
   const RetrievalPlan p = plan_retrieval(c, N);
   if (workspace_bytes < p.total + 256) return fail(RANGE_ERR_WORKSPACE, "retrieve workspace too small");
   RetrievalArgs a;
-  int r = fill_args(c, mode, N, q16, qxyz, temp, geo_temp, p, &a);
-  if (r) return r;
   char* ws = reinterpret_cast<char*>(align_up(reinterpret_cast<size_t>(workspace), 256));
   cudaStream_t s = cudaStream_t(stream);
+  int r = fill_args(c, mode, N, q16, qxyz, temp, geo_temp, p, ws, s, &a);
+  if (r) return r;
   float* rowc = reinterpret_cast<float*>(ws + p.off_rowc);
   CUDA_TRY(launch_row_constants(sums, maxs, qxyz, int(N), a.geo, beta, a.a_sem, a.a_geo, 1.f / c->vscale, rowc, s));
   float* part_out = p.splits > 1 ? reinterpret_cast<float*>(ws + p.off_part_out) : O;
@@ -470,13 +533,18 @@ int range_retrieve(range_ctx* c, int mode, int64_t N, const void* q16, const flo
                               workspace_bytes, stream);
 }
 
-int range_concat(range_ctx* c, int64_t N, const float* O, const double* q64, void* out, int out_dtype,
-                 void* stream) {
+int range_concat_scatter(range_ctx* c, int64_t N, const float* O, const double* q64, const int32_t* perm, void* out,
+                         int out_dtype, void* stream) {
   if (!c || N <= 0 || !O || !q64 || !out) return fail(RANGE_ERR_INVALID, "bad arguments");
   if (out_dtype != RANGE_OUT_F64 && out_dtype != RANGE_OUT_F32) return fail(RANGE_ERR_INVALID, "unknown out dtype");
-  CUDA_TRY(launch_concat(O, q64, int(N), kDimV, kDimK, out, out_dtype, cudaStream_t(stream)));
+  CUDA_TRY(launch_concat(O, q64, int(N), kDimV, kDimK, perm, out, out_dtype, cudaStream_t(stream)));
   g_launches += 1;
   return RANGE_OK;
+}
+
+int range_concat(range_ctx* c, int64_t N, const float* O, const double* q64, void* out, int out_dtype,
+                 void* stream) {
+  return range_concat_scatter(c, N, O, q64, nullptr, out, out_dtype, stream);
 }
 
 }  // extern "C"

@@ -199,16 +199,17 @@ normalize_kernel(const double* __restrict__ e, const double* __restrict__ lonlat
 }
 
 __global__ void __launch_bounds__(256)
-concat_kernel(const float* __restrict__ O, const double* __restrict__ q64, int N, int DO, int DQ, void* out,
-              int dtype) {
+concat_kernel(const float* __restrict__ O, const double* __restrict__ q64, int N, int DO, int DQ,
+              const int* __restrict__ perm, void* out, int dtype) {
   const int W = DO + DQ;
   const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= size_t(N) * W) return;
   const size_t n = i / W;
   const int c = int(i - n * W);
   const double v = c < DO ? double(O[n * DO + c]) : q64[n * DQ + (c - DO)];
-  if (dtype == 0) reinterpret_cast<double*>(out)[i] = v;
-  else reinterpret_cast<float*>(out)[i] = float(v);
+  const size_t o = perm ? size_t(perm[n]) * W + c : i;      // row n was computed for the caller's row perm[n]
+  if (dtype == 0) reinterpret_cast<double*>(out)[o] = v;
+  else reinterpret_cast<float*>(out)[o] = float(v);
 }
 
 }  // namespace
@@ -240,11 +241,11 @@ cudaError_t launch_normalize(const double* e, const double* lonlat, int N, int D
   return cudaGetLastError();
 }
 
-cudaError_t launch_concat(const float* O, const double* q64, int N, int DO, int DQ, void* out, int dtype,
-                          cudaStream_t s) {
+cudaError_t launch_concat(const float* O, const double* q64, int N, int DO, int DQ, const int* perm, void* out,
+                          int dtype, cudaStream_t s) {
   if (N <= 0) return cudaSuccess;
   const size_t total = size_t(N) * (DO + DQ);
-  concat_kernel<<<unsigned((total + 255) / 256), 256, 0, s>>>(O, q64, N, DO, DQ, out, dtype);
+  concat_kernel<<<unsigned((total + 255) / 256), 256, 0, s>>>(O, q64, N, DO, DQ, perm, out, dtype);
   return cudaGetLastError();
 }
 

@@ -340,6 +340,12 @@ __device__ __forceinline__ float ex2_poly(float x) {
   p = fmaf(p, f, 0.9999992847442627f);
   return __int_as_float(__float_as_int(p) + (__float_as_int(xr) << 23));
 }
+// three-input maximum (FMNMX3 on sm_100): one instruction per two new candidates
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float y;
+  asm("max.ftz.f32 %0, %1, %2, %3;" : "=f"(y) : "f"(a), "f"(b), "f"(c));
+  return y;
+}
 __device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
   __half2 h = __floats2half2_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);

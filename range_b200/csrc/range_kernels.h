@@ -41,9 +41,15 @@ cudaError_t launch_siren_tc(const CUtensorMap& tmAh, const CUtensorMap& tmAl, co
 // e [N][D] fp64 row-major -> q64 [N][D] (ld = ldq), q16 [N][D] fp16, qxyz [N][4] fp32 from lonlat
 cudaError_t launch_normalize(const double* e, const double* lonlat, int N, int D, double* q64, size_t ldq,
                              void* q16, float* qxyz, cudaStream_t s);
-// out[n] = [O[n][0:DO] | q64[n][0:DQ]]  as fp64 (dtype 0) or fp32 (dtype 1)
-cudaError_t launch_concat(const float* O, const double* q64, int N, int DO, int DQ, void* out, int dtype,
-                          cudaStream_t s);
+// out[perm ? perm[n] : n] = [O[n][0:DO] | q64[n][0:DQ]]  as fp64 (dtype 0) or fp32 (dtype 1)
+cudaError_t launch_concat(const float* O, const double* q64, int N, int DO, int DQ, const int* perm, void* out,
+                          int dtype, cudaStream_t s);
+
+// ---- spatial batching of the queries (sort.cu) ----------------------------------------------------
+size_t sort_workspace_bytes(int N);
+// perm[i] = caller's row of sorted row i; lonlat_sorted[i] = lonlat[perm[i]]  (deterministic)
+cudaError_t launch_sort_queries(const double* lonlat, int N, double* lonlat_sorted, int32_t* perm, void* workspace,
+                                cudaStream_t s);
 
 // ---- K2: retrieval (retrieval.cu) ---------------------------------------------------------------
 struct RetrievalArgs {
@@ -68,8 +74,8 @@ int retrieval_stats_smem_bytes();
 int retrieval_apply_smem_bytes();
 cudaError_t launch_stats(const RetrievalArgs& a, float* part_sum, float* part_max, cudaStream_t s);
 // skip bits from the query tiles' and database tiles' bounding caps (retrieval.cu: geo_mask_kernel)
-cudaError_t launch_geo_mask(const float* q_xyz, int N, const float* caps, int n_tiles, float delta, uint32_t* mask,
-                            int words, cudaStream_t s);
+cudaError_t launch_geo_mask(const float* q_xyz, int N, int rows, const float* caps, int n_tiles, float delta,
+                            uint32_t* mask, int words, cudaStream_t s);
 cudaError_t launch_reduce_stats(const float* part_sum, const float* part_max, int N, int splits, float* sums,
                                 float* maxs, cudaStream_t s);
 cudaError_t launch_row_constants(const float* sums, const float* maxs, const float* q_xyz, int N, int geo,

@@ -261,26 +261,38 @@ range_stats_kernel(const __grid_constant__ CUtensorMap tmK, const __half* __rest
       const uint32_t kxyz = ptx::smem_u32(smem + L::xyz + b * kXyzBytes) + grp * 32 * 16;
       const int nvalid = M - key0;            // >= 32 except in the last tile
       const bool with_geo = kGeo && !skip_geo(t_begin + j);
-      auto body = [&](auto masked) {
+      // the geo part is selected per TILE (warp-uniform): two straight-line bodies, no branch inside the unrolled loop
+      auto body = [&](auto masked, auto geo) {
+        constexpr bool kM = decltype(masked)::value, kG = decltype(geo)::value;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float s = __uint_as_float(s0[i]);
-          const bool valid = !decltype(masked)::value || (i < nvalid);
-          float es = ptx::ex2(fmaf(s, a_sem, -a_sem));
-          if (!valid) es = 0.f;
-          sum_s += es;
-          max_s = fmaxf(max_s, valid ? s : -2.f);
-          if (kGeo && with_geo) {
-            const float4 k = ptx::lds_f4(kxyz + i * 16);
-            const float g = fmaf(gx, k.x, fmaf(gy, k.y, fmaf(gz, k.z, -a_geo)));   // a_geo (g - 1)
-            float eg = ptx::ex2(g);
-            if (!valid) eg = 0.f;
-            sum_g += eg;
-            max_g = fmaxf(max_g, valid ? g : -3.0e38f);
+        for (int i = 0; i < 32; i += 2) {
+          float sv[2], gv[2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const float s = __uint_as_float(s0[i + u]);
+            const bool valid = !kM || (i + u < nvalid);
+            float es = ptx::ex2(fmaf(s, a_sem, -a_sem));
+            if (!valid) es = 0.f;
+            sum_s += es;
+            sv[u] = valid ? s : -2.f;
+            if (kG) {
+              const float4 k = ptx::lds_f4(kxyz + (i + u) * 16);
+              const float g = fmaf(gx, k.x, fmaf(gy, k.y, fmaf(gz, k.z, -a_geo)));   // a_geo (g - 1)
+              float eg = ptx::ex2(g);
+              if (!valid) eg = 0.f;
+              sum_g += eg;
+              gv[u] = valid ? g : -3.0e38f;
+            }
           }
+          max_s = ptx::max3(max_s, sv[0], sv[1]);
+          if (kG) max_g = ptx::max3(max_g, gv[0], gv[1]);
         }
       };
-      if (nvalid >= 32) body(std::false_type{}); else body(std::true_type{});
+      if (nvalid >= 32) {
+        if (with_geo) body(std::false_type{}, std::true_type{}); else body(std::false_type{}, std::false_type{});
+      } else {
+        if (with_geo) body(std::true_type{}, std::true_type{}); else body(std::true_type{}, std::false_type{});
+      }
       if (kGeo) {
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&bars[L::b_xyz_empty + b]);
@@ -568,7 +580,9 @@ range_apply_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       const int nvalid = M - key0;            // >= 32 except in the last tile
       const bool with_geo = kGeo && !skip_geo(t_begin + j);
       uint32_t packed[16];
-      auto body = [&](auto masked) {
+      // the geo part is selected per TILE (warp-uniform): separate straight-line bodies
+      auto body = [&](auto masked, auto geo) {
+        constexpr bool kM = decltype(masked)::value, kG = decltype(geo)::value;
 #pragma unroll
         for (int w = 0; w < 16; ++w) {
           float pv[2];
@@ -576,17 +590,21 @@ range_apply_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
           for (int u = 0; u < 2; ++u) {
             const int i = 2 * w + u;
             float p = ptx::ex2(fmaf(__uint_as_float(cur[i]), a_sem, cs));
-            if (kGeo && with_geo) {
+            if (kG) {
               const float4 k = ptx::lds_f4(kxyz + i * 16);
               p += ptx::ex2(fmaf(gx, k.x, fmaf(gy, k.y, fmaf(gz, k.z, cg))));
             }
-            if (decltype(masked)::value && i >= nvalid) p = 0.f;
+            if (kM && i >= nvalid) p = 0.f;
             pv[u] = p;
           }
           packed[w] = ptx::pack_half2(pv[0], pv[1]);
         }
       };
-      if (nvalid >= 32) body(std::false_type{}); else body(std::true_type{});
+      if (nvalid >= 32) {
+        if (with_geo) body(std::false_type{}, std::true_type{}); else body(std::false_type{}, std::false_type{});
+      } else {
+        if (with_geo) body(std::true_type{}, std::true_type{}); else body(std::true_type{}, std::false_type{});
+      }
       PROF_ADD(2, 3);
       // P'(row, 32 entries) as 16 packed columns over the first half of the 32 S columns it came from
       ptx::tmem_st16(taddr, packed);
@@ -778,9 +796,10 @@ cudaError_t launch_stats(const RetrievalArgs& a, float* part_sum, float* part_ma
   return cudaGetLastError();
 }
 
-cudaError_t launch_geo_mask(const float* q_xyz, int N, const float* caps, int n_tiles, float delta, uint32_t* mask,
-                            int words, cudaStream_t stream) {
-  geo_mask_kernel<<<(N + 127) / 128, 128, 0, stream>>>(reinterpret_cast<const float4*>(q_xyz), N,
+cudaError_t launch_geo_mask(const float* q_xyz, int N, int rows, const float* caps, int n_tiles, float delta,
+                            uint32_t* mask, int words, cudaStream_t stream) {
+  // rows >= ceil(N / 128): all-padding query tiles (the CTA-pair grid is rounded up to even) get an all-zero row
+  geo_mask_kernel<<<rows, 128, 0, stream>>>(reinterpret_cast<const float4*>(q_xyz), N,
                                                        reinterpret_cast<const float4*>(caps), n_tiles, delta, mask, words);
   return cudaGetLastError();
 }

@@ -6,7 +6,13 @@ Device layout (what include/range_b200.h:range_ctx_set_db takes):
   Vt  (1024, Mpad) fp16  values TRANSPOSED (entries contiguous) x vscale -> TMA boxes [256 dims x 64 entries];
                          K-major B operand of the P.V tensor-core product, same descriptor as the keys
   xyz (Mpad, 4)    fp32  unit vectors of the entry locations (x, y, z, 0)
+  caps (Mpad/128, 4) fp32 bounding cap of every 128-entry tile: (unit centre, angular radius [rad])
 Mpad = M rounded up to 128; padding is zero and masked in-kernel.
+
+Row order: the reference's results do not depend on the order of the database rows (softmax-weighted sums,
+range/range.py:213-238), so the rows are stored sorted along a cube-map Morton curve.  Consecutive 128-entry
+tiles are then spatially compact, which lets the RANGE+ kernels skip the geographic term for tiles far from a
+query tile (include/range_b200.h: range_ctx_set_db_caps).
 """
 import math
 
@@ -28,16 +34,67 @@ def prepare_reference_arrays(db):
     return K, V, xyz
 
 
+def _spread_bits(v):
+    v = v.astype(np.uint64) & np.uint64(0xFFFF)
+    v = (v | (v << np.uint64(8))) & np.uint64(0x00FF00FF)
+    v = (v | (v << np.uint64(4))) & np.uint64(0x0F0F0F0F)
+    v = (v | (v << np.uint64(2))) & np.uint64(0x33333333)
+    v = (v | (v << np.uint64(1))) & np.uint64(0x55555555)
+    return v
+
+
+def morton_order(xyz, bits=12):
+    """stable argsort of unit vectors along a cube-map (equal-angle) Morton curve"""
+    x, y, z = (np.asarray(xyz[:, i], dtype=np.float64) for i in range(3))
+    ax, ay, az = np.abs(x), np.abs(y), np.abs(z)
+    fx = (ax >= ay) & (ax >= az)
+    fy = ~fx & (ay >= az)
+    fz = ~fx & ~fy
+    face = np.where(fx, np.where(x >= 0, 0, 1), np.where(fy, np.where(y >= 0, 2, 3), np.where(z >= 0, 4, 5)))
+    m = np.maximum(np.where(fx, ax, np.where(fy, ay, az)), 1e-30)
+    u = np.where(fx, y, x) / m
+    v = np.where(fz, y, z) / m
+    g = 1 << bits
+    iu = np.clip(((np.arctan(u) * (4 / np.pi) + 1) * 0.5 * g).astype(np.int64), 0, g - 1)
+    iv = np.clip(((np.arctan(v) * (4 / np.pi) + 1) * 0.5 * g).astype(np.int64), 0, g - 1)
+    key = (face.astype(np.uint64) << np.uint64(2 * bits)) | _spread_bits(iu) | (_spread_bits(iv) << np.uint64(1))
+    return np.argsort(key, kind="stable")
+
+
+def tile_caps(xyz, block=BLOCK):
+    """(ceil(M/block), 4) fp32: unit mean direction and the largest angle to it, per tile of `block` rows"""
+    M = xyz.shape[0]
+    T = (M + block - 1) // block
+    pad = T * block - M
+    p = np.asarray(xyz, dtype=np.float64)
+    if pad:
+        p = np.concatenate([p, np.repeat(p[-1:], pad, axis=0)], axis=0)     # repeat a real entry: caps unchanged
+    p = p.reshape(T, block, 3)
+    c = p.sum(1)
+    n = np.linalg.norm(c, axis=1, keepdims=True)
+    c = np.where(n > 1e-9, c / np.maximum(n, 1e-30), np.array([0.0, 0.0, 1.0]))
+    cosang = np.clip(np.einsum("tbi,ti->tb", p, c) / np.maximum(np.linalg.norm(p, axis=2), 1e-30), -1.0, 1.0)
+    r = np.arccos(cosang).max(1)
+    r = np.where(n[:, 0] > 1e-9, r, np.pi)                                    # degenerate tile: covers the sphere
+    return np.concatenate([c, r[:, None]], axis=1).astype(np.float32)
+
+
 class DeviceDatabase:
-    def __init__(self, db, device, shard=None):
+    def __init__(self, db, device, shard=None, spatial_sort=True):
         """db: mapping with locs / satclip_embeddings / image_embeddings (an opened .npz works).
-        shard=(rank, world): keep rows [rank*M/world, (rank+1)*M/world) only (M-sharding)."""
+        shard=(rank, world): keep rows [rank*M/world, (rank+1)*M/world) of the (sorted) database only (M-sharding).
+        spatial_sort: store the rows along a Morton curve and build the tile caps (geo-term skipping)."""
         K, V, xyz = prepare_reference_arrays(db)
         self.M_total = K.shape[0]
+        self.order = None
+        if spatial_sort and self.M_total > 0:
+            self.order = morton_order(xyz)
+            K, xyz = K[self.order], xyz[self.order]         # V is gathered chunk-wise below (it is the big one)
         if shard is not None:
             r, w = shard
             lo, hi = (self.M_total * r) // w, (self.M_total * (r + 1)) // w
-            K, V, xyz = K[lo:hi], V[lo:hi], xyz[lo:hi]
+            K, xyz = K[lo:hi], xyz[lo:hi]
+            V = V[lo:hi] if self.order is None else V
             self.row_range = (lo, hi)
         else:
             self.row_range = (0, self.M_total)
@@ -55,11 +112,14 @@ class DeviceDatabase:
         self.vscale = 1.0 if vmax == 0.0 or not math.isfinite(vmax) else 2.0 ** math.floor(math.log2(256.0 / vmax))
         self.Vt = torch.zeros(1024, Mpad, dtype=torch.float16, device=dev)
         step = 1 << 18
+        row0 = self.row_range[0]
         for lo in range(0, M, step):                       # bounded staging memory for 10M-entry databases
             hi = min(M, lo + step)
-            self.Vt[:, lo:hi] = (torch.from_numpy(V[lo:hi]).to(dev) * self.vscale).half().t()
+            rows = V[lo:hi] if self.order is None else V[self.order[row0 + lo:row0 + hi]]
+            self.Vt[:, lo:hi] = (torch.from_numpy(np.ascontiguousarray(rows)).to(dev) * self.vscale).half().t()
         self.xyz = torch.zeros(Mpad, 4, dtype=torch.float32, device=dev)
         self.xyz[:M, :3] = torch.from_numpy(np.ascontiguousarray(xyz)).to(dev)
+        self.caps = torch.from_numpy(tile_caps(xyz)).to(dev) if self.order is not None else None
 
     def nbytes(self):
         return sum(t.numel() * t.element_size() for t in (self.Kh, self.Vt, self.xyz))

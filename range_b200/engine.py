@@ -93,6 +93,8 @@ class RangeEngine:
     def set_database(self, db):
         _lib.check(self.lib.range_ctx_set_db(self.ctx, db.M, db.Mpad, _ptr(db.Kh), _ptr(db.Vt), _ptr(db.xyz),
                                              float(db.vscale)))
+        if getattr(db, "caps", None) is not None:
+            _lib.check(self.lib.range_ctx_set_db_caps(self.ctx, db.caps.shape[0], _ptr(db.caps), db.M_total))
         self.db = db
 
     def _workspace(self, key, nbytes):
@@ -112,6 +114,30 @@ class RangeEngine:
         with torch.cuda.device(self.index):
             _lib.check(self.lib.range_sh_features(self.ctx, N, _ptr(lonlat), _ptr(Yt), ld, _stream()))
         return Yt[:, :N].t()
+
+    def sort_queries(self, lonlat):
+        """(N,2) fp64 device tensor -> (lonlat_sorted (N,2), perm (N,) int32): spatial batching for RANGE+.
+        perm[i] is the caller's row of sorted row i; hand it to concat()."""
+        lonlat = lonlat.to(self.device, torch.float64).contiguous()
+        N = lonlat.shape[0]
+        out = torch.empty_like(lonlat)
+        perm = torch.empty(N, dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.index):
+            ws = self._workspace("sort", self.lib.range_sort_workspace_bytes(self.ctx, N))
+            _lib.check(self.lib.range_sort_queries(self.ctx, N, _ptr(lonlat), _ptr(out), _ptr(perm), _ptr(ws),
+                                                   ws.numel(), _stream()))
+        return out, perm
+
+    def geo_mask(self, qxyz, geo_temp):
+        """diagnostic: (query tiles, database tiles) bool tensor, True = the geo term of that tile pair is skipped"""
+        N = qxyz.shape[0]
+        rows, words = c_int32(), c_int32()
+        _lib.check(self.lib.range_geo_mask_shape(self.ctx, N, ctypes.byref(rows), ctypes.byref(words)))
+        mask = torch.zeros(rows.value, words.value, dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.index):
+            _lib.check(self.lib.range_geo_mask(self.ctx, N, _ptr(qxyz), float(geo_temp), _ptr(mask), _stream()))
+        bits = (mask.unsqueeze(-1) >> torch.arange(32, device=self.device, dtype=torch.int32)) & 1
+        return bits.reshape(rows.value, -1)[: (N + 127) // 128, : self.db.Mpad // 128].bool()
 
     def encode(self, lonlat, q64=None, q16=None, qxyz=None):
         lonlat = lonlat.to(self.device, torch.float64).contiguous()
@@ -159,10 +185,13 @@ class RangeEngine:
                                                      _ptr(O), _ptr(ws), ws.numel(), _stream()))
         return O
 
-    def concat(self, O, q64, out=None, dtype=torch.float64):
+    def concat(self, O, q64, out=None, dtype=torch.float64, perm=None):
+        """[O | q64] -> (N,1280); with perm (from sort_queries) row n is written to out[perm[n]]"""
         N = O.shape[0]
         out = torch.empty(N, 1280, dtype=dtype, device=self.device) if out is None else out
         code = _lib.RANGE_OUT_F64 if out.dtype == torch.float64 else _lib.RANGE_OUT_F32
         with torch.cuda.device(self.index):
-            _lib.check(self.lib.range_concat(self.ctx, N, _ptr(O), _ptr(q64), _ptr(out), code, _stream()))
+            _lib.check(self.lib.range_concat_scatter(self.ctx, N, _ptr(O), _ptr(q64),
+                                                     c_void_p(None) if perm is None else _ptr(perm), _ptr(out), code,
+                                                     _stream()))
         return out

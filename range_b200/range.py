@@ -53,6 +53,10 @@ class LocationEncoder(nn.Module):
     def embed(self, coords, out=None, out_dtype=torch.float32):
         """Device-resident path: coords (N,2) fp64 on the device -> (N,1280) device tensor."""
         eng, a = self.engine, self.args
+        perm = None
+        if self.location_model_name == 'RANGE+' and eng.db is not None and eng.db.caps is not None:
+            # spatial batching: the geo softmax is local, tiles of nearby queries skip far database tiles
+            coords, perm = eng.sort_queries(coords)
         q64, q16, qxyz = eng.encode(coords)
         beta = getattr(a, 'beta', None)
         geo_temp = float(getattr(a, 'geo_temp', 0.0))
@@ -61,7 +65,7 @@ class LocationEncoder(nn.Module):
         else:
             from .distributed import sharded_retrieve
             O = sharded_retrieve(eng, self.location_model_name, q16, qxyz, a.temp, geo_temp, beta, self.group)
-        return eng.concat(O, q64, out=out, dtype=out_dtype)
+        return eng.concat(O, q64, out=out, dtype=out_dtype, perm=perm)
 
     @torch.no_grad()
     def forward(self, coords):

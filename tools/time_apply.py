@@ -13,6 +13,8 @@ db = dict(locs=O.area_uniform(M, rng), satclip_embeddings=rng.standard_normal((M
 eng = RangeEngine(dev, L=40, database=DeviceDatabase(db, dev))
 q = torch.randn(N, 256, device=dev); q = (q / q.norm(dim=1, keepdim=True)).half()
 c = torch.tensor(O.area_uniform(N, np.random.default_rng(1)))
+if os.environ.get("SORT", "1") == "1":      # spatially batched queries (what range.py does for RANGE+)
+    c = eng.sort_queries(c)[0].cpu()
 xyz = torch.zeros(N, 4); xyz[:, :3] = torch.tensor(O.rad_to_cart(c.numpy() * np.pi / 180)).float(); xyz = xyz.to(dev)
 def timeit(fn, reps=3):
     fn(); torch.cuda.synchronize(); ts = []
@@ -20,6 +22,8 @@ def timeit(fn, reps=3):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(); fn(); b.record(); torch.cuda.synchronize(); ts.append(a.elapsed_time(b))
     return min(ts)
+if eng.db.caps is not None:
+    print(f"geo-skip fraction: {eng.geo_mask(xyz, 40.0).float().mean().item():.3f}")
 sums, maxs = eng.retrieve_stats("RANGE+", q, xyz, 12.0, 40.0)
 t_st = timeit(lambda: eng.retrieve_stats("RANGE+", q, xyz, 12.0, 40.0))
 t_ap = timeit(lambda: eng.retrieve_apply("RANGE+", q, xyz, 12.0, 40.0, 0.5, sums, maxs))
