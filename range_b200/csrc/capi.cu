@@ -2,6 +2,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -66,6 +67,22 @@ int make_tmap(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, ui
   return RANGE_OK;
 }
 
+// 2-D view [rows][2048 B] (256 x uint64) of a byte buffer, box [8 rows][2048 B], no swizzle: the P' ring of the
+// producer/consumer apply kernel (one row = one 8-entry key chunk of a tile: [128 query rows][16 B])
+int make_tmap_rows2k(CUtensorMap* m, const void* base, uint64_t rows) {
+  auto fn = get_encode_fn();
+  if (!fn) return fail(RANGE_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
+  cuuint64_t gdim[2] = {256, rows};
+  cuuint64_t gstr[1] = {2048};
+  cuuint32_t box[2] = {256, 8};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(RANGE_ERR_CUDA, "cuTensorMapEncodeTiled (ring) failed (%d)", int(r));
+  return RANGE_OK;
+}
+
 }  // namespace
 
 struct range_ctx {
@@ -98,8 +115,19 @@ struct RetrievalPlan {
   int splits, tiles_per_split;              // apply kernel
   int stats_splits, stats_tiles_per_split;  // stats kernel
   int mask_rows, mask_words;                // geo-skip mask: [even-padded query tiles][ceil(tiles / 32)]
-  size_t off_part_sum, off_part_max, off_sums, off_maxs, off_rowc, off_mask, off_part_out, total;
+  bool pc;                                  // apply with the producer/consumer kernel (retrieval_pc.cu)
+  size_t off_part_sum, off_part_max, off_sums, off_maxs, off_rowc, off_mask, off_ring, off_flags, off_part_out, total;
 };
+
+// 0 = choose by batch size, 1 = always the single-role CTA-pair kernel, 2 = producer/consumer whenever possible
+int apply_kernel_override() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("RANGE_APPLY_KERNEL");
+    v = !e ? 0 : (!strcmp(e, "pair") ? 1 : (!strcmp(e, "pc") ? 2 : 0));
+  }
+  return v;
+}
 
 // Database splits: enough CTAs to fill the SMs when there are few query tiles.
 RetrievalPlan plan_retrieval(const range_ctx* c, int64_t N) {
@@ -134,6 +162,14 @@ RetrievalPlan plan_retrieval(const range_ctx* c, int64_t N) {
   p.mask_rows = int((qtiles + 1) / 2 * 2);
   p.mask_words = int((tiles + 31) / 32);
   p.off_mask = o;     o += c->caps ? align_up(size_t(p.mask_rows) * p.mask_words * 4, 256) : 0;
+  // producer/consumer apply: needs the whole database per CTA (no splits) and enough query-tile pairs to give
+  // every unit (2 producer + 4 consumer SMs) at least two rounds
+  const int units = apply_pc_units(c->sm_count);
+  const int64_t qpairs = (qtiles + 1) / 2;
+  const int ov = apply_kernel_override();
+  p.pc = units > 0 && p.splits == 1 && ov != 1 && (ov == 2 || qpairs >= 2 * units);
+  p.off_ring = o;     o += p.pc ? align_up(apply_pc_ring_bytes(c->sm_count), 1024) : 0;
+  p.off_flags = o;    o += p.pc ? align_up(apply_pc_flag_bytes(c->sm_count), 256) : 0;
   p.off_part_out = o; o += p.splits > 1 ? align_up(size_t(p.splits) * N * kDimV * 4, 256) : 0;
   p.total = o;
   return p;
@@ -508,6 +544,15 @@ int range_retrieve_apply(range_ctx* c, int mode, int64_t N, const void* q16, con
   CUDA_TRY(launch_row_constants(sums, maxs, qxyz, int(N), a.geo, beta, a.a_sem, a.a_geo, 1.f / c->vscale, rowc, s));
   float* part_out = p.splits > 1 ? reinterpret_cast<float*>(ws + p.off_part_out) : O;
   const size_t stride = size_t(N) * kDimV;
+  if (p.pc) {
+    CUtensorMap tmP;
+    void* ring = ws + p.off_ring;
+    r = make_tmap_rows2k(&tmP, ring, uint64_t(apply_pc_ring_rows(c->sm_count)));
+    if (r) return r;
+    CUDA_TRY(launch_apply_pc(a, tmP, rowc, O, ring, ws + p.off_flags, c->sm_count, s));
+    g_launches += 2;
+    return RANGE_OK;
+  }
   CUDA_TRY(launch_apply(a, rowc, part_out, stride, s));
   g_launches += 2;
   if (p.splits > 1) {

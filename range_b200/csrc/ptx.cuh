@@ -121,6 +121,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // registers -> TMEM, 32 lanes x N consecutive 32-bit columns (thread t writes lane base_lane + t)
@@ -157,6 +166,17 @@ __device__ __forceinline__ uint64_t umma_desc_kmajor_sw128(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(1024 >> 4) << 32;
   d |= static_cast<uint64_t>(1) << 46;
   d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+// Same, no swizzle ("interleave"): 8-row x 16-byte core matrices, each 128 contiguous bytes; SBO = distance
+// between 8-row groups, LBO = distance between the two 16-byte K chunks of one K = 16 step
+// (cute/atom/mma_traits_sm100.hpp: ((8,n),2):((1,SBO),LBO) in 16-byte units).
+__device__ __forceinline__ uint64_t umma_desc_kmajor_nosw(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
   return d;
 }
 // Instruction descriptor, kind::f16: A,B = f16 (format 0), D = f32 (1), both K-major, dense.
@@ -349,6 +369,36 @@ __device__ __forceinline__ float max3(float a, float b, float c) {
 __device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
   __half2 h = __floats2half2_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);
+}
+
+
+// ------------------------------------------------------------------ flags in global memory (CTA <-> CTA through L2)
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void st_relaxed_gpu(uint32_t* p, uint32_t v) {
+  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// orders generic-proxy accesses (the acquire above, plain stores) against later async-proxy ones (TMA)
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void stg_u4(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+// Bounded spin on a monotonically increasing counter (never hang the GPU box on a protocol bug)
+__device__ __forceinline__ void wait_flag_ge(const uint32_t* p, uint32_t want) {
+  uint32_t spins = 0;
+  while (int32_t(ld_acquire_gpu(p) - want) < 0) {
+    if (++spins > (1u << 24)) {
+      printf("range_b200: global flag wait timed out (block %d thread %d, want %u have %u)\n", blockIdx.x,
+             threadIdx.x, want, ld_acquire_gpu(p));
+      __trap();
+    }
+  }
 }
 
 }  // namespace ptx

@@ -82,6 +82,14 @@ cudaError_t launch_row_constants(const float* sums, const float* maxs, const flo
                                  float beta, float a_sem, float a_geo, float inv_vscale, float* rowc, cudaStream_t s);
 cudaError_t launch_apply(const RetrievalArgs& a, const float* rowc, float* out, size_t out_split_stride,
                          cudaStream_t s);
+// role-specialised persistent apply kernel for large batches (retrieval_pc.cu): P' computed once per tile pair by
+// producer CTAs, handed to the value-slice consumers through an L2-resident ring
+int apply_pc_units(int sm_count);
+size_t apply_pc_ring_bytes(int sm_count);
+size_t apply_pc_flag_bytes(int sm_count);
+int apply_pc_ring_rows(int sm_count);          // ring as a 2-D tensor [rows][2 KB]
+cudaError_t launch_apply_pc(const RetrievalArgs& a, const CUtensorMap& tmP, const float* rowc, float* out, void* ring,
+                            void* flags, int sm_count, cudaStream_t s);
 cudaError_t launch_reduce_out(const float* part, size_t split_stride, int splits, size_t total, float* out,
                               cudaStream_t s);
 

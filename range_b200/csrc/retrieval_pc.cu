@@ -1,0 +1,608 @@
+// K2b (large batches) - apply as a role-specialised persistent kernel.
+//
+// The single-role apply kernel (retrieval.cu) is bound by TMEM capacity: a 128-query tile's 1024-wide fp32
+// output needs 1024 of an SM's 512 TMEM columns, so four CTAs each own a 256-wide slice and each of them
+// recomputes Q.K^T and the softmax (reference: range/range.py:213-215,231-234) - half of its tensor cycles and
+// all of its MUFU cycles are redundant work.  Here the two halves of the computation live on different SMs:
+//
+//   producer pair  (2 CTAs, cta_group::2)  S = Q.K^T -> P' = 2^(a s + cs) + 2^(gam g + cg)  (fp16), ONCE per
+//                                          (query tile, database tile); P' goes to a ring in global memory
+//                                          (it stays in L2: 32 KB per tile, 4 slots per producer CTA)
+//   consumer pairs (2 x 2 CTAs)            O[128 queries x 512 dims] += P' . Vt   (all 512 TMEM columns are
+//                                          accumulators); P' arrives by TMA as the SWIZZLE_128B A operand,
+//                                          Vt halves are shared by the pair as in retrieval.cu
+//
+// One unit = 3 clusters of 2 CTAs = two query tiles x 1024 value dims; 148 SMs = 24 units (+ 2 idle clusters).
+// Producers are MUFU-bound (2 ex2 per pair, 16/clk/SM), consumers tensor-bound (2048 clk per 128x128 tile),
+// both ~2048 clk per tile; nothing is computed twice.  Hand-off through L2 is ordered with
+// st.release.gpu / ld.acquire.gpu flags that count tiles (monotonic, zeroed by the host before the launch):
+//   full[p]      tiles producer CTA p has published        (publisher warp, after the softmax warps' stores)
+//   done[p][c]   tiles consumer pair c has copied to smem  (consumer leader, after the TMA load completed)
+// All CTAs must be co-resident: the launch is cooperative (the runtime refuses it otherwise).
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <type_traits>
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include "ptx.cuh"
+#include "range_kernels.h"
+
+namespace {
+
+constexpr int kBlockQ = 128, kKeys = 128, kXyzBytes = kKeys * 16;
+constexpr int kSoftmaxWarps = 16;
+constexpr int kWarpTma = 16, kWarpMma = 17, kWarpPublish = 18, kWarpXyz = 19;
+constexpr int kThreads = 20 * 32;
+#ifndef RANGE_PC_RING
+#define RANGE_PC_RING 16
+#endif
+constexpr int kRing = RANGE_PC_RING;             // P' slots per producer CTA
+constexpr int kPublishBatch = 4;                 // tiles per release of the `full` counter (kRing >= 3 batches)
+constexpr int kFlagStride = 32;                  // uint32 per flag line (128 B)
+constexpr int kFlagsPerProducer = 3 * kFlagStride;   // full, done[0], done[1]
+
+struct ProdSmem {
+  static constexpr int NS = 4, NB = 4;           // K stages (32 KB: this CTA's 64 entries x 256 dims), S buffers
+  static constexpr int q = 0;                    // 4 x [128 rows x 64 dims] SW128
+  static constexpr int stages = q + 65536;
+  static constexpr int xyz = stages + NS * 32768;
+  static constexpr int bars = xyz + NB * kXyzBytes;
+  static constexpr int b_q_full = 0, b_q_pair = 1, b_q_empty = 2;
+  static constexpr int b_stage_full = 3;
+  static constexpr int b_stage_empty = b_stage_full + NS;
+  static constexpr int b_s_full = b_stage_empty + NS;
+  static constexpr int b_s_empty = b_s_full + NB;
+  static constexpr int b_xyz_empty = b_s_empty + NB;
+  static constexpr int b_slot_free = b_xyz_empty + NB;
+  static constexpr int b_p_written = b_slot_free + kRing;
+  static constexpr int n_bars = b_p_written + kRing;
+  static constexpr int tmem_slot = bars + n_bars * 8;
+  static constexpr int total = tmem_slot + 16;
+};
+struct ConsSmem {
+  // half tiles (64 entries).  Vt: 3 stages of [2 blocks][128 dims x 64 entries] SW128 (32 KB); P': 6 stages of
+  // [8 key chunks][128 rows][16 B] (16 KB, no-swizzle K-major core matrices) - P' buffers three tiles ahead so the
+  // L2 round trips of the hand-off stay off the tensor pipe's critical path.
+  static constexpr int NV = 3, NP = 6, kStageV = 32768, kStageP = 16384;
+  static constexpr int v = 0;
+  static constexpr int p = v + NV * kStageV;
+  static constexpr int bars = p + NP * kStageP;
+  static constexpr int b_v_full = 0;
+  static constexpr int b_v_empty = b_v_full + NV;
+  static constexpr int b_p_full = b_v_empty + NV;
+  static constexpr int b_p_empty = b_p_full + NP;
+  static constexpr int b_o_full = b_p_empty + NP;
+  static constexpr int b_o_empty = b_o_full + 1;
+  static constexpr int n_bars = b_o_empty + 1;
+  static constexpr int tmem_slot = bars + n_bars * 8;
+  static constexpr int total = tmem_slot + 16;
+};
+constexpr int kDynamicSmem = (ProdSmem::total > ConsSmem::total ? ProdSmem::total : ConsSmem::total) + 1024;
+
+struct PipeState {
+  int idx = 0;
+  uint32_t phase = 0;
+  template <int N>
+  __device__ __forceinline__ void advance() {
+    if (++idx == N) {
+      idx = 0;
+      phase ^= 1;
+    }
+  }
+};
+
+template <bool kGeo>
+__global__ void __launch_bounds__(kThreads, 1)
+range_apply_pc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK64,
+                      const __grid_constant__ CUtensorMap tmV128, const __grid_constant__ CUtensorMap tmP,
+                      const float4* __restrict__ db_xyz, const float4* __restrict__ rowc, int N, int M, float a_sem,
+                      float* __restrict__ out, const uint32_t* __restrict__ geo_mask, int mask_words,
+                      __half* __restrict__ ring, uint32_t* __restrict__ flags, int n_units, int dbg,
+                      long long* __restrict__ prof) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();
+  // developer instrumentation (tools/time_apply.py): wait-cycle accounting of unit 1's leader CTAs
+  long long pacc[6] = {0, 0, 0, 0, 0, 0};
+  const bool prof_on = prof != nullptr && (blockIdx.x >> 1) / 3 == 1 && rank == 0;
+#define PC_T0() long long _t0 = prof_on ? clock64() : 0
+#define PC_ADD(k) do { if (prof_on) { long long _t1 = clock64(); pacc[k] += _t1 - _t0; _t0 = _t1; } } while (0)
+#define PC_OUT(base) do { if (prof_on) { for (int _k = 0; _k < 6; ++_k) prof[(base) + _k] = pacc[_k]; } } while (0)
+  const bool leader = rank == 0;
+  const int cid = blockIdx.x >> 1;
+  const int unit = cid / 3, role = cid % 3;                 // role 0: producer pair; 1, 2: consumer pairs
+  const bool active = unit < n_units;
+  const bool producer = role == 0;
+  const int T = (M + kKeys - 1) / kKeys;
+  const int QP = ((N + kBlockQ - 1) / kBlockQ + 1) / 2;     // query-tile pairs
+  const int rounds = active && unit < QP ? (QP - unit + n_units - 1) / n_units : 0;
+  const int prod_id = unit * 2 + int(rank);                 // the producer CTA this CTA is / listens to
+  uint32_t* full_flag = flags + size_t(prod_id) * kFlagsPerProducer;
+
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (producer ? ProdSmem::bars : ConsSmem::bars));
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + (producer ? ProdSmem::tmem_slot : ConsSmem::tmem_slot));
+
+  if (threadIdx.x == 0 && active) {
+    if (producer) {
+      using L = ProdSmem;
+      ptx::mbar_init(&bars[L::b_q_full], 1);
+      ptx::mbar_init(&bars[L::b_q_pair], 2);
+      ptx::mbar_init(&bars[L::b_q_empty], 1);
+      for (int i = 0; i < L::NS; ++i) {
+        ptx::mbar_init(&bars[L::b_stage_full + i], 1);
+        ptx::mbar_init(&bars[L::b_stage_empty + i], 1);
+      }
+      for (int i = 0; i < L::NB; ++i) {
+        ptx::mbar_init(&bars[L::b_s_full + i], kGeo ? 2 : 1);            // MMA commit (+ this CTA's xyz bytes)
+        ptx::mbar_init(&bars[L::b_s_empty + i], 2 * 4);                  // the owning group's 4 warps in both CTAs
+        ptx::mbar_init(&bars[L::b_xyz_empty + i], 4);
+      }
+      for (int i = 0; i < kRing; ++i) {
+        ptx::mbar_init(&bars[L::b_slot_free + i], 1);
+        ptx::mbar_init(&bars[L::b_p_written + i], 4);
+      }
+    } else {
+      using L = ConsSmem;
+      for (int i = 0; i < L::NV; ++i) {
+        ptx::mbar_init(&bars[L::b_v_full + i], 1);
+        ptx::mbar_init(&bars[L::b_v_empty + i], 1);
+      }
+      for (int i = 0; i < L::NP; ++i) {
+        ptx::mbar_init(&bars[L::b_p_full + i], 1);
+        ptx::mbar_init(&bars[L::b_p_empty + i], 1);
+      }
+      ptx::mbar_init(&bars[L::b_o_full], 1);
+      ptx::mbar_init(&bars[L::b_o_empty], 8);                            // 4 epilogue warps x 2 CTAs
+    }
+    ptx::fence_mbar_init();
+  }
+  if (active && warp == kWarpMma) ptx::tmem_alloc_2sm<512>(tmem_slot);
+  ptx::tc_fence_before();
+  ptx::cluster_sync();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = active ? __shfl_sync(0xffffffffu, *tmem_slot, 0) : 0u;
+  const uint32_t smem_u = __shfl_sync(0xffffffffu, ptx::smem_u32(smem), 0);
+
+  if (active && rounds > 0 && producer) {
+    // =====================================================================================================
+    // producer pair: query tiles 2 qp (leader) and 2 qp + 1 (peer)
+    // =====================================================================================================
+    using L = ProdSmem;
+    const uint32_t bars_u = smem_u + L::bars;
+    if (warp == kWarpTma) {
+      if (lane == 0) {
+        ptx::prefetch_tmap(&tmQ);
+        ptx::prefetch_tmap(&tmK64);
+        PipeState st;
+        uint32_t it = 0;
+        for (int r = 0; r < rounds; ++r) {
+          const int qt = 2 * (unit + r * n_units) + int(rank);
+          if (r > 0) ptx::mbar_wait(&bars[L::b_q_empty], (r - 1) & 1);        // every Q.K^T of the last round has read Q
+          ptx::mbar_expect_tx(&bars[L::b_q_full], 65536);
+          for (int c = 0; c < 4; ++c)
+            ptx::tma_load_2d(smem + L::q + c * 16384, &tmQ, &bars[L::b_q_full], c * 64, qt * kBlockQ);
+          for (int j = 0; j < T; ++j, ++it) {
+            const int key0 = j * kKeys;
+            PC_T0();
+            ptx::mbar_wait(&bars[L::b_stage_empty + st.idx], st.phase ^ 1);
+            PC_ADD(0);
+            uint8_t* dst = smem + L::stages + st.idx * 32768;
+            if (leader) ptx::mbar_expect_tx(&bars[L::b_stage_full + st.idx], 65536);
+#pragma unroll
+            for (int c = 0; c < 4; ++c)       // this CTA's 64 entries x 256 dims, as 4 [64 x 64] boxes
+              ptx::tma_load_2d_2sm(dst + c * 8192, &tmK64, &bars[L::b_stage_full + st.idx], c * 64, key0 + int(rank) * 64);
+            st.advance<L::NS>();
+          }
+        }
+        PC_OUT(0);
+      }
+    } else if (warp == kWarpXyz) {
+      // ----- xyz loader: entry unit vectors of tile it -> slot it & 3, bytes credited to the barrier S(it) arrives on.
+      // Its own warp: the slot frees only when softmax(it - 4) is done, and no K load may queue behind that wait.
+      if (kGeo && lane == 0) {
+        uint32_t it = 0;
+        for (int r = 0; r < rounds; ++r) {
+          const int qt = 2 * (unit + r * n_units) + int(rank);
+          const uint32_t* mask_row = geo_mask ? geo_mask + size_t(qt) * mask_words : nullptr;
+          for (int j = 0; j < T; ++j, ++it) {
+            const int x = it & (L::NB - 1);
+            PC_T0();
+            ptx::mbar_wait(&bars[L::b_xyz_empty + x], ((it / L::NB) & 1) ^ 1);
+            PC_ADD(2);
+            const bool skip = mask_row != nullptr && ((__ldg(mask_row + (j >> 5)) >> (j & 31)) & 1u);
+            if (skip) {
+              ptx::mbar_arrive(&bars[L::b_s_full + x]);
+            } else {
+              ptx::mbar_expect_tx(&bars[L::b_s_full + x], kXyzBytes);
+              ptx::bulk_load_1d(smem + L::xyz + x * kXyzBytes, db_xyz + j * kKeys, kXyzBytes, &bars[L::b_s_full + x]);
+            }
+          }
+        }
+      }
+    } else if (warp == kWarpMma) {
+      constexpr uint32_t idesc_qk = ptx::umma_idesc_f16(2 * kBlockQ, kKeys);
+      PipeState st;
+      uint32_t it = 0;
+      for (int r = 0; r < rounds; ++r) {
+        ptx::mbar_wait(&bars[L::b_q_full], r & 1);
+        if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&bars[L::b_q_pair]), 0));
+        __syncwarp();
+        if (!leader) continue;
+        ptx::mbar_wait_cluster(&bars[L::b_q_pair], r & 1);
+        for (int j = 0; j < T; ++j, ++it) {
+          const int b = it & (L::NB - 1);
+          PC_T0();
+          ptx::mbar_wait_cluster(&bars[L::b_s_empty + b], ((it / L::NB) & 1) ^ 1);   // S(it - 4) is in registers
+          PC_ADD(0);
+          ptx::mbar_wait(&bars[L::b_stage_full + st.idx], st.phase);
+          PC_ADD(1);
+          ptx::tc_fence_after();
+          if (ptx::elect_one()) {
+            const uint32_t b_base = smem_u + L::stages + st.idx * 32768;
+            const uint32_t a_base = smem_u + L::q;
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk)
+                ptx::umma_f16_ss_2sm(tmem_base + b * kKeys, ptx::umma_desc_kmajor_sw128(a_base + c * 16384 + kk * 32),
+                                     ptx::umma_desc_kmajor_sw128(b_base + c * 8192 + kk * 32), idesc_qk, (c | kk) != 0);
+            ptx::umma_commit_2sm_u32(bars_u + 8 * (L::b_stage_empty + st.idx));
+            ptx::umma_commit_2sm_u32(bars_u + 8 * (L::b_s_full + b));
+          }
+          __syncwarp();
+          PC_ADD(2);
+          st.advance<L::NS>();
+        }
+        if (ptx::elect_one()) ptx::umma_commit_2sm_u32(bars_u + 8 * L::b_q_empty);
+        __syncwarp();
+      }
+      if (lane == 0) PC_OUT(8);
+    } else if (warp == kWarpPublish) {
+      // ----- ring bookkeeping (one thread, two interleaved non-blocking streams) -----
+      //   gate:    slot it % kRing is free once both consumer pairs have copied tile it - kRing (their `done` counters)
+      //   publish: once the owning softmax group has stored tile it, advance the `full` counter.  A gpu-scope release
+      //            costs ~1500 clk here (every store the SM has in flight must be acknowledged), so tiles are
+      //            published in batches of kPublishBatch; the ring absorbs the added latency.
+      if (lane == 0) {
+        const uint32_t total = uint32_t(rounds) * uint32_t(T);
+        uint32_t pub = 0, gate = 0, seen = 0, spins = 0;
+        while (pub < total || gate < total) {
+          bool progress = false;
+          if (gate < total) {
+            const uint32_t need = gate >= uint32_t(kRing) && !(dbg & 2) ? gate - kRing + 1 : 0u;
+            if (seen < need) {
+              const uint32_t d0 = ptx::ld_acquire_gpu(full_flag + kFlagStride), d1 = ptx::ld_acquire_gpu(full_flag + 2 * kFlagStride);
+              seen = d0 < d1 ? d0 : d1;
+            }
+            if (seen >= need) {
+              ptx::mbar_arrive(&bars[L::b_slot_free + (gate % kRing)]);
+              ++gate;
+              progress = true;
+            }
+          }
+          if (pub < total && ptx::mbar_try_wait(&bars[L::b_p_written + (pub % kRing)], (pub / kRing) & 1)) {
+            ++pub;
+            if (pub % kPublishBatch == 0 || pub == total) ptx::st_release_gpu(full_flag, pub);
+            progress = true;
+          }
+          if (progress) spins = 0;
+          else if (++spins > (1u << 24)) {
+            printf("range_b200: ring bookkeeping stalled (block %d, published %u gated %u of %u)\n", blockIdx.x, pub, gate, total);
+            __trap();
+          }
+        }
+      }
+    } else {
+      // ----- softmax warps: S (TMEM fp32) -> P' (fp16) -> ring in global memory -----
+      // Four groups of four warps (one warp per TMEM lane quarter).  Group g owns S buffer g, i.e. the tiles
+      // it = g (mod 4), and walks a tile in four 32-entry chunks.  The groups drift apart, so while one waits
+      // for its next S tile, a TMEM load or the ring, the SM sub-partition's MUFU pipe is fed by the other three.
+      const int grp = warp >> 2, quarter = warp & 3;
+      const int row = quarter * 32 + lane;
+      const int b = grp;
+      const uint32_t s_empty_leader = ptx::mapa(ptx::smem_u32(&bars[L::b_s_empty + b]), 0);
+      const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + b * kKeys;
+      // slot s of this producer: ring + (prod_id * kRing + s) * 128 * 128 halves, laid out [16 key chunks][128 rows][8]
+      __half* ring_row = ring + size_t(prod_id) * kRing * 128 * 128 + row * 8;
+      const uint32_t total = uint32_t(rounds) * uint32_t(T);
+      int cur_r = -1, n = 0;
+      const uint32_t* mask_row = nullptr;
+      float cs = -INFINITY, cg = -INFINITY, gx = 0.f, gy = 0.f, gz = 0.f;
+      for (uint32_t it = uint32_t(grp); it < total; it += L::NB) {
+        const int r = int(it / uint32_t(T)), j = int(it - uint32_t(r) * uint32_t(T));
+        if (r != cur_r) {
+          cur_r = r;
+          const int qt = 2 * (unit + r * n_units) + int(rank);
+          n = qt * kBlockQ + row;
+          mask_row = (kGeo && geo_mask) ? geo_mask + size_t(qt) * mask_words : nullptr;
+          cs = -INFINITY; cg = -INFINITY; gx = gy = gz = 0.f;
+          if (n < N) {
+            const float4 c0 = rowc[2 * n], c1 = rowc[2 * n + 1];
+            cs = c0.x; cg = c0.y; gx = c0.z; gy = c0.w; gz = c1.x;
+          }
+        }
+        const int slot = it % kRing;
+        const bool with_geo = kGeo && !(mask_row != nullptr && ((__ldg(mask_row + (j >> 5)) >> (j & 31)) & 1u));
+        __half* dst = ring_row + size_t(slot) * 128 * 128;
+        PC_T0();
+        ptx::mbar_wait(&bars[L::b_s_full + b], (it / L::NB) & 1);      // S(it) in TMEM and xyz(it) in smem
+        PC_ADD(0);
+        ptx::tc_fence_after();
+        // eight 16-entry pieces; the TMEM load of piece h + 1 is in flight while piece h is evaluated
+        uint32_t bufA[16], bufB[16];
+        auto piece = [&](const uint32_t (&cur)[16], int h) {
+          const uint32_t kxyz = smem_u + L::xyz + b * kXyzBytes + h * 16 * 16;
+          const int nvalid = M - (j * kKeys + h * 16);            // >= 16 except in the last tile
+          uint32_t packed[8];
+          auto body = [&](auto masked, auto geo) {
+            constexpr bool kM = decltype(masked)::value, kG = decltype(geo)::value;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) {
+              float pv[2];
+#pragma unroll
+              for (int u = 0; u < 2; ++u) {
+                const int i = 2 * w + u;
+                float p = ptx::ex2(fmaf(__uint_as_float(cur[i]), a_sem, cs));
+                if (kG) {
+                  const float4 k = ptx::lds_f4(kxyz + i * 16);
+                  p += ptx::ex2(fmaf(gx, k.x, fmaf(gy, k.y, fmaf(gz, k.z, cg))));
+                }
+                if (kM && i >= nvalid) p = 0.f;
+                pv[u] = p;
+              }
+              packed[w] = ptx::pack_half2(pv[0], pv[1]);
+            }
+          };
+          if (dbg & 8) {                                  // developer switch: no exponentials (consumer-bound run)
+#pragma unroll
+            for (int w = 0; w < 8; ++w) packed[w] = cur[2 * w] & 0x3c003c00u;
+          } else if (nvalid >= 16) {
+            if (with_geo) body(std::false_type{}, std::true_type{}); else body(std::false_type{}, std::false_type{});
+          } else {
+            if (with_geo) body(std::true_type{}, std::true_type{}); else body(std::true_type{}, std::false_type{});
+          }
+          PC_ADD(2);
+          if (h == 0) ptx::mbar_wait(&bars[L::b_slot_free + slot], (it / kRing) & 1);   // both consumers copied tile it - kRing
+          PC_ADD(3);
+          // ring tile layout [16 key chunks][128 rows][8 entries]: a warp's store covers 512 contiguous bytes
+          ptx::stg_u4(dst + ((2 * h) * 128) * 8, packed[0], packed[1], packed[2], packed[3]);
+          ptx::stg_u4(dst + ((2 * h + 1) * 128) * 8, packed[4], packed[5], packed[6], packed[7]);
+          PC_ADD(4);
+        };
+        ptx::tmem_ld16(taddr, bufA);
+#pragma unroll 1
+        for (int hp = 0; hp < 4; ++hp) {
+          ptx::tmem_ld_wait();
+          PC_ADD(1);
+          ptx::tmem_ld16(taddr + (2 * hp + 1) * 16, bufB);
+          piece(bufA, 2 * hp);
+          ptx::tmem_ld_wait();
+          PC_ADD(1);
+          if (hp < 3) {
+            ptx::tmem_ld16(taddr + (2 * hp + 2) * 16, bufA);
+          } else {                              // the whole S tile is in registers: the MMA warp may overwrite the buffer
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if (leader) ptx::mbar_arrive(&bars[L::b_s_empty + b]);
+              else ptx::mbar_arrive_cluster_relaxed(s_empty_leader);
+            }
+          }
+          piece(bufB, 2 * hp + 1);
+        }
+        __syncwarp();
+        if (lane == 0) {
+          ptx::mbar_arrive(&bars[L::b_p_written + slot]);
+          if (kGeo) ptx::mbar_arrive(&bars[L::b_xyz_empty + b]);
+        }
+        PC_ADD(4);
+      }
+      if (threadIdx.x == 0) PC_OUT(32);
+    }
+  } else if (active && rounds > 0) {
+    // =====================================================================================================
+    // consumer pair: value dims [512 (role - 1), +512) of the unit's two query tiles
+    // =====================================================================================================
+    using L = ConsSmem;
+    const uint32_t bars_u = smem_u + L::bars;
+    const int cp = role - 1;
+    const int dimbase = cp * 512;
+    if (warp == 0) {
+      // ----- Vt loader: never waits on the producer -----
+      if (lane == 0) {
+        ptx::prefetch_tmap(&tmV128);
+        PipeState st;
+        for (int r = 0; r < rounds; ++r) {
+          for (int j = 0; j < T; ++j) {
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+              const int key0 = j * kKeys + half * 64;
+              PC_T0();
+              ptx::mbar_wait(&bars[L::b_v_empty + st.idx], st.phase ^ 1);
+              PC_ADD(0);
+              uint8_t* dst = smem + L::v + st.idx * L::kStageV;
+              if (leader) ptx::mbar_expect_tx(&bars[L::b_v_full + st.idx], 2 * L::kStageV);
+#pragma unroll
+              for (int nb = 0; nb < 2; ++nb)     // this CTA's 128 dims of each 256-wide block x 64 entries
+                ptx::tma_load_2d_2sm(dst + nb * 16384, &tmV128, &bars[L::b_v_full + st.idx], key0,
+                                     dimbase + nb * 256 + int(rank) * 128);
+              st.advance<L::NV>();
+            }
+          }
+        }
+        if (role == 1) PC_OUT(40);
+      }
+    } else if (warp == 6) {
+      // ----- P' loader: follows the producer's `full` counter -----
+      if (lane == 0) {
+        ptx::prefetch_tmap(&tmP);
+        PipeState st;
+        uint32_t it = 0, seen = 0;
+        for (int r = 0; r < rounds; ++r) {
+          for (int j = 0; j < T; ++j, ++it) {
+            const int slot = it % kRing;
+            PC_T0();
+            if (seen < it + 1 && !(dbg & 1)) {               // the counter advances in batches: one poll + proxy fence per batch
+              uint32_t spins = 0;
+              while ((seen = ptx::ld_acquire_gpu(full_flag)) < it + 1) {
+                if (++spins > (1u << 24)) {
+                  printf("range_b200: consumer %d waits for tile %u, producer published %u\n", blockIdx.x, it, seen);
+                  __trap();
+                }
+              }
+              PC_ADD(0);
+              ptx::fence_proxy_async_all();
+              PC_ADD(1);
+            }
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+              ptx::mbar_wait(&bars[L::b_p_empty + st.idx], st.phase ^ 1);
+              PC_ADD(2);
+              if (leader) ptx::mbar_expect_tx(&bars[L::b_p_full + st.idx], 2 * L::kStageP);
+              // 8 key chunks x 2 KB: rows (prod * kRing + slot) * 16 + half * 8 .. + 8 of the ring viewed as [.][2 KB]
+              ptx::tma_load_2d_2sm(smem + L::p + st.idx * L::kStageP, &tmP, &bars[L::b_p_full + st.idx], 0,
+                                   (prod_id * kRing + slot) * 16 + half * 8);
+              st.advance<L::NP>();
+            }
+          }
+        }
+        if (role == 1) PC_OUT(48);
+      }
+    } else if (warp == 1) {
+      if (leader) {
+        constexpr uint32_t idesc_pv = ptx::umma_idesc_f16(2 * kBlockQ, 256);
+        uint32_t* done0 = flags + size_t(unit * 2) * kFlagsPerProducer + (1 + cp) * kFlagStride;       // producer rank 0
+        uint32_t* done1 = flags + size_t(unit * 2 + 1) * kFlagsPerProducer + (1 + cp) * kFlagStride;   // producer rank 1
+        PipeState sv, sp;
+        uint32_t it = 0;
+        for (int r = 0; r < rounds; ++r) {
+          if (r > 0) {
+            ptx::mbar_wait_cluster(&bars[L::b_o_empty], (r - 1) & 1);     // both epilogues have read O
+            ptx::tc_fence_after();
+          }
+          for (int j = 0; j < T; ++j, ++it) {
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+              PC_T0();
+              ptx::mbar_wait(&bars[L::b_p_full + sp.idx], sp.phase);
+              PC_ADD(0);
+              if (half == 1 && ptx::elect_one()) {
+                // both halves of both CTAs' P'(it) are in shared memory: the ring slots are free.  Relaxed is enough:
+                // the TMA reads of the slot completed (mbarrier complete_tx) before these stores issue.
+                ptx::st_relaxed_gpu(done0, it + 1);
+                ptx::st_relaxed_gpu(done1, it + 1);
+              }
+              ptx::mbar_wait(&bars[L::b_v_full + sv.idx], sv.phase);
+              PC_ADD(2);
+              ptx::tc_fence_after();
+              if (ptx::elect_one()) {
+                const uint32_t a_base = smem_u + L::p + sp.idx * L::kStageP;
+                const uint32_t b_base = smem_u + L::v + sv.idx * L::kStageV;
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+                  for (int nb = 0; nb < 2; ++nb)
+                    if (!(dbg & 4))                          // developer switch: no P.V (producer-bound run)
+                    ptx::umma_f16_ss_2sm(tmem_base + nb * 256, ptx::umma_desc_kmajor_nosw(a_base + kk * 4096, 2048, 128),
+                                         ptx::umma_desc_kmajor_sw128(b_base + nb * 16384 + kk * 32), idesc_pv,
+                                         (j | half | kk) != 0);
+                ptx::umma_commit_2sm_u32(bars_u + 8 * (L::b_v_empty + sv.idx));
+                ptx::umma_commit_2sm_u32(bars_u + 8 * (L::b_p_empty + sp.idx));
+              }
+              __syncwarp();
+              PC_ADD(1);
+              sv.advance<L::NV>();
+              sp.advance<L::NP>();
+            }
+          }
+          if (ptx::elect_one()) ptx::umma_commit_2sm_u32(bars_u + 8 * L::b_o_full);
+          __syncwarp();
+        }
+        if (role == 1 && lane == 0) PC_OUT(56);
+      }
+    } else if (warp >= 2 && warp < 6) {
+      // ----- epilogue warps: O (TMEM, 128 lanes x 512 columns) -> global fp32, scaled -----
+      const int quarter = warp & 3;
+      const int row = quarter * 32 + lane;
+      const uint32_t o_empty_leader = ptx::mapa(ptx::smem_u32(&bars[L::b_o_empty]), 0);
+      for (int r = 0; r < rounds; ++r) {
+        const int qt = 2 * (unit + r * n_units) + int(rank);
+        const int n = qt * kBlockQ + row;
+        const float out_scale = n < N ? rowc[2 * n + 1].y : 0.f;
+        ptx::mbar_wait(&bars[L::b_o_full], r & 1);
+        ptx::tc_fence_after();
+        float* orow = out + size_t(n) * 1024 + dimbase;
+#pragma unroll 1
+        for (int cc = 0; cc < 16; ++cc) {
+          uint32_t v[32];
+          ptx::tmem_ld32(tmem_base + (uint32_t(quarter * 32) << 16) + cc * 32, v);
+          ptx::tmem_ld_wait();
+          if (n < N) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              float4 o;
+              o.x = __uint_as_float(v[i]) * out_scale;
+              o.y = __uint_as_float(v[i + 1]) * out_scale;
+              o.z = __uint_as_float(v[i + 2]) * out_scale;
+              o.w = __uint_as_float(v[i + 3]) * out_scale;
+              *reinterpret_cast<float4*>(orow + cc * 32 + i) = o;
+            }
+          }
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive_cluster(o_empty_leader);
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  ptx::cluster_sync();                           // neither CTA may free TMEM / exit while the pair is in flight
+  if (active && warp == kWarpMma) ptx::tmem_dealloc_2sm<512>(tmem_base);
+}
+
+}  // namespace
+
+namespace rangeb200 {
+
+extern long long* g_prof_buffer;      // retrieval.cu (developer instrumentation)
+
+int apply_pc_units(int sm_count) { return (sm_count / 2) / 3; }
+size_t apply_pc_ring_bytes(int sm_count) { return size_t(apply_pc_units(sm_count)) * 2 * kRing * 128 * 128 * 2; }
+size_t apply_pc_flag_bytes(int sm_count) { return size_t(apply_pc_units(sm_count)) * 2 * kFlagsPerProducer * 4; }
+int apply_pc_ring_rows(int sm_count) { return apply_pc_units(sm_count) * 2 * kRing * 16; }   // rows of 2 KB
+
+cudaError_t launch_apply_pc(const RetrievalArgs& a, const CUtensorMap& tmP, const float* rowc, float* out, void* ring,
+                            void* flags, int sm_count, cudaStream_t stream) {
+  const int units = apply_pc_units(sm_count);
+  static const int dbg = getenv("RANGE_PC_DBG") ? atoi(getenv("RANGE_PC_DBG")) : 0;   // developer switch: decouple the roles
+  cudaError_t e = cudaMemsetAsync(flags, 0, apply_pc_flag_bytes(sm_count), stream);
+  if (e != cudaSuccess) return e;
+  auto kern = a.geo ? range_apply_pc_kernel<true> : range_apply_pc_kernel<false>;
+  if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynamicSmem)) != cudaSuccess) return e;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(unsigned(sm_count / 2 * 2));
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = size_t(kDynamicSmem);
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeCooperative;      // every CTA must be resident: roles wait on each other
+  attr[1].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 2;
+  e = cudaLaunchKernelEx(&cfg, kern, a.tmQ, a.tmK64, a.tmV128, tmP, a.db_xyz, reinterpret_cast<const float4*>(rowc),
+                         a.N, a.M, a.a_sem, out, a.geo_mask, a.mask_words, reinterpret_cast<__half*>(ring),
+                         reinterpret_cast<uint32_t*>(flags), units, dbg, g_prof_buffer);
+  if (e != cudaSuccess)
+    fprintf(stderr, "range_b200: producer/consumer apply launch failed (%s); grid %u smem %d\n", cudaGetErrorString(e),
+            cfg.gridDim.x, kDynamicSmem);
+  return e;
+}
+
+}  // namespace rangeb200

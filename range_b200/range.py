@@ -14,8 +14,8 @@ from .checkpoint import load_satclip_location_encoder
 from .database import DeviceDatabase
 from .engine import RangeEngine
 
-# one wave of the stats kernel / four of the apply kernel on 148 SMs: 148 query tiles of 128
-DEFAULT_CHUNK = 148 * 128
+# four rounds of the producer/consumer apply kernel on 148 SMs (24 units x 2 query tiles of 128 per round)
+DEFAULT_CHUNK = 4 * 24 * 256
 
 
 class LocationEncoder(nn.Module):

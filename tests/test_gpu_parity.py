@@ -222,3 +222,30 @@ def test_load_model_api(tmp_path, golden, sh_entries):
     assert m2.args.temp == 15.0 and rel_rows(out2[:, :1024], g["O_range"]).max() <= 2e-3
     with pytest.raises(ValueError):
         load_model("RANGE++", str(ckpt), device="cuda", db_path=str(dbfile))
+
+
+def test_large_batch_producer_consumer_apply(sh_entries):
+    """batches of >= 48 query-tile pairs run the role-specialised apply kernel (retrieval_pc.cu): ragged N and M,
+    spatially batched queries (geo-term skipping active), against the exact oracle"""
+    from range_b200.engine import RangeEngine
+    from range_b200.database import DeviceDatabase
+    N, M = 12_300 + 37, 3000 + 5
+    db = O.synthetic_db(M, seed=6, kind="iid")
+    ws = O.siren_init(40, 64, 2, 256, seed=3)
+    eng = RangeEngine(DEV, encoder=dict(L=40, dims=[1600, 64, 64, 256], weights=ws), database=DeviceDatabase(db, DEV))
+    c = O.area_uniform(N, np.random.default_rng(21))
+    cs, perm = eng.sort_queries(torch.tensor(c))
+    q64, q16, qxyz = eng.encode(cs)
+    p = perm.cpu().numpy().astype(np.int64)
+    sub = np.linspace(0, N - 1, 400).astype(np.int64)               # oracle on a spread of sorted rows
+    for name, beta in [("RANGE+", 0.5), ("RANGE", None), ("RANGE+", 0.0)]:
+        orc = O.RangeOracle(name, ws, sh_entries, db, beta=beta, exact=True)
+        Ot = eng.retrieve(name, q16, qxyz, orc.temp, 40.0, beta).cpu().numpy()
+        assert np.isfinite(Ot).all()
+        ref = orc(c[p[sub]])[:, :1024]
+        r = rel_rows(Ot[sub], ref)
+        assert r.max() <= 2e-3 and r.mean() <= 6e-4, (name, beta, r.max(), r.mean())
+    # and the same rows through the single-role kernel (small batch): same arithmetic, same P' rounding
+    small = eng.retrieve("RANGE+", q16[:1000], qxyz[:1000], 12.0, 40.0, 0.5)
+    big = eng.retrieve("RANGE+", q16, qxyz, 12.0, 40.0, 0.5)[:1000]
+    assert rel_rows(big.cpu().numpy(), small.cpu().numpy()).max() <= 5e-4     # fp16 rounding of P' (row sums differ in the last bit)

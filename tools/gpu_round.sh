@@ -11,6 +11,6 @@ timeout 300 python tools/time_apply.py > gpurun_out/${tag}_time_apply.log 2>&1; 
 if [ "${NCU:-1}" = "1" ]; then
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches.csv \
   python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/${tag}_ncu_bench.log 2>&1; echo "ncu list exit $?"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'range_(apply_pair|stats)_kernel' -s 6 -c 2 \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'range_(apply_pc|apply_pair|stats)_kernel' -s 6 -c 2 \
   -o gpurun_out/${tag}_k2 -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/${tag}_ncu_full.log 2>&1; echo "ncu full exit $?"
 fi

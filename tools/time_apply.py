@@ -38,7 +38,20 @@ if os.environ.get("PROF"):
     eng.lib.range_debug_set_profile_buffer(ctypes.c_void_p(buf.data_ptr()))
     eng.retrieve_apply("RANGE+", q, xyz, 12.0, 40.0, 0.5, sums, maxs); torch.cuda.synchronize()
     eng.lib.range_debug_set_profile_buffer(None)
-    b = buf.cpu().numpy().astype(float); T = max(1, b[22])
+    b = buf.cpu().numpy().astype(float)
+    if os.environ.get("RANGE_APPLY_KERNEL") == "pc":
+        T = 17.0 * ((M + 127) // 128)          # rounds of unit 1 x tiles
+        f = lambda lo, n: " ".join(f"{x / T:7.0f}" for x in b[lo:lo + n])
+        print(f"per-tile cycles, unit 1 leader CTAs (T = {T:.0f} tiles):")
+        print(f" producer tma      wait_stage_empty | issue K | wait_xyz_empty : {f(0, 3)}")
+        print(f" producer mma      wait_s_empty | wait_stage_full | issue+commit : {f(8, 3)}")
+        print(f" (publish+gate merged: not instrumented)")
+        print(f" producer softmax  wait_s_full | tmem_ld | compute | wait_slot_free | store+arrive : {f(32, 5)}")
+        print(f" consumer Vt load  wait_v_empty (per tile = 2 stages)            : {f(40, 1)}")
+        print(f" consumer P load   wait_full flag | proxy fence | wait_p_empty   : {f(48, 3)}")
+        print(f" consumer mma      wait_p_full | issue | wait_v_full (per tile)   : {f(56, 3)}")
+        sys.exit(0)
+    T = max(1, b[22])
     print(f"tiles {T}; per-tile cycles:")
     print(f" producer: wait_empty(K) {b[0]/T:.0f} wait_empty(V) {b[1]/T:.0f} total {b[2]/T:.0f}")
     print(f" mma: wait_stage_qk {b[8]/T:.0f} issue_qk {b[9]/T:.0f} wait_p {b[10]/T:.0f} wait_stage_pv {b[11]/T:.0f} issue_pv {b[12]/T:.0f} total {b[13]/T:.0f}")
