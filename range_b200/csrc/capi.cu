@@ -169,7 +169,7 @@ RetrievalPlan plan_retrieval(const range_ctx* c, int64_t N) {
   const int ov = apply_kernel_override();
   p.pc = units > 0 && p.splits == 1 && ov != 1 && (ov == 2 || qpairs >= 2 * units);
   p.off_ring = o;     o += p.pc ? align_up(apply_pc_ring_bytes(c->sm_count), 1024) : 0;
-  p.off_flags = o;    o += p.pc ? align_up(apply_pc_flag_bytes(c->sm_count), 256) : 0;
+  p.off_flags = o;    o += p.pc ? align_up(apply_pc_flag_bytes(c->sm_count, N, c->M), 256) : 0;
   p.off_part_out = o; o += p.splits > 1 ? align_up(size_t(p.splits) * N * kDimV * 4, 256) : 0;
   p.total = o;
   return p;

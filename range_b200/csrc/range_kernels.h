@@ -86,7 +86,7 @@ cudaError_t launch_apply(const RetrievalArgs& a, const float* rowc, float* out, 
 // producer CTAs, handed to the value-slice consumers through an L2-resident ring
 int apply_pc_units(int sm_count);
 size_t apply_pc_ring_bytes(int sm_count);
-size_t apply_pc_flag_bytes(int sm_count);
+size_t apply_pc_flag_bytes(int sm_count, int64_t N, int64_t M);
 int apply_pc_ring_rows(int sm_count);          // ring as a 2-D tensor [rows][2 KB]
 cudaError_t launch_apply_pc(const RetrievalArgs& a, const CUtensorMap& tmP, const float* rowc, float* out, void* ring,
                             void* flags, int sm_count, cudaStream_t s);

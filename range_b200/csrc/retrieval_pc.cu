@@ -40,6 +40,7 @@ constexpr int kThreads = 20 * 32;
 #endif
 constexpr int kRing = RANGE_PC_RING;             // P' slots per producer CTA
 constexpr int kPublishBatch = 4;                 // tiles per release of the `full` counter (kRing >= 3 batches)
+constexpr int kWindow = 64;                      // tiles per cross-unit synchronisation window (8192 entries, 21 MB of database)
 constexpr int kFlagStride = 32;                  // uint32 per flag line (128 B)
 constexpr int kFlagsPerProducer = 3 * kFlagStride;   // full, done[0], done[1]
 
@@ -62,10 +63,10 @@ struct ProdSmem {
   static constexpr int total = tmem_slot + 16;
 };
 struct ConsSmem {
-  // half tiles (64 entries).  Vt: 3 stages of [2 blocks][128 dims x 64 entries] SW128 (32 KB); P': 6 stages of
+  // half tiles (64 entries).  Vt: 4 stages of [2 blocks][128 dims x 64 entries] SW128 (32 KB); P': 6 stages of
   // [8 key chunks][128 rows][16 B] (16 KB, no-swizzle K-major core matrices) - P' buffers three tiles ahead so the
   // L2 round trips of the hand-off stay off the tensor pipe's critical path.
-  static constexpr int NV = 3, NP = 6, kStageV = 32768, kStageP = 16384;
+  static constexpr int NV = 4, NP = 6, kStageV = 32768, kStageP = 16384;
   static constexpr int v = 0;
   static constexpr int p = v + NV * kStageV;
   static constexpr int bars = p + NP * kStageP;
@@ -99,8 +100,8 @@ range_apply_pc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
                       const __grid_constant__ CUtensorMap tmV128, const __grid_constant__ CUtensorMap tmP,
                       const float4* __restrict__ db_xyz, const float4* __restrict__ rowc, int N, int M, float a_sem,
                       float* __restrict__ out, const uint32_t* __restrict__ geo_mask, int mask_words,
-                      __half* __restrict__ ring, uint32_t* __restrict__ flags, int n_units, int dbg,
-                      long long* __restrict__ prof) {
+                      __half* __restrict__ ring, uint32_t* __restrict__ flags, uint32_t* __restrict__ windows,
+                      int n_units, int dbg, long long* __restrict__ prof) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -119,6 +120,8 @@ range_apply_pc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   const int T = (M + kKeys - 1) / kKeys;
   const int QP = ((N + kBlockQ - 1) / kBlockQ + 1) / 2;     // query-tile pairs
   const int rounds = active && unit < QP ? (QP - unit + n_units - 1) / n_units : 0;
+  const int sync_units = QP < n_units ? QP : n_units;       // units that have work
+  const int n_windows = int((uint32_t((QP + n_units - 1) / n_units) * uint32_t(T) + kWindow - 1) / kWindow);
   const int prod_id = unit * 2 + int(rank);                 // the producer CTA this CTA is / listens to
   uint32_t* full_flag = flags + size_t(prod_id) * kFlagsPerProducer;
 
@@ -186,6 +189,13 @@ range_apply_pc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
             ptx::tma_load_2d(smem + L::q + c * 16384, &tmQ, &bars[L::b_q_full], c * 64, qt * kBlockQ);
           for (int j = 0; j < T; ++j, ++it) {
             const int key0 = j * kKeys;
+            if (leader && (it % kWindow) == 0) {
+              // Keep the units within two windows of each other: they all stream the same database, and only tiles
+              // the other units touched recently are still in L2 (measured without this: 33 GB of DRAM reads per launch).
+              const uint32_t w = it / kWindow;
+              atomicAdd(&windows[w], 1u);
+              if (w > 0) ptx::wait_flag_ge(&windows[w - 1], uint32_t(sync_units));
+            }
             PC_T0();
             ptx::mbar_wait(&bars[L::b_stage_empty + st.idx], st.phase ^ 1);
             PC_ADD(0);
@@ -197,6 +207,8 @@ range_apply_pc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
             st.advance<L::NS>();
           }
         }
+        if (leader)       // units with fewer rounds: check in for the windows the others still have to pass
+          for (uint32_t w = (it + kWindow - 1) / kWindow; w < uint32_t(n_windows); ++w) atomicAdd(&windows[w], 1u);
         PC_OUT(0);
       }
     } else if (warp == kWarpXyz) {
@@ -571,14 +583,21 @@ extern long long* g_prof_buffer;      // retrieval.cu (developer instrumentation
 
 int apply_pc_units(int sm_count) { return (sm_count / 2) / 3; }
 size_t apply_pc_ring_bytes(int sm_count) { return size_t(apply_pc_units(sm_count)) * 2 * kRing * 128 * 128 * 2; }
-size_t apply_pc_flag_bytes(int sm_count) { return size_t(apply_pc_units(sm_count)) * 2 * kFlagsPerProducer * 4; }
+static size_t pc_window_count(int sm_count, int64_t N, int64_t M) {
+  const int64_t units = apply_pc_units(sm_count), qp = ((N + kBlockQ - 1) / kBlockQ + 1) / 2, T = (M + kKeys - 1) / kKeys;
+  return size_t(((qp + units - 1) / units * T + kWindow - 1) / kWindow + 1);
+}
+static size_t pc_ring_flag_bytes(int sm_count) { return size_t(apply_pc_units(sm_count)) * 2 * kFlagsPerProducer * 4; }
+size_t apply_pc_flag_bytes(int sm_count, int64_t N, int64_t M) {
+  return pc_ring_flag_bytes(sm_count) + pc_window_count(sm_count, N, M) * 4;
+}
 int apply_pc_ring_rows(int sm_count) { return apply_pc_units(sm_count) * 2 * kRing * 16; }   // rows of 2 KB
 
 cudaError_t launch_apply_pc(const RetrievalArgs& a, const CUtensorMap& tmP, const float* rowc, float* out, void* ring,
                             void* flags, int sm_count, cudaStream_t stream) {
   const int units = apply_pc_units(sm_count);
   static const int dbg = getenv("RANGE_PC_DBG") ? atoi(getenv("RANGE_PC_DBG")) : 0;   // developer switch: decouple the roles
-  cudaError_t e = cudaMemsetAsync(flags, 0, apply_pc_flag_bytes(sm_count), stream);
+  cudaError_t e = cudaMemsetAsync(flags, 0, apply_pc_flag_bytes(sm_count, a.N, a.M), stream);
   if (e != cudaSuccess) return e;
   auto kern = a.geo ? range_apply_pc_kernel<true> : range_apply_pc_kernel<false>;
   if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynamicSmem)) != cudaSuccess) return e;
@@ -595,10 +614,15 @@ cudaError_t launch_apply_pc(const RetrievalArgs& a, const CUtensorMap& tmP, cons
   attr[1].id = cudaLaunchAttributeCooperative;      // every CTA must be resident: roles wait on each other
   attr[1].val.cooperative = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 2;
+  // RANGE_PC_COOP=0: plain cluster launch (profilers that cannot replay cooperative launches); co-residency then
+  // rests on grid = one CTA per SM on an otherwise idle device
+  static const bool coop = !(getenv("RANGE_PC_COOP") && atoi(getenv("RANGE_PC_COOP")) == 0);
+  cfg.numAttrs = coop ? 2 : 1;
   e = cudaLaunchKernelEx(&cfg, kern, a.tmQ, a.tmK64, a.tmV128, tmP, a.db_xyz, reinterpret_cast<const float4*>(rowc),
                          a.N, a.M, a.a_sem, out, a.geo_mask, a.mask_words, reinterpret_cast<__half*>(ring),
-                         reinterpret_cast<uint32_t*>(flags), units, dbg, g_prof_buffer);
+                         reinterpret_cast<uint32_t*>(flags),
+                         reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(flags) + pc_ring_flag_bytes(sm_count)), units, dbg,
+                         g_prof_buffer);
   if (e != cudaSuccess)
     fprintf(stderr, "range_b200: producer/consumer apply launch failed (%s); grid %u smem %d\n", cudaGetErrorString(e),
             cfg.gridDim.x, kDynamicSmem);

@@ -1,3 +1,3 @@
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
-RANGE_APPLY_KERNEL=pc timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
-timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/r1e_bench.json 2> gpurun_out/r1e_bench.err; cat gpurun_out/r1e_bench.json
+RANGE_APPLY_KERNEL=pc timeout 120 python tools/check_pc.py 2>&1 | tail -2
+timeout 200 python tools/time_apply.py 2>&1 | grep -v "^$" | tail -1
+PROF=1 RANGE_APPLY_KERNEL=pc timeout 200 python tools/time_apply.py 2>&1 | grep -v "^$" | tail -8
