@@ -92,7 +92,7 @@ int range_geo_mask_shape(range_ctx* ctx, int64_t N, int32_t* rows, int32_t* word
 int range_geo_mask(range_ctx* ctx, int64_t N, const float* qxyz, float geo_temp, uint32_t* mask, void* stream);
 
 /* Spatial batching of a query batch (no reference counterpart: rows are independent, range/range.py:213-240).
- * perm[i] = caller's row index of sorted row i, lonlat_sorted[i] = lonlat[perm[i]]; cube-map Morton cells,
+ * perm[i] = caller's row index of sorted row i, lonlat_sorted[i] = lonlat[perm[i]]; cube-map Hilbert cells,
  * deterministic.  Run the encoder / retrieval on lonlat_sorted and hand perm to range_concat_scatter. */
 size_t range_sort_workspace_bytes(range_ctx* ctx, int64_t N);
 int range_sort_queries(range_ctx* ctx, int64_t N, const double* lonlat, double* lonlat_sorted, int32_t* perm,

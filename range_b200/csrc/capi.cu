@@ -35,7 +35,7 @@ int fail(int code, const char* fmt, ...) {
   } while (0)
 
 constexpr int kDimK = 256, kDimV = 1024, kBlockQ = 128, kBlockKeys = 128;
-constexpr int64_t kEncodeChunk = 32768;   // queries per encoder pass (bounds the feature workspace)
+constexpr int64_t kEncodeChunk = 131072;   // queries per encoder pass (bounds the feature workspace)
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

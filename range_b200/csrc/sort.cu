@@ -2,10 +2,10 @@
 // range/range.py:213-240 are all row-wise).  The geographic softmax of RANGE+ is local - exp(40 (cos d - 1)) -
 // so when the 128 queries of a tile are close to each other whole database tiles can skip the geo term
 // (retrieval.cu: geo_mask_kernel).  Queries arrive in arbitrary order; this file computes a permutation that
-// groups them by a cube-map Morton cell (deterministic counting sort), the encoder and retrieval run on the
+// groups them by a cube-map Hilbert cell (deterministic counting sort), the encoder and retrieval run on the
 // permuted rows and range_concat scatters the results back to the caller's order.
 //
-//   cell_hist_kernel    key[i] = face * 4^k + morton(u, v);  hist[key]++
+//   cell_hist_kernel    key[i] = face * 4^k + hilbert(u, v);  hist[key]++
 //   cell_scan_kernel    start[c] = exclusive prefix sum (single CTA; <= 6 * 4^7 + 1 cells)
 //   cell_scatter_kernel tmp[cursor[key[i]]++] = i                      (order inside a cell: arbitrary)
 //   cell_rank_kernel    orders each cell's members by original index  (-> deterministic permutation)
@@ -19,13 +19,19 @@ namespace {
 constexpr int kMaxBits = 7;            // up to 6 * 4^7 = 98 304 cells
 constexpr int kRankLimit = 64;         // cells larger than this keep the scatter order (still a valid permutation)
 
-__device__ __forceinline__ uint32_t spread_bits(uint32_t v) {   // 0b abcdefg -> 0b 0a0b0c0d0e0f0g
-  v &= 0xffffu;
-  v = (v | (v << 8)) & 0x00ff00ffu;
-  v = (v | (v << 4)) & 0x0f0f0f0fu;
-  v = (v | (v << 2)) & 0x33333333u;
-  v = (v | (v << 1)) & 0x55555555u;
-  return v;
+// position of grid cell (x, y) of a 2^bits x 2^bits grid along the Hilbert curve (the classic xy2d walk)
+__device__ __forceinline__ uint32_t hilbert_index(uint32_t x, uint32_t y, int bits) {
+  const uint32_t n = 1u << bits;
+  uint32_t d = 0;
+  for (uint32_t s = n >> 1; s > 0; s >>= 1) {
+    const uint32_t rx = (x & s) ? 1u : 0u, ry = (y & s) ? 1u : 0u;
+    d += s * s * ((3u * rx) ^ ry);
+    if (ry == 0) {
+      if (rx == 1) { x = n - 1 - x; y = n - 1 - y; }
+      const uint32_t t = x; x = y; y = t;
+    }
+  }
+  return d;
 }
 
 __device__ __forceinline__ uint32_t cell_key(double lon_deg, double lat_deg, int bits) {
@@ -47,7 +53,7 @@ __device__ __forceinline__ uint32_t cell_key(double lon_deg, double lat_deg, int
   int iu = int((fu + 1.f) * 0.5f * float(g)), iv = int((fv + 1.f) * 0.5f * float(g));
   iu = min(max(iu, 0), g - 1);
   iv = min(max(iv, 0), g - 1);
-  return (uint32_t(face) << (2 * bits)) | spread_bits(uint32_t(iu)) | (spread_bits(uint32_t(iv)) << 1);
+  return (uint32_t(face) << (2 * bits)) | hilbert_index(uint32_t(iu), uint32_t(iv), bits);
 }
 
 __global__ void __launch_bounds__(256)

@@ -1,7 +1,7 @@
 """Spatial ordering of the database / queries and the geographic tile-skip bound.
 
 The reference's result does not depend on row order (range/range.py:213-238 are row-wise sums), so these
-are properties of OUR layout: the Morton order is a permutation, every tile's cap contains its entries, and a
+are properties of OUR layout: the Hilbert order is a permutation, every tile's cap contains its entries, and a
 skipped (query tile, database tile) pair only ever holds pairs whose geo weight is below 2^-24 of the row's
 normaliser."""
 import numpy as np
@@ -11,11 +11,11 @@ import torch
 from oracle import range_oracle as O
 
 
-def test_morton_order_and_caps_cpu():
-    from range_b200.database import morton_order, tile_caps, prepare_reference_arrays
+def test_hilbert_order_and_caps_cpu():
+    from range_b200.database import hilbert_order, tile_caps, prepare_reference_arrays
     db = O.synthetic_db(5000, seed=7, kind="iid")
     _, _, xyz = prepare_reference_arrays(db)
-    order = morton_order(xyz)
+    order = hilbert_order(xyz)
     assert sorted(order.tolist()) == list(range(5000))
     s = xyz[order]
     caps = tile_caps(s)
@@ -24,11 +24,11 @@ def test_morton_order_and_caps_cpu():
         pts = s[t * 128:(t + 1) * 128].astype(np.float64)
         ang = np.arccos(np.clip(pts @ caps[t, :3].astype(np.float64), -1, 1))
         assert ang.max() <= caps[t, 3] + 1e-5
-    # locality: Morton tiles are far smaller than tiles of the unsorted rows
+    # locality: Hilbert tiles are far smaller than tiles of the unsorted rows
     assert np.median(caps[:, 3]) < 0.25 * np.median(tile_caps(xyz)[:, 3])
     # identical points / tiny inputs
     one = np.repeat(xyz[:1], 3, axis=0)
-    assert tile_caps(one)[0, 3] < 1e-3 and morton_order(one).tolist() == [0, 1, 2]
+    assert tile_caps(one)[0, 3] < 1e-3 and hilbert_order(one).tolist() == [0, 1, 2]
 
 
 @pytest.mark.gpu

@@ -1,0 +1,102 @@
+"""BASELINE.json configs 2-5 on however many GPUs torchrun gives (1 GPU: plain python).  Prints one JSON line per
+config; device-resident timing (CUDA events, max over ranks), synthetic data, random-init SatCLIP-L40 (H = 512).
+  C2  RANGE+ beta=0.5, 100k queries x 100k entries                       (bench.py's workload, here for reference)
+  C3  RANGE+ beta in {0, .25, .5, .75, 1}, 1M queries, query-sharded
+  C4  database scaling M = 100k .. M_MAX, 100k queries; with > 1 rank the database is sharded along M (NCCL merge)
+  C5  dense lat/lon raster (visualize_embeddings.py:29-39 coord_grid), RASTER_POINTS points, query-sharded
+"""
+import json, os, sys, time
+import numpy as np, torch, torch.distributed as dist
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
+from argparse import Namespace
+from oracle import range_oracle as O
+from range_b200.range import LocationEncoder
+from range_b200.distributed import shard_rows
+
+world, rank, local = int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0))
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+if world > 1:
+    dist.init_process_group("nccl", device_id=dev)
+M_MAX = int(os.environ.get("M_MAX", 1_000_000))
+RASTER = int(os.environ.get("RASTER_POINTS", 10_000_000))
+CHUNK = 98_304                                    # 16 rounds of the producer/consumer apply kernel
+enc = dict(L=40, dims=[1600, 512, 512, 256], weights=O.siren_init(40, 512, 2, 256, seed=0))
+
+
+def make_db(M, seed=0):
+    rng = np.random.default_rng(seed)
+    return dict(locs=O.area_uniform(M, rng), satclip_embeddings=rng.standard_normal((M, 256), dtype=np.float32),
+                image_embeddings=rng.standard_normal((M, 1024), dtype=np.float32))
+
+
+def model_for(db, beta, **kw):
+    import contextlib
+    with contextlib.redirect_stdout(sys.stderr):
+        return LocationEncoder(Namespace(location_model_name="RANGE+", pretrained_path=enc, device=dev, range_db=db, beta=beta, **kw))
+
+
+def timed(fn, reps=2):
+    fn(); torch.cuda.synchronize()
+    if world > 1: dist.barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps): fn()
+    b.record(); torch.cuda.synchronize()
+    t = torch.tensor([a.elapsed_time(b) / reps], device=dev)
+    if world > 1: dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t[0]) * 1e-3
+
+
+def run_chunks(model, coords, out):
+    for lo in range(0, coords.shape[0], CHUNK):
+        hi = min(coords.shape[0], lo + CHUNK)
+        model.embed(coords[lo:hi], out=out[: hi - lo])
+
+
+def emit(**kw):
+    if rank == 0: print(json.dumps(kw), flush=True)
+
+
+out = torch.empty(CHUNK, 1280, dtype=torch.float32, device=dev)
+db = make_db(100_000)
+which = os.environ.get("CONFIGS", "2,3,4,5").split(",")
+
+if "2" in which or "3" in which:
+    N = 1_000_000
+    lo, hi = shard_rows(N, rank, world)
+    coords = torch.tensor(O.area_uniform(N, np.random.default_rng(1))[lo:hi], device=dev)
+    for beta in ([0.5] if "3" not in which else [0.0, 0.25, 0.5, 0.75, 1.0]):
+        m = model_for(db, beta)
+        t = timed(lambda: run_chunks(m, coords, out), reps=1)
+        emit(config="C3 beta sweep", beta=beta, queries=N, M=100_000, n_gpus=world, seconds=t, queries_per_s=N / t,
+             parallelism=f"query-sharded x{world}")
+        del m
+
+if "4" in which:
+    N = 100_000
+    coords = torch.tensor(O.area_uniform(N, np.random.default_rng(1)), device=dev)
+    M = 100_000
+    while M <= M_MAX:
+        dbm = make_db(M)
+        kw = dict(db_shard=(rank, world), db_group=dist.group.WORLD) if world > 1 else {}
+        m = model_for(dbm, 0.5, **kw)
+        t = timed(lambda: run_chunks(m, coords, out), reps=1)
+        emit(config="C4 database scaling", queries=N, M=M, n_gpus=world, seconds=t, queries_per_s=N / t,
+             pair_rate_per_s=N * M / t, parallelism=(f"database sharded along M x{world}, NCCL SUM/MAX merge" if world > 1 else "one GPU"))
+        del m, dbm
+        M *= (10 if M * 10 <= M_MAX else 10**9) if os.environ.get("M_DECADES") else 3 if M * 3 <= M_MAX else 10**9
+
+if "5" in which:
+    # coord_grid (visualize_embeddings.py:29-39): lon = linspace(-180, 180, W), lat = linspace(90, -90, H) in float32
+    H = int(round((RASTER / 2) ** 0.5)); W = 2 * H
+    lon = torch.linspace(-180, 180, W, dtype=torch.float32); lat = torch.linspace(90, -90, H, dtype=torch.float32)
+    grid = torch.stack(torch.meshgrid(lon, lat, indexing="xy"), dim=-1).reshape(-1, 2).double()
+    lo, hi = shard_rows(grid.shape[0], rank, world)
+    coords = grid[lo:hi].to(dev)
+    m = model_for(db, 0.5)
+    t = timed(lambda: run_chunks(m, coords, out), reps=1)
+    emit(config="C5 dense raster", H=H, W=W, queries=grid.shape[0], M=100_000, n_gpus=world, seconds=t,
+         queries_per_s=grid.shape[0] / t, parallelism=f"query-sharded x{world}")
+if world > 1:
+    dist.destroy_process_group()
