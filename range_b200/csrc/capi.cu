@@ -116,6 +116,7 @@ struct RetrievalPlan {
   int stats_splits, stats_tiles_per_split;  // stats kernel
   int mask_rows, mask_words;                // geo-skip mask: [even-padded query tiles][ceil(tiles / 32)]
   bool pc;                                  // apply with the producer/consumer kernel (retrieval_pc.cu)
+  bool stats_pc;                            // statistics with the CTA-pair / four-group kernel (retrieval_pc.cu)
   size_t off_part_sum, off_part_max, off_sums, off_maxs, off_rowc, off_mask, off_ring, off_flags, off_part_out, total;
 };
 
@@ -150,6 +151,18 @@ RetrievalPlan plan_retrieval(const range_ctx* c, int64_t N) {
     const double waves = double((qtiles * sp + c->sm_count - 1) / c->sm_count);
     const double cost = waves / double(sp) * (1.0 + 0.004 * double(sp));      // small per-CTA fixed cost
     if (cost < best_cost - 1e-9) { best_cost = cost; best = sp; }
+  }
+  // large batches: CTA pairs (two query tiles per cluster) -> waves are counted in clusters
+  const int64_t qpairs0 = (qtiles + 1) / 2, slots = c->sm_count / 2;
+  p.stats_pc = apply_kernel_override() != 1 && slots > 0 && qpairs0 * 2 >= slots;
+  if (p.stats_pc) {
+    best = 1;
+    best_cost = 1e30;
+    for (int64_t sp = 1; sp <= 16 && sp <= (tiles / 32 > 0 ? tiles / 32 : 1); ++sp) {
+      const double waves = double((qpairs0 * sp + slots - 1) / slots);
+      const double cost = waves / double(sp) * (1.0 + 0.004 * double(sp));
+      if (cost < best_cost - 1e-9) { best_cost = cost; best = sp; }
+    }
   }
   p.stats_tiles_per_split = int((tiles + best - 1) / best);
   p.stats_splits = int((tiles + p.stats_tiles_per_split - 1) / p.stats_tiles_per_split);
@@ -516,7 +529,8 @@ int range_retrieve_stats(range_ctx* c, int mode, int64_t N, const void* q16, con
   if (r) return r;
   float* part_sum = p.stats_splits > 1 ? reinterpret_cast<float*>(ws + p.off_part_sum) : sums;
   float* part_max = p.stats_splits > 1 ? reinterpret_cast<float*>(ws + p.off_part_max) : maxs;
-  CUDA_TRY(launch_stats(a, part_sum, part_max, s));
+  if (p.stats_pc) CUDA_TRY(launch_stats_pc(a, part_sum, part_max, s));
+  else CUDA_TRY(launch_stats(a, part_sum, part_max, s));
   g_launches += 1;
   if (p.stats_splits > 1) {
     CUDA_TRY(launch_reduce_stats(part_sum, part_max, int(N), p.stats_splits, sums, maxs, s));

@@ -41,6 +41,15 @@ constexpr int kThreads = 20 * 32;
 constexpr int kRing = RANGE_PC_RING;             // P' slots per producer CTA
 constexpr int kPublishBatch = 4;                 // tiles per release of the `full` counter (kRing >= 3 batches)
 constexpr int kWindow = 64;                      // tiles per cross-unit synchronisation window (8192 entries, 21 MB of database)
+// Every kPolyEvery-th semantic exponential is evaluated on the FMA pipe (ptx::ex2_poly, rel. error 2.7e-6) instead of
+// MUFU: the softmax warps are MUFU-bound with issue slots to spare.  0 = never.
+#ifndef RANGE_PC_POLY
+#define RANGE_PC_POLY 0
+#endif
+constexpr int kPolyEvery = RANGE_PC_POLY;
+__device__ __forceinline__ float ex2_mixed(float x, int i) {
+  return (kPolyEvery > 0 && (i % (kPolyEvery > 0 ? kPolyEvery : 1)) == kPolyEvery - 1) ? ptx::ex2_poly(x) : ptx::ex2(x);
+}
 constexpr int kFlagStride = 32;                  // uint32 per flag line (128 B)
 constexpr int kFlagsPerProducer = 3 * kFlagStride;   // full, done[0], done[1]
 
@@ -357,7 +366,7 @@ range_apply_pc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 #pragma unroll
               for (int u = 0; u < 2; ++u) {
                 const int i = 2 * w + u;
-                float p = ptx::ex2(fmaf(__uint_as_float(cur[i]), a_sem, cs));
+                float p = ex2_mixed(fmaf(__uint_as_float(cur[i]), a_sem, cs), i);
                 if (kG) {
                   const float4 k = ptx::lds_f4(kxyz + i * 16);
                   p += ptx::ex2(fmaf(gx, k.x, fmaf(gy, k.y, fmaf(gz, k.z, cg))));
@@ -575,6 +584,239 @@ range_apply_pc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   if (active && warp == kWarpMma) ptx::tmem_dealloc_2sm<512>(tmem_base);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// K2a (large batches): row statistics with the producer's structure - CTA pairs (two query tiles, half a K tile
+// loaded per CTA), four S buffers, four desynchronised softmax groups, pipelined 16-column TMEM loads.  The
+// exponentials are the whole cost of this pass (the MUFU pipe), so what matters is that some warp of every SM
+// sub-partition always has exponentials to issue; the 16-warp lockstep kernel in retrieval.cu reaches 78 % of the
+// MUFU peak, this one ~95 %.  Per row: sum_j 2^(a (s_j - 1)), max_j s_j (and the same for g) over the tiles
+// [split * tiles_per_split, ...) - partials over splits / ranks merge with SUM and MAX (reference: the softmax
+// denominators of range/range.py:215,234).
+// ---------------------------------------------------------------------------------------------------
+struct StatSmem {
+  static constexpr int NS = 4, NB = 4;           // K stages (32 KB: this CTA's 64 entries x 256 dims), S buffers
+  static constexpr int q = 0;
+  static constexpr int stages = q + 65536;
+  static constexpr int xyz = stages + NS * 32768;
+  static constexpr int red = xyz + NB * kXyzBytes;             // cross-group reduction scratch [3][128] float4
+  static constexpr int bars = red + 3 * kBlockQ * 16;
+  static constexpr int b_q_full = 0, b_q_pair = 1;
+  static constexpr int b_stage_full = 2;
+  static constexpr int b_stage_empty = b_stage_full + NS;
+  static constexpr int b_s_full = b_stage_empty + NS;
+  static constexpr int b_s_empty = b_s_full + NB;
+  static constexpr int b_xyz_empty = b_s_empty + NB;
+  static constexpr int n_bars = b_xyz_empty + NB;
+  static constexpr int tmem_slot = bars + n_bars * 8;
+  static constexpr int total = tmem_slot + 16;
+  static constexpr int dynamic_bytes = total + 1024;
+};
+
+template <bool kGeo>
+__global__ void __launch_bounds__(kThreads, 1)
+range_stats_pc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK64,
+                      const float4* __restrict__ db_xyz, const float4* __restrict__ q_xyz, int N, int M,
+                      int tiles_per_split, float a_sem, float a_geo, float* __restrict__ part_sum,
+                      float* __restrict__ part_max, const uint32_t* __restrict__ geo_mask, int mask_words) {
+  using L = StatSmem;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::bars);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::tmem_slot);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const bool leader = rank == 0;
+  const int qt = blockIdx.x;                       // cluster (2,1,1): blockIdx.x = 2 * pair + rank
+  const int split = blockIdx.y;
+  const int total_tiles = (M + kKeys - 1) / kKeys;
+  const int t_begin = split * tiles_per_split;
+  const int T = min(total_tiles, t_begin + tiles_per_split) - t_begin;
+  const uint32_t* mask_row = (kGeo && geo_mask) ? geo_mask + size_t(qt) * mask_words : nullptr;
+  auto skip_geo = [&](int t) { return mask_row != nullptr && ((__ldg(mask_row + (t >> 5)) >> (t & 31)) & 1u); };
+
+  if (threadIdx.x == 0) {
+    ptx::mbar_init(&bars[L::b_q_full], 1);
+    ptx::mbar_init(&bars[L::b_q_pair], 2);
+    for (int i = 0; i < L::NS; ++i) {
+      ptx::mbar_init(&bars[L::b_stage_full + i], 1);
+      ptx::mbar_init(&bars[L::b_stage_empty + i], 1);
+    }
+    for (int i = 0; i < L::NB; ++i) {
+      ptx::mbar_init(&bars[L::b_s_full + i], kGeo ? 2 : 1);            // MMA commit (+ this CTA's xyz bytes)
+      ptx::mbar_init(&bars[L::b_s_empty + i], 2 * 4);                  // the owning group's 4 warps in both CTAs
+      ptx::mbar_init(&bars[L::b_xyz_empty + i], 4);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == kWarpMma) ptx::tmem_alloc_2sm<512>(tmem_slot);
+  ptx::tc_fence_before();
+  ptx::cluster_sync();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  const uint32_t smem_u = __shfl_sync(0xffffffffu, ptx::smem_u32(smem), 0);
+  const uint32_t bars_u = smem_u + L::bars;
+
+  if (warp == kWarpTma) {
+    if (lane == 0 && T > 0) {
+      ptx::prefetch_tmap(&tmQ);
+      ptx::prefetch_tmap(&tmK64);
+      ptx::mbar_expect_tx(&bars[L::b_q_full], 65536);
+      for (int c = 0; c < 4; ++c) ptx::tma_load_2d(smem + L::q + c * 16384, &tmQ, &bars[L::b_q_full], c * 64, qt * kBlockQ);
+      PipeState st;
+      for (int j = 0; j < T; ++j) {
+        ptx::mbar_wait(&bars[L::b_stage_empty + st.idx], st.phase ^ 1);
+        uint8_t* dst = smem + L::stages + st.idx * 32768;
+        if (leader) ptx::mbar_expect_tx(&bars[L::b_stage_full + st.idx], 65536);
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          ptx::tma_load_2d_2sm(dst + c * 8192, &tmK64, &bars[L::b_stage_full + st.idx], c * 64,
+                               (t_begin + j) * kKeys + int(rank) * 64);
+        st.advance<L::NS>();
+      }
+    }
+  } else if (warp == kWarpXyz) {
+    if (kGeo && lane == 0) {
+      for (int j = 0; j < T; ++j) {
+        const int x = j & (L::NB - 1);
+        ptx::mbar_wait(&bars[L::b_xyz_empty + x], ((j / L::NB) & 1) ^ 1);
+        if (skip_geo(t_begin + j)) {
+          ptx::mbar_arrive(&bars[L::b_s_full + x]);
+        } else {
+          ptx::mbar_expect_tx(&bars[L::b_s_full + x], kXyzBytes);
+          ptx::bulk_load_1d(smem + L::xyz + x * kXyzBytes, db_xyz + (t_begin + j) * kKeys, kXyzBytes, &bars[L::b_s_full + x]);
+        }
+      }
+    }
+  } else if (warp == kWarpMma) {
+    if (T > 0) {
+      ptx::mbar_wait(&bars[L::b_q_full], 0);
+      if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&bars[L::b_q_pair]), 0));
+      __syncwarp();
+    }
+    if (leader && T > 0) {
+      constexpr uint32_t idesc_qk = ptx::umma_idesc_f16(2 * kBlockQ, kKeys);
+      ptx::mbar_wait_cluster(&bars[L::b_q_pair], 0);
+      PipeState st;
+      for (int j = 0; j < T; ++j) {
+        const int b = j & (L::NB - 1);
+        ptx::mbar_wait_cluster(&bars[L::b_s_empty + b], ((j / L::NB) & 1) ^ 1);
+        ptx::mbar_wait(&bars[L::b_stage_full + st.idx], st.phase);
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) {
+          const uint32_t b_base = smem_u + L::stages + st.idx * 32768;
+          const uint32_t a_base = smem_u + L::q;
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+              ptx::umma_f16_ss_2sm(tmem_base + b * kKeys, ptx::umma_desc_kmajor_sw128(a_base + c * 16384 + kk * 32),
+                                   ptx::umma_desc_kmajor_sw128(b_base + c * 8192 + kk * 32), idesc_qk, (c | kk) != 0);
+          ptx::umma_commit_2sm_u32(bars_u + 8 * (L::b_stage_empty + st.idx));
+          ptx::umma_commit_2sm_u32(bars_u + 8 * (L::b_s_full + b));
+        }
+        __syncwarp();
+        st.advance<L::NS>();
+      }
+    }
+  } else if (warp < kSoftmaxWarps) {
+    const int grp = warp >> 2, quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const int n = qt * kBlockQ + row;
+    const int b = grp;
+    const uint32_t s_empty_leader = ptx::mapa(ptx::smem_u32(&bars[L::b_s_empty + b]), 0);
+    const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + b * kKeys;
+    float4 qx = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (kGeo && n < N) qx = q_xyz[n];
+    const float gx = qx.x * a_geo, gy = qx.y * a_geo, gz = qx.z * a_geo;
+    float sum_s = 0.f, sum_g = 0.f, max_s = -2.f, max_g = -3.0e38f;
+    for (int j = grp; j < T; j += L::NB) {
+      const int t = t_begin + j;
+      const bool with_geo = kGeo && !skip_geo(t);
+      ptx::mbar_wait(&bars[L::b_s_full + b], (j / L::NB) & 1);      // S(j) in TMEM and xyz(j) in smem
+      ptx::tc_fence_after();
+      uint32_t bufA[16], bufB[16];
+      auto piece = [&](const uint32_t (&cur)[16], int h) {
+        const uint32_t kxyz = smem_u + L::xyz + b * kXyzBytes + h * 16 * 16;
+        const int nvalid = M - (t * kKeys + h * 16);            // >= 16 except in the last tile
+        auto body = [&](auto masked, auto geo) {
+          constexpr bool kM = decltype(masked)::value, kG = decltype(geo)::value;
+#pragma unroll
+          for (int i = 0; i < 16; i += 2) {
+            float sv[2], gv[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const float s = __uint_as_float(cur[i + u]);
+              const bool valid = !kM || (i + u < nvalid);
+              float es = ex2_mixed(fmaf(s, a_sem, -a_sem), i + u);
+              if (!valid) es = 0.f;
+              sum_s += es;
+              sv[u] = valid ? s : -2.f;
+              if (kG) {
+                const float4 k = ptx::lds_f4(kxyz + (i + u) * 16);
+                const float g = fmaf(gx, k.x, fmaf(gy, k.y, fmaf(gz, k.z, -a_geo)));   // a_geo (g - 1)
+                float eg = ptx::ex2(g);
+                if (!valid) eg = 0.f;
+                sum_g += eg;
+                gv[u] = valid ? g : -3.0e38f;
+              }
+            }
+            max_s = ptx::max3(max_s, sv[0], sv[1]);
+            if (kG) max_g = ptx::max3(max_g, gv[0], gv[1]);
+          }
+        };
+        if (nvalid >= 16) {
+          if (with_geo) body(std::false_type{}, std::true_type{}); else body(std::false_type{}, std::false_type{});
+        } else {
+          if (with_geo) body(std::true_type{}, std::true_type{}); else body(std::true_type{}, std::false_type{});
+        }
+      };
+      ptx::tmem_ld16(taddr, bufA);
+#pragma unroll 1
+      for (int hp = 0; hp < 4; ++hp) {
+        ptx::tmem_ld_wait();
+        ptx::tmem_ld16(taddr + (2 * hp + 1) * 16, bufB);
+        piece(bufA, 2 * hp);
+        ptx::tmem_ld_wait();
+        if (hp < 3) {
+          ptx::tmem_ld16(taddr + (2 * hp + 2) * 16, bufA);
+        } else {                              // the whole S tile is in registers: the MMA warp may overwrite the buffer
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (leader) ptx::mbar_arrive(&bars[L::b_s_empty + b]);
+            else ptx::mbar_arrive_cluster_relaxed(s_empty_leader);
+          }
+        }
+        piece(bufB, 2 * hp + 1);
+      }
+      if (kGeo) {
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&bars[L::b_xyz_empty + b]);
+      }
+    }
+    // combine the four groups (each saw a quarter of the tiles), write this split's partials
+    float4* red = reinterpret_cast<float4*>(smem + L::red);
+    if (grp > 0) red[(grp - 1) * kBlockQ + row] = make_float4(sum_s, sum_g, max_s, max_g);
+    asm volatile("bar.sync 1, %0;" ::"n"(kSoftmaxWarps * 32) : "memory");
+    if (grp == 0 && n < N) {
+#pragma unroll
+      for (int g2 = 0; g2 < 3; ++g2) {
+        const float4 o = red[g2 * kBlockQ + row];
+        sum_s += o.x;
+        sum_g += o.y;
+        max_s = fmaxf(max_s, o.z);
+        max_g = fmaxf(max_g, o.w);
+      }
+      const float raw_g = kGeo ? (max_g / a_geo + 1.f) : 0.f;      // max_g holds a_geo (g - 1); store the raw cosine
+      reinterpret_cast<float2*>(part_sum)[size_t(split) * N + n] = make_float2(sum_s, sum_g);
+      reinterpret_cast<float2*>(part_max)[size_t(split) * N + n] = make_float2(max_s, raw_g);
+    }
+  }
+  ptx::tc_fence_before();
+  ptx::cluster_sync();
+  if (warp == kWarpMma) ptx::tmem_dealloc_2sm<512>(tmem_base);
+}
+
 }  // namespace
 
 namespace rangeb200 {
@@ -627,6 +869,28 @@ cudaError_t launch_apply_pc(const RetrievalArgs& a, const CUtensorMap& tmP, cons
     fprintf(stderr, "range_b200: producer/consumer apply launch failed (%s); grid %u smem %d\n", cudaGetErrorString(e),
             cfg.gridDim.x, kDynamicSmem);
   return e;
+}
+
+// stats over pairs of query tiles; grid (2 * ceil(qtiles / 2), splits), cluster (2,1,1)
+cudaError_t launch_stats_pc(const RetrievalArgs& a, float* part_sum, float* part_max, cudaStream_t stream) {
+  auto kern = a.geo ? range_stats_pc_kernel<true> : range_stats_pc_kernel<false>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, StatSmem::dynamic_bytes);
+  if (e != cudaSuccess) return e;
+  const int qtiles = (a.N + kBlockQ - 1) / kBlockQ;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(unsigned((qtiles + 1) / 2 * 2), unsigned(a.stats_splits), 1);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = size_t(StatSmem::dynamic_bytes);
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, a.tmQ, a.tmK64, a.db_xyz, a.q_xyz, a.N, a.M, a.stats_tiles_per_split, a.a_sem,
+                            a.a_geo, part_sum, part_max, a.geo_mask, a.mask_words);
 }
 
 }  // namespace rangeb200

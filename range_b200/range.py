@@ -16,6 +16,7 @@ from .engine import RangeEngine
 
 # four rounds of the producer/consumer apply kernel on 148 SMs (24 units x 2 query tiles of 128 per round)
 DEFAULT_CHUNK = 4 * 24 * 256
+DEFAULT_TAIL = 24 * 256          # one round: the unoverlapped last copy is 63 MB instead of 252 MB
 
 
 class LocationEncoder(nn.Module):
@@ -41,6 +42,8 @@ class LocationEncoder(nn.Module):
         self.location_feature_dim = 1024 + 256                                             # range.py:86
         self.engine = RangeEngine(args.device, encoder=enc, database=DeviceDatabase(db, args.device, shard=shard))
         self.chunk = int(getattr(args, 'chunk', DEFAULT_CHUNK))
+        self.tail = max(1, min(self.chunk, int(getattr(args, 'tail', DEFAULT_TAIL))))
+        self.super_batch = max(self.chunk, int(getattr(args, 'super_batch', 1 << 20)) // self.chunk * self.chunk)
         self.group = getattr(args, 'db_group', None)       # torch.distributed group when the DB is M-sharded
         self._copy_stream = None
         self.eval()
@@ -49,28 +52,48 @@ class LocationEncoder(nn.Module):
     def _apply(self, fn, recurse=True):
         return self
 
-    @torch.no_grad()
-    def embed(self, coords, out=None, out_dtype=torch.float32):
-        """Device-resident path: coords (N,2) fp64 on the device -> (N,1280) device tensor."""
+    def _sorts(self):
+        eng = self.engine
+        return self.location_model_name == 'RANGE+' and eng.db is not None and eng.db.caps is not None
+
+    def _retrieve(self, q16, qxyz):
         eng, a = self.engine, self.args
-        perm = None
-        if self.location_model_name == 'RANGE+' and eng.db is not None and eng.db.caps is not None:
-            # spatial batching: the geo softmax is local, tiles of nearby queries skip far database tiles
-            coords, perm = eng.sort_queries(coords)
-        q64, q16, qxyz = eng.encode(coords)
         beta = getattr(a, 'beta', None)
         geo_temp = float(getattr(a, 'geo_temp', 0.0))
         if self.group is None:
-            O = eng.retrieve(self.location_model_name, q16, qxyz, a.temp, geo_temp, beta)
-        else:
-            from .distributed import sharded_retrieve
-            O = sharded_retrieve(eng, self.location_model_name, q16, qxyz, a.temp, geo_temp, beta, self.group)
-        return eng.concat(O, q64, out=out, dtype=out_dtype, perm=perm)
+            return eng.retrieve(self.location_model_name, q16, qxyz, a.temp, geo_temp, beta)
+        from .distributed import sharded_retrieve
+        return sharded_retrieve(eng, self.location_model_name, q16, qxyz, a.temp, geo_temp, beta, self.group)
+
+    @torch.no_grad()
+    def embed(self, coords, out=None, out_dtype=torch.float32):
+        """Device-resident path: coords (N,2) fp64 on the device -> (N,1280) device tensor."""
+        eng = self.engine
+        perm = None
+        if self._sorts():
+            # spatial batching: the geo softmax is local, tiles of nearby queries skip far database tiles
+            coords, perm = eng.sort_queries(coords)
+        q64, q16, qxyz = eng.encode(coords)
+        return eng.concat(self._retrieve(q16, qxyz), q64, out=out, dtype=out_dtype, perm=perm)
+
+    @staticmethod
+    def _chunks(N, chunk, tail):
+        """[lo, hi) slices: full chunks, then the remainder with a short last piece - the last device->host copy is
+        the only one nothing overlaps"""
+        cuts, lo = [], 0
+        while N - lo > chunk:
+            cuts.append((lo, lo + chunk)); lo += chunk
+        if N - lo > 2 * tail:
+            cuts.append((lo, N - tail)); lo = N - tail
+        cuts.append((lo, N))
+        return cuts
 
     @torch.no_grad()
     def forward(self, coords):
-        """range.py:206-242.  Returns numpy float64 (N, 1280); chunks are computed on the current stream while
-        the previous chunk's result travels to pinned host memory on a copy stream."""
+        """range.py:206-242.  Returns numpy float64 (N, 1280).  Per super-batch (<= 1M queries): every chunk is
+        batched spatially, the encoder runs once over the whole super-batch (full-width launches), then chunk after
+        chunk is retrieved on the current stream while the previous chunk's rows travel to pinned host memory on a
+        copy stream."""
         if 'RANGE' not in self.location_model_name:
             raise NotImplementedError(f'{self.location_model_name} not implemented')
         eng = self.engine
@@ -86,22 +109,34 @@ class LocationEncoder(nn.Module):
             if self._copy_stream is None:
                 self._copy_stream = torch.cuda.Stream(device=eng.device)
             chunk = min(self.chunk, N)
-            bufs = [torch.empty(chunk, 1280, dtype=torch.float64, device=eng.device) for _ in range(2 if N > chunk else 1)]
+            bufs = [torch.empty(chunk, 1280, dtype=torch.float64, device=eng.device) for _ in range(2 if N > self.tail else 1)]
             freed = [None] * len(bufs)
             cur = torch.cuda.current_stream()
-            for i, lo in enumerate(range(0, N, chunk)):
-                hi = min(N, lo + chunk)
-                k = i % len(bufs)
-                if freed[k] is not None:
-                    cur.wait_event(freed[k])
-                buf = bufs[k][: hi - lo]
-                self.embed(dev_coords[lo:hi], out=buf)
-                ready = torch.cuda.Event()
-                ready.record(cur)
-                self._copy_stream.wait_event(ready)
-                with torch.cuda.stream(self._copy_stream):
-                    host[lo:hi].copy_(buf, non_blocking=True)
-                    freed[k] = torch.cuda.Event()
-                    freed[k].record(self._copy_stream)
+            i = 0
+            for s0 in range(0, N, self.super_batch):
+                s1 = min(N, s0 + self.super_batch)
+                cuts = self._chunks(s1 - s0, chunk, self.tail)
+                sub = dev_coords[s0:s1]
+                perms = None
+                if self._sorts():
+                    parts = [eng.sort_queries(sub[lo:hi]) for lo, hi in cuts]
+                    sub = torch.cat([p[0] for p in parts]) if len(parts) > 1 else parts[0][0]
+                    perms = [p[1] for p in parts]
+                q64, q16, qxyz = eng.encode(sub)
+                for c, (lo, hi) in enumerate(cuts):
+                    k = i % len(bufs)
+                    i += 1
+                    if freed[k] is not None:
+                        cur.wait_event(freed[k])
+                    buf = bufs[k][: hi - lo]
+                    eng.concat(self._retrieve(q16[lo:hi], qxyz[lo:hi]), q64[lo:hi], out=buf,
+                               perm=None if perms is None else perms[c])
+                    ready = torch.cuda.Event()
+                    ready.record(cur)
+                    self._copy_stream.wait_event(ready)
+                    with torch.cuda.stream(self._copy_stream):
+                        host[s0 + lo:s0 + hi].copy_(buf, non_blocking=True)
+                        freed[k] = torch.cuda.Event()
+                        freed[k].record(self._copy_stream)
             self._copy_stream.synchronize()
         return host.numpy()                                                               # range.py:222,240
