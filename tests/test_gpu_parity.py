@@ -249,3 +249,59 @@ def test_large_batch_producer_consumer_apply(sh_entries):
     small = eng.retrieve("RANGE+", q16[:1000], qxyz[:1000], 12.0, 40.0, 0.5)
     big = eng.retrieve("RANGE+", q16, qxyz, 12.0, 40.0, 0.5)[:1000]
     assert rel_rows(big.cpu().numpy(), small.cpu().numpy()).max() <= 5e-4     # fp16 rounding of P' (row sums differ in the last bit)
+
+
+def test_full_size_properties(sh_entries):
+    """BASELINE.json config 2 at full size (100 000 queries x 100 000 entries, H = 512) through the public module:
+    sampled rows against the exact oracle, linearity in beta over every row, unit-norm location columns."""
+    from argparse import Namespace
+    from range_b200.range import LocationEncoder
+    N = M = 100_000
+    rng = np.random.default_rng(0)
+    db = dict(locs=O.area_uniform(M, rng), satclip_embeddings=rng.standard_normal((M, 256), dtype=np.float32),
+              image_embeddings=rng.standard_normal((M, 1024), dtype=np.float32))
+    ws = O.siren_init(40, 512, 2, 256, seed=0)
+    enc = dict(L=40, dims=[1600, 512, 512, 256], weights=ws)
+    c = O.area_uniform(N, np.random.default_rng(1))
+    dc = torch.tensor(c, device=DEV)
+    outs = {}
+    for beta in (0.0, 0.5, 1.0):
+        m = LocationEncoder(Namespace(location_model_name="RANGE+", pretrained_path=enc, device=DEV, range_db=db, beta=beta))
+        outs[beta] = m.embed(dc, out_dtype=torch.float64)
+        del m
+    mid = outs[0.5][:, :1024]
+    lin = 0.5 * outs[0.0][:, :1024] + 0.5 * outs[1.0][:, :1024]
+    rel = ((mid - lin).norm(dim=1) / mid.norm(dim=1))
+    assert rel.max().item() <= 2e-3 and rel.mean().item() <= 3e-4, (rel.max().item(), rel.mean().item())
+    qn = outs[0.5][:, 1024:].norm(dim=1)
+    assert (qn - 1).abs().max().item() < 1e-12
+    assert torch.equal(outs[0.0][:, 1024:], outs[1.0][:, 1024:])
+    sub = np.linspace(0, N - 1, 192).astype(np.int64)
+    ref = O.RangeOracle("RANGE+", ws, sh_entries, db, beta=0.5, exact=True)(c[sub])
+    got = outs[0.5][torch.tensor(sub, device=DEV)].cpu().numpy()
+    r = rel_rows(got[:, :1024], ref[:, :1024])
+    assert r.max() <= 2e-3 and r.mean() <= 6e-4, (r.max(), r.mean())
+    assert cos_rows(got[:, :1024], ref[:, :1024]).min() >= 0.99999
+    lat = np.abs(c[sub, 1])
+    dq = np.abs(got[:, 1024:] - ref[:, 1024:])
+    assert dq[lat < 60].max() <= 5e-5 and dq.max() <= 2e-3
+
+
+@pytest.mark.parametrize("N,M", [(13_000, 77), (12_288, 128), (20_000, 129)])
+def test_large_batch_tiny_database(N, M, sh_entries):
+    """producer/consumer kernels with one or two database tiles (most softmax groups idle, ragged last tile)"""
+    from range_b200.engine import RangeEngine
+    from range_b200.database import DeviceDatabase
+    db = O.synthetic_db(M, seed=9, kind="iid")
+    d = DeviceDatabase(db, DEV)
+    eng = RangeEngine(DEV, L=40, database=d)
+    g = torch.Generator(device="cpu").manual_seed(5)
+    q = torch.randn(N, 256, generator=g); q = (q / q.norm(dim=1, keepdim=True)).half().to(DEV)
+    c = O.area_uniform(N, np.random.default_rng(2))
+    xyz = torch.zeros(N, 4); xyz[:, :3] = torch.tensor(O.rad_to_cart(c * np.pi / 180)).float(); xyz = xyz.to(DEV)
+    K = d.Kh[:M].float(); V = d.Vt[:, :M].float().t() / d.vscale; X = d.xyz[:M, :3]
+    out = eng.retrieve("RANGE+", q, xyz, 12.0, 40.0, 0.25)
+    P = 0.25 * torch.softmax((q.float() @ K.t()) * 12.0, dim=1) + 0.75 * torch.softmax((xyz[:, :3] @ X.t()) * 40.0, dim=1)
+    ref = P @ V
+    rel = ((out - ref).norm(dim=1) / ref.norm(dim=1))
+    assert torch.isfinite(out).all() and rel.max().item() <= 2e-3, rel.max().item()
