@@ -19,6 +19,18 @@
 //   full[p]      tiles producer CTA p has published        (publisher warp, after the softmax warps' stores)
 //   done[p][c]   tiles consumer pair c has copied to smem  (consumer leader, after the TMA load completed)
 // All CTAs must be co-resident: the launch is cooperative (the runtime refuses it otherwise).
+//
+// Measured on B200 at 100 000 x 100 000 (tools/time_apply.py; PROF=1 prints per-role wait cycles):
+//   single-role CTA-pair kernel (retrieval.cu)                                  32.7 ms
+//   first working version (row-major ring, release per tile, 16 lockstep warps) 35.3 ms   <- gpu-scope release: 3300 clk/tile
+//   + batched release, separate Vt / P' loaders, relaxed `done`                 30.9 ms
+//   + coalesced ring layout, no-swizzle A operand, pipelined TMEM loads,
+//     6-stage P' ring in the consumer, four desynchronised softmax groups       24.5 ms
+//   + cross-unit window barrier (DRAM reads 33 GB -> 5.5 GB), 4 Vt stages        22.9 ms
+//   + Hilbert-ordered tiles (geo skip 44 % -> 52 %)                              22.6 ms
+//   + three softmax groups over four S buffers                                  21.6 ms
+// Dead ends: 64-entry S half tiles with double-buffered groups (UMMA N = 64 is operand-fetch bound: 24.7 ms);
+// every 3rd-6th exponential on the FMA pipe (no gain: the SM is power-capped, not MUFU-issue-bound).
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -32,9 +44,19 @@
 namespace {
 
 constexpr int kBlockQ = 128, kKeys = 128, kXyzBytes = kKeys * 16;
-constexpr int kSoftmaxWarps = 16;
-constexpr int kWarpTma = 16, kWarpMma = 17, kWarpPublish = 18, kWarpXyz = 19;
-constexpr int kThreads = 20 * 32;
+// Softmax warps: kGroups groups of 4 (one warp per TMEM lane quarter).  Tile it belongs to group it % kGroups and
+// lives in S buffer it % 4.  With THREE groups over FOUR buffers there is always a spare buffer: when a group
+// finishes tile it, Q.K^T of its next tile it + 3 went into a buffer that was released a whole tile earlier, so the
+// group never waits for the tensor core (4 groups x 4 buffers: 395 clk per tile waiting for S).
+#ifndef RANGE_PC_GROUPS
+#define RANGE_PC_GROUPS 3
+#endif
+constexpr int kGroups = RANGE_PC_GROUPS;
+constexpr int kSoftmaxWarps = 4 * kGroups;
+constexpr int kWarpTma = kSoftmaxWarps, kWarpMma = kSoftmaxWarps + 1, kWarpPublish = kSoftmaxWarps + 2,
+              kWarpXyz = kSoftmaxWarps + 3;
+constexpr int kThreads = (kSoftmaxWarps + 4) * 32;
+static_assert(kSoftmaxWarps + 4 >= 7, "the consumer roles use warps 0..6");
 #ifndef RANGE_PC_RING
 #define RANGE_PC_RING 16
 #endif
@@ -323,17 +345,17 @@ range_apply_pc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       // for its next S tile, a TMEM load or the ring, the SM sub-partition's MUFU pipe is fed by the other three.
       const int grp = warp >> 2, quarter = warp & 3;
       const int row = quarter * 32 + lane;
-      const int b = grp;
-      const uint32_t s_empty_leader = ptx::mapa(ptx::smem_u32(&bars[L::b_s_empty + b]), 0);
-      const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + b * kKeys;
+      const uint32_t s_empty_leader0 = ptx::mapa(ptx::smem_u32(&bars[L::b_s_empty]), 0);
       // slot s of this producer: ring + (prod_id * kRing + s) * 128 * 128 halves, laid out [16 key chunks][128 rows][8]
       __half* ring_row = ring + size_t(prod_id) * kRing * 128 * 128 + row * 8;
       const uint32_t total = uint32_t(rounds) * uint32_t(T);
       int cur_r = -1, n = 0;
       const uint32_t* mask_row = nullptr;
       float cs = -INFINITY, cg = -INFINITY, gx = 0.f, gy = 0.f, gz = 0.f;
-      for (uint32_t it = uint32_t(grp); it < total; it += L::NB) {
+      for (uint32_t it = uint32_t(grp); it < total; it += kGroups) {
         const int r = int(it / uint32_t(T)), j = int(it - uint32_t(r) * uint32_t(T));
+        const int b = it & (L::NB - 1);
+        const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + b * kKeys;
         if (r != cur_r) {
           cur_r = r;
           const int qt = 2 * (unit + r * n_units) + int(rank);
@@ -409,7 +431,7 @@ range_apply_pc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
             __syncwarp();
             if (lane == 0) {
               if (leader) ptx::mbar_arrive(&bars[L::b_s_empty + b]);
-              else ptx::mbar_arrive_cluster_relaxed(s_empty_leader);
+              else ptx::mbar_arrive_cluster_relaxed(s_empty_leader0 + 8 * b);
             }
           }
           piece(bufB, 2 * hp + 1);
@@ -598,7 +620,7 @@ struct StatSmem {
   static constexpr int q = 0;
   static constexpr int stages = q + 65536;
   static constexpr int xyz = stages + NS * 32768;
-  static constexpr int red = xyz + NB * kXyzBytes;             // cross-group reduction scratch [3][128] float4
+  static constexpr int red = xyz + NB * kXyzBytes;             // cross-group reduction scratch [groups - 1][128] float4
   static constexpr int bars = red + 3 * kBlockQ * 16;
   static constexpr int b_q_full = 0, b_q_pair = 1;
   static constexpr int b_stage_full = 2;
@@ -722,15 +744,15 @@ range_stats_pc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     const int grp = warp >> 2, quarter = warp & 3;
     const int row = quarter * 32 + lane;
     const int n = qt * kBlockQ + row;
-    const int b = grp;
-    const uint32_t s_empty_leader = ptx::mapa(ptx::smem_u32(&bars[L::b_s_empty + b]), 0);
-    const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + b * kKeys;
+    const uint32_t s_empty_leader0 = ptx::mapa(ptx::smem_u32(&bars[L::b_s_empty]), 0);
     float4 qx = make_float4(0.f, 0.f, 0.f, 0.f);
     if (kGeo && n < N) qx = q_xyz[n];
     const float gx = qx.x * a_geo, gy = qx.y * a_geo, gz = qx.z * a_geo;
     float sum_s = 0.f, sum_g = 0.f, max_s = -2.f, max_g = -3.0e38f;
-    for (int j = grp; j < T; j += L::NB) {
+    for (int j = grp; j < T; j += kGroups) {
       const int t = t_begin + j;
+      const int b = j & (L::NB - 1);
+      const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + b * kKeys;
       const bool with_geo = kGeo && !skip_geo(t);
       ptx::mbar_wait(&bars[L::b_s_full + b], (j / L::NB) & 1);      // S(j) in TMEM and xyz(j) in smem
       ptx::tc_fence_after();
@@ -784,7 +806,7 @@ range_stats_pc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           __syncwarp();
           if (lane == 0) {
             if (leader) ptx::mbar_arrive(&bars[L::b_s_empty + b]);
-            else ptx::mbar_arrive_cluster_relaxed(s_empty_leader);
+            else ptx::mbar_arrive_cluster_relaxed(s_empty_leader0 + 8 * b);
           }
         }
         piece(bufB, 2 * hp + 1);
@@ -800,7 +822,7 @@ range_stats_pc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     asm volatile("bar.sync 1, %0;" ::"n"(kSoftmaxWarps * 32) : "memory");
     if (grp == 0 && n < N) {
 #pragma unroll
-      for (int g2 = 0; g2 < 3; ++g2) {
+      for (int g2 = 0; g2 < kGroups - 1; ++g2) {
         const float4 o = red[g2 * kBlockQ + row];
         sum_s += o.x;
         sum_g += o.y;
