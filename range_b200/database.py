@@ -129,5 +129,35 @@ class DeviceDatabase:
         self.xyz[:M, :3] = torch.from_numpy(np.ascontiguousarray(xyz)).to(dev)
         self.caps = torch.from_numpy(tile_caps(xyz)).to(dev) if self.order is not None else None
 
+    # ---- device-resident format on disk: skips normalisation / sorting / transposition at start-up
+    CACHE_VERSION = 1
+
+    def save_cache(self, path):
+        """write the prepared layout (fp16 keys / transposed values, xyz, tile caps, row order) as an .npz"""
+        np.savez(path, version=self.CACHE_VERSION, M=self.M, Mpad=self.Mpad, M_total=self.M_total,
+                 row_range=np.asarray(self.row_range), vscale=self.vscale,
+                 Kh=self.Kh.cpu().numpy(), Vt=self.Vt.cpu().numpy(), xyz=self.xyz.cpu().numpy(),
+                 caps=np.zeros((0, 4), np.float32) if self.caps is None else self.caps.cpu().numpy(),
+                 order=np.zeros(0, np.int64) if self.order is None else self.order)
+
+    @classmethod
+    def from_cache(cls, path, device):
+        z = np.load(path)
+        if int(z["version"]) != cls.CACHE_VERSION:
+            raise ValueError(f"{path}: database cache version {int(z['version'])}, expected {cls.CACHE_VERSION}")
+        self = cls.__new__(cls)
+        dev = torch.device(device)
+        self.M, self.Mpad, self.M_total = int(z["M"]), int(z["Mpad"]), int(z["M_total"])
+        self.row_range = tuple(int(v) for v in z["row_range"])
+        self.vscale = float(z["vscale"])
+        self.Kh = torch.from_numpy(z["Kh"]).to(dev)
+        self.Vt = torch.from_numpy(z["Vt"]).to(dev)
+        self.xyz = torch.from_numpy(z["xyz"]).to(dev)
+        self.caps = torch.from_numpy(z["caps"]).to(dev) if z["caps"].shape[0] else None
+        self.order = z["order"] if z["order"].shape[0] else None
+        if self.Kh.shape != (self.Mpad, 256) or self.Vt.shape != (1024, self.Mpad) or self.Kh.dtype != torch.float16:
+            raise ValueError(f"{path}: malformed database cache")
+        return self
+
     def nbytes(self):
         return sum(t.numel() * t.element_size() for t in (self.Kh, self.Vt, self.xyz))

@@ -15,7 +15,8 @@ def load_model(model_name='RANGE+', pretrained_path=None, device='cuda', **kwarg
       * names containing 'RANGE' need `db_path`                         (load_model.py:33-35)
       * `beta` defaults to 0.5                                          (load_model.py:37-40)
     Extra, optional keywords (not in the reference): `chunk` (queries per pipelined chunk),
-    `db_shard=(rank, world)` + `db_group` (torch.distributed group) for an M-sharded database.
+    `db_shard=(rank, world)` + `db_group` (torch.distributed group) for an M-sharded database, `db_cache` (path
+    of the prepared device layout: written on first use, read afterwards).
     """
     if pretrained_path is None:
         raise ValueError("Please provide the pretrained model path.")
@@ -27,7 +28,7 @@ def load_model(model_name='RANGE+', pretrained_path=None, device='cuda', **kwarg
         raise NotImplementedError(f"{model_name}: range_b200 implements the RANGE and RANGE+ encoders only")
     args = Namespace(location_model_name=model_name, pretrained_path=pretrained_path, device=device,
                      range_db=db_path, beta=beta)
-    for k in ('chunk', 'db_shard', 'db_group'):
+    for k in ('chunk', 'db_shard', 'db_group', 'db_cache', 'tail', 'super_batch'):
         if k in kwargs:
             setattr(args, k, kwargs[k])
     model = LocationEncoder(args)

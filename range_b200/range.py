@@ -40,7 +40,15 @@ class LocationEncoder(nn.Module):
         enc = load_satclip_location_encoder(args.pretrained_path) if isinstance(args.pretrained_path, str) \
             else args.pretrained_path
         self.location_feature_dim = 1024 + 256                                             # range.py:86
-        self.engine = RangeEngine(args.device, encoder=enc, database=DeviceDatabase(db, args.device, shard=shard))
+        cache = getattr(args, 'db_cache', None)        # optional: prepared device layout on disk (database.py)
+        import os
+        if cache is not None and os.path.exists(cache):
+            ddb = DeviceDatabase.from_cache(cache, args.device)
+        else:
+            ddb = DeviceDatabase(db, args.device, shard=shard)
+            if cache is not None:
+                ddb.save_cache(cache)
+        self.engine = RangeEngine(args.device, encoder=enc, database=ddb)
         self.chunk = int(getattr(args, 'chunk', DEFAULT_CHUNK))
         self.tail = max(1, min(self.chunk, int(getattr(args, 'tail', DEFAULT_TAIL))))
         self.super_batch = max(self.chunk, int(getattr(args, 'super_batch', 1 << 20)) // self.chunk * self.chunk)
@@ -75,6 +83,22 @@ class LocationEncoder(nn.Module):
             coords, perm = eng.sort_queries(coords)
         q64, q16, qxyz = eng.encode(coords)
         return eng.concat(self._retrieve(q16, qxyz), q64, out=out, dtype=out_dtype, perm=perm)
+
+    @torch.no_grad()
+    def embed_sweep(self, coords, betas, out_dtype=torch.float32):
+        """RANGE+ for several beta on the same queries (multi-resolution use, Readme.md:27-31): the encoder and the
+        statistics pass do not depend on beta and run once; each beta costs one apply pass.  Returns a list of
+        (N,1280) device tensors."""
+        if self.location_model_name != 'RANGE+' or self.group is not None:
+            raise NotImplementedError('embed_sweep: RANGE+ with an unsharded database')
+        eng, a = self.engine, self.args
+        perm = None
+        if self._sorts():
+            coords, perm = eng.sort_queries(coords)
+        q64, q16, qxyz = eng.encode(coords)
+        sums, maxs = eng.retrieve_stats('RANGE+', q16, qxyz, a.temp, a.geo_temp)
+        return [eng.concat(eng.retrieve_apply('RANGE+', q16, qxyz, a.temp, a.geo_temp, float(b), sums, maxs), q64,
+                           dtype=out_dtype, perm=perm) for b in betas]
 
     @staticmethod
     def _chunks(N, chunk, tail):

@@ -305,3 +305,26 @@ def test_large_batch_tiny_database(N, M, sh_entries):
     ref = P @ V
     rel = ((out - ref).norm(dim=1) / ref.norm(dim=1))
     assert torch.isfinite(out).all() and rel.max().item() <= 2e-3, rel.max().item()
+
+
+def test_beta_sweep_and_database_cache(tmp_path, sh_entries):
+    """embed_sweep (statistics shared across beta) == one model per beta; the on-disk device layout round-trips"""
+    from argparse import Namespace
+    from range_b200.range import LocationEncoder
+    db = O.synthetic_db(4000, seed=8, kind="iid")
+    ws = O.siren_init(40, 64, 2, 256, seed=4)
+    enc = dict(L=40, dims=[1600, 64, 64, 256], weights=ws)
+    c = torch.tensor(O.area_uniform(700, np.random.default_rng(5)), device=DEV)
+    cache = str(tmp_path / "db_layout.npz")
+    mk = lambda beta, **kw: LocationEncoder(Namespace(location_model_name="RANGE+", pretrained_path=enc, device=DEV,
+                                                      range_db=db, beta=beta, **kw))
+    m = mk(0.5, db_cache=cache)                   # builds and writes the cache
+    betas = [0.0, 0.25, 0.5, 0.75, 1.0]
+    sweep = m.embed_sweep(c, betas)
+    for beta, got in zip(betas, sweep):
+        one = mk(beta, db_cache=cache).embed(c)   # reads the cache
+        assert torch.equal(got, one), beta
+    ref = O.RangeOracle("RANGE+", ws, sh_entries, db, beta=0.25, exact=True)(c.cpu().numpy())
+    assert rel_rows(sweep[1][:, :1024].cpu().numpy(), ref[:, :1024]).max() <= 2e-3
+    fresh = mk(0.25).embed(c)
+    assert torch.equal(fresh, sweep[1])

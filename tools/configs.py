@@ -69,9 +69,17 @@ if "2" in which or "3" in which:
     for beta in ([0.5] if "3" not in which else [0.0, 0.25, 0.5, 0.75, 1.0]):
         m = model_for(db, beta)
         t = timed(lambda: run_chunks(m, coords, out), reps=1)
-        emit(config="C3 beta sweep", beta=beta, queries=N, M=100_000, n_gpus=world, seconds=t, queries_per_s=N / t,
-             parallelism=f"query-sharded x{world}")
-        del m
+        emit(config="C3 beta sweep, one pass per beta", beta=beta, queries=N, M=100_000, n_gpus=world, seconds=t,
+             queries_per_s=N / t, parallelism=f"query-sharded x{world}")
+    if "3" in which:                  # all five beta in one call: encoder + statistics shared, five apply passes
+        betas = [0.0, 0.25, 0.5, 0.75, 1.0]
+        def sweep():
+            for lo in range(0, coords.shape[0], CHUNK):
+                m.embed_sweep(coords[lo:lo + CHUNK], betas)
+        t = timed(sweep, reps=1)
+        emit(config="C3 beta sweep, embed_sweep (shared statistics)", betas=betas, queries=N, M=100_000, n_gpus=world,
+             seconds=t, embeddings_per_s=N * len(betas) / t, parallelism=f"query-sharded x{world}")
+    del m
 
 if "4" in which:
     N = 100_000
