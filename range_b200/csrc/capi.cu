@@ -117,7 +117,7 @@ struct RetrievalPlan {
   int mask_rows, mask_words;                // geo-skip mask: [even-padded query tiles][ceil(tiles / 32)]
   bool pc;                                  // apply with the producer/consumer kernel (retrieval_pc.cu)
   bool stats_pc;                            // statistics with the CTA-pair / four-group kernel (retrieval_pc.cu)
-  size_t off_part_sum, off_part_max, off_sums, off_maxs, off_rowc, off_mask, off_ring, off_flags, off_part_out, total;
+  size_t off_part_sum, off_part_max, off_sums, off_maxs, off_rowc, off_mask, off_ring, off_flags, off_pc_part, off_part_out, total;
 };
 
 // 0 = choose by batch size, 1 = always the single-role CTA-pair kernel, 2 = producer/consumer whenever possible
@@ -183,6 +183,7 @@ RetrievalPlan plan_retrieval(const range_ctx* c, int64_t N) {
   p.pc = units > 0 && p.splits == 1 && ov != 1 && (ov == 2 || qpairs >= 2 * units);
   p.off_ring = o;     o += p.pc ? align_up(apply_pc_ring_bytes(c->sm_count), 1024) : 0;
   p.off_flags = o;    o += p.pc ? align_up(apply_pc_flag_bytes(c->sm_count, N, c->M), 256) : 0;
+  p.off_pc_part = o;  o += p.pc ? align_up(apply_pc_part_bytes(c->sm_count, N, c->M), 256) : 0;
   p.off_part_out = o; o += p.splits > 1 ? align_up(size_t(p.splits) * N * kDimV * 4, 256) : 0;
   p.total = o;
   return p;
@@ -563,8 +564,8 @@ int range_retrieve_apply(range_ctx* c, int mode, int64_t N, const void* q16, con
     void* ring = ws + p.off_ring;
     r = make_tmap_rows2k(&tmP, ring, uint64_t(apply_pc_ring_rows(c->sm_count)));
     if (r) return r;
-    CUDA_TRY(launch_apply_pc(a, tmP, rowc, O, ring, ws + p.off_flags, c->sm_count, s));
-    g_launches += 2;
+    CUDA_TRY(launch_apply_pc(a, tmP, rowc, O, ring, ws + p.off_flags, ws + p.off_pc_part, c->sm_count, s));
+    g_launches += 2 + (apply_pc_part_bytes(c->sm_count, N, c->M) > 0);
     return RANGE_OK;
   }
   CUDA_TRY(launch_apply(a, rowc, part_out, stride, s));

@@ -77,19 +77,41 @@ sh_rowmajor_kernel(const double* __restrict__ lonlat, int N, int L, const double
       spow *= s;
       sincos(double(am) * phi, &sm, &cm);
     }
-    for (int l = am; l < L; ++l, ++e) {
+    // Horner chains of consecutive degrees l = am + 2k, am + 2k + 1 have the same length (k + 1 terms): two
+    // independent chains per iteration hide the fp64 FMA and table-load latency (a thread owns a whole query)
+    auto finish = [&](double acc, int ee) {
+      if (__ldg(par + ee)) acc *= c;
+      if (am == 0) {
+        emit(acc);
+      } else {
+        const double leg = (__ldg(pref + ee) * spow) * acc;
+        emit(leg * cm);
+        emit(leg * sm);
+      }
+    };
+    int l = am;
+    for (; l + 1 < L; l += 2, e += 2) {
+      int k0 = __ldg(off + e);
+      int k1 = __ldg(off + e + 1);
+      const int n0 = k1 - k0, n1 = __ldg(off + e + 2) - k1;
+      double a0 = __ldg(coef + k0), a1 = __ldg(coef + k1);
+      const int nmin = min(n0, n1);
+      for (int t = 1; t < nmin; ++t) {
+        a0 = fma(a0, c2, __ldg(coef + k0 + t));
+        a1 = fma(a1, c2, __ldg(coef + k1 + t));
+      }
+      for (int t = nmin; t < n0; ++t) a0 = fma(a0, c2, __ldg(coef + k0 + t));
+      for (int t = nmin; t < n1; ++t) a1 = fma(a1, c2, __ldg(coef + k1 + t));
+      finish(a0, e);
+      finish(a1, e + 1);
+    }
+    if (l < L) {
       int k = __ldg(off + e);
       const int kend = __ldg(off + e + 1);
       double acc = __ldg(coef + k);
       for (++k; k < kend; ++k) acc = fma(acc, c2, __ldg(coef + k));
-      if (__ldg(par + e)) acc *= c;
-      if (am == 0) {
-        emit(acc);
-      } else {
-        const double leg = (__ldg(pref + e) * spow) * acc;
-        emit(leg * cm);
-        emit(leg * sm);
-      }
+      finish(acc, e);
+      ++e;
     }
   }
 }

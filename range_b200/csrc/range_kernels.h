@@ -88,8 +88,9 @@ int apply_pc_units(int sm_count);
 size_t apply_pc_ring_bytes(int sm_count);
 size_t apply_pc_flag_bytes(int sm_count, int64_t N, int64_t M);
 int apply_pc_ring_rows(int sm_count);          // ring as a 2-D tensor [rows][2 KB]
+size_t apply_pc_part_bytes(int sm_count, int64_t N, int64_t M);   // partial outputs of the split tail pairs
 cudaError_t launch_apply_pc(const RetrievalArgs& a, const CUtensorMap& tmP, const float* rowc, float* out, void* ring,
-                            void* flags, int sm_count, cudaStream_t s);
+                            void* flags, void* part, int sm_count, cudaStream_t s);
 // statistics pass with the producer's structure (retrieval_pc.cu); same partials as launch_stats
 cudaError_t launch_stats_pc(const RetrievalArgs& a, float* part_sum, float* part_max, cudaStream_t s);
 cudaError_t launch_reduce_out(const float* part, size_t split_stride, int splits, size_t total, float* out,

@@ -125,14 +125,36 @@ struct PipeState {
   }
 };
 
+// Work decomposition.  Unit u handles query-tile pair r * n_units + u in round r < full_rounds (whole database,
+// output written directly).  The remaining tail_pairs pairs would keep only tail_pairs of the units busy for a
+// whole round, so each of them is split over tail_split database ranges of tail_tiles tiles: tail_pairs *
+// tail_split units work for 1 / tail_split of a round and write partial outputs that the host sums.
+struct PcPlan {
+  int n_units, full_rounds, tail_pairs, tail_split, tail_tiles;
+  int tail_row0;              // first query row of the tail pairs
+  size_t part_stride;         // floats between the partial outputs of two splits
+};
+struct PcWork {
+  int qp, t0, t1, split;      // query-tile pair, database tiles [t0, t1), split index or -1 (direct output)
+};
+__device__ __forceinline__ int pc_rounds(const PcPlan& p, int unit) {
+  return p.full_rounds + (unit < p.tail_pairs * p.tail_split ? 1 : 0);
+}
+__device__ __forceinline__ PcWork pc_work(const PcPlan& p, int unit, int r, int T) {
+  if (r < p.full_rounds) return PcWork{r * p.n_units + unit, 0, T, -1};
+  const int s = unit % p.tail_split;
+  const int t0 = s * p.tail_tiles;
+  return PcWork{p.full_rounds * p.n_units + unit / p.tail_split, t0, min(T, t0 + p.tail_tiles), p.tail_split > 1 ? s : -1};
+}
+
 template <bool kGeo>
 __global__ void __launch_bounds__(kThreads, 1)
 range_apply_pc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK64,
                       const __grid_constant__ CUtensorMap tmV128, const __grid_constant__ CUtensorMap tmP,
                       const float4* __restrict__ db_xyz, const float4* __restrict__ rowc, int N, int M, float a_sem,
                       float* __restrict__ out, const uint32_t* __restrict__ geo_mask, int mask_words,
-                      __half* __restrict__ ring, uint32_t* __restrict__ flags, uint32_t* __restrict__ windows,
-                      int n_units, int dbg, long long* __restrict__ prof) {
+                      float* __restrict__ part, __half* __restrict__ ring, uint32_t* __restrict__ flags,
+                      uint32_t* __restrict__ windows, const PcPlan plan, int dbg, long long* __restrict__ prof) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -146,13 +168,19 @@ range_apply_pc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   const bool leader = rank == 0;
   const int cid = blockIdx.x >> 1;
   const int unit = cid / 3, role = cid % 3;                 // role 0: producer pair; 1, 2: consumer pairs
+  const int n_units = plan.n_units;
   const bool active = unit < n_units;
   const bool producer = role == 0;
   const int T = (M + kKeys - 1) / kKeys;
-  const int QP = ((N + kBlockQ - 1) / kBlockQ + 1) / 2;     // query-tile pairs
-  const int rounds = active && unit < QP ? (QP - unit + n_units - 1) / n_units : 0;
-  const int sync_units = QP < n_units ? QP : n_units;       // units that have work
-  const int n_windows = int((uint32_t((QP + n_units - 1) / n_units) * uint32_t(T) + kWindow - 1) / kWindow);
+  const int rounds = active ? pc_rounds(plan, unit) : 0;
+  const int tail_items = plan.tail_pairs * plan.tail_split;
+  const int tail_len = tail_items ? (plan.tail_split > 1 ? plan.tail_tiles : T) : 0;       // longest tail item, tiles
+  const int sync_units = plan.full_rounds > 0 ? n_units : tail_items;                       // units that have work
+  const int n_windows = int((uint32_t(plan.full_rounds) * uint32_t(T) + uint32_t(tail_len) + kWindow - 1) / kWindow);
+  // tiles this unit processes over the whole launch (ring positions, `full` / `done` counters count these)
+  const uint32_t my_tiles = uint32_t(plan.full_rounds) * uint32_t(T) +
+                            (rounds > plan.full_rounds ? uint32_t(pc_work(plan, unit, plan.full_rounds, T).t1 -
+                                                                  pc_work(plan, unit, plan.full_rounds, T).t0) : 0u);
   const int prod_id = unit * 2 + int(rank);                 // the producer CTA this CTA is / listens to
   uint32_t* full_flag = flags + size_t(prod_id) * kFlagsPerProducer;
 
@@ -213,12 +241,13 @@ range_apply_pc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         PipeState st;
         uint32_t it = 0;
         for (int r = 0; r < rounds; ++r) {
-          const int qt = 2 * (unit + r * n_units) + int(rank);
+          const PcWork wk = pc_work(plan, unit, r, T);
+          const int qt = 2 * wk.qp + int(rank);
           if (r > 0) ptx::mbar_wait(&bars[L::b_q_empty], (r - 1) & 1);        // every Q.K^T of the last round has read Q
           ptx::mbar_expect_tx(&bars[L::b_q_full], 65536);
           for (int c = 0; c < 4; ++c)
             ptx::tma_load_2d(smem + L::q + c * 16384, &tmQ, &bars[L::b_q_full], c * 64, qt * kBlockQ);
-          for (int j = 0; j < T; ++j, ++it) {
+          for (int j = wk.t0; j < wk.t1; ++j, ++it) {
             const int key0 = j * kKeys;
             if (leader && (it % kWindow) == 0) {
               // Keep the units within two windows of each other: they all stream the same database, and only tiles
@@ -248,9 +277,10 @@ range_apply_pc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       if (kGeo && lane == 0) {
         uint32_t it = 0;
         for (int r = 0; r < rounds; ++r) {
-          const int qt = 2 * (unit + r * n_units) + int(rank);
+          const PcWork wk = pc_work(plan, unit, r, T);
+          const int qt = 2 * wk.qp + int(rank);
           const uint32_t* mask_row = geo_mask ? geo_mask + size_t(qt) * mask_words : nullptr;
-          for (int j = 0; j < T; ++j, ++it) {
+          for (int j = wk.t0; j < wk.t1; ++j, ++it) {
             const int x = it & (L::NB - 1);
             PC_T0();
             ptx::mbar_wait(&bars[L::b_xyz_empty + x], ((it / L::NB) & 1) ^ 1);
@@ -275,7 +305,8 @@ range_apply_pc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         __syncwarp();
         if (!leader) continue;
         ptx::mbar_wait_cluster(&bars[L::b_q_pair], r & 1);
-        for (int j = 0; j < T; ++j, ++it) {
+        const PcWork wk = pc_work(plan, unit, r, T);
+        for (int j = wk.t0; j < wk.t1; ++j, ++it) {
           const int b = it & (L::NB - 1);
           PC_T0();
           ptx::mbar_wait_cluster(&bars[L::b_s_empty + b], ((it / L::NB) & 1) ^ 1);   // S(it - 4) is in registers
@@ -310,7 +341,7 @@ range_apply_pc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       //            costs ~1500 clk here (every store the SM has in flight must be acknowledged), so tiles are
       //            published in batches of kPublishBatch; the ring absorbs the added latency.
       if (lane == 0) {
-        const uint32_t total = uint32_t(rounds) * uint32_t(T);
+        const uint32_t total = my_tiles;
         uint32_t pub = 0, gate = 0, seen = 0, spins = 0;
         while (pub < total || gate < total) {
           bool progress = false;
@@ -348,17 +379,19 @@ range_apply_pc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       const uint32_t s_empty_leader0 = ptx::mapa(ptx::smem_u32(&bars[L::b_s_empty]), 0);
       // slot s of this producer: ring + (prod_id * kRing + s) * 128 * 128 halves, laid out [16 key chunks][128 rows][8]
       __half* ring_row = ring + size_t(prod_id) * kRing * 128 * 128 + row * 8;
-      const uint32_t total = uint32_t(rounds) * uint32_t(T);
-      int cur_r = -1, n = 0;
+      const uint32_t total = my_tiles, base_tail = uint32_t(plan.full_rounds) * uint32_t(T);
+      int cur_r = -1, n = 0, tail_t0 = 0;
       const uint32_t* mask_row = nullptr;
       float cs = -INFINITY, cg = -INFINITY, gx = 0.f, gy = 0.f, gz = 0.f;
       for (uint32_t it = uint32_t(grp); it < total; it += kGroups) {
-        const int r = int(it / uint32_t(T)), j = int(it - uint32_t(r) * uint32_t(T));
+        const int r = it < base_tail ? int(it / uint32_t(T)) : plan.full_rounds;
         const int b = it & (L::NB - 1);
         const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + b * kKeys;
         if (r != cur_r) {
           cur_r = r;
-          const int qt = 2 * (unit + r * n_units) + int(rank);
+          const PcWork wk = pc_work(plan, unit, r, T);
+          tail_t0 = wk.t0;
+          const int qt = 2 * wk.qp + int(rank);
           n = qt * kBlockQ + row;
           mask_row = (kGeo && geo_mask) ? geo_mask + size_t(qt) * mask_words : nullptr;
           cs = -INFINITY; cg = -INFINITY; gx = gy = gz = 0.f;
@@ -367,6 +400,7 @@ range_apply_pc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
             cs = c0.x; cg = c0.y; gx = c0.z; gy = c0.w; gz = c1.x;
           }
         }
+        const int j = it < base_tail ? int(it - uint32_t(r) * uint32_t(T)) : tail_t0 + int(it - base_tail);   // database tile
         const int slot = it % kRing;
         const bool with_geo = kGeo && !(mask_row != nullptr && ((__ldg(mask_row + (j >> 5)) >> (j & 31)) & 1u));
         __half* dst = ring_row + size_t(slot) * 128 * 128;
@@ -459,7 +493,8 @@ range_apply_pc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         ptx::prefetch_tmap(&tmV128);
         PipeState st;
         for (int r = 0; r < rounds; ++r) {
-          for (int j = 0; j < T; ++j) {
+          const PcWork wk = pc_work(plan, unit, r, T);
+          for (int j = wk.t0; j < wk.t1; ++j) {
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
               const int key0 = j * kKeys + half * 64;
@@ -483,9 +518,9 @@ range_apply_pc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       if (lane == 0) {
         ptx::prefetch_tmap(&tmP);
         PipeState st;
-        uint32_t it = 0, seen = 0;
-        for (int r = 0; r < rounds; ++r) {
-          for (int j = 0; j < T; ++j, ++it) {
+        uint32_t seen = 0;
+        {
+          for (uint32_t it = 0; it < my_tiles; ++it) {
             const int slot = it % kRing;
             PC_T0();
             if (seen < it + 1 && !(dbg & 1)) {               // the counter advances in batches: one poll + proxy fence per batch
@@ -526,7 +561,8 @@ range_apply_pc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
             ptx::mbar_wait_cluster(&bars[L::b_o_empty], (r - 1) & 1);     // both epilogues have read O
             ptx::tc_fence_after();
           }
-          for (int j = 0; j < T; ++j, ++it) {
+          const PcWork wk = pc_work(plan, unit, r, T);
+          for (int j = 0; j < wk.t1 - wk.t0; ++j, ++it) {
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
               PC_T0();
@@ -572,12 +608,15 @@ range_apply_pc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       const int row = quarter * 32 + lane;
       const uint32_t o_empty_leader = ptx::mapa(ptx::smem_u32(&bars[L::b_o_empty]), 0);
       for (int r = 0; r < rounds; ++r) {
-        const int qt = 2 * (unit + r * n_units) + int(rank);
+        const PcWork wk = pc_work(plan, unit, r, T);
+        const int qt = 2 * wk.qp + int(rank);
         const int n = qt * kBlockQ + row;
         const float out_scale = n < N ? rowc[2 * n + 1].y : 0.f;
         ptx::mbar_wait(&bars[L::b_o_full], r & 1);
         ptx::tc_fence_after();
-        float* orow = out + size_t(n) * 1024 + dimbase;
+        // whole database: the final rows; one range of a split tail pair: that split's partial rows (summed by the host)
+        float* orow = (wk.split < 0 ? out + size_t(n) * 1024
+                                    : part + size_t(wk.split) * plan.part_stride + size_t(n - plan.tail_row0) * 1024) + dimbase;
 #pragma unroll 1
         for (int cc = 0; cc < 16; ++cc) {
           uint32_t v[32];
@@ -847,19 +886,45 @@ extern long long* g_prof_buffer;      // retrieval.cu (developer instrumentation
 
 int apply_pc_units(int sm_count) { return (sm_count / 2) / 3; }
 size_t apply_pc_ring_bytes(int sm_count) { return size_t(apply_pc_units(sm_count)) * 2 * kRing * 128 * 128 * 2; }
-static size_t pc_window_count(int sm_count, int64_t N, int64_t M) {
-  const int64_t units = apply_pc_units(sm_count), qp = ((N + kBlockQ - 1) / kBlockQ + 1) / 2, T = (M + kKeys - 1) / kKeys;
-  return size_t(((qp + units - 1) / units * T + kWindow - 1) / kWindow + 1);
+int apply_pc_ring_rows(int sm_count) { return apply_pc_units(sm_count) * 2 * kRing * 16; }   // rows of 2 KB
+
+static PcPlan pc_plan(int sm_count, int64_t N, int64_t M) {
+  PcPlan p{};
+  const int64_t qp = ((N + kBlockQ - 1) / kBlockQ + 1) / 2, T = (M + kKeys - 1) / kKeys;
+  p.n_units = apply_pc_units(sm_count);
+  p.full_rounds = int(qp / p.n_units);
+  p.tail_pairs = int(qp % p.n_units);
+  p.tail_split = 1;
+  if (p.tail_pairs > 0) {          // spread the leftover pairs over the idle units, >= 32 tiles per range, <= 4 ranges
+    int k = p.n_units / p.tail_pairs;
+    if (k > 4) k = 4;
+    while (k > 1 && T / k < 32) --k;
+    p.tail_split = k < 1 ? 1 : k;
+  }
+  p.tail_tiles = int((T + p.tail_split - 1) / p.tail_split);
+  p.tail_row0 = p.full_rounds * p.n_units * 2 * kBlockQ;
+  const int64_t tail_rows = N - p.tail_row0 > 0 ? N - p.tail_row0 : 0;
+  p.part_stride = size_t(tail_rows) * 1024;
+  return p;
+}
+static size_t pc_window_count(const PcPlan& p, int64_t M) {
+  const int64_t T = (M + kKeys - 1) / kKeys;
+  const int64_t tail_len = p.tail_pairs ? (p.tail_split > 1 ? p.tail_tiles : T) : 0;
+  return size_t((int64_t(p.full_rounds) * T + tail_len + kWindow - 1) / kWindow + 1);
 }
 static size_t pc_ring_flag_bytes(int sm_count) { return size_t(apply_pc_units(sm_count)) * 2 * kFlagsPerProducer * 4; }
 size_t apply_pc_flag_bytes(int sm_count, int64_t N, int64_t M) {
-  return pc_ring_flag_bytes(sm_count) + pc_window_count(sm_count, N, M) * 4;
+  return pc_ring_flag_bytes(sm_count) + pc_window_count(pc_plan(sm_count, N, M), M) * 4;
 }
-int apply_pc_ring_rows(int sm_count) { return apply_pc_units(sm_count) * 2 * kRing * 16; }   // rows of 2 KB
+// partial outputs of the split tail pairs: [tail_split][tail rows][1024] fp32 (0 when nothing is split)
+size_t apply_pc_part_bytes(int sm_count, int64_t N, int64_t M) {
+  const PcPlan p = pc_plan(sm_count, N, M);
+  return p.tail_split > 1 ? size_t(p.tail_split) * p.part_stride * 4 : 0;
+}
 
 cudaError_t launch_apply_pc(const RetrievalArgs& a, const CUtensorMap& tmP, const float* rowc, float* out, void* ring,
-                            void* flags, int sm_count, cudaStream_t stream) {
-  const int units = apply_pc_units(sm_count);
+                            void* flags, void* part, int sm_count, cudaStream_t stream) {
+  const PcPlan plan = pc_plan(sm_count, a.N, a.M);
   static const int dbg = getenv("RANGE_PC_DBG") ? atoi(getenv("RANGE_PC_DBG")) : 0;   // developer switch: decouple the roles
   cudaError_t e = cudaMemsetAsync(flags, 0, apply_pc_flag_bytes(sm_count, a.N, a.M), stream);
   if (e != cudaSuccess) return e;
@@ -883,14 +948,20 @@ cudaError_t launch_apply_pc(const RetrievalArgs& a, const CUtensorMap& tmP, cons
   static const bool coop = !(getenv("RANGE_PC_COOP") && atoi(getenv("RANGE_PC_COOP")) == 0);
   cfg.numAttrs = coop ? 2 : 1;
   e = cudaLaunchKernelEx(&cfg, kern, a.tmQ, a.tmK64, a.tmV128, tmP, a.db_xyz, reinterpret_cast<const float4*>(rowc),
-                         a.N, a.M, a.a_sem, out, a.geo_mask, a.mask_words, reinterpret_cast<__half*>(ring),
+                         a.N, a.M, a.a_sem, out, a.geo_mask, a.mask_words, reinterpret_cast<float*>(part),
+                         reinterpret_cast<__half*>(ring),
                          reinterpret_cast<uint32_t*>(flags),
-                         reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(flags) + pc_ring_flag_bytes(sm_count)), units, dbg,
+                         reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(flags) + pc_ring_flag_bytes(sm_count)), plan, dbg,
                          g_prof_buffer);
-  if (e != cudaSuccess)
+  if (e != cudaSuccess) {
     fprintf(stderr, "range_b200: producer/consumer apply launch failed (%s); grid %u smem %d\n", cudaGetErrorString(e),
             cfg.gridDim.x, kDynamicSmem);
-  return e;
+    return e;
+  }
+  if (plan.tail_split > 1)      // sum the partial outputs of the split tail pairs into the last rows of out
+    return launch_reduce_out(reinterpret_cast<const float*>(part), plan.part_stride, plan.tail_split, plan.part_stride,
+                             out + size_t(plan.tail_row0) * 1024, stream);
+  return cudaSuccess;
 }
 
 // stats over pairs of query tiles; grid (2 * ceil(qtiles / 2), splits), cluster (2,1,1)
