@@ -8,10 +8,10 @@ tail -3 gpurun_out/${tag}_pytest.log
 timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err; echo "bench exit $?"
 cat gpurun_out/${tag}_bench.json
 timeout 300 python tools/time_apply.py > gpurun_out/${tag}_time_apply.log 2>&1; cat gpurun_out/${tag}_time_apply.log | tail -3
-RANGE_PC_COOP=0 timeout 300 python tools/time_apply.py 2>&1 | tail -1
+RANGE_PC_COOP=1 timeout 300 python tools/time_apply.py 2>&1 | tail -1
 if [ "${NCU:-1}" = "1" ]; then
-RANGE_PC_COOP=0 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches.csv \
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches.csv \
   python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/${tag}_ncu_bench.log 2>&1; echo "ncu list exit $?"
-RANGE_PC_COOP=0 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'range_(apply_pc|apply_pair|stats)_kernel' -s 6 -c 2 \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'range_(apply_pc|stats_pc)_kernel' -s 4 -c 2 \
   -o gpurun_out/${tag}_k2 -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/${tag}_ncu_full.log 2>&1; echo "ncu full exit $?"
 fi
