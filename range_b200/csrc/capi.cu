@@ -98,7 +98,7 @@ struct range_ctx {
   const void* Vt = nullptr;
   const float* xyz = nullptr;
   float vscale = 1.f;
-  CUtensorMap tmK128, tmV, tmK64, tmV128;
+  CUtensorMap tmK128, tmK64, tmV128;
   const float* caps = nullptr;     // (Mpad / 128, 4) bounding caps of the database tiles, or null
   int64_t M_total = 0;             // entries of the whole (unsharded) database: sets the geo-skip threshold
   // tensor-core encoder (3xTF32): prepared weights live in a caller-provided buffer
@@ -198,7 +198,6 @@ int fill_args(range_ctx* c, int mode, int64_t N, const void* q16, const float* q
   int r = make_tmap(&a->tmQ, q16, uint64_t(N), kDimK, kBlockQ);
   if (r) return r;
   a->tmK128 = c->tmK128;
-  a->tmV = c->tmV;
   a->tmK64 = c->tmK64;
   a->tmV128 = c->tmV128;
   a->q16 = reinterpret_cast<const __half*>(q16);
@@ -297,8 +296,6 @@ int range_ctx_set_db(range_ctx* c, int64_t M, int64_t Mpad, const void* Kh, cons
   if (M > (int64_t(1) << 30)) return fail(RANGE_ERR_UNSUPPORTED, "M too large");
   CUDA_TRY(cudaSetDevice(c->device));
   int r = make_tmap(&c->tmK128, Kh, uint64_t(Mpad), kDimK, 128);
-  if (r) return r;
-  r = make_tmap(&c->tmV, Vt, kDimV, uint64_t(Mpad), 256);
   if (r) return r;
   r = make_tmap(&c->tmK64, Kh, uint64_t(Mpad), kDimK, 64);
   if (r) return r;

@@ -55,7 +55,6 @@ cudaError_t launch_sort_queries(const double* lonlat, int N, double* lonlat_sort
 struct RetrievalArgs {
   CUtensorMap tmQ;      // queries, box [128 rows x 64 dims]
   CUtensorMap tmK128;   // keys, box [128 entries x 64 dims]
-  CUtensorMap tmV;      // values^T, box [256 dims x 64 entries]
   CUtensorMap tmK64;    // keys, box [64 entries x 64 dims]          (CTA-pair kernel: half a K tile per CTA)
   CUtensorMap tmV128;   // values^T, box [128 dims x 64 entries]    (CTA-pair kernel: half a Vt tile per CTA)
   const __half* q16;
