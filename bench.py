@@ -181,7 +181,6 @@ def main():
     q64 = torch.empty(N_QUERIES, 256, dtype=torch.float64, device=dev)
     q16 = torch.empty(N_QUERIES, 256, dtype=torch.float16, device=dev)
     qxyz = torch.empty(N_QUERIES, 4, dtype=torch.float32, device=dev)
-    O = torch.empty(N_QUERIES, 1024, dtype=torch.float32, device=dev)
 
     marks = []
 
@@ -194,11 +193,10 @@ def main():
         if record: ev[1].record()
         sums, maxs = eng.retrieve_stats("RANGE+", q16, qxyz, 12.0, 40.0)
         if record: ev[2].record()
-        eng.retrieve_apply("RANGE+", q16, qxyz, 12.0, 40.0, BETA, sums, maxs, O)
-        if record: ev[3].record()
-        eng.concat(O, q64, out=out, perm=perm)
+        # apply pass: its epilogue writes the (N,1280) result (rows back in the caller's order); then the location columns
+        eng.retrieve_apply_concat("RANGE+", q16, qxyz, 12.0, 40.0, BETA, sums, maxs, q64, out=out, perm=perm)
         if record:
-            ev[4].record()
+            ev[3].record()
             marks.append(ev)
 
     def barrier():
@@ -221,8 +219,8 @@ def main():
         clocks.mark_end()
     launches = _lib.launch_count() - launches0
     ms = t0.elapsed_time(t1)
-    seg = np.array([[e[i].elapsed_time(e[i + 1]) for i in range(4)] + [e[5].elapsed_time(e[0])]
-                    for e in marks]).mean(0)                                   # enc, stats, apply, cat, sort
+    seg = np.array([[e[i].elapsed_time(e[i + 1]) for i in range(3)] + [0.0, e[5].elapsed_time(e[0])]
+                    for e in marks]).mean(0)                                   # enc, stats, apply+concat, -, sort
 
     # e2e through the public API: pinned host coords -> numpy float64 (N,1280)
     for _ in range(3):
@@ -252,7 +250,7 @@ def main():
             "config": {"workload": f"RANGE+ beta={BETA}, {N_QUERIES} queries/GPU x M={M_DB} (range_db_large shape), "
                                    f"SatCLIP-L40 H={H} random-init", "parallelism": f"query-sharded x{world}, DB replicated",
                        "l2": "inputs larger than L2 (DB 257 MB fp16 streamed every step; 512 MB output)",
-                       "segments_ms": {"sort_queries": seg[4], "encode": seg[0], "retrieve_stats": seg[1], "retrieve_apply": seg[2], "concat": seg[3]}},
+                       "segments_ms": {"sort_queries": seg[4], "encode": seg[0], "retrieve_stats": seg[1], "retrieve_apply_concat": seg[2]}},
             # dominant kernel = the apply pass (all 2566 algorithmic flop per pair live there); the stats pass that
             # precedes it is algorithmically redundant work, so the stricter figure over both kernels is given too
             "roofline": {"bound": "tensor", "kernel": "range_apply_pc_kernel (K2b: Q.K^T + softmax blend + P.V)",

@@ -125,6 +125,16 @@ int range_retrieve_apply(range_ctx* ctx, int mode, int64_t N, const void* q16, c
 int range_retrieve(range_ctx* ctx, int mode, int64_t N, const void* q16, const float* qxyz, float temp,
                    float geo_temp, float beta, float* O, void* workspace, size_t workspace_bytes, void* stream);
 
+/* K2 apply + K3 in one call: this shard-less variant writes the retrieved feature straight into the caller's
+ * (N,1280) result - row n to out row perm[n] (perm from range_sort_queries, NULL = identity), as fp64
+ * (RANGE_OUT_F64, what range/range.py:222,240 returns) or fp32 - followed by the location columns q64.  For
+ * large batches the apply kernel's epilogue does the concat itself (no (N,1024) intermediate); small batches run
+ * apply + range_concat_scatter internally. */
+int range_retrieve_apply_concat(range_ctx* ctx, int mode, int64_t N, const void* q16, const float* qxyz, float temp,
+                                float geo_temp, float beta, const float* sums, const float* maxs, const double* q64,
+                                const int32_t* perm, void* out, int out_dtype, void* workspace, size_t workspace_bytes,
+                                void* stream);
+
 /* K3: out (N,1280) = [O | q64] as fp64 (RANGE_OUT_F64, what the reference returns: range/range.py:222,240)
  * or fp32. */
 int range_concat(range_ctx* ctx, int64_t N, const float* O, const double* q64, void* out, int out_dtype,

@@ -41,6 +41,9 @@ PROTOTYPES = {
                                      c_void_p, c_void_p, c_size_t, c_void_p]),
     "range_retrieve_apply": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_float, c_float, c_float,
                                      c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "range_retrieve_apply_concat": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_float, c_float, c_float,
+                                            c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_size_t,
+                                            c_void_p]),
     "range_retrieve": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_float, c_float, c_float, c_void_p,
                                c_void_p, c_size_t, c_void_p]),
     "range_concat": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),

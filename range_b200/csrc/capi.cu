@@ -117,7 +117,7 @@ struct RetrievalPlan {
   int mask_rows, mask_words;                // geo-skip mask: [even-padded query tiles][ceil(tiles / 32)]
   bool pc;                                  // apply with the producer/consumer kernel (retrieval_pc.cu)
   bool stats_pc;                            // statistics with the CTA-pair / four-group kernel (retrieval_pc.cu)
-  size_t off_part_sum, off_part_max, off_sums, off_maxs, off_rowc, off_mask, off_ring, off_flags, off_pc_part, off_part_out, total;
+  size_t off_part_sum, off_part_max, off_sums, off_maxs, off_rowc, off_mask, off_ring, off_flags, off_pc_part, off_part_out, off_O, total;
 };
 
 // 0 = choose by batch size, 1 = always the single-role CTA-pair kernel, 2 = producer/consumer whenever possible
@@ -185,6 +185,7 @@ RetrievalPlan plan_retrieval(const range_ctx* c, int64_t N) {
   p.off_flags = o;    o += p.pc ? align_up(apply_pc_flag_bytes(c->sm_count, N, c->M), 256) : 0;
   p.off_pc_part = o;  o += p.pc ? align_up(apply_pc_part_bytes(c->sm_count, N, c->M), 256) : 0;
   p.off_part_out = o; o += p.splits > 1 ? align_up(size_t(p.splits) * N * kDimV * 4, 256) : 0;
+  p.off_O = o;        o += p.pc ? 0 : align_up(size_t(N) * kDimV * 4, 256);   // scratch O of range_retrieve_apply_concat (small batches)
   p.total = o;
   return p;
 }
@@ -537,14 +538,17 @@ int range_retrieve_stats(range_ctx* c, int mode, int64_t N, const void* q16, con
   return RANGE_OK;
 }
 
-int range_retrieve_apply(range_ctx* c, int mode, int64_t N, const void* q16, const float* qxyz, float temp,
-                         float geo_temp, float beta, const float* sums, const float* maxs, float* O,
-                         void* workspace, size_t workspace_bytes, void* stream) {
+// apply pass; the result goes either to O (N,1024) fp32 or, fused with the concat of range/range.py:222,240, to the
+// caller's (N,1280) array `out` (rows through `perm`, fp32 or fp64) together with the location columns q64
+static int apply_impl(range_ctx* c, int mode, int64_t N, const void* q16, const float* qxyz, float temp, float geo_temp,
+                      float beta, const float* sums, const float* maxs, float* O, const double* q64, const int32_t* perm,
+                      void* out, int out_dtype, void* workspace, size_t workspace_bytes, void* stream) {
   if (!c || !c->Kh) return fail(RANGE_ERR_INVALID, "database not set");
-  if (!q16 || !qxyz || !sums || !maxs || !O || !workspace) return fail(RANGE_ERR_INVALID, "null argument");
+  if (!q16 || !qxyz || !sums || !maxs || !workspace || (!O && !(out && q64))) return fail(RANGE_ERR_INVALID, "null argument");
   if (N <= 0) return fail(RANGE_ERR_INVALID, "N must be positive");
   if (mode == RANGE_MODE_RANGE_PLUS && !(beta >= 0.f && beta <= 1.f))
     return fail(RANGE_ERR_INVALID, "beta must be in [0,1]");
+  if (out && out_dtype != RANGE_OUT_F64 && out_dtype != RANGE_OUT_F32) return fail(RANGE_ERR_INVALID, "unknown out dtype");
   const RetrievalPlan p = plan_retrieval(c, N);
   if (workspace_bytes < p.total + 256) return fail(RANGE_ERR_WORKSPACE, "retrieve workspace too small");
   RetrievalArgs a;
@@ -554,24 +558,55 @@ int range_retrieve_apply(range_ctx* c, int mode, int64_t N, const void* q16, con
   if (r) return r;
   float* rowc = reinterpret_cast<float*>(ws + p.off_rowc);
   CUDA_TRY(launch_row_constants(sums, maxs, qxyz, int(N), a.geo, beta, a.a_sem, a.a_geo, 1.f / c->vscale, rowc, s));
-  float* part_out = p.splits > 1 ? reinterpret_cast<float*>(ws + p.off_part_out) : O;
   const size_t stride = size_t(N) * kDimV;
+  const int W = kDimV + kDimK;
   if (p.pc) {
     CUtensorMap tmP;
     void* ring = ws + p.off_ring;
     r = make_tmap_rows2k(&tmP, ring, uint64_t(apply_pc_ring_rows(c->sm_count)));
     if (r) return r;
-    CUDA_TRY(launch_apply_pc(a, tmP, rowc, O, ring, ws + p.off_flags, ws + p.off_pc_part, c->sm_count, s));
+    if (out) {      // consumers write straight into the (N,1280) result; the location columns follow
+      CUDA_TRY(launch_apply_pc(a, tmP, rowc, out, W, out_dtype == RANGE_OUT_F64, perm, ring, ws + p.off_flags,
+                               ws + p.off_pc_part, c->sm_count, s));
+      CUDA_TRY(launch_concat_q(q64, int(N), kDimK, perm, out, W, kDimV, out_dtype, s));
+      g_launches += 1;
+    } else {
+      CUDA_TRY(launch_apply_pc(a, tmP, rowc, O, kDimV, 0, nullptr, ring, ws + p.off_flags, ws + p.off_pc_part,
+                               c->sm_count, s));
+    }
     g_launches += 2 + (apply_pc_part_bytes(c->sm_count, N, c->M) > 0);
     return RANGE_OK;
   }
+  float* Odst = O ? O : reinterpret_cast<float*>(ws + p.off_O);
+  float* part_out = p.splits > 1 ? reinterpret_cast<float*>(ws + p.off_part_out) : Odst;
   CUDA_TRY(launch_apply(a, rowc, part_out, stride, s));
   g_launches += 2;
   if (p.splits > 1) {
-    CUDA_TRY(launch_reduce_out(part_out, stride, p.splits, stride, O, s));
+    CUDA_TRY(launch_reduce_out(part_out, stride, p.splits, stride, Odst, s));
+    g_launches += 1;
+  }
+  if (out) {
+    CUDA_TRY(launch_concat(Odst, q64, int(N), kDimV, kDimK, perm, out, out_dtype, s));
     g_launches += 1;
   }
   return RANGE_OK;
+}
+
+int range_retrieve_apply(range_ctx* c, int mode, int64_t N, const void* q16, const float* qxyz, float temp,
+                         float geo_temp, float beta, const float* sums, const float* maxs, float* O,
+                         void* workspace, size_t workspace_bytes, void* stream) {
+  if (!O) return fail(RANGE_ERR_INVALID, "null argument");
+  return apply_impl(c, mode, N, q16, qxyz, temp, geo_temp, beta, sums, maxs, O, nullptr, nullptr, nullptr, 0, workspace,
+                    workspace_bytes, stream);
+}
+
+int range_retrieve_apply_concat(range_ctx* c, int mode, int64_t N, const void* q16, const float* qxyz, float temp,
+                                float geo_temp, float beta, const float* sums, const float* maxs, const double* q64,
+                                const int32_t* perm, void* out, int out_dtype, void* workspace, size_t workspace_bytes,
+                                void* stream) {
+  if (!out || !q64) return fail(RANGE_ERR_INVALID, "null argument");
+  return apply_impl(c, mode, N, q16, qxyz, temp, geo_temp, beta, sums, maxs, nullptr, q64, perm, out, out_dtype, workspace,
+                    workspace_bytes, stream);
 }
 
 int range_retrieve(range_ctx* c, int mode, int64_t N, const void* q16, const float* qxyz, float temp,

@@ -212,6 +212,18 @@ concat_kernel(const float* __restrict__ O, const double* __restrict__ q64, int N
   else reinterpret_cast<float*>(out)[o] = float(v);
 }
 
+__global__ void __launch_bounds__(256)
+concat_q_kernel(const double* __restrict__ q64, int N, int DQ, const int* __restrict__ perm, void* out, int ld, int col0,
+                int dtype) {
+  const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= size_t(N) * DQ) return;
+  const size_t n = i / DQ;
+  const int c = int(i - n * DQ);
+  const size_t o = size_t(perm ? perm[n] : n) * ld + col0 + c;
+  if (dtype == 0) reinterpret_cast<double*>(out)[o] = q64[i];
+  else reinterpret_cast<float*>(out)[o] = float(q64[i]);
+}
+
 }  // namespace
 
 namespace rangeb200 {
@@ -246,6 +258,14 @@ cudaError_t launch_concat(const float* O, const double* q64, int N, int DO, int 
   if (N <= 0) return cudaSuccess;
   const size_t total = size_t(N) * (DO + DQ);
   concat_kernel<<<unsigned((total + 255) / 256), 256, 0, s>>>(O, q64, N, DO, DQ, perm, out, dtype);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_concat_q(const double* q64, int N, int DQ, const int* perm, void* out, int ld, int col0, int dtype,
+                            cudaStream_t s) {
+  if (N <= 0) return cudaSuccess;
+  const size_t total = size_t(N) * DQ;
+  concat_q_kernel<<<unsigned((total + 255) / 256), 256, 0, s>>>(q64, N, DQ, perm, out, ld, col0, dtype);
   return cudaGetLastError();
 }
 

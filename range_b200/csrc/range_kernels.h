@@ -44,6 +44,9 @@ cudaError_t launch_normalize(const double* e, const double* lonlat, int N, int D
 // out[perm ? perm[n] : n] = [O[n][0:DO] | q64[n][0:DQ]]  as fp64 (dtype 0) or fp32 (dtype 1)
 cudaError_t launch_concat(const float* O, const double* q64, int N, int DO, int DQ, const int* perm, void* out,
                           int dtype, cudaStream_t s);
+// only the location columns: out[perm ? perm[n] : n][col0 .. col0 + DQ) = q64[n]  (row length ld)
+cudaError_t launch_concat_q(const double* q64, int N, int DQ, const int* perm, void* out, int ld, int col0, int dtype,
+                            cudaStream_t s);
 
 // ---- spatial batching of the queries (sort.cu) ----------------------------------------------------
 size_t sort_workspace_bytes(int N);
@@ -88,8 +91,10 @@ size_t apply_pc_ring_bytes(int sm_count);
 size_t apply_pc_flag_bytes(int sm_count, int64_t N, int64_t M);
 int apply_pc_ring_rows(int sm_count);          // ring as a 2-D tensor [rows][2 KB]
 size_t apply_pc_part_bytes(int sm_count, int64_t N, int64_t M);   // partial outputs of the split tail pairs
-cudaError_t launch_apply_pc(const RetrievalArgs& a, const CUtensorMap& tmP, const float* rowc, float* out, void* ring,
-                            void* flags, void* part, int sm_count, cudaStream_t s);
+// row n of the result goes to out + (perm ? perm[n] : n) * out_ld (+ column), fp32 or fp64
+cudaError_t launch_apply_pc(const RetrievalArgs& a, const CUtensorMap& tmP, const float* rowc, void* out, int out_ld,
+                            int out_f64, const int* perm, void* ring, void* flags, void* part, int sm_count,
+                            cudaStream_t s);
 // statistics pass with the producer's structure (retrieval_pc.cu); same partials as launch_stats
 cudaError_t launch_stats_pc(const RetrievalArgs& a, float* part_sum, float* part_max, cudaStream_t s);
 cudaError_t launch_reduce_out(const float* part, size_t split_stride, int splits, size_t total, float* out,

@@ -133,6 +133,10 @@ struct PcPlan {
   int n_units, full_rounds, tail_pairs, tail_split, tail_tiles;
   int tail_row0;              // first query row of the tail pairs
   size_t part_stride;         // floats between the partial outputs of two splits
+  // where finished rows go: row n -> out + (perm ? perm[n] : n) * out_ld + column, as fp32 or fp64 (fused concat:
+  // the caller's (N, 1280) result, range/range.py:222,240) - or the plain (N, 1024) fp32 O
+  int out_ld, out_f64;
+  const int* perm;
 };
 struct PcWork {
   int qp, t0, t1, split;      // query-tile pair, database tiles [t0, t1), split index or -1 (direct output)
@@ -152,7 +156,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 range_apply_pc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK64,
                       const __grid_constant__ CUtensorMap tmV128, const __grid_constant__ CUtensorMap tmP,
                       const float4* __restrict__ db_xyz, const float4* __restrict__ rowc, int N, int M, float a_sem,
-                      float* __restrict__ out, const uint32_t* __restrict__ geo_mask, int mask_words,
+                      void* __restrict__ out, const uint32_t* __restrict__ geo_mask, int mask_words,
                       float* __restrict__ part, __half* __restrict__ ring, uint32_t* __restrict__ flags,
                       uint32_t* __restrict__ windows, const PcPlan plan, int dbg, long long* __restrict__ prof) {
   extern __shared__ uint8_t smem_raw[];
@@ -614,23 +618,35 @@ range_apply_pc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         const float out_scale = n < N ? rowc[2 * n + 1].y : 0.f;
         ptx::mbar_wait(&bars[L::b_o_full], r & 1);
         ptx::tc_fence_after();
-        // whole database: the final rows; one range of a split tail pair: that split's partial rows (summed by the host)
-        float* orow = (wk.split < 0 ? out + size_t(n) * 1024
-                                    : part + size_t(wk.split) * plan.part_stride + size_t(n - plan.tail_row0) * 1024) + dimbase;
+        // whole database: the final rows (caller's layout, dtype and row order); one range of a split tail pair: that
+        // split's fp32 partial rows (summed and placed by the host's reduce kernel)
+        const bool direct = wk.split < 0;
+        const size_t drow = direct ? size_t(plan.perm && n < N ? plan.perm[n] : n) * plan.out_ld : 0;
+        float* orow32 = direct ? reinterpret_cast<float*>(out) + drow + dimbase
+                               : part + size_t(wk.split) * plan.part_stride + size_t(n - plan.tail_row0) * 1024 + dimbase;
+        double* orow64 = reinterpret_cast<double*>(out) + drow + dimbase;
+        const bool f64 = direct && plan.out_f64;
 #pragma unroll 1
         for (int cc = 0; cc < 16; ++cc) {
           uint32_t v[32];
           ptx::tmem_ld32(tmem_base + (uint32_t(quarter * 32) << 16) + cc * 32, v);
           ptx::tmem_ld_wait();
           if (n < N) {
+            if (f64) {
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              float4 o;
-              o.x = __uint_as_float(v[i]) * out_scale;
-              o.y = __uint_as_float(v[i + 1]) * out_scale;
-              o.z = __uint_as_float(v[i + 2]) * out_scale;
-              o.w = __uint_as_float(v[i + 3]) * out_scale;
-              *reinterpret_cast<float4*>(orow + cc * 32 + i) = o;
+              for (int i = 0; i < 32; i += 2)
+                *reinterpret_cast<double2*>(orow64 + cc * 32 + i) =
+                    make_double2(double(__uint_as_float(v[i]) * out_scale), double(__uint_as_float(v[i + 1]) * out_scale));
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) {
+                float4 o;
+                o.x = __uint_as_float(v[i]) * out_scale;
+                o.y = __uint_as_float(v[i + 1]) * out_scale;
+                o.z = __uint_as_float(v[i + 2]) * out_scale;
+                o.w = __uint_as_float(v[i + 3]) * out_scale;
+                *reinterpret_cast<float4*>(orow32 + cc * 32 + i) = o;
+              }
             }
           }
         }
@@ -922,9 +938,33 @@ size_t apply_pc_part_bytes(int sm_count, int64_t N, int64_t M) {
   return p.tail_split > 1 ? size_t(p.tail_split) * p.part_stride * 4 : 0;
 }
 
-cudaError_t launch_apply_pc(const RetrievalArgs& a, const CUtensorMap& tmP, const float* rowc, float* out, void* ring,
-                            void* flags, void* part, int sm_count, cudaStream_t stream) {
-  const PcPlan plan = pc_plan(sm_count, a.N, a.M);
+// partials [splits][rows][1024] fp32 -> rows row0.. of the caller's output (layout / dtype / row order of PcPlan)
+__global__ void reduce_tail_kernel(const float4* __restrict__ part, size_t stride4, int splits, int rows, int row0,
+                                   const int* __restrict__ perm, void* __restrict__ out, int out_ld, int out_f64) {
+  const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= size_t(rows) * 256) return;
+  float4 a = part[i];
+  for (int k = 1; k < splits; ++k) {
+    const float4 b = part[size_t(k) * stride4 + i];
+    a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+  }
+  const int n = row0 + int(i / 256), c = int(i % 256) * 4;
+  const size_t o = size_t(perm ? perm[n] : n) * out_ld + c;
+  if (out_f64) {
+    double* d = reinterpret_cast<double*>(out) + o;
+    d[0] = a.x; d[1] = a.y; d[2] = a.z; d[3] = a.w;
+  } else {
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + o) = a;
+  }
+}
+
+cudaError_t launch_apply_pc(const RetrievalArgs& a, const CUtensorMap& tmP, const float* rowc, void* out, int out_ld,
+                            int out_f64, const int* perm, void* ring, void* flags, void* part, int sm_count,
+                            cudaStream_t stream) {
+  PcPlan plan = pc_plan(sm_count, a.N, a.M);
+  plan.out_ld = out_ld;
+  plan.out_f64 = out_f64;
+  plan.perm = perm;
   static const int dbg = getenv("RANGE_PC_DBG") ? atoi(getenv("RANGE_PC_DBG")) : 0;   // developer switch: decouple the roles
   cudaError_t e = cudaMemsetAsync(flags, 0, apply_pc_flag_bytes(sm_count, a.N, a.M), stream);
   if (e != cudaSuccess) return e;
@@ -968,9 +1008,13 @@ cudaError_t launch_apply_pc(const RetrievalArgs& a, const CUtensorMap& tmP, cons
             cfg.gridDim.x, kDynamicSmem);
     return e;
   }
-  if (plan.tail_split > 1)      // sum the partial outputs of the split tail pairs into the last rows of out
-    return launch_reduce_out(reinterpret_cast<const float*>(part), plan.part_stride, plan.tail_split, plan.part_stride,
-                             out + size_t(plan.tail_row0) * 1024, stream);
+  if (plan.tail_split > 1) {    // sum the partial outputs of the split tail pairs into the last rows of out
+    const int rows = a.N - plan.tail_row0;
+    reduce_tail_kernel<<<unsigned((size_t(rows) * 256 + 255) / 256), 256, 0, stream>>>(
+        reinterpret_cast<const float4*>(part), plan.part_stride / 4, plan.tail_split, rows, plan.tail_row0, perm, out, out_ld,
+        out_f64);
+    return cudaGetLastError();
+  }
   return cudaSuccess;
 }
 

@@ -185,6 +185,20 @@ class RangeEngine:
                                                      _ptr(O), _ptr(ws), ws.numel(), _stream()))
         return O
 
+    def retrieve_apply_concat(self, mode, q16, qxyz, temp, geo_temp, beta, sums, maxs, q64, out=None,
+                              dtype=torch.float64, perm=None):
+        """apply pass + concat in one call: (N,1280) = [retrieved feature | q64], row n at out[perm[n]]"""
+        N = q16.shape[0]
+        out = torch.empty(N, 1280, dtype=dtype, device=self.device) if out is None else out
+        code = _lib.RANGE_OUT_F64 if out.dtype == torch.float64 else _lib.RANGE_OUT_F32
+        with torch.cuda.device(self.index):
+            ws = self._ret_ws(N)
+            _lib.check(self.lib.range_retrieve_apply_concat(
+                self.ctx, MODE[mode], N, _ptr(q16), _ptr(qxyz), temp, geo_temp, 0.0 if beta is None else float(beta),
+                _ptr(sums), _ptr(maxs), _ptr(q64), c_void_p(None) if perm is None else _ptr(perm), _ptr(out), code,
+                _ptr(ws), ws.numel(), _stream()))
+        return out
+
     def concat(self, O, q64, out=None, dtype=torch.float64, perm=None):
         """[O | q64] -> (N,1280); with perm (from sort_queries) row n is written to out[perm[n]]"""
         N = O.shape[0]

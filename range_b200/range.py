@@ -64,14 +64,19 @@ class LocationEncoder(nn.Module):
         eng = self.engine
         return self.location_model_name == 'RANGE+' and eng.db is not None and eng.db.caps is not None
 
-    def _retrieve(self, q16, qxyz):
+    def _retrieve_concat(self, q16, qxyz, q64, out, out_dtype, perm):
+        """statistics, apply and concat: (N,1280) = [retrieved feature | q64] with row n at out[perm[n]]"""
         eng, a = self.engine, self.args
+        name = self.location_model_name
         beta = getattr(a, 'beta', None)
         geo_temp = float(getattr(a, 'geo_temp', 0.0))
         if self.group is None:
-            return eng.retrieve(self.location_model_name, q16, qxyz, a.temp, geo_temp, beta)
-        from .distributed import sharded_retrieve
-        return sharded_retrieve(eng, self.location_model_name, q16, qxyz, a.temp, geo_temp, beta, self.group)
+            sums, maxs = eng.retrieve_stats(name, q16, qxyz, a.temp, geo_temp)
+            return eng.retrieve_apply_concat(name, q16, qxyz, a.temp, geo_temp, beta, sums, maxs, q64, out=out,
+                                             dtype=out_dtype, perm=perm)
+        from .distributed import sharded_retrieve      # M-sharded: the partial outputs are summed over NCCL first
+        O = sharded_retrieve(eng, name, q16, qxyz, a.temp, geo_temp, beta, self.group)
+        return eng.concat(O, q64, out=out, dtype=out_dtype, perm=perm)
 
     @torch.no_grad()
     def embed(self, coords, out=None, out_dtype=torch.float32):
@@ -82,7 +87,7 @@ class LocationEncoder(nn.Module):
             # spatial batching: the geo softmax is local, tiles of nearby queries skip far database tiles
             coords, perm = eng.sort_queries(coords)
         q64, q16, qxyz = eng.encode(coords)
-        return eng.concat(self._retrieve(q16, qxyz), q64, out=out, dtype=out_dtype, perm=perm)
+        return self._retrieve_concat(q16, qxyz, q64, out, out_dtype, perm)
 
     @torch.no_grad()
     def embed_sweep(self, coords, betas, out_dtype=torch.float32):
@@ -97,8 +102,8 @@ class LocationEncoder(nn.Module):
             coords, perm = eng.sort_queries(coords)
         q64, q16, qxyz = eng.encode(coords)
         sums, maxs = eng.retrieve_stats('RANGE+', q16, qxyz, a.temp, a.geo_temp)
-        return [eng.concat(eng.retrieve_apply('RANGE+', q16, qxyz, a.temp, a.geo_temp, float(b), sums, maxs), q64,
-                           dtype=out_dtype, perm=perm) for b in betas]
+        return [eng.retrieve_apply_concat('RANGE+', q16, qxyz, a.temp, a.geo_temp, float(b), sums, maxs, q64,
+                                          dtype=out_dtype, perm=perm) for b in betas]
 
     @staticmethod
     def _chunks(N, chunk, tail):
@@ -153,8 +158,8 @@ class LocationEncoder(nn.Module):
                     if freed[k] is not None:
                         cur.wait_event(freed[k])
                     buf = bufs[k][: hi - lo]
-                    eng.concat(self._retrieve(q16[lo:hi], qxyz[lo:hi]), q64[lo:hi], out=buf,
-                               perm=None if perms is None else perms[c])
+                    self._retrieve_concat(q16[lo:hi], qxyz[lo:hi], q64[lo:hi], buf, torch.float64,
+                                          None if perms is None else perms[c])
                     ready = torch.cuda.Event()
                     ready.record(cur)
                     self._copy_stream.wait_event(ready)
