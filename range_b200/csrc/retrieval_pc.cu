@@ -61,8 +61,14 @@ static_assert(kSoftmaxWarps + 4 >= 7, "the consumer roles use warps 0..6");
 #define RANGE_PC_RING 16
 #endif
 constexpr int kRing = RANGE_PC_RING;             // P' slots per producer CTA
-constexpr int kPublishBatch = 4;                 // tiles per release of the `full` counter (kRing >= 3 batches)
-constexpr int kWindow = 64;                      // tiles per cross-unit synchronisation window (8192 entries, 21 MB of database)
+#ifndef RANGE_PC_BATCH
+#define RANGE_PC_BATCH 4
+#endif
+constexpr int kPublishBatch = RANGE_PC_BATCH;                 // tiles per release of the `full` counter (kRing >= 3 batches)
+#ifndef RANGE_PC_WINDOW
+#define RANGE_PC_WINDOW 64
+#endif
+constexpr int kWindow = RANGE_PC_WINDOW;                      // tiles per cross-unit synchronisation window (8192 entries, 21 MB of database)
 // Every kPolyEvery-th semantic exponential is evaluated on the FMA pipe (ptx::ex2_poly, rel. error 2.7e-6) instead of
 // MUFU: the softmax warps are MUFU-bound with issue slots to spare.  0 = never.
 #ifndef RANGE_PC_POLY

@@ -1,2 +1,4 @@
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
-timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['config']['segments_ms'], d['roofline']['frac'], d['roofline']['stats_plus_apply']['frac'], 'e2e', d['e2e']['value'], d['gpu_launches'])"
+for cfg in "-DRANGE_PC_BATCH=2" "-DRANGE_PC_BATCH=8 -DRANGE_PC_RING=32" "-DRANGE_PC_WINDOW=32" "-DRANGE_PC_WINDOW=128" "-DRANGE_PC_RING=32" ""; do
+  NVCC_EXTRA="$cfg" bash range_b200/csrc/build.sh > /dev/null 2>&1
+  echo "== [$cfg]"; for i in 1 2; do timeout 200 python tools/time_apply.py 2>&1 | grep -v "^$" | tail -1; done
+done
