@@ -154,7 +154,7 @@ RetrievalPlan plan_retrieval(const range_ctx* c, int64_t N) {
   }
   // large batches: CTA pairs (two query tiles per cluster) -> waves are counted in clusters
   const int64_t qpairs0 = (qtiles + 1) / 2, slots = c->sm_count / 2;
-  p.stats_pc = apply_kernel_override() != 1 && slots > 0 && qpairs0 * 2 >= slots;
+  p.stats_pc = apply_kernel_override() != 1 && slots > 0 && qpairs0 >= apply_pc_units(c->sm_count);
   if (p.stats_pc) {
     best = 1;
     best_cost = 1e30;
@@ -175,16 +175,15 @@ RetrievalPlan plan_retrieval(const range_ctx* c, int64_t N) {
   p.mask_rows = int((qtiles + 1) / 2 * 2);
   p.mask_words = int((tiles + 31) / 32);
   p.off_mask = o;     o += c->caps ? align_up(size_t(p.mask_rows) * p.mask_words * 4, 256) : 0;
-  // producer/consumer apply: needs the whole database per CTA (no splits) and enough query-tile pairs to give
-  // every unit (2 producer + 4 consumer SMs) at least two rounds
+  // producer/consumer apply: enough query-tile pairs to give every unit (2 producer + 4 consumer SMs) a full round
   const int units = apply_pc_units(c->sm_count);
   const int64_t qpairs = (qtiles + 1) / 2;
   const int ov = apply_kernel_override();
-  p.pc = units > 0 && p.splits == 1 && ov != 1 && (ov == 2 || qpairs >= 2 * units);
+  p.pc = units > 0 && ov != 1 && (ov == 2 || qpairs >= units);
   p.off_ring = o;     o += p.pc ? align_up(apply_pc_ring_bytes(c->sm_count), 1024) : 0;
   p.off_flags = o;    o += p.pc ? align_up(apply_pc_flag_bytes(c->sm_count, N, c->M), 256) : 0;
   p.off_pc_part = o;  o += p.pc ? align_up(apply_pc_part_bytes(c->sm_count, N, c->M), 256) : 0;
-  p.off_part_out = o; o += p.splits > 1 ? align_up(size_t(p.splits) * N * kDimV * 4, 256) : 0;
+  p.off_part_out = o; o += (p.splits > 1 && !p.pc) ? align_up(size_t(p.splits) * N * kDimV * 4, 256) : 0;
   p.off_O = o;        o += p.pc ? 0 : align_up(size_t(N) * kDimV * 4, 256);   // scratch O of range_retrieve_apply_concat (small batches)
   p.total = o;
   return p;

@@ -107,11 +107,15 @@ class LocationEncoder(nn.Module):
 
     @staticmethod
     def _chunks(N, chunk, tail):
-        """[lo, hi) slices: full chunks, then the remainder with a short last piece - the last device->host copy is
-        the only one nothing overlaps"""
+        """[lo, hi) slices: full chunks, half chunks over the last two chunks' worth of rows, and a short last piece.
+        Every chunk's device->host copy overlaps the next chunk's computation except the last one, so the pieces get
+        smaller towards the end (half a chunk is still two full rounds of the producer/consumer apply kernel)."""
         cuts, lo = [], 0
-        while N - lo > chunk:
+        half = max(tail, chunk // 2)
+        while N - lo > 2 * chunk:
             cuts.append((lo, lo + chunk)); lo += chunk
+        while N - lo > half + tail:
+            cuts.append((lo, lo + half)); lo += half
         if N - lo > 2 * tail:
             cuts.append((lo, N - tail)); lo = N - tail
         cuts.append((lo, N))
@@ -138,7 +142,8 @@ class LocationEncoder(nn.Module):
             if self._copy_stream is None:
                 self._copy_stream = torch.cuda.Stream(device=eng.device)
             chunk = min(self.chunk, N)
-            bufs = [torch.empty(chunk, 1280, dtype=torch.float64, device=eng.device) for _ in range(2 if N > self.tail else 1)]
+            rows = max(hi - lo for lo, hi in self._chunks(min(N, self.super_batch), chunk, self.tail))
+            bufs = [torch.empty(rows, 1280, dtype=torch.float64, device=eng.device) for _ in range(2 if N > rows else 1)]
             freed = [None] * len(bufs)
             cur = torch.cuda.current_stream()
             i = 0

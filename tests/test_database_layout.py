@@ -70,3 +70,6 @@ def test_forward_chunking_covers_every_row():
         assert cuts[0][0] == 0 and cuts[-1][1] == N and all(a[1] == b[0] for a, b in zip(cuts, cuts[1:]))
         assert all(0 < hi - lo <= 24576 for lo, hi in cuts)
         assert cuts[-1][1] - cuts[-1][0] <= 12288            # the unoverlapped last copy stays short
+    for N, chunk, tail in [(64, 24, 24), (64, 24, 5), (7, 3, 3), (100, 1, 1)]:          # degenerate settings still tile [0, N)
+        cuts = LocationEncoder._chunks(N, chunk, tail)
+        assert cuts[0][0] == 0 and cuts[-1][1] == N and all(a[1] == b[0] for a, b in zip(cuts, cuts[1:]))
