@@ -87,9 +87,12 @@ int range_ctx_set_db_caps(range_ctx* ctx, int64_t n_tiles, const float* caps, in
 
 /* Diagnostic: the skip mask the RANGE+ kernels would use for these queries - mask [rows][words] uint32, bit t of
  * row r set = query tile r (128 rows of qxyz) skips the geo term of database tile t.  Shape from
- * range_geo_mask_shape (rows = query tiles rounded up to even). */
+ * range_geo_mask_shape (rows = query tiles rounded up to even).  sums = NULL: the mask of the statistics pass (bound
+ * from the nearest database tile); sums = the (N,2) output of range_retrieve_stats: the tighter mask of the apply
+ * pass (the geo normalisers are known: an entry is negligible iff exp(T (g - 1)) <= 2^-24 l_g / M_total). */
 int range_geo_mask_shape(range_ctx* ctx, int64_t N, int32_t* rows, int32_t* words);
-int range_geo_mask(range_ctx* ctx, int64_t N, const float* qxyz, float geo_temp, uint32_t* mask, void* stream);
+int range_geo_mask(range_ctx* ctx, int64_t N, const float* qxyz, float geo_temp, const float* sums, uint32_t* mask,
+                   void* stream);
 
 /* Spatial batching of a query batch (no reference counterpart: rows are independent, range/range.py:213-240).
  * perm[i] = caller's row index of sorted row i, lonlat_sorted[i] = lonlat[perm[i]]; cube-map Hilbert cells,

@@ -29,7 +29,7 @@ PROTOTYPES = {
     "range_ctx_set_db": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_float]),
     "range_ctx_set_db_caps": (c_int, [c_void_p, c_int64, c_void_p, c_int64]),
     "range_geo_mask_shape": (c_int, [c_void_p, c_int64, POINTER(c_int32), POINTER(c_int32)]),
-    "range_geo_mask": (c_int, [c_void_p, c_int64, c_void_p, c_float, c_void_p, c_void_p]),
+    "range_geo_mask": (c_int, [c_void_p, c_int64, c_void_p, c_float, c_void_p, c_void_p, c_void_p]),
     "range_sort_workspace_bytes": (c_size_t, [c_void_p, c_int64]),
     "range_sort_queries": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "range_sh_features": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p]),

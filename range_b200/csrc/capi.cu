@@ -191,7 +191,7 @@ RetrievalPlan plan_retrieval(const range_ctx* c, int64_t N) {
 
 // ws: aligned workspace base; when the database carries bounding caps the geo-skip mask is (re)computed here
 int fill_args(range_ctx* c, int mode, int64_t N, const void* q16, const float* qxyz, float temp, float geo_temp,
-              const RetrievalPlan& p, char* ws, cudaStream_t stream, RetrievalArgs* a) {
+              const RetrievalPlan& p, char* ws, cudaStream_t stream, RetrievalArgs* a, const float* sums = nullptr) {
   if (!c || !c->Kh) return fail(RANGE_ERR_INVALID, "database not set");
   if (mode != RANGE_MODE_RANGE && mode != RANGE_MODE_RANGE_PLUS) return fail(RANGE_ERR_INVALID, "unknown mode %d", mode);
   if (N <= 0 || N > (int64_t(1) << 30)) return fail(RANGE_ERR_INVALID, "N out of range");
@@ -217,10 +217,12 @@ int fill_args(range_ctx* c, int mode, int64_t N, const void* q16, const float* q
   a->mask_words = 0;
   if (a->geo && c->caps && geo_temp > 0.f) {
     // entries with g <= g_max - delta together carry < 2^-24 of the row's geo normaliser (retrieval.cu)
-    const float delta = (logf(float(c->M_total)) + 24.f * 0.6931471805599453f) / geo_temp;
+    const float thr_ln = logf(float(c->M_total)) + 24.f * 0.6931471805599453f;
+    const float delta = thr_ln / geo_temp;
     uint32_t* mask = reinterpret_cast<uint32_t*>(ws + p.off_mask);
-    CUDA_TRY(launch_geo_mask(qxyz, int(N), p.mask_rows, c->caps, int(c->Mpad / kBlockKeys), delta, mask, p.mask_words,
-                             stream));
+    // apply pass: the (global) row normalisers are known and tighten the bound
+    CUDA_TRY(launch_geo_mask(qxyz, int(N), p.mask_rows, c->caps, int(c->Mpad / kBlockKeys), delta, sums, thr_ln,
+                             geo_temp, mask, p.mask_words, stream));
     g_launches += 1;
     a->geo_mask = mask;
     a->mask_words = p.mask_words;
@@ -325,13 +327,14 @@ int range_geo_mask_shape(range_ctx* c, int64_t N, int32_t* rows, int32_t* words)
   return RANGE_OK;
 }
 
-int range_geo_mask(range_ctx* c, int64_t N, const float* qxyz, float geo_temp, uint32_t* mask, void* stream) {
+int range_geo_mask(range_ctx* c, int64_t N, const float* qxyz, float geo_temp, const float* sums, uint32_t* mask,
+                   void* stream) {
   if (!c || !c->Kh || !c->caps) return fail(RANGE_ERR_INVALID, "database caps not set");
   if (N <= 0 || !qxyz || !mask || !(geo_temp > 0.f)) return fail(RANGE_ERR_INVALID, "bad arguments");
   const RetrievalPlan p = plan_retrieval(c, N);
-  const float delta = (logf(float(c->M_total)) + 24.f * 0.6931471805599453f) / geo_temp;
-  CUDA_TRY(launch_geo_mask(qxyz, int(N), p.mask_rows, c->caps, int(c->Mpad / kBlockKeys), delta, mask, p.mask_words,
-                           cudaStream_t(stream)));
+  const float thr_ln = logf(float(c->M_total)) + 24.f * 0.6931471805599453f;
+  CUDA_TRY(launch_geo_mask(qxyz, int(N), p.mask_rows, c->caps, int(c->Mpad / kBlockKeys), thr_ln / geo_temp, sums, thr_ln,
+                           geo_temp, mask, p.mask_words, cudaStream_t(stream)));
   g_launches += 1;
   return RANGE_OK;
 }
@@ -553,7 +556,7 @@ static int apply_impl(range_ctx* c, int mode, int64_t N, const void* q16, const 
   RetrievalArgs a;
   char* ws = reinterpret_cast<char*>(align_up(reinterpret_cast<size_t>(workspace), 256));
   cudaStream_t s = cudaStream_t(stream);
-  int r = fill_args(c, mode, N, q16, qxyz, temp, geo_temp, p, ws, s, &a);
+  int r = fill_args(c, mode, N, q16, qxyz, temp, geo_temp, p, ws, s, &a, sums);
   if (r) return r;
   float* rowc = reinterpret_cast<float*>(ws + p.off_rowc);
   CUDA_TRY(launch_row_constants(sums, maxs, qxyz, int(N), a.geo, beta, a.a_sem, a.a_geo, 1.f / c->vscale, rowc, s));

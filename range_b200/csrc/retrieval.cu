@@ -670,9 +670,13 @@ __device__ __forceinline__ float block128_reduce(float v, bool is_max, float* sc
   return is_max ? fmaxf(fmaxf(a, b), fmaxf(c, d)) : (a + b) + (c + d);
 }
 
+// Once the statistics pass has run, the row normalisers l_g are KNOWN (sums[n].y = sum_j exp(T (g_j - 1))): an entry
+// carries at most 2^-24 / M_total of the row's geo mass iff g <= 1 + (ln l_g - ln M_total - 24 ln 2) / T, which is at
+// least as tight as the bound from the nearest entry alone (l_g >= exp(T (g_max - 1))) and much tighter where the
+// database is dense around the query.  `sums` != null selects it (apply pass); thr_ln = ln M_total + 24 ln 2.
 __global__ void __launch_bounds__(128)
 geo_mask_kernel(const float4* __restrict__ q_xyz, int N, const float4* __restrict__ caps, int n_tiles, float delta,
-                uint32_t* __restrict__ mask, int words) {
+                const float2* __restrict__ sums, float thr_ln, float geo_temp, uint32_t* __restrict__ mask, int words) {
   __shared__ float scratch[4];
   const int n = blockIdx.x * 128 + threadIdx.x;
   const bool valid = n < N;
@@ -697,7 +701,12 @@ geo_mask_kernel(const float4* __restrict__ q_xyz, int N, const float4* __restric
     if (far < kPi) glb = fmaxf(glb, cosf(far));
   }
   glb = block128_reduce(glb, true, scratch);
-  const float thr = glb - delta;
+  float thr = glb - delta;
+  if (sums != nullptr) {
+    // smallest normaliser of the tile's rows (padding rows do not count); -(max of -l)
+    const float lmin = -block128_reduce(valid ? -sums[n].y : -3.0e38f, true, scratch);
+    if (lmin > 0.f && lmin < 3.0e38f) thr = fmaxf(thr, 1.f + (logf(lmin) - thr_ln) / geo_temp - 1e-6f);
+  }
   for (int w = threadIdx.x; w < words; w += 128) {
     uint32_t bits = 0;
     for (int b = 0; b < 32; ++b) {
@@ -797,10 +806,12 @@ cudaError_t launch_stats(const RetrievalArgs& a, float* part_sum, float* part_ma
 }
 
 cudaError_t launch_geo_mask(const float* q_xyz, int N, int rows, const float* caps, int n_tiles, float delta,
-                            uint32_t* mask, int words, cudaStream_t stream) {
+                            const float* sums, float thr_ln, float geo_temp, uint32_t* mask, int words,
+                            cudaStream_t stream) {
   // rows >= ceil(N / 128): all-padding query tiles (the CTA-pair grid is rounded up to even) get an all-zero row
   geo_mask_kernel<<<rows, 128, 0, stream>>>(reinterpret_cast<const float4*>(q_xyz), N,
-                                                       reinterpret_cast<const float4*>(caps), n_tiles, delta, mask, words);
+                                                       reinterpret_cast<const float4*>(caps), n_tiles, delta,
+                                            reinterpret_cast<const float2*>(sums), thr_ln, geo_temp, mask, words);
   return cudaGetLastError();
 }
 

@@ -128,14 +128,16 @@ class RangeEngine:
                                                    ws.numel(), _stream()))
         return out, perm
 
-    def geo_mask(self, qxyz, geo_temp):
-        """diagnostic: (query tiles, database tiles) bool tensor, True = the geo term of that tile pair is skipped"""
+    def geo_mask(self, qxyz, geo_temp, sums=None):
+        """diagnostic: (query tiles, database tiles) bool tensor, True = the geo term of that tile pair is skipped;
+        sums (from retrieve_stats) selects the tighter mask of the apply pass"""
         N = qxyz.shape[0]
         rows, words = c_int32(), c_int32()
         _lib.check(self.lib.range_geo_mask_shape(self.ctx, N, ctypes.byref(rows), ctypes.byref(words)))
         mask = torch.zeros(rows.value, words.value, dtype=torch.int32, device=self.device)
         with torch.cuda.device(self.index):
-            _lib.check(self.lib.range_geo_mask(self.ctx, N, _ptr(qxyz), float(geo_temp), _ptr(mask), _stream()))
+            _lib.check(self.lib.range_geo_mask(self.ctx, N, _ptr(qxyz), float(geo_temp),
+                                               c_void_p(None) if sums is None else _ptr(sums), _ptr(mask), _stream()))
         bits = (mask.unsqueeze(-1) >> torch.arange(32, device=self.device, dtype=torch.int32)) & 1
         return bits.reshape(rows.value, -1)[: (N + 127) // 128, : self.db.Mpad // 128].bool()
 

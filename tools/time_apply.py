@@ -25,6 +25,8 @@ def timeit(fn, reps=3):
 if eng.db.caps is not None:
     print(f"geo-skip fraction: {eng.geo_mask(xyz, 40.0).float().mean().item():.3f}")
 sums, maxs = eng.retrieve_stats("RANGE+", q, xyz, 12.0, 40.0)
+if eng.db.caps is not None:
+    print(f"geo-skip fraction, apply pass (known normalisers): {eng.geo_mask(xyz, 40.0, sums=sums).float().mean().item():.3f}")
 t_st = timeit(lambda: eng.retrieve_stats("RANGE+", q, xyz, 12.0, 40.0))
 t_ap = timeit(lambda: eng.retrieve_apply("RANGE+", q, xyz, 12.0, 40.0, 0.5, sums, maxs))
 s2, m2 = eng.retrieve_stats("RANGE", q, xyz, 15.0, 0.0)
