@@ -221,7 +221,7 @@ int fill_args(range_ctx* c, int mode, int64_t N, const void* q16, const float* q
     const float delta = thr_ln / geo_temp;
     uint32_t* mask = reinterpret_cast<uint32_t*>(ws + p.off_mask);
     // apply pass: the (global) row normalisers are known and tighten the bound
-    CUDA_TRY(launch_geo_mask(qxyz, int(N), p.mask_rows, c->caps, int(c->Mpad / kBlockKeys), delta, sums, thr_ln,
+    CUDA_TRY(launch_geo_mask(qxyz, int(N), p.mask_rows, c->caps, int(c->Mpad / kBlockKeys), int(c->M), delta, sums, thr_ln,
                              geo_temp, mask, p.mask_words, stream));
     g_launches += 1;
     a->geo_mask = mask;
@@ -333,7 +333,7 @@ int range_geo_mask(range_ctx* c, int64_t N, const float* qxyz, float geo_temp, c
   if (N <= 0 || !qxyz || !mask || !(geo_temp > 0.f)) return fail(RANGE_ERR_INVALID, "bad arguments");
   const RetrievalPlan p = plan_retrieval(c, N);
   const float thr_ln = logf(float(c->M_total)) + 24.f * 0.6931471805599453f;
-  CUDA_TRY(launch_geo_mask(qxyz, int(N), p.mask_rows, c->caps, int(c->Mpad / kBlockKeys), thr_ln / geo_temp, sums, thr_ln,
+  CUDA_TRY(launch_geo_mask(qxyz, int(N), p.mask_rows, c->caps, int(c->Mpad / kBlockKeys), int(c->M), thr_ln / geo_temp, sums, thr_ln,
                            geo_temp, mask, p.mask_words, cudaStream_t(stream)));
   g_launches += 1;
   return RANGE_OK;

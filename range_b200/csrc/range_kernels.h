@@ -77,7 +77,7 @@ int retrieval_apply_smem_bytes();
 cudaError_t launch_stats(const RetrievalArgs& a, float* part_sum, float* part_max, cudaStream_t s);
 // skip bits from the query tiles' and database tiles' bounding caps (retrieval.cu: geo_mask_kernel)
 // sums (N,2) != null: use the known geo normalisers (apply pass), thr_ln = ln M_total + 24 ln 2
-cudaError_t launch_geo_mask(const float* q_xyz, int N, int rows, const float* caps, int n_tiles, float delta,
+cudaError_t launch_geo_mask(const float* q_xyz, int N, int rows, const float* caps, int n_tiles, int M, float delta,
                             const float* sums, float thr_ln, float geo_temp, uint32_t* mask, int words, cudaStream_t s);
 cudaError_t launch_reduce_stats(const float* part_sum, const float* part_max, int N, int splits, float* sums,
                                 float* maxs, cudaStream_t s);

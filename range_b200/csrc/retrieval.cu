@@ -675,7 +675,7 @@ __device__ __forceinline__ float block128_reduce(float v, bool is_max, float* sc
 // least as tight as the bound from the nearest entry alone (l_g >= exp(T (g_max - 1))) and much tighter where the
 // database is dense around the query.  `sums` != null selects it (apply pass); thr_ln = ln M_total + 24 ln 2.
 __global__ void __launch_bounds__(128)
-geo_mask_kernel(const float4* __restrict__ q_xyz, int N, const float4* __restrict__ caps, int n_tiles, float delta,
+geo_mask_kernel(const float4* __restrict__ q_xyz, int N, const float4* __restrict__ caps, int n_tiles, int M, float delta,
                 const float2* __restrict__ sums, float thr_ln, float geo_temp, uint32_t* __restrict__ mask, int words) {
   __shared__ float scratch[4];
   const int n = blockIdx.x * 128 + threadIdx.x;
@@ -693,15 +693,22 @@ geo_mask_kernel(const float4* __restrict__ q_xyz, int N, const float4* __restric
     const float d = valid ? acosf(fminf(1.f, fmaxf(-1.f, cx * x.x + cy * x.y + cz * x.z))) : 0.f;
     r_q = block128_reduce(d, true, scratch) + kEps;
   }
-  // lower bound of every row's g_max: the farthest point of the closest database tile
-  float glb = -1.f;
+  // Lower bounds valid for every row of the tile: g_max >= cos(far) of the closest database tile, and the geo
+  // normaliser l_g = sum_j exp(T (g_j - 1)) >= sum over tiles of (entries in the tile) exp(T (cos(far_t) - 1)).
+  float glb = -1.f, llb = 0.f;
   for (int t = threadIdx.x; t < n_tiles; t += 128) {
     const float4 c = caps[t];
     const float far = acosf(fminf(1.f, fmaxf(-1.f, cx * c.x + cy * c.y + cz * c.z))) + r_q + c.w + kEps;
-    if (far < kPi) glb = fmaxf(glb, cosf(far));
+    if (far < kPi) {
+      const float cf = cosf(far);
+      glb = fmaxf(glb, cf);
+      llb += float(min(128, M - t * 128)) * __expf(geo_temp * (cf - 1.f));
+    }
   }
   glb = block128_reduce(glb, true, scratch);
+  llb = block128_reduce(llb, false, scratch);
   float thr = glb - delta;
+  if (llb > 0.f) thr = fmaxf(thr, 1.f + (logf(llb) - thr_ln) / geo_temp - 1e-6f);
   if (sums != nullptr) {
     // smallest normaliser of the tile's rows (padding rows do not count); -(max of -l)
     const float lmin = -block128_reduce(valid ? -sums[n].y : -3.0e38f, true, scratch);
@@ -805,12 +812,12 @@ cudaError_t launch_stats(const RetrievalArgs& a, float* part_sum, float* part_ma
   return cudaGetLastError();
 }
 
-cudaError_t launch_geo_mask(const float* q_xyz, int N, int rows, const float* caps, int n_tiles, float delta,
+cudaError_t launch_geo_mask(const float* q_xyz, int N, int rows, const float* caps, int n_tiles, int M, float delta,
                             const float* sums, float thr_ln, float geo_temp, uint32_t* mask, int words,
                             cudaStream_t stream) {
   // rows >= ceil(N / 128): all-padding query tiles (the CTA-pair grid is rounded up to even) get an all-zero row
   geo_mask_kernel<<<rows, 128, 0, stream>>>(reinterpret_cast<const float4*>(q_xyz), N,
-                                                       reinterpret_cast<const float4*>(caps), n_tiles, delta,
+                                                       reinterpret_cast<const float4*>(caps), n_tiles, M, delta,
                                             reinterpret_cast<const float2*>(sums), thr_ln, geo_temp, mask, words);
   return cudaGetLastError();
 }
