@@ -245,7 +245,7 @@ def main():
         line = {
             "metric": METRIC, "value": world * N_QUERIES * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f16 operands / f32 accumulate (retrieval); f64 SH + 3xTF32 SIREN (encoder)",
+            "scaling": "weak", "vs_baseline": None, "dtype": "f16 operands / f32 accumulate (retrieval); f64 SH + split-fp16 (f16x3) SIREN (encoder)",
             "data": "synthetic",
             "config": {"workload": f"RANGE+ beta={BETA}, {N_QUERIES} queries/GPU x M={M_DB} (range_db_large shape), "
                                    f"SatCLIP-L40 H={H} random-init", "parallelism": f"query-sharded x{world}, DB replicated",

@@ -57,13 +57,15 @@ int range_ctx_set_sh_table(range_ctx* ctx, int L, int n_entries, const double* p
 int range_ctx_set_encoder(range_ctx* ctx, int n_layers, const int32_t* dims, const double* const* W,
                           const double* const* b, double w0_first, double w0_hidden);
 
-/* Optional tensor-core encoder: the SIREN layers as 3xTF32 tcgen05 GEMMs (fp32-class accuracy; the
- * reference's fp64 SIREN sits on spherical-harmonic input that carries >= 1e-3 of its own rounding noise).
- * Needs every layer width % 256 == 0.  The prepared (split / permuted) weights live in `buf`, a device
+/* Optional tensor-core encoder: the SIREN layers as split-precision tcgen05 GEMMs - every operand as hi + lo fp16,
+ * three kind::f16 products per term, fp32 accumulation (fp32-class accuracy; the reference's fp64 SIREN sits on
+ * spherical-harmonic input that carries >= 1e-3 of its own rounding noise).
+ * Needs every layer width % 256 == 0 and input width % 64 == 0.  The prepared (split / permuted) weights live in `buf`, a device
  * buffer of range_encoder_prepared_bytes() the caller keeps alive; after a successful prepare the ctx
- * encodes in RANGE_ENC_TF32X3 until range_ctx_set_encoder_precision(ctx, RANGE_ENC_F64). */
+ * encodes in RANGE_ENC_F16X3 until range_ctx_set_encoder_precision(ctx, RANGE_ENC_F64). */
 #define RANGE_ENC_F64 0
-#define RANGE_ENC_TF32X3 1
+#define RANGE_ENC_F16X3 1
+#define RANGE_ENC_TF32X3 RANGE_ENC_F16X3 /* earlier name of the same mode */
 size_t range_encoder_prepared_bytes(range_ctx* ctx);
 int range_ctx_prepare_encoder(range_ctx* ctx, void* buf, size_t bytes, void* stream);
 int range_ctx_set_encoder_precision(range_ctx* ctx, int mode);

@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(_HERE, "librange_b200.so")
 
 RANGE_MODE_RANGE, RANGE_MODE_RANGE_PLUS = 0, 1
 RANGE_OUT_F64, RANGE_OUT_F32 = 0, 1
-RANGE_ENC_F64, RANGE_ENC_TF32X3 = 0, 1
+RANGE_ENC_F64, RANGE_ENC_F16X3 = 0, 1
 
 # every symbol include/range_b200.h declares: name -> (restype, argtypes)
 PROTOTYPES = {

@@ -101,11 +101,10 @@ struct range_ctx {
   CUtensorMap tmK128, tmK64, tmV128;
   const float* caps = nullptr;     // (Mpad / 128, 4) bounding caps of the database tiles, or null
   int64_t M_total = 0;             // entries of the whole (unsharded) database: sets the geo-skip threshold
-  // tensor-core encoder (3xTF32): prepared weights live in a caller-provided buffer
+  // tensor-core encoder (split fp16): prepared weights live in a caller-provided buffer
   int enc_precision = RANGE_ENC_F64;
   bool enc_prepared = false;
   const int* perm = nullptr;
-  std::vector<const float*> Wh, Wl;
   std::vector<CUtensorMap> tmWh, tmWl;
 };
 
@@ -365,20 +364,20 @@ int range_sh_features(range_ctx* c, int64_t N, const double* lonlat, double* Yt,
 static bool tc_supported(const range_ctx* c) {
   if (!c || !c->n_layers) return false;
   for (int i = 0; i < c->n_layers; ++i)
-    if (c->dims[i] % 32 || c->dims[i + 1] % 256) return false;
+    if (c->dims[i] % 64 || c->dims[i + 1] % 256) return false;
   return true;
 }
 
 size_t range_encoder_prepared_bytes(range_ctx* c) {
   if (!tc_supported(c)) return 0;
   size_t b = align_up(size_t(c->dims[0]) * 4, 256);
-  for (int i = 0; i < c->n_layers; ++i) b += 2 * align_up(size_t(c->dims[i]) * c->dims[i + 1] * 4, 256);
+  for (int i = 0; i < c->n_layers; ++i) b += 2 * align_up(size_t(c->dims[i]) * c->dims[i + 1] * 2, 256);   // hi + lo fp16
   return b + 256;
 }
 
 int range_ctx_prepare_encoder(range_ctx* c, void* buf, size_t bytes, void* stream) {
   if (!c || !c->sh.pref || !c->n_layers) return fail(RANGE_ERR_INVALID, "encoder / SH table not set");
-  if (!tc_supported(c)) return fail(RANGE_ERR_UNSUPPORTED, "tensor-core encoder needs layer widths %% 256 == 0 and inputs %% 32 == 0");
+  if (!tc_supported(c)) return fail(RANGE_ERR_UNSUPPORTED, "tensor-core encoder needs layer widths %% 256 == 0 and inputs %% 64 == 0");
   if (!buf || bytes < range_encoder_prepared_bytes(c)) return fail(RANGE_ERR_WORKSPACE, "prepared-encoder buffer too small");
   const int L = c->sh.L, F = L * L;
   if (c->dims[0] != F) return fail(RANGE_ERR_INVALID, "encoder input dim %d != L*L", c->dims[0]);
@@ -397,28 +396,27 @@ int range_ctx_prepare_encoder(range_ctx* c, void* buf, size_t bytes, void* strea
   CUDA_TRY(cudaStreamSynchronize(s));          // perm is a stack-lifetime host vector
   p += align_up(size_t(F) * 4, 256);
   c->perm = dperm;
-  c->Wh.clear(); c->Wl.clear(); c->tmWh.assign(c->n_layers, CUtensorMap{}); c->tmWl.assign(c->n_layers, CUtensorMap{});
+  c->tmWh.assign(c->n_layers, CUtensorMap{}); c->tmWl.assign(c->n_layers, CUtensorMap{});
   for (int i = 0; i < c->n_layers; ++i) {
     const int K = c->dims[i], H = c->dims[i + 1];
-    float* wh = reinterpret_cast<float*>(p); p += align_up(size_t(K) * H * 4, 256);
-    float* wl = reinterpret_cast<float*>(p); p += align_up(size_t(K) * H * 4, 256);
+    void* wh = p; p += align_up(size_t(K) * H * 2, 256);
+    void* wl = p; p += align_up(size_t(K) * H * 2, 256);
     CUDA_TRY(launch_split_weights(c->W[i], H, K, i == 0 ? dperm : nullptr, wh, wl, s));
     g_launches += 1;
-    int r = make_tmap(&c->tmWh[i], wh, uint64_t(H), uint64_t(K), 256, true);
+    int r = make_tmap(&c->tmWh[i], wh, uint64_t(H), uint64_t(K), 256);
     if (r) return r;
-    r = make_tmap(&c->tmWl[i], wl, uint64_t(H), uint64_t(K), 256, true);
+    r = make_tmap(&c->tmWl[i], wl, uint64_t(H), uint64_t(K), 256);
     if (r) return r;
-    c->Wh.push_back(wh); c->Wl.push_back(wl);
   }
   c->enc_prepared = true;
-  c->enc_precision = RANGE_ENC_TF32X3;
+  c->enc_precision = RANGE_ENC_F16X3;
   return RANGE_OK;
 }
 
 int range_ctx_set_encoder_precision(range_ctx* c, int mode) {
   if (!c) return fail(RANGE_ERR_INVALID, "null ctx");
-  if (mode == RANGE_ENC_TF32X3 && !c->enc_prepared) return fail(RANGE_ERR_INVALID, "call range_ctx_prepare_encoder first");
-  if (mode != RANGE_ENC_F64 && mode != RANGE_ENC_TF32X3) return fail(RANGE_ERR_INVALID, "unknown encoder precision %d", mode);
+  if (mode == RANGE_ENC_F16X3 && !c->enc_prepared) return fail(RANGE_ERR_INVALID, "call range_ctx_prepare_encoder first");
+  if (mode != RANGE_ENC_F64 && mode != RANGE_ENC_F16X3) return fail(RANGE_ERR_INVALID, "unknown encoder precision %d", mode);
   c->enc_precision = mode;
   return RANGE_OK;
 }
@@ -426,13 +424,14 @@ int range_ctx_set_encoder_precision(range_ctx* c, int mode) {
 static size_t encode_ws_tc(const range_ctx* c, int64_t chunk) {
   size_t widest = 0;
   for (int i = 1; i < c->n_layers; ++i) widest = widest > size_t(c->dims[i]) ? widest : size_t(c->dims[i]);
-  return 2 * align_up(size_t(chunk) * c->dims[0] * 4, 256) + 4 * align_up(size_t(chunk) * widest * 4, 256) +
+  // features hi + lo, two ping-pong hidden buffers hi + lo (all fp16), row-major fp64 embedding
+  return 2 * align_up(size_t(chunk) * c->dims[0] * 2, 256) + 4 * align_up(size_t(chunk) * widest * 2, 256) +
          size_t(chunk) * kDimK * 8 + 1024;
 }
 
 size_t range_encode_workspace_bytes(range_ctx* c, int64_t N) {
   if (!c || !c->n_layers || N <= 0) return 0;
-  if (c->enc_precision == RANGE_ENC_TF32X3) return encode_ws_tc(c, N < kEncodeChunk ? N : kEncodeChunk);
+  if (c->enc_precision == RANGE_ENC_F16X3) return encode_ws_tc(c, N < kEncodeChunk ? N : kEncodeChunk);
   const int64_t chunk = N < kEncodeChunk ? N : kEncodeChunk;
   const size_t ld = align_up(size_t(chunk), 128);
   size_t widest = 0;
@@ -451,28 +450,28 @@ int range_encode(range_ctx* c, int64_t N, const double* lonlat, double* q64, voi
     return fail(RANGE_ERR_WORKSPACE, "encode workspace too small");
   cudaStream_t s = cudaStream_t(stream);
   const int64_t chunk = N < kEncodeChunk ? N : kEncodeChunk;
-  if (c->enc_precision == RANGE_ENC_TF32X3) {
+  if (c->enc_precision == RANGE_ENC_F16X3) {
     size_t widest = 0;
     for (int i = 1; i < c->n_layers; ++i) widest = widest > size_t(c->dims[i]) ? widest : size_t(c->dims[i]);
     char* p = reinterpret_cast<char*>(align_up(reinterpret_cast<size_t>(workspace), 256));
     const int F = c->dims[0];
-    float* Yh = reinterpret_cast<float*>(p); p += align_up(size_t(chunk) * F * 4, 256);
-    float* Yl = reinterpret_cast<float*>(p); p += align_up(size_t(chunk) * F * 4, 256);
-    float* hid[2][2];
+    void* Yh = p; p += align_up(size_t(chunk) * F * 2, 256);
+    void* Yl = p; p += align_up(size_t(chunk) * F * 2, 256);
+    void* hid[2][2];
     for (int a = 0; a < 2; ++a)
-      for (int b = 0; b < 2; ++b) { hid[a][b] = reinterpret_cast<float*>(p); p += align_up(size_t(chunk) * widest * 4, 256); }
+      for (int b = 0; b < 2; ++b) { hid[a][b] = p; p += align_up(size_t(chunk) * widest * 2, 256); }
     double* emb = reinterpret_cast<double*>(p);
     for (int64_t n0 = 0; n0 < N; n0 += chunk) {
       const int n = int(N - n0 < chunk ? N - n0 : chunk);
       CUDA_TRY(launch_sh_rowmajor(c->sh, lonlat + 2 * n0, n, Yh, Yl, s));
-      const float *ah = Yh, *al = Yl;
+      const void *ah = Yh, *al = Yl;
       for (int i = 0; i < c->n_layers; ++i) {
         const bool last = i == c->n_layers - 1;
         const int K = c->dims[i], H = c->dims[i + 1];
         CUtensorMap tmAh, tmAl;
-        int r = make_tmap(&tmAh, ah, uint64_t(n), uint64_t(K), 128, true);
+        int r = make_tmap(&tmAh, ah, uint64_t(n), uint64_t(K), 128);
         if (r) return r;
-        r = make_tmap(&tmAl, al, uint64_t(n), uint64_t(K), 128, true);
+        r = make_tmap(&tmAl, al, uint64_t(n), uint64_t(K), 128);
         if (r) return r;
         CUDA_TRY(launch_siren_tc(tmAh, tmAl, c->tmWh[i], c->tmWl[i], c->b[i], n, K, H,
                                  last ? 0.0 : (i == 0 ? c->w0_first : c->w0_hidden), last ? nullptr : hid[i & 1][0],

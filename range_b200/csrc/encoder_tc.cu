@@ -1,20 +1,24 @@
-// K1/K1b on the tensor cores: the SIREN layers as 3xTF32 tcgen05 GEMMs (fp32-class accuracy).
+// K1/K1b on the tensor cores: the SIREN layers as split-precision (3 x fp16) tcgen05 GEMMs (fp32-class accuracy).
 //
 // The reference runs the SIREN in fp64 (model_old.py:326-330), but its own spherical-harmonic input carries
 // 1e-3 .. 5e-2 of fp64 rounding noise; an fp32-accurate SIREN moves the normalised
-// embedding by ~3e-7 (measured, tests/test_gpu_parity.py::test_encoder_tf32x3_vs_fp64), far below that.
-// Every operand x is split x = hi + lo with hi holding the 10 mantissa bits the TF32 datapath keeps, and
+// embedding by ~1e-6 (measured, tests/test_gpu_parity.py::test_encoder_split_vs_fp64), far below that.
+// Every operand x is split x = hi + lo into two fp16 values (11 + 11 significant bits, what a 3xTF32 split keeps too) and
 //     A.B  ~=  A_hi.B_hi + A_hi.B_lo + A_lo.B_hi          (dropped term: 2^-22 relative)
-// accumulated in fp32 in TMEM.  Bias add and the sine's argument reduction are done in fp64 in the epilogue.
+// accumulated in fp32 in TMEM with kind::f16 MMAs - twice the TF32 rate and half the operand bytes (the TF32 version of
+// this kernel was shared-memory-bandwidth bound: 156 B/clk of operand traffic).  Weights are pre-scaled by 2^10 so
+// their low parts stay in fp16's normal range (|W| <= 1/1600 in the first layer); the epilogue scales back.  Bias add
+// and the sine's argument reduction are done in fp64 in the epilogue.
 //
 //   sh_rowmajor_kernel   features in PRODUCTION order (|m|-major; the first layer's columns are permuted to
-//                        match) as hi/lo fp32, row-major [N][L*L], through a per-warp 32x32 smem transpose
+//                        match) as hi/lo fp16, row-major [N][L*L], through a per-warp 32x32 smem transpose
 //                        so global writes are coalesced although a thread owns a whole query.
-//   split_weights_kernel W fp64 [H][K] -> W_hi, W_lo fp32 [H][K] (optionally with the column permutation)
-//   siren_tc_kernel      CTA = 128 queries x 256 outputs, K-blocks of 32: TMA (SWIZZLE_128B) -> smem ring ->
-//                        12 x tcgen05.mma kind::tf32 (128x256x8) per block -> TMEM -> epilogue warps.
+//   split_weights_kernel W fp64 [H][K] -> hi, lo fp16 of 2^10 W, [H][K] (optionally with the column permutation)
+//   siren_tc_kernel      CTA = 128 queries x 256 outputs, K-blocks of 64: TMA (SWIZZLE_128B) -> smem ring ->
+//                        12 x tcgen05.mma kind::f16 (128x256x16) per block -> TMEM -> epilogue warps.
 #include <cstdint>
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <math_constants.h>
 
@@ -25,10 +29,11 @@ namespace {
 
 constexpr double kDeg2Rad = 0.017453292519943295769236907684886;
 
-__device__ __forceinline__ void split_tf32(double x, float& hi, float& lo) {
-  const float f = float(x);
-  hi = __uint_as_float(__float_as_uint(f) & 0xFFFFE000u);      // the 19 bits kind::tf32 reads
-  lo = float(x - double(hi));
+constexpr float kWScale = 1024.f;        // weights are stored as 2^10 W (hi + lo fp16)
+
+__device__ __forceinline__ void split_f16(double x, __half& hi, __half& lo) {
+  hi = __float2half_rn(float(x));
+  lo = __float2half_rn(float(x - double(__half2float(hi))));
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -38,8 +43,8 @@ constexpr int kShWarps = 4;
 __global__ void __launch_bounds__(kShWarps * 32)
 sh_rowmajor_kernel(const double* __restrict__ lonlat, int N, int L, const double* __restrict__ pref,
                    const int* __restrict__ off, const double* __restrict__ coef, const int* __restrict__ par,
-                   float* __restrict__ Yh, float* __restrict__ Yl) {
-  __shared__ float tile[kShWarps][2][32][33];
+                   __half* __restrict__ Yh, __half* __restrict__ Yl) {
+  __shared__ __half tile[kShWarps][2][32][34];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = (blockIdx.x * kShWarps + warp) * 32;
   if (n0 >= N) return;
@@ -55,8 +60,8 @@ sh_rowmajor_kernel(const double* __restrict__ lonlat, int N, int L, const double
   double spow = 1.0;
   int e = 0, cnt = 0, f0 = 0;
   auto emit = [&](double v) {
-    float hi, lo;
-    split_tf32(v, hi, lo);
+    __half hi, lo;
+    split_f16(v, hi, lo);
     tile[warp][0][lane][cnt] = hi;
     tile[warp][1][lane][cnt] = lo;
     if (++cnt == 32) {
@@ -116,14 +121,14 @@ sh_rowmajor_kernel(const double* __restrict__ lonlat, int N, int L, const double
   }
 }
 
-// W fp64 [H][K] -> hi/lo fp32 [H][K]; column f of the output reads column perm[f] of the input (perm may be null)
+// W fp64 [H][K] -> hi/lo fp16 of 2^10 W, [H][K]; column f of the output reads column perm[f] of the input (perm may be null)
 __global__ void split_weights_kernel(const double* __restrict__ W, int H, int K, const int* __restrict__ perm,
-                                     float* __restrict__ Wh, float* __restrict__ Wl) {
+                                     __half* __restrict__ Wh, __half* __restrict__ Wl) {
   const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= size_t(H) * K) return;
   const int h = int(i / K), f = int(i % K);
-  float hi, lo;
-  split_tf32(W[size_t(h) * K + (perm ? perm[f] : f)], hi, lo);
+  __half hi, lo;
+  split_f16(double(kWScale) * W[size_t(h) * K + (perm ? perm[f] : f)], hi, lo);
   Wh[i] = hi;
   Wl[i] = lo;
 }
@@ -140,15 +145,15 @@ constexpr int kTcSmem = kTcStages * kTcStageBytes + 256 + 1024;
 __global__ void __launch_bounds__(kTcThreads, 1)
 siren_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                 const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
-                const double* __restrict__ bias, int N, int K, int H, double act_w0, float* __restrict__ out_hi,
-                float* __restrict__ out_lo, double* __restrict__ out_f64) {
+                const double* __restrict__ bias, int N, int K, int H, double act_w0, __half* __restrict__ out_hi,
+                __half* __restrict__ out_lo, double* __restrict__ out_f64) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kTcStages * kTcStageBytes);   // full[S] | empty[S] | done
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kTcStages + 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row0 = blockIdx.x * 128, col0 = blockIdx.y * 256;
-  const int KB = K / 32;
+  const int KB = K / 64;                  // K blocks of 64 fp16 = one 128-byte swizzle row
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kTcStages; ++i) {
@@ -174,15 +179,15 @@ siren_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
         ptx::mbar_wait(&bars[kTcStages + idx], phase ^ 1);
         uint8_t* st = smem + idx * kTcStageBytes;
         ptx::mbar_expect_tx(&bars[idx], kTcStageBytes);
-        ptx::tma_load_2d(st, &tmAh, &bars[idx], kb * 32, row0);
-        ptx::tma_load_2d(st + 16384, &tmAl, &bars[idx], kb * 32, row0);
-        ptx::tma_load_2d(st + 32768, &tmBh, &bars[idx], kb * 32, col0);
-        ptx::tma_load_2d(st + 65536, &tmBl, &bars[idx], kb * 32, col0);
+        ptx::tma_load_2d(st, &tmAh, &bars[idx], kb * 64, row0);
+        ptx::tma_load_2d(st + 16384, &tmAl, &bars[idx], kb * 64, row0);
+        ptx::tma_load_2d(st + 32768, &tmBh, &bars[idx], kb * 64, col0);
+        ptx::tma_load_2d(st + 65536, &tmBl, &bars[idx], kb * 64, col0);
         if (++idx == kTcStages) { idx = 0; phase ^= 1; }
       }
     }
   } else if (warp == kTcEpiWarps + 1) {
-    constexpr uint32_t idesc = ptx::umma_idesc_tf32(128, 256);
+    constexpr uint32_t idesc = ptx::umma_idesc_f16(128, 256);
     int idx = 0; uint32_t phase = 0;
     for (int kb = 0; kb < KB; ++kb) {
       ptx::mbar_wait(&bars[idx], phase);
@@ -195,9 +200,9 @@ siren_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
           const uint64_t al = ptx::umma_desc_kmajor_sw128(st + 16384 + kk * 32);
           const uint64_t bh = ptx::umma_desc_kmajor_sw128(st + 32768 + kk * 32);
           const uint64_t bl = ptx::umma_desc_kmajor_sw128(st + 65536 + kk * 32);
-          ptx::umma_tf32_ss(tmem_base, al, bh, idesc, (kb | kk) != 0);   // small terms first
-          ptx::umma_tf32_ss(tmem_base, ah, bl, idesc, 1);
-          ptx::umma_tf32_ss(tmem_base, ah, bh, idesc, 1);
+          ptx::umma_f16_ss(tmem_base, al, bh, idesc, (kb | kk) != 0);   // small terms first
+          ptx::umma_f16_ss(tmem_base, ah, bl, idesc, 1);
+          ptx::umma_f16_ss(tmem_base, ah, bh, idesc, 1);
         }
         ptx::umma_commit_u32(bars_u + 8 * (kTcStages + idx));
         if (kb == KB - 1) ptx::umma_commit_u32(bars_u + 8 * (2 * kTcStages));
@@ -222,25 +227,32 @@ siren_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
           double* o = out_f64 + size_t(n) * H + col0 + c0;
 #pragma unroll
           for (int i = 0; i < 32; i += 2)
-            *reinterpret_cast<double2*>(o + i) = make_double2(double(__uint_as_float(v[i])) + __ldg(bias + col0 + c0 + i),
-                                                              double(__uint_as_float(v[i + 1])) + __ldg(bias + col0 + c0 + i + 1));
+            *reinterpret_cast<double2*>(o + i) =
+                make_double2(double(__uint_as_float(v[i]) * (1.f / kWScale)) + __ldg(bias + col0 + c0 + i),
+                             double(__uint_as_float(v[i + 1]) * (1.f / kWScale)) + __ldg(bias + col0 + c0 + i + 1));
         } else {
-          float hi[32], lo[32];
+          uint32_t hi[16], lo[16];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            // sin(w0 (acc + b)): argument reduced in fp64 (phases reach tens of radians), sine in fp32
-            const double t = act_w0 * (double(__uint_as_float(v[i])) + __ldg(bias + col0 + c0 + i));
-            const double r = fma(-rint(t * 0.15915494309189535), 6.283185307179586, t);
-            const float sv = sinf(float(r));
-            hi[i] = __uint_as_float(__float_as_uint(sv) & 0xFFFFE000u);
-            lo[i] = sv - hi[i];
+          for (int i = 0; i < 32; i += 2) {
+            float sv[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              // sin(w0 (acc + b)): argument reduced in fp64 (phases reach tens of radians), sine in fp32
+              const double t = act_w0 * (double(__uint_as_float(v[i + u]) * (1.f / kWScale)) + __ldg(bias + col0 + c0 + i + u));
+              const double r = fma(-rint(t * 0.15915494309189535), 6.283185307179586, t);
+              sv[u] = sinf(float(r));
+            }
+            const __half2 h = __floats2half2_rn(sv[0], sv[1]);
+            const __half2 l = __floats2half2_rn(sv[0] - __low2float(h), sv[1] - __high2float(h));
+            hi[i / 2] = *reinterpret_cast<const uint32_t*>(&h);
+            lo[i / 2] = *reinterpret_cast<const uint32_t*>(&l);
           }
-          float4* oh = reinterpret_cast<float4*>(out_hi + size_t(n) * H + col0 + c0);
-          float4* ol = reinterpret_cast<float4*>(out_lo + size_t(n) * H + col0 + c0);
+          uint4* oh = reinterpret_cast<uint4*>(out_hi + size_t(n) * H + col0 + c0);
+          uint4* ol = reinterpret_cast<uint4*>(out_lo + size_t(n) * H + col0 + c0);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            oh[i] = make_float4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
-            ol[i] = make_float4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+          for (int i = 0; i < 4; ++i) {
+            oh[i] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
+            ol[i] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
           }
         }
       }
@@ -255,30 +267,31 @@ siren_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
 
 namespace rangeb200 {
 
-cudaError_t launch_sh_rowmajor(const ShTable& t, const double* lonlat, int N, float* Yh, float* Yl, cudaStream_t s) {
+cudaError_t launch_sh_rowmajor(const ShTable& t, const double* lonlat, int N, void* Yh, void* Yl, cudaStream_t s) {
   if (N <= 0) return cudaSuccess;
   const int per_block = kShWarps * 32;
   sh_rowmajor_kernel<<<(N + per_block - 1) / per_block, per_block, 0, s>>>(lonlat, N, t.L, t.pref, t.off, t.coef,
-                                                                           t.par, Yh, Yl);
+                                                                           t.par, reinterpret_cast<__half*>(Yh), reinterpret_cast<__half*>(Yl));
   return cudaGetLastError();
 }
 
-cudaError_t launch_split_weights(const double* W, int H, int K, const int* perm, float* Wh, float* Wl, cudaStream_t s) {
+cudaError_t launch_split_weights(const double* W, int H, int K, const int* perm, void* Wh, void* Wl, cudaStream_t s) {
   const size_t total = size_t(H) * K;
-  split_weights_kernel<<<unsigned((total + 255) / 256), 256, 0, s>>>(W, H, K, perm, Wh, Wl);
+  split_weights_kernel<<<unsigned((total + 255) / 256), 256, 0, s>>>(W, H, K, perm, reinterpret_cast<__half*>(Wh),
+                                                                     reinterpret_cast<__half*>(Wl));
   return cudaGetLastError();
 }
 
 cudaError_t launch_siren_tc(const CUtensorMap& tmAh, const CUtensorMap& tmAl, const CUtensorMap& tmBh,
                             const CUtensorMap& tmBl, const double* bias, int N, int K, int H, double act_w0,
-                            float* out_hi, float* out_lo, double* out_f64, cudaStream_t s) {
+                            void* out_hi, void* out_lo, double* out_f64, cudaStream_t s) {
   if (N <= 0) return cudaSuccess;
-  if (K % 32 || H % 256) return cudaErrorInvalidValue;
+  if (K % 64 || H % 256) return cudaErrorInvalidValue;
   cudaError_t e = cudaFuncSetAttribute(siren_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem);
   if (e != cudaSuccess) return e;
   dim3 grid((N + 127) / 128, H / 256);
-  siren_tc_kernel<<<grid, kTcThreads, kTcSmem, s>>>(tmAh, tmAl, tmBh, tmBl, bias, N, K, H, act_w0, out_hi, out_lo,
-                                                    out_f64);
+  siren_tc_kernel<<<grid, kTcThreads, kTcSmem, s>>>(tmAh, tmAl, tmBh, tmBl, bias, N, K, H, act_w0,
+                                                    reinterpret_cast<__half*>(out_hi), reinterpret_cast<__half*>(out_lo), out_f64);
   return cudaGetLastError();
 }
 

@@ -26,16 +26,16 @@ cudaError_t launch_sh(const ShTable& t, const double* lonlat, int N, double* Yt,
 cudaError_t launch_siren_layer(const double* W, const double* b, const double* Xt, size_t ldx, int H, int K, int N,
                                double act_w0, double* out, size_t ldo, int out_rowmajor, cudaStream_t s);
 
-// ---- K1/K1b on the tensor cores: 3xTF32 tcgen05 GEMMs (encoder_tc.cu) ----------------------------------
-// features as hi/lo fp32, row-major [N][L*L], in PRODUCTION order (|m|-major: for am: for l >= am: cos, sin)
-cudaError_t launch_sh_rowmajor(const ShTable& t, const double* lonlat, int N, float* Yh, float* Yl, cudaStream_t s);
-// W fp64 [H][K] -> hi/lo fp32 [H][K]; output column f = input column perm[f] (perm may be null)
-cudaError_t launch_split_weights(const double* W, int H, int K, const int* perm, float* Wh, float* Wl, cudaStream_t s);
-// out = act(A . B^T + bias): A hi/lo [N][K], B hi/lo [H][K] (tensor maps: fp32, box [rows x 32], SWIZZLE_128B);
-// act_w0 > 0 -> sin(act_w0 x) written as hi/lo fp32 [N][H]; out_f64 != null -> plain fp64 [N][H]
+// ---- K1/K1b on the tensor cores: split-precision (3 x fp16) tcgen05 GEMMs (encoder_tc.cu) ------------------
+// features as hi/lo fp16, row-major [N][L*L], in PRODUCTION order (|m|-major: for am: for l >= am: cos, sin)
+cudaError_t launch_sh_rowmajor(const ShTable& t, const double* lonlat, int N, void* Yh, void* Yl, cudaStream_t s);
+// W fp64 [H][K] -> hi/lo fp16 of 2^10 W, [H][K]; output column f = input column perm[f] (perm may be null)
+cudaError_t launch_split_weights(const double* W, int H, int K, const int* perm, void* Wh, void* Wl, cudaStream_t s);
+// out = act(A . B^T + bias): A hi/lo [N][K], B hi/lo [H][K] (tensor maps: fp16, box [rows x 64], SWIZZLE_128B);
+// act_w0 > 0 -> sin(act_w0 x) written as hi/lo fp16 [N][H]; out_f64 != null -> plain fp64 [N][H]
 cudaError_t launch_siren_tc(const CUtensorMap& tmAh, const CUtensorMap& tmAl, const CUtensorMap& tmBh,
                             const CUtensorMap& tmBl, const double* bias, int N, int K, int H, double act_w0,
-                            float* out_hi, float* out_lo, double* out_f64, cudaStream_t s);
+                            void* out_hi, void* out_lo, double* out_f64, cudaStream_t s);
 
 // ---- K3: normalise / concat (encoder.cu) ----------------------------------------------------------
 // e [N][D] fp64 row-major -> q64 [N][D] (ld = ldq), q16 [N][D] fp16, qxyz [N][4] fp32 from lonlat

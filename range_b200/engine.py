@@ -26,8 +26,8 @@ class RangeEngine:
     def __init__(self, device, encoder=None, database=None, L=None, encoder_precision="auto"):
         """encoder: dict from checkpoint.load_satclip_location_encoder (or None: SH only with `L`);
         database: database.DeviceDatabase or None;
-        encoder_precision: 'fp64' (the reference's arithmetic, DMMA), 'tf32x3' (tensor cores, fp32-class
-        accuracy) or 'auto' (= tf32x3 when the layer widths allow it, else fp64)."""
+        encoder_precision: 'fp64' (the reference's arithmetic, DMMA), 'f16x3' (tensor cores, split fp16 operands,
+        fp32-class accuracy; 'tf32x3' is accepted as an alias) or 'auto' (= f16x3 when the layer widths allow it, else fp64)."""
         self.encoder_precision = encoder_precision
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -80,15 +80,15 @@ class RangeEngine:
         self.dims = list(enc["dims"])
         self._prepared = None
         self.precision = "fp64"
-        want = self.encoder_precision
+        want = "f16x3" if self.encoder_precision == "tf32x3" else self.encoder_precision
         nbytes = self.lib.range_encoder_prepared_bytes(self.ctx)
-        if want == "tf32x3" and nbytes == 0:
-            raise _lib.RangeError("encoder_precision='tf32x3' needs every SIREN width to be a multiple of 256")
-        if want in ("auto", "tf32x3") and nbytes > 0:
+        if want == "f16x3" and nbytes == 0:
+            raise _lib.RangeError("encoder_precision='f16x3' needs every SIREN width to be a multiple of 256")
+        if want in ("auto", "f16x3") and nbytes > 0:
             self._prepared = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
             with torch.cuda.device(self.index):
                 _lib.check(self.lib.range_ctx_prepare_encoder(self.ctx, _ptr(self._prepared), int(nbytes), _stream()))
-            self.precision = "tf32x3"
+            self.precision = "f16x3"
 
     def set_database(self, db):
         _lib.check(self.lib.range_ctx_set_db(self.ctx, db.M, db.Mpad, _ptr(db.Kh), _ptr(db.Vt), _ptr(db.xyz),

@@ -93,14 +93,14 @@ def test_encoder_vs_reference(gold_setup):
     assert np.abs(qxyz.cpu().numpy()[:, :3] - xyz).max() <= 1.2e-7
 
 
-def test_encoder_tf32x3_vs_fp64(sh_entries):
-    """tensor-core SIREN (3xTF32, fp32-class) against the fp64 DMMA path and the oracle, H = 512; ragged N"""
+def test_encoder_split_vs_fp64(sh_entries):
+    """tensor-core SIREN (split fp16 operands, fp32-class) against the fp64 DMMA path and the oracle, H = 512; ragged N"""
     from range_b200.engine import RangeEngine
     ws = O.siren_init(40, 512, 2, 256, seed=0)
     enc = dict(L=40, dims=[1600, 512, 512, 256], weights=ws)
     e64 = RangeEngine(DEV, encoder=enc, encoder_precision="fp64")
     etc = RangeEngine(DEV, encoder=enc, encoder_precision="auto")
-    assert e64.precision == "fp64" and etc.precision == "tf32x3"
+    assert e64.precision == "fp64" and etc.precision == "f16x3"
     for N in (1, 129, 3000):
         c = O.area_uniform(N, np.random.default_rng(N))
         c[0] = [0.0, 90.0]
@@ -115,7 +115,7 @@ def test_encoder_tf32x3_vs_fp64(sh_entries):
     assert d[lat < 60].max() <= 5e-5 and d.max() <= 2e-3
     with pytest.raises(Exception):
         RangeEngine(DEV, encoder=dict(L=40, dims=[1600, 64, 64, 256], weights=O.siren_init(40, 64, 2, 256)),
-                    encoder_precision="tf32x3")
+                    encoder_precision="f16x3")
 
 
 def test_retrieval_vs_reference_golden(gold_setup):

@@ -8,7 +8,7 @@ dev = "cuda:0"
 ws = O.siren_init(40, 512, 2, 256, seed=0)
 enc = dict(L=40, dims=[1600, 512, 512, 256], weights=ws)
 e64 = RangeEngine(dev, encoder=enc, encoder_precision="fp64")
-etc = RangeEngine(dev, encoder=enc, encoder_precision="tf32x3")
+etc = RangeEngine(dev, encoder=enc, encoder_precision="f16x3")
 print("precisions:", e64.precision, etc.precision)
 c = O.area_uniform(5000, np.random.default_rng(7))
 c[:4] = [[0, 90], [0, -90], [180, 0], [-180, 0]]
@@ -16,11 +16,11 @@ ct = torch.tensor(c)
 qa, qa16, xa = e64.encode(ct)
 qb, qb16, xb = etc.encode(ct)
 d = (qa - qb).abs().max(1).values.cpu().numpy()
-print("tf32x3 vs fp64 (GPU): max abs", d.max(), " mean", d.mean(), " nan", int(torch.isnan(qb).sum()))
+print("f16x3 vs fp64 (GPU): max abs", d.max(), " mean", d.mean(), " nan", int(torch.isnan(qb).sum()))
 ref = O.RangeOracle.__new__(O.RangeOracle); ref.L, ref.entries, ref.weights = 40, load_entries(40), ws
 qr = ref.encode(ct).numpy()
 lat = np.abs(c[:, 1])
-for nm, q in (("fp64", qa), ("tf32x3", qb)):
+for nm, q in (("fp64", qa), ("f16x3", qb)):
     dd = np.abs(q.cpu().numpy() - qr).max(1)
     print(f"{nm} vs oracle: |lat|<60 {dd[lat < 60].max():.3e}  >=60 {dd[lat >= 60].max():.3e}")
 # ragged N
@@ -35,4 +35,4 @@ def timeit(fn, reps=5):
         a.record(); fn(); b.record(); torch.cuda.synchronize(); ts.append(a.elapsed_time(b))
     return min(ts)
 big = torch.tensor(O.area_uniform(100000, np.random.default_rng(1)), device=dev)
-print("encode 100k: fp64 %.2f ms   tf32x3 %.2f ms" % (timeit(lambda: e64.encode(big)), timeit(lambda: etc.encode(big))))
+print("encode 100k: fp64 %.2f ms   f16x3 %.2f ms" % (timeit(lambda: e64.encode(big)), timeit(lambda: etc.encode(big))))
