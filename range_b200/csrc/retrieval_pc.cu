@@ -78,6 +78,15 @@ constexpr int kPolyEvery = RANGE_PC_POLY;
 __device__ __forceinline__ float ex2_mixed(float x, int i) {
   return (kPolyEvery > 0 && (i % (kPolyEvery > 0 ? kPolyEvery : 1)) == kPolyEvery - 1) ? ptx::ex2_poly(x) : ptx::ex2(x);
 }
+// columns of S a softmax warp evaluates per step (one TMEM load in flight while the previous piece is evaluated)
+// Measured: apply 16 (20.2 ms; 32 spills under the 128-register cap: 21.9 ms), statistics 32 (4.56 vs 4.65 ms).
+constexpr int kPieceApply = 16, kPieceStats = 32;
+template <int W>
+__device__ __forceinline__ void tmem_ld_piece(uint32_t taddr, uint32_t (&v)[W]) {
+  static_assert(W == 16 || W == 32, "piece width");
+  if constexpr (W == 16) ptx::tmem_ld16(taddr, v);
+  else ptx::tmem_ld32(taddr, v);
+}
 constexpr int kFlagStride = 32;                  // uint32 per flag line (128 B)
 constexpr int kFlagsPerProducer = 3 * kFlagStride;   // full, done[0], done[1]
 
@@ -393,6 +402,8 @@ range_apply_pc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       int cur_r = -1, n = 0, tail_t0 = 0;
       const uint32_t* mask_row = nullptr;
       float cs = -INFINITY, cg = -INFINITY, gx = 0.f, gy = 0.f, gz = 0.f;
+      uint32_t bufA[kPieceApply], bufB[kPieceApply];
+      bool prefetched = false;        // the first piece of this tile's S was requested at the end of the last tile
       for (uint32_t it = uint32_t(grp); it < total; it += kGroups) {
         const int r = it < base_tail ? int(it / uint32_t(T)) : plan.full_rounds;
         const int b = it & (L::NB - 1);
@@ -415,19 +426,21 @@ range_apply_pc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         const bool with_geo = kGeo && !(mask_row != nullptr && ((__ldg(mask_row + (j >> 5)) >> (j & 31)) & 1u));
         __half* dst = ring_row + size_t(slot) * 128 * 128;
         PC_T0();
-        ptx::mbar_wait(&bars[L::b_s_full + b], (it / L::NB) & 1);      // S(it) in TMEM and xyz(it) in smem
+        if (!prefetched) {
+          ptx::mbar_wait(&bars[L::b_s_full + b], (it / L::NB) & 1);      // S(it) in TMEM and xyz(it) in smem
+          ptx::tc_fence_after();
+          tmem_ld_piece(taddr, bufA);
+        }
         PC_ADD(0);
-        ptx::tc_fence_after();
-        // eight 16-entry pieces; the TMEM load of piece h + 1 is in flight while piece h is evaluated
-        uint32_t bufA[16], bufB[16];
-        auto piece = [&](const uint32_t (&cur)[16], int h) {
-          const uint32_t kxyz = smem_u + L::xyz + b * kXyzBytes + h * 16 * 16;
-          const int nvalid = M - (j * kKeys + h * 16);            // >= 16 except in the last tile
-          uint32_t packed[8];
+        // 128 / kPieceApply pieces; the TMEM load of piece h + 1 is in flight while piece h is evaluated
+        auto piece = [&](const uint32_t (&cur)[kPieceApply], int h) {
+          const uint32_t kxyz = smem_u + L::xyz + b * kXyzBytes + h * kPieceApply * 16;
+          const int nvalid = M - (j * kKeys + h * kPieceApply);            // >= kPieceApply except in the last tile
+          uint32_t packed[kPieceApply / 2];
           auto body = [&](auto masked, auto geo) {
             constexpr bool kM = decltype(masked)::value, kG = decltype(geo)::value;
 #pragma unroll
-            for (int w = 0; w < 8; ++w) {
+            for (int w = 0; w < kPieceApply / 2; ++w) {
               float pv[2];
 #pragma unroll
               for (int u = 0; u < 2; ++u) {
@@ -445,8 +458,8 @@ range_apply_pc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           };
           if (dbg & 8) {                                  // developer switch: no exponentials (consumer-bound run)
 #pragma unroll
-            for (int w = 0; w < 8; ++w) packed[w] = cur[2 * w] & 0x3c003c00u;
-          } else if (nvalid >= 16) {
+            for (int w = 0; w < kPieceApply / 2; ++w) packed[w] = cur[2 * w] & 0x3c003c00u;
+          } else if (nvalid >= kPieceApply) {
             if (with_geo) body(std::false_type{}, std::true_type{}); else body(std::false_type{}, std::false_type{});
           } else {
             if (with_geo) body(std::true_type{}, std::true_type{}); else body(std::true_type{}, std::false_type{});
@@ -455,27 +468,38 @@ range_apply_pc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           if (h == 0) ptx::mbar_wait(&bars[L::b_slot_free + slot], (it / kRing) & 1);   // both consumers copied tile it - kRing
           PC_ADD(3);
           // ring tile layout [16 key chunks][128 rows][8 entries]: a warp's store covers 512 contiguous bytes
-          ptx::stg_u4(dst + ((2 * h) * 128) * 8, packed[0], packed[1], packed[2], packed[3]);
-          ptx::stg_u4(dst + ((2 * h + 1) * 128) * 8, packed[4], packed[5], packed[6], packed[7]);
+#pragma unroll
+          for (int e = 0; e < kPieceApply / 8; ++e)
+            ptx::stg_u4(dst + ((h * (kPieceApply / 8) + e) * 128) * 8, packed[4 * e], packed[4 * e + 1], packed[4 * e + 2],
+                        packed[4 * e + 3]);
           PC_ADD(4);
         };
-        ptx::tmem_ld16(taddr, bufA);
+        constexpr int kPairs = 128 / (2 * kPieceApply);
 #pragma unroll 1
-        for (int hp = 0; hp < 4; ++hp) {
+        for (int hp = 0; hp < kPairs; ++hp) {
           ptx::tmem_ld_wait();
           PC_ADD(1);
-          ptx::tmem_ld16(taddr + (2 * hp + 1) * 16, bufB);
+          tmem_ld_piece(taddr + (2 * hp + 1) * kPieceApply, bufB);
           piece(bufA, 2 * hp);
           ptx::tmem_ld_wait();
           PC_ADD(1);
-          if (hp < 3) {
-            ptx::tmem_ld16(taddr + (2 * hp + 2) * 16, bufA);
+          if (hp < kPairs - 1) {
+            tmem_ld_piece(taddr + (2 * hp + 2) * kPieceApply, bufA);
           } else {                              // the whole S tile is in registers: the MMA warp may overwrite the buffer
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) {
               if (leader) ptx::mbar_arrive(&bars[L::b_s_empty + b]);
               else ptx::mbar_arrive_cluster_relaxed(s_empty_leader0 + 8 * b);
+            }
+            // the group's next tile normally sits in the spare buffer already: start its first TMEM load now, so the
+            // barrier wait and the load latency hide behind the last piece of this tile
+            const uint32_t nx = it + kGroups;
+            prefetched = __all_sync(0xffffffffu, nx < total && ptx::mbar_try_wait(&bars[L::b_s_full + (nx & (L::NB - 1))],
+                                                                                 (nx / L::NB) & 1));
+            if (prefetched) {
+              ptx::tc_fence_after();
+              tmem_ld_piece(tmem_base + (uint32_t(quarter * 32) << 16) + (nx & (L::NB - 1)) * kKeys, bufA);
             }
           }
           piece(bufB, 2 * hp + 1);
@@ -810,21 +834,25 @@ range_stats_pc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     if (kGeo && n < N) qx = q_xyz[n];
     const float gx = qx.x * a_geo, gy = qx.y * a_geo, gz = qx.z * a_geo;
     float sum_s = 0.f, sum_g = 0.f, max_s = -2.f, max_g = -3.0e38f;
+    uint32_t bufA[kPieceStats], bufB[kPieceStats];
+    bool prefetched = false;          // the first piece of this tile's S was requested at the end of the last tile
     for (int j = grp; j < T; j += kGroups) {
       const int t = t_begin + j;
       const int b = j & (L::NB - 1);
       const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + b * kKeys;
       const bool with_geo = kGeo && !skip_geo(t);
-      ptx::mbar_wait(&bars[L::b_s_full + b], (j / L::NB) & 1);      // S(j) in TMEM and xyz(j) in smem
-      ptx::tc_fence_after();
-      uint32_t bufA[16], bufB[16];
-      auto piece = [&](const uint32_t (&cur)[16], int h) {
-        const uint32_t kxyz = smem_u + L::xyz + b * kXyzBytes + h * 16 * 16;
-        const int nvalid = M - (t * kKeys + h * 16);            // >= 16 except in the last tile
+      if (!prefetched) {
+        ptx::mbar_wait(&bars[L::b_s_full + b], (j / L::NB) & 1);      // S(j) in TMEM and xyz(j) in smem
+        ptx::tc_fence_after();
+        tmem_ld_piece(taddr, bufA);
+      }
+      auto piece = [&](const uint32_t (&cur)[kPieceStats], int h) {
+        const uint32_t kxyz = smem_u + L::xyz + b * kXyzBytes + h * kPieceStats * 16;
+        const int nvalid = M - (t * kKeys + h * kPieceStats);            // >= kPieceStats except in the last tile
         auto body = [&](auto masked, auto geo) {
           constexpr bool kM = decltype(masked)::value, kG = decltype(geo)::value;
 #pragma unroll
-          for (int i = 0; i < 16; i += 2) {
+          for (int i = 0; i < kPieceStats; i += 2) {
             float sv[2], gv[2];
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
@@ -847,27 +875,34 @@ range_stats_pc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
             if (kG) max_g = ptx::max3(max_g, gv[0], gv[1]);
           }
         };
-        if (nvalid >= 16) {
+        if (nvalid >= kPieceStats) {
           if (with_geo) body(std::false_type{}, std::true_type{}); else body(std::false_type{}, std::false_type{});
         } else {
           if (with_geo) body(std::true_type{}, std::true_type{}); else body(std::true_type{}, std::false_type{});
         }
       };
-      ptx::tmem_ld16(taddr, bufA);
+      constexpr int kPairs = 128 / (2 * kPieceStats);
 #pragma unroll 1
-      for (int hp = 0; hp < 4; ++hp) {
+      for (int hp = 0; hp < kPairs; ++hp) {
         ptx::tmem_ld_wait();
-        ptx::tmem_ld16(taddr + (2 * hp + 1) * 16, bufB);
+        tmem_ld_piece(taddr + (2 * hp + 1) * kPieceStats, bufB);
         piece(bufA, 2 * hp);
         ptx::tmem_ld_wait();
-        if (hp < 3) {
-          ptx::tmem_ld16(taddr + (2 * hp + 2) * 16, bufA);
+        if (hp < kPairs - 1) {
+          tmem_ld_piece(taddr + (2 * hp + 2) * kPieceStats, bufA);
         } else {                              // the whole S tile is in registers: the MMA warp may overwrite the buffer
           ptx::tc_fence_before();
           __syncwarp();
           if (lane == 0) {
             if (leader) ptx::mbar_arrive(&bars[L::b_s_empty + b]);
             else ptx::mbar_arrive_cluster_relaxed(s_empty_leader0 + 8 * b);
+          }
+          const int nx = j + kGroups;         // start the next tile's first TMEM load behind this tile's last piece
+          prefetched = __all_sync(0xffffffffu, nx < T && ptx::mbar_try_wait(&bars[L::b_s_full + (nx & (L::NB - 1))],
+                                                                             (nx / L::NB) & 1));
+          if (prefetched) {
+            ptx::tc_fence_after();
+            tmem_ld_piece(tmem_base + (uint32_t(quarter * 32) << 16) + (nx & (L::NB - 1)) * kKeys, bufA);
           }
         }
         piece(bufB, 2 * hp + 1);
