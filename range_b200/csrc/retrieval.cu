@@ -5,7 +5,9 @@
 //   RANGE :  P = softmax(15 S)                              O = P V
 //   RANGE+:  P = beta softmax(12 S) + (1-beta) softmax(40 G) O = P V     ((1-b) Pg V + b Ps V == (..) V)
 //
-// The N x M similarity matrix never exists in memory.  Two kernels, both streaming the database once:
+// The N x M similarity matrix never exists in memory.  Two passes, both streaming the database once.  This file holds
+// the kernels for SMALL batches (fewer than 24 query-tile pairs; database split over CTAs to fill the SMs) and the
+// geo-skip mask; large batches run the role-specialised kernels of retrieval_pc.cu.
 //
 //   range_stats_kernel   per query row: sum_j exp(t (s_j - 1)), max_j s_j (and the same for g).  Because
 //                        |s|,|g| <= 1 the offset "-1" is a fixed, data-independent softmax max, so partial
@@ -326,7 +328,7 @@ range_stats_kernel(const __grid_constant__ CUtensorMap tmK, const __half* __rest
 
 // ---------------------------------------------------------------------------------------------------
 // K2b: apply  (O slice = P' . Vt).  Tile = 128 entries.  SS-mode Q.K^T with Q resident in shared memory,
-// TS-mode P.V with P' in TMEM.  Measured dead ends (profiles/r1b_notes.md): a 64-entry tile with Q in TMEM
+// TS-mode P.V with P' in TMEM.  Measured dead ends: a 64-entry tile with Q in TMEM
 // (a TS-mode MMA fetches its 128x16 A tile from TMEM in ~64 clk, which dominates UMMA_N = 64), sharing P'
 // between the four value-slice CTAs over DSMEM (9 B/clk/SM with the whole chip active).
 // rowc[n] = {cs, cg, qx*a_geo, qy*a_geo, qz*a_geo, out_scale, -, -}
