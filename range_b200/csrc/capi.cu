@@ -236,6 +236,8 @@ extern "C" {
 const char* range_last_error(void) { return g_err; }
 int range_version(void) { return 100; }
 int64_t range_launch_count(void) { return g_launches.load(); }
+// not in the public header: work decomposition of the producer/consumer apply kernel (tests/test_capi.py; host code only)
+void range_debug_apply_plan(int sm_count, int64_t N, int64_t M, int32_t* out7) { apply_pc_describe_plan(sm_count, N, M, out7); }
 // not in the public header: developer hook used by tools/time_apply.py
 void range_debug_set_profile_buffer(void* device_buffer) { set_profile_buffer(reinterpret_cast<long long*>(device_buffer)); }
 

@@ -91,7 +91,8 @@ int apply_pc_units(int sm_count);
 size_t apply_pc_ring_bytes(int sm_count);
 size_t apply_pc_flag_bytes(int sm_count, int64_t N, int64_t M);
 int apply_pc_ring_rows(int sm_count);          // ring as a 2-D tensor [rows][2 KB]
-size_t apply_pc_part_bytes(int sm_count, int64_t N, int64_t M);   // partial outputs of the split tail pairs
+size_t apply_pc_part_bytes(int sm_count, int64_t N, int64_t M);
+void apply_pc_describe_plan(int sm_count, int64_t N, int64_t M, int32_t out[7]);   // test hook   // partial outputs of the split tail pairs
 // row n of the result goes to out + (perm ? perm[n] : n) * out_ld (+ column), fp32 or fp64
 cudaError_t launch_apply_pc(const RetrievalArgs& a, const CUtensorMap& tmP, const float* rowc, void* out, int out_ld,
                             int out_f64, const int* perm, void* ring, void* flags, void* part, int sm_count,

@@ -973,6 +973,12 @@ static size_t pc_ring_flag_bytes(int sm_count) { return size_t(apply_pc_units(sm
 size_t apply_pc_flag_bytes(int sm_count, int64_t N, int64_t M) {
   return pc_ring_flag_bytes(sm_count) + pc_window_count(pc_plan(sm_count, N, M), M) * 4;
 }
+// developer / test hook: {n_units, full_rounds, tail_pairs, tail_split, tail_tiles, tail_row0, windows}
+void apply_pc_describe_plan(int sm_count, int64_t N, int64_t M, int32_t out[7]) {
+  const PcPlan p = pc_plan(sm_count, N, M);
+  out[0] = p.n_units; out[1] = p.full_rounds; out[2] = p.tail_pairs; out[3] = p.tail_split; out[4] = p.tail_tiles;
+  out[5] = p.tail_row0; out[6] = int32_t(pc_window_count(p, M));
+}
 // partial outputs of the split tail pairs: [tail_split][tail rows][1024] fp32 (0 when nothing is split)
 size_t apply_pc_part_bytes(int sm_count, int64_t N, int64_t M) {
   const PcPlan p = pc_plan(sm_count, N, M);

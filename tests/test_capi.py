@@ -90,3 +90,40 @@ def test_database_preparation_matches_reference_rules():
     assert K.dtype == np.float32 and xyz.dtype == np.float32
     assert np.array_equal(K, Kr) and np.array_equal(V, Vr) and np.array_equal(xyz, xr)
     assert np.allclose(np.linalg.norm(K, axis=1), 1, atol=1e-6)
+
+
+def test_apply_work_plan_covers_every_query_tile_pair_once():
+    """host-side decomposition of the producer/consumer apply kernel (csrc/retrieval_pc.cu: pc_plan / pc_work):
+    every query-tile pair is processed for every database tile exactly once, by one unit per round"""
+    import ctypes
+    from range_b200 import _lib
+    lib = _lib.load()
+    lib.range_debug_apply_plan.argtypes = [ctypes.c_int, ctypes.c_int64, ctypes.c_int64, ctypes.POINTER(ctypes.c_int32)]
+    lib.range_debug_apply_plan.restype = None
+    for sm, N, M in [(148, 100_000, 100_000), (148, 6_144, 50_000), (148, 24_576, 3_005), (148, 12_337, 77),
+                     (148, 7_900, 1_000_000), (132, 100_000, 100_000), (148, 300, 5_000), (148, 1 << 20, 10_000_000)]:
+        out = (ctypes.c_int32 * 7)()
+        lib.range_debug_apply_plan(sm, N, M, out)
+        units, full, tail_pairs, split, tail_tiles, row0, windows = list(out)
+        T = -(-M // 128)
+        qp = (-(-N // 128) + 1) // 2
+        assert units == (sm // 2) // 3 and full * units + tail_pairs == qp and 0 <= tail_pairs < units
+        assert row0 == full * units * 256
+        assert 1 <= split <= 4 and (tail_pairs == 0 or tail_pairs * split <= units)
+        assert split == 1 or T // split >= 32                      # a split range keeps at least 32 tiles
+        covered = {}
+        for unit in range(units):                                   # the device-side pc_work(), restated
+            for r in range(full + (1 if unit < tail_pairs * split else 0)):
+                if r < full:
+                    pair, t0, t1 = r * units + unit, 0, T
+                else:
+                    s = unit % split
+                    pair, t0, t1 = full * units + unit // split, s * tail_tiles, min(T, (s + 1) * tail_tiles)
+                assert t0 < t1
+                covered.setdefault(pair, []).append((t0, t1))
+        assert sorted(covered) == list(range(qp))
+        for pair, ranges in covered.items():
+            ranges.sort()
+            assert ranges[0][0] == 0 and ranges[-1][1] == T and all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
+        longest = full * T + (0 if tail_pairs == 0 else (tail_tiles if split > 1 else T))
+        assert windows >= -(-longest // 64)
