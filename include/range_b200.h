@@ -49,6 +49,11 @@ int range_ctx_destroy(range_ctx* ctx);
 int range_ctx_set_sh_table(range_ctx* ctx, int L, int n_entries, const double* pref, const int32_t* off,
                            const double* coef, const int32_t* par);
 
+/* harmonics_calculation == 'closed-form' checkpoints (positional_encoding/spherical_harmonics_closed_form.py:8-40):
+ * associated-Legendre recurrence instead of the generated polynomials.  norm: device array of L (L + 1) / 2
+ * factors, |m|-major (for am: for l >= am): SH_renormalization(l, am), times sqrt(2) for am > 0.  Borrowed. */
+int range_ctx_set_sh_closed_form(range_ctx* ctx, int L, int n_entries, const double* norm);
+
 /* SIREN weights - replaces SirenNet's parameters, location_encoder.py:73-112 (checkpoint keys
  * model.location.nnet.layers.{i}.{weight,bias}, model.location.nnet.last_layer.{weight,bias}).
  * dims: host array of n_layers+1 ints (dims[0] == L*L); W, b: host arrays of n_layers device pointers,

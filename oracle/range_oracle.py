@@ -69,6 +69,61 @@ def sh_analytic(lonlat, L, entries):
     return Y
 
 
+def closed_form_norms(L):
+    """(sqrt(2) *) SH_renormalization(l, m) exactly as spherical_harmonics_closed_form.py:28-40 computes them in Python
+    floats; returned |m|-major: for am in range(L): for l in range(am, L)"""
+    out = []
+    for am in range(L):
+        for l in range(am, L):
+            renorm = math.sqrt((2.0 * l + 1.0) * math.factorial(l - am) / (4 * math.pi * math.factorial(l + am)))
+            out.append(renorm if am == 0 else math.sqrt(2.0) * renorm)
+    return np.asarray(out, np.float64)
+
+
+def sh_closed_form(lonlat, L):
+    """harmonics_calculation='closed-form': spherical_harmonics.py:27-42 with spherical_harmonics_closed_form.py:8-40
+    (unnormalised associated-Legendre recurrence WITH Condon-Shortley phase, orthonormal m = 0), same operation order."""
+    lonlat = torch.as_tensor(lonlat, dtype=torch.float64)
+    phi = torch.deg2rad(lonlat[:, 0] + 180)
+    theta = torch.deg2rad(lonlat[:, 1] + 90)
+    x = torch.cos(theta)
+    Y = torch.empty(lonlat.shape[0], L * L, dtype=torch.float64)
+
+    def legendre(l, m):                                      # closed_form.py:8-26
+        pmm = torch.ones_like(x)
+        if m > 0:
+            somx2 = torch.sqrt((1 - x) * (1 + x))
+            fact = 1.0
+            for _ in range(1, m + 1):
+                pmm = pmm * (-fact) * somx2
+                fact += 2.0
+        if l == m:
+            return pmm
+        pmmp1 = x * (2.0 * m + 1.0) * pmm
+        if l == m + 1:
+            return pmmp1
+        pll = torch.zeros_like(x)
+        for ll in range(m + 2, l + 1):
+            pll = ((2.0 * ll - 1.0) * x * pmmp1 - (ll + m - 1.0) * pmm) / (ll - m)
+            pmm = pmmp1
+            pmmp1 = pll
+        return pll
+
+    def renorm(l, m):                                        # :28-30
+        return math.sqrt((2.0 * l + 1.0) * math.factorial(l - m) / (4 * math.pi * math.factorial(l + m)))
+
+    for l in range(L):
+        for m in range(-l, l + 1):
+            if m == 0:
+                y = renorm(l, 0) * legendre(l, 0)
+            elif m > 0:
+                y = math.sqrt(2.0) * renorm(l, m) * torch.cos(m * phi) * legendre(l, m)
+            else:
+                y = math.sqrt(2.0) * renorm(l, -m) * torch.sin(-m * phi) * legendre(l, -m)
+            Y[:, l * l + l + m] = y
+    return Y
+
+
 def sh_exact(lonlat, L):
     """Mathematically exact harmonics in the SAME convention (stable recurrence, fp64): the accuracy
     yardstick that shows how far the reference's 15-digit polynomials are from the true functions."""
@@ -140,10 +195,11 @@ def prepare_db(locs, satclip_embeddings, image_embeddings):
 class RangeOracle:
     """Restatement of range.py's LocationEncoder for 'RANGE' / 'RANGE+'."""
 
-    def __init__(self, model_name, weights, entries, db, L=40, beta=0.5, exact=False):
+    def __init__(self, model_name, weights, entries, db, L=40, beta=0.5, exact=False, harmonics="analytic"):
         if model_name not in SEM_TEMP:
             raise ValueError("Unimplemented RANGE model")                        # range.py:114
         self.model_name, self.L, self.entries = model_name, L, entries
+        self.harmonics = harmonics          # 'analytic' (generated closed forms) or 'closed-form' (recurrence)
         self.weights = [(torch.as_tensor(W, dtype=torch.float64), torch.as_tensor(b, dtype=torch.float64))
                         for W, b in weights]
         K, V, xyz = prepare_db(db["locs"], db["satclip_embeddings"], db["image_embeddings"])
@@ -154,7 +210,8 @@ class RangeOracle:
         self.location_feature_dim = 1024 + 256                                    # :86
 
     def encode(self, coords):
-        Y = sh_analytic(coords, self.L, self.entries)
+        Y = (sh_analytic(coords, self.L, self.entries) if getattr(self, "harmonics", "analytic") == "analytic"
+             else sh_closed_form(coords, self.L))
         e = siren(Y, self.weights)
         return e / e.norm(p=2, dim=-1, keepdim=True)                              # :212
 

@@ -21,6 +21,7 @@ PROTOTYPES = {
     "range_ctx_create": (c_int, [c_int, POINTER(c_void_p)]),
     "range_ctx_destroy": (c_int, [c_void_p]),
     "range_ctx_set_sh_table": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "range_ctx_set_sh_closed_form": (c_int, [c_void_p, c_int, c_int, c_void_p]),
     "range_ctx_set_encoder": (c_int, [c_void_p, c_int, POINTER(c_int32), POINTER(c_void_p), POINTER(c_void_p),
                                       c_double, c_double]),
     "range_encoder_prepared_bytes": (c_size_t, [c_void_p]),

@@ -20,8 +20,8 @@ def load_satclip_location_encoder(ckpt_path):
         raise NotImplementedError("range_b200 implements the SatCLIP spherical-harmonics + SIREN location encoder "
                                   f"only (got le_type={hp.get('le_type')}, pe_type={hp.get('pe_type')})")
     calc = hp.get("harmonics_calculation", "analytic")
-    if calc != "analytic":
-        raise NotImplementedError(f"harmonics_calculation={calc!r}: only the 'analytic' closed forms are built")
+    if calc not in ("analytic", "closed-form"):                                   # spherical_harmonics.py:22-25
+        raise NotImplementedError(f"harmonics_calculation={calc!r}: expected 'analytic' or 'closed-form'")
     L = int(hp["legendre_polys"])
     sd = ckpt["state_dict"]
     n_hidden = int(hp.get("num_hidden_layers", 2))

@@ -270,6 +270,18 @@ int range_ctx_set_sh_table(range_ctx* c, int L, int n_entries, const double* pre
   return RANGE_OK;
 }
 
+int range_ctx_set_sh_closed_form(range_ctx* c, int L, int n_entries, const double* norm) {
+  if (!c || L <= 0 || n_entries != L * (L + 1) / 2 || !norm)
+    return fail(RANGE_ERR_INVALID, "bad closed-form harmonics arguments (L=%d, entries=%d)", L, n_entries);
+  c->sh = ShTable{};
+  c->sh.L = L;
+  c->sh.n_entries = n_entries;
+  c->sh.pref = norm;              // "a table is set" marker for the entry checks; unused by the closed-form kernels
+  c->sh.closed_form = 1;
+  c->sh.norm = norm;
+  return RANGE_OK;
+}
+
 int range_ctx_set_encoder(range_ctx* c, int n_layers, const int32_t* dims, const double* const* W,
                           const double* const* b, double w0_first, double w0_hidden) {
   if (!c || n_layers < 1 || !dims || !W || !b) return fail(RANGE_ERR_INVALID, "bad encoder arguments");

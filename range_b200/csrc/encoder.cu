@@ -8,6 +8,7 @@
 #include <math_constants.h>
 
 #include "range_kernels.h"
+#include "sh_closed_form.cuh"
 
 namespace {
 
@@ -21,7 +22,7 @@ constexpr double kDeg2Rad = 0.017453292519943295769236907684886;   // torch.deg2
 __global__ void __launch_bounds__(128)
 sh_kernel(const double* __restrict__ lonlat, int N, int L, const double* __restrict__ pref,
           const int* __restrict__ off, const double* __restrict__ coef, const int* __restrict__ par,
-          double* __restrict__ Yt, size_t ld) {
+          int closed_form, const double* __restrict__ norm, double* __restrict__ Yt, size_t ld) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
   const double lon = lonlat[2 * n], lat = lonlat[2 * n + 1];
@@ -33,11 +34,27 @@ sh_kernel(const double* __restrict__ lonlat, int N, int L, const double* __restr
   const double s = sqrt(s2);
   double spow = 1.0;                                // (1 - c^2)^(am/2)
   int e = 0;
+  rangeb200::ClosedFormLegendre cf;
+  cf.init(c);
   for (int am = 0; am < L; ++am) {
     double cm = 1.0, sm = 0.0;
     if (am > 0) {
       spow *= s;
       sincos(double(am) * phi, &sm, &cm);
+    }
+    if (closed_form) {                              // spherical_harmonics_closed_form.py:32-40
+      cf.start_order(am);
+      for (int l = am; l < L; ++l, ++e) {
+        const double p = cf.next(l, am), nf = __ldg(norm + e);
+        const size_t f0 = size_t(l) * l + l;
+        if (am == 0) {
+          Yt[f0 * ld + n] = nf * p;
+        } else {
+          Yt[(f0 + am) * ld + n] = (nf * cm) * p;
+          Yt[(f0 - am) * ld + n] = (nf * sm) * p;
+        }
+      }
+      continue;
     }
     for (int l = am; l < L; ++l, ++e) {
       int k = __ldg(off + e);
@@ -230,7 +247,7 @@ namespace rangeb200 {
 
 cudaError_t launch_sh(const ShTable& t, const double* lonlat, int N, double* Yt, size_t ld, cudaStream_t s) {
   if (N <= 0) return cudaSuccess;
-  sh_kernel<<<(N + 127) / 128, 128, 0, s>>>(lonlat, N, t.L, t.pref, t.off, t.coef, t.par, Yt, ld);
+  sh_kernel<<<(N + 127) / 128, 128, 0, s>>>(lonlat, N, t.L, t.pref, t.off, t.coef, t.par, t.closed_form, t.norm, Yt, ld);
   return cudaGetLastError();
 }
 

@@ -24,6 +24,7 @@
 
 #include "ptx.cuh"
 #include "range_kernels.h"
+#include "sh_closed_form.cuh"
 
 namespace {
 
@@ -43,7 +44,7 @@ constexpr int kShWarps = 4;
 __global__ void __launch_bounds__(kShWarps * 32)
 sh_rowmajor_kernel(const double* __restrict__ lonlat, int N, int L, const double* __restrict__ pref,
                    const int* __restrict__ off, const double* __restrict__ coef, const int* __restrict__ par,
-                   __half* __restrict__ Yh, __half* __restrict__ Yl) {
+                   int closed_form, const double* __restrict__ norm, __half* __restrict__ Yh, __half* __restrict__ Yl) {
   __shared__ __half tile[kShWarps][2][32][34];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = (blockIdx.x * kShWarps + warp) * 32;
@@ -76,11 +77,26 @@ sh_rowmajor_kernel(const double* __restrict__ lonlat, int N, int L, const double
       f0 += 32;
     }
   };
+  rangeb200::ClosedFormLegendre cf;
+  cf.init(c);
   for (int am = 0; am < L; ++am) {
     double cm = 1.0, sm = 0.0;
     if (am > 0) {
       spow *= s;
       sincos(double(am) * phi, &sm, &cm);
+    }
+    if (closed_form) {                              // spherical_harmonics_closed_form.py:32-40, same production order
+      cf.start_order(am);
+      for (int l = am; l < L; ++l, ++e) {
+        const double p = cf.next(l, am), nf = __ldg(norm + e);
+        if (am == 0) {
+          emit(nf * p);
+        } else {
+          emit((nf * cm) * p);
+          emit((nf * sm) * p);
+        }
+      }
+      continue;
     }
     // Horner chains of consecutive degrees l = am + 2k, am + 2k + 1 have the same length (k + 1 terms): two
     // independent chains per iteration hide the fp64 FMA and table-load latency (a thread owns a whole query)
@@ -271,7 +287,8 @@ cudaError_t launch_sh_rowmajor(const ShTable& t, const double* lonlat, int N, vo
   if (N <= 0) return cudaSuccess;
   const int per_block = kShWarps * 32;
   sh_rowmajor_kernel<<<(N + per_block - 1) / per_block, per_block, 0, s>>>(lonlat, N, t.L, t.pref, t.off, t.coef,
-                                                                           t.par, reinterpret_cast<__half*>(Yh), reinterpret_cast<__half*>(Yl));
+                                                                           t.par, t.closed_form, t.norm, reinterpret_cast<__half*>(Yh),
+                                                                           reinterpret_cast<__half*>(Yl));
   return cudaGetLastError();
 }
 

@@ -16,6 +16,10 @@ struct ShTable {
   const int* off = nullptr;       // [n_entries + 1]
   const double* coef = nullptr;   // Horner coefficients in c^2, highest power first
   const int* par = nullptr;       // [n_entries] polynomial parity
+  // harmonics_calculation == 'closed-form' (spherical_harmonics_closed_form.py): no polynomial table, only the
+  // normalisation factors (sqrt(2) *) SH_renormalization(l, |m|), |m|-major like the entries above
+  int closed_form = 0;
+  const double* norm = nullptr;   // [n_entries]
 };
 // Yt[f * ld + n] for f < L*L, n < N   (feature-major so a thread per query writes coalesced)
 cudaError_t launch_sh(const ShTable& t, const double* lonlat, int N, double* Yt, size_t ld, cudaStream_t s);

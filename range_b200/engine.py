@@ -9,7 +9,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .sh_table import build_table
+from .sh_table import build_table, closed_form_norms
 
 MODE = {"RANGE": _lib.RANGE_MODE_RANGE, "RANGE+": _lib.RANGE_MODE_RANGE_PLUS}
 
@@ -23,7 +23,7 @@ def _stream():
 
 
 class RangeEngine:
-    def __init__(self, device, encoder=None, database=None, L=None, encoder_precision="auto"):
+    def __init__(self, device, encoder=None, database=None, L=None, encoder_precision="auto", harmonics=None):
         """encoder: dict from checkpoint.load_satclip_location_encoder (or None: SH only with `L`);
         database: database.DeviceDatabase or None;
         encoder_precision: 'fp64' (the reference's arithmetic, DMMA), 'f16x3' (tensor cores, split fp16 operands,
@@ -45,15 +45,23 @@ class RangeEngine:
         self._ws = {}
         self.db = None
         self.L = int(encoder["L"]) if encoder is not None else int(L)
-        # spherical-harmonics table
-        t = build_table(self.L)
-        self._tab = dict(pref=torch.from_numpy(t["pref"]).to(self.device),
-                         off=torch.from_numpy(t["off"]).to(self.device),
-                         coef=torch.from_numpy(t["coef"]).to(self.device),
-                         par=torch.from_numpy(t["par"]).to(self.device))
-        _lib.check(self.lib.range_ctx_set_sh_table(self.ctx, self.L, len(t["pref"]), _ptr(self._tab["pref"]),
-                                                   _ptr(self._tab["off"]), _ptr(self._tab["coef"]),
-                                                   _ptr(self._tab["par"])))
+        # spherical harmonics: the generated polynomials ('analytic', the SatCLIP-L40 checkpoint) or the recurrence
+        self.harmonics = harmonics or (encoder or {}).get("harmonics_calculation", "analytic")
+        if self.harmonics == "analytic":
+            t = build_table(self.L)
+            self._tab = dict(pref=torch.from_numpy(t["pref"]).to(self.device),
+                             off=torch.from_numpy(t["off"]).to(self.device),
+                             coef=torch.from_numpy(t["coef"]).to(self.device),
+                             par=torch.from_numpy(t["par"]).to(self.device))
+            _lib.check(self.lib.range_ctx_set_sh_table(self.ctx, self.L, len(t["pref"]), _ptr(self._tab["pref"]),
+                                                       _ptr(self._tab["off"]), _ptr(self._tab["coef"]),
+                                                       _ptr(self._tab["par"])))
+        elif self.harmonics == "closed-form":
+            self._tab = dict(norm=torch.from_numpy(closed_form_norms(self.L)).to(self.device))
+            _lib.check(self.lib.range_ctx_set_sh_closed_form(self.ctx, self.L, self._tab["norm"].numel(),
+                                                             _ptr(self._tab["norm"])))
+        else:
+            raise ValueError(f"harmonics_calculation={self.harmonics!r}: expected 'analytic' or 'closed-form'")
         self.dims = None
         if encoder is not None:
             self.set_encoder(encoder)

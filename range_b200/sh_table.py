@@ -140,3 +140,16 @@ def build_table(L=40, entries=None):
             off.append(len(coef))
     return dict(pref=np.asarray(pref, np.float64), off=np.asarray(off, np.int32),
                 coef=np.asarray(coef, np.float64), par=np.asarray(par, np.int32), index=index, L=L)
+
+
+def closed_form_norms(L):
+    """Normalisation factors of harmonics_calculation='closed-form' (spherical_harmonics_closed_form.py:28-40), computed
+    in Python floats exactly as the reference does: SH_renormalization(l, m) = sqrt((2l+1) (l-m)! / (4 pi (l+m)!)),
+    times sqrt(2) for m != 0.  |m|-major order (for am in range(L): for l in range(am, L)), float64."""
+    import math
+    out = []
+    for am in range(L):
+        for l in range(am, L):
+            renorm = math.sqrt((2.0 * l + 1.0) * math.factorial(l - am) / (4 * math.pi * math.factorial(l + am)))
+            out.append(renorm if am == 0 else math.sqrt(2.0) * renorm)
+    return np.asarray(out, np.float64)

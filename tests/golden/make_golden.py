@@ -202,6 +202,27 @@ def main():
     np.savez_compressed(path, **gold)
     print("wrote", path, os.path.getsize(path), "bytes")
 
+    # ---- harmonics_calculation='closed-form' (spherical_harmonics_closed_form.py): separate small fixture ----------
+    from range.location_models.satclip.positional_encoding.spherical_harmonics import SphericalHarmonics
+    from range.location_models.satclip.location_encoder import get_neural_network
+    with torch.no_grad():
+        posenc = SphericalHarmonics(legendre_polys=40, harmonics_calculation="closed-form").double()
+        Ycf = posenc(torch.tensor(coords)).numpy()
+        nnet = get_neural_network("siren", input_dim=1600, num_classes=256, dim_hidden=H, num_layers=2).double()
+        sd = {"layers.0.weight": weights[0][0], "layers.0.bias": weights[0][1], "layers.1.weight": weights[1][0],
+              "layers.1.bias": weights[1][1], "last_layer.weight": weights[2][0], "last_layer.bias": weights[2][1]}
+        nnet.load_state_dict(sd)
+        nnet.eval()                                      # dropout in the hidden Siren layers is identity in eval mode
+        ecf = nnet(torch.tensor(Ycf))
+        qcf = (ecf / ecf.norm(p=2, dim=-1, keepdim=True)).numpy()
+    Yo = O.sh_closed_form(coords, 40).numpy()
+    qo = O.RangeOracle("RANGE", weights, entries, db, harmonics="closed-form").encode(torch.tensor(coords)).numpy()
+    print("closed-form SH oracle vs reference: max abs", np.abs(Yo - Ycf).max(), " q max abs", np.abs(qo - qcf).max(),
+          " closed-form vs analytic max abs", np.abs(Ycf - gold["Y"]).max())
+    cf_path = os.path.join(HERE, "closed_form_golden.npz")
+    np.savez_compressed(cf_path, coords=coords, Y=Ycf, q=qcf)
+    print("wrote", cf_path, os.path.getsize(cf_path), "bytes")
+
     if "--big" in sys.argv:
         H, M, N = 512, 20000, 10000
         ckpt = os.path.join(tmp, "satclip_h512.ckpt")

@@ -76,6 +76,9 @@ def test_checkpoint_reader(tmp_path, golden):
         load_satclip_location_encoder(str(p))
     hp3 = dict(hp, harmonics_calculation="closed-form")
     torch.save({"hyper_parameters": hp3, "state_dict": sd}, p)
+    assert load_satclip_location_encoder(str(p))["harmonics_calculation"] == "closed-form"
+    hp4 = dict(hp, harmonics_calculation="discretized")
+    torch.save({"hyper_parameters": hp4, "state_dict": sd}, p)
     with pytest.raises(NotImplementedError):
         load_satclip_location_encoder(str(p))
 

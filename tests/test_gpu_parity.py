@@ -328,3 +328,29 @@ def test_beta_sweep_and_database_cache(tmp_path, sh_entries):
     assert rel_rows(sweep[1][:, :1024].cpu().numpy(), ref[:, :1024]).max() <= 2e-3
     fresh = mk(0.25).embed(c)
     assert torch.equal(fresh, sweep[1])
+
+
+def test_closed_form_harmonics_vs_reference(golden):
+    """harmonics_calculation='closed-form' through both encoder paths against the reference's own output"""
+    import os
+    from range_b200.engine import RangeEngine
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "closed_form_golden.npz"))
+    weights = [(torch.tensor(golden[f"W{i}"]), torch.tensor(golden[f"b{i}"])) for i in range(3)]
+    enc = dict(L=40, dims=[1600, 64, 64, 256], weights=weights, harmonics_calculation="closed-form")
+    eng = RangeEngine(DEV, encoder=enc, encoder_precision="fp64")
+    assert eng.harmonics == "closed-form"
+    Y = eng.sh_features(torch.tensor(g["coords"])).cpu().numpy()
+    # the recurrence is evaluated in the reference's operation order: only libm-vs-CUDA cos / sin / sqrt differ
+    assert np.abs(Y - g["Y"]).max() <= 1e-12 * max(1.0, np.abs(g["Y"]).max())
+    q64, _, _ = eng.encode(torch.tensor(g["coords"]))
+    assert np.abs(q64.cpu().numpy() - g["q"]).max() <= 1e-10
+    # tensor-core encoder (needs widths % 256 == 0): H = 512 against the oracle
+    ws = O.siren_init(40, 512, 2, 256, seed=0)
+    etc = RangeEngine(DEV, encoder=dict(L=40, dims=[1600, 512, 512, 256], weights=ws, harmonics_calculation="closed-form"))
+    assert etc.precision == "f16x3"
+    c = O.area_uniform(777, np.random.default_rng(4))
+    q, _, _ = etc.encode(torch.tensor(c))
+    ref = O.RangeOracle.__new__(O.RangeOracle)
+    ref.L, ref.entries, ref.harmonics = 40, None, "closed-form"
+    ref.weights = [(torch.as_tensor(W, dtype=torch.float64), torch.as_tensor(b, dtype=torch.float64)) for W, b in ws]
+    assert np.abs(q.cpu().numpy() - ref.encode(torch.tensor(c)).numpy()).max() <= 5e-6

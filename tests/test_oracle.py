@@ -68,3 +68,24 @@ def test_beta_limits_and_exact_mode(golden, sh_entries):
     assert rel.max() < 1e-5
     with pytest.raises(ValueError):
         O.RangeOracle("RANGE++", w, sh_entries, db)
+
+
+def test_closed_form_harmonics_match_reference(golden):
+    """harmonics_calculation='closed-form' (spherical_harmonics_closed_form.py): fixture written by the unmodified
+    reference (tests/golden/make_golden.py)"""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "closed_form_golden.npz"))
+    assert np.array_equal(g["coords"], golden["coords"])
+    Y = O.sh_closed_form(g["coords"], 40).numpy()
+    assert np.abs(Y - g["Y"]).max() <= 4e-16 * np.abs(g["Y"]).max()
+    q = O.RangeOracle("RANGE", _weights(golden), None, _db(golden), harmonics="closed-form").encode(
+        torch.tensor(g["coords"])).numpy()
+    assert np.abs(q - g["q"]).max() <= 1e-14
+    # known answers: orthonormal Y_00, and the Condon-Shortley sign of m = 1
+    pts = np.array([[10.0, 20.0], [-120.0, -45.0]])
+    y = O.sh_closed_form(pts, 2).numpy()
+    theta, phi = np.deg2rad(pts[:, 1] + 90), np.deg2rad(pts[:, 0] + 180)
+    assert np.allclose(y[:, 0], 0.5 / np.sqrt(np.pi))
+    assert np.allclose(y[:, 3], -np.sqrt(3 / (4 * np.pi)) * np.sin(theta) * np.cos(phi))
+    from range_b200.sh_table import closed_form_norms
+    assert np.array_equal(closed_form_norms(40), O.closed_form_norms(40))
