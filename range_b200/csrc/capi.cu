@@ -457,8 +457,12 @@ size_t range_encode_workspace_bytes(range_ctx* c, int64_t N) {
 int range_encode(range_ctx* c, int64_t N, const double* lonlat, double* q64, void* q16, float* qxyz,
                  void* workspace, size_t workspace_bytes, void* stream) {
   if (!c || !c->sh.pref || !c->n_layers) return fail(RANGE_ERR_INVALID, "encoder not set");
-  if (c->dims[0] != c->sh.L * c->sh.L)
-    return fail(RANGE_ERR_INVALID, "encoder input dim %d != L*L = %d", c->dims[0], c->sh.L * c->sh.L);
+  // the first layer may be zero-padded up to the next multiple of 16 input columns (L*L = 100 for SatCLIP-L10)
+  const int F = c->sh.L * c->sh.L;
+  if (c->dims[0] < F || c->dims[0] - F >= 16)
+    return fail(RANGE_ERR_INVALID, "encoder input dim %d does not match L*L = %d", c->dims[0], F);
+  if (c->dims[0] != F && c->enc_precision != RANGE_ENC_F64)
+    return fail(RANGE_ERR_UNSUPPORTED, "padded first layer (%d > L*L = %d) needs the fp64 encoder", c->dims[0], F);
   if (N <= 0 || !lonlat || !q64 || !q16 || !qxyz) return fail(RANGE_ERR_INVALID, "bad arguments");
   if (workspace_bytes < range_encode_workspace_bytes(c, N) || !workspace)
     return fail(RANGE_ERR_WORKSPACE, "encode workspace too small");
@@ -507,6 +511,8 @@ int range_encode(range_ctx* c, int64_t N, const double* lonlat, double* q64, voi
   for (int64_t n0 = 0; n0 < N; n0 += chunk) {
     const int n = int(N - n0 < chunk ? N - n0 : chunk);
     CUDA_TRY(launch_sh(c->sh, lonlat + 2 * n0, n, Yt, ld, s));
+    if (c->dims[0] > F)       // zero rows for the padded input columns of the first layer
+      CUDA_TRY(cudaMemsetAsync(Yt + size_t(F) * ld, 0, size_t(c->dims[0] - F) * ld * sizeof(double), s));
     const double* in = Yt;
     for (int i = 0; i < c->n_layers; ++i) {
       const bool last = i == c->n_layers - 1;

@@ -80,12 +80,18 @@ class RangeEngine:
     def set_encoder(self, enc, w0_first=30.0, w0_hidden=1.0):
         self._weights = [(w.to(self.device, torch.float64).contiguous(), b.to(self.device, torch.float64).contiguous())
                          for w, b in enc["weights"]]
+        enc_dims = [int(d) for d in enc["dims"]]
+        if enc_dims[0] % 16:            # e.g. SatCLIP-L10: 100 features -> zero-padded input columns (fp64 encoder)
+            pad = 16 - enc_dims[0] % 16
+            w0, b0 = self._weights[0]
+            self._weights[0] = (torch.nn.functional.pad(w0, (0, pad)).contiguous(), b0)
+            enc_dims[0] += pad
         n = len(self._weights)
-        dims = (c_int32 * (n + 1))(*[int(d) for d in enc["dims"]])
+        dims = (c_int32 * (n + 1))(*enc_dims)
         W = (c_void_p * n)(*[w.data_ptr() for w, _ in self._weights])
         B = (c_void_p * n)(*[b.data_ptr() for _, b in self._weights])
         _lib.check(self.lib.range_ctx_set_encoder(self.ctx, n, dims, W, B, w0_first, w0_hidden))
-        self.dims = list(enc["dims"])
+        self.dims = enc_dims
         self._prepared = None
         self.precision = "fp64"
         want = "f16x3" if self.encoder_precision == "tf32x3" else self.encoder_precision

@@ -354,3 +354,29 @@ def test_closed_form_harmonics_vs_reference(golden):
     ref.L, ref.entries, ref.harmonics = 40, None, "closed-form"
     ref.weights = [(torch.as_tensor(W, dtype=torch.float64), torch.as_tensor(b, dtype=torch.float64)) for W, b in ws]
     assert np.abs(q.cpu().numpy() - ref.encode(torch.tensor(c)).numpy()).max() <= 5e-6
+
+
+@pytest.mark.parametrize("L", [10, 20, 32])
+def test_other_legendre_degrees(L, sh_entries):
+    """checkpoints with legendre_polys != 40: L = 10 (100 features -> zero-padded first layer, fp64 encoder), L = 20
+    (fp64 encoder), L = 32 (1024 features: tensor-core encoder) - against the oracle, both harmonics flavours"""
+    from range_b200.engine import RangeEngine
+    H = 256
+    ws = O.siren_init(L, H, 2, 256, seed=L)
+    c = O.area_uniform(300, np.random.default_rng(L))
+    for flavour in ("analytic", "closed-form"):
+        eng = RangeEngine(DEV, encoder=dict(L=L, dims=[L * L, H, H, 256], weights=ws, harmonics_calculation=flavour))
+        assert eng.precision == ("f16x3" if (L * L) % 64 == 0 else "fp64")
+        q64, q16, qxyz = eng.encode(torch.tensor(c))
+        ref = O.RangeOracle.__new__(O.RangeOracle)
+        ref.L, ref.entries, ref.harmonics = L, sh_entries, flavour
+        ref.weights = [(torch.as_tensor(W, dtype=torch.float64), torch.as_tensor(b, dtype=torch.float64)) for W, b in ws]
+        d = np.abs(q64.cpu().numpy() - ref.encode(torch.tensor(c)).numpy()).max()
+        assert d <= (5e-6 if eng.precision == "f16x3" else (1e-9 if flavour == "closed-form" or L <= 20 else 1e-5)), (L, flavour, d)
+        Y = eng.sh_features(torch.tensor(c)).cpu().numpy()
+        Yref = (O.sh_analytic(c, L, sh_entries) if flavour == "analytic" else O.sh_closed_form(c, L)).numpy()
+        assert Y.shape == (300, L * L)
+        lo = min(L, 20) ** 2                       # l < 20: no cancellation in the generated polynomials
+        assert np.abs(Y - Yref)[:, :lo].max() <= 1e-9
+        # l >= 20 ('analytic' only): the reference's own fp64 noise on its cancelling 15-digit polynomials (DESIGN.md 2)
+        assert np.abs(Y - Yref).max() <= (1e-3 if flavour == "analytic" else 1e-9)
