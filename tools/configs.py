@@ -95,6 +95,28 @@ if "4" in which:
         del m, dbm
         M *= (10 if M * 10 <= M_MAX else 10**9) if os.environ.get("M_DECADES") else 3 if M * 3 <= M_MAX else 10**9
 
+if "4big" in which:
+    # M = 10 M entries on ONE GPU (25.7 GB of fp16 keys / values resident): database generated on the device
+    from range_b200.database import DeviceDatabase
+    from range_b200.engine import RangeEngine
+    Mbig = int(os.environ.get("M_BIG", 10_000_000))
+    N = 100_000
+    t0 = time.time()
+    eng = RangeEngine(dev, encoder=enc, database=DeviceDatabase.synthetic(Mbig, dev))
+    t_build = time.time() - t0
+    coords = torch.tensor(O.area_uniform(N, np.random.default_rng(1)), device=dev)
+    def big():
+        c, perm = eng.sort_queries(coords)
+        q64, q16, qxyz = eng.encode(c)
+        sums, maxs = eng.retrieve_stats("RANGE+", q16, qxyz, 12.0, 40.0)
+        return eng.retrieve_apply_concat("RANGE+", q16, qxyz, 12.0, 40.0, 0.5, sums, maxs, q64, dtype=torch.float32, perm=perm)
+    t = timed(big, reps=1)
+    res = big()
+    emit(config="C4 database scaling, 10 M entries on one GPU", queries=N, M=Mbig, n_gpus=1, seconds=t, queries_per_s=N / t,
+         pair_rate_per_s=N * Mbig / t, database_build_s=t_build, database_bytes=eng.db.nbytes(),
+         finite=bool(torch.isfinite(res).all()), unit_norm=float((res[:, 1024:].double().norm(dim=1) - 1).abs().max()))
+    del eng, res
+
 if "5" in which:
     # coord_grid (visualize_embeddings.py:29-39): lon = linspace(-180, 180, W), lat = linspace(90, -90, H) in float32
     H = int(round((RASTER / 2) ** 0.5)); W = 2 * H

@@ -1,1 +1,2 @@
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -6
+free -g | head -2
+CONFIGS=4big M_BIG=10000000 timeout 900 python tools/configs.py 2>gpurun_out/big.err | tee gpurun_out/r1_config_10M.jsonl; tail -3 gpurun_out/big.err
