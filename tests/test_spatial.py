@@ -31,6 +31,38 @@ def test_hilbert_order_and_caps_cpu():
     assert tile_caps(one)[0, 3] < 1e-3 and hilbert_order(one).tolist() == [0, 1, 2]
 
 
+@pytest.mark.parametrize("regional", [False, True])
+def test_geo_skip_rule_is_exact_cpu(regional):
+    """the skip decision (numpy restatement of geo_mask_kernel, oracle/geo_skip.py) never drops an entry that carries more
+    than 2^-24 / M of its row's geo mass - statistics-pass and apply-pass flavours, global and regional databases"""
+    from oracle import geo_skip as GS
+    from range_b200.database import hilbert_order, prepare_reference_arrays
+    M, N = 6000, 3000
+    db = O.synthetic_db(M, seed=11, kind="iid")
+    if regional:
+        db["locs"][:, 1] = 30.0 + 0.5 * db["locs"][:, 1]
+        db["locs"][:, 0] = 0.25 * db["locs"][:, 0]
+    _, _, xyz = prepare_reference_arrays(db)
+    xyz = xyz[hilbert_order(xyz)].astype(np.float64)
+    q = O.rad_to_cart(O.area_uniform(N, np.random.default_rng(12)) * np.pi / 180).reshape(-1, 3)
+    q = q[hilbert_order(q)]
+    m1 = GS.skip_mask(q, xyz, M)
+    slack, lg = GS.exactness_slack(q, xyz, M, m1)
+    assert slack >= -1e-9
+    m2 = GS.skip_mask(q, xyz, M, lg=lg)
+    assert (m2 | ~m1).all() and m2.sum() >= m1.sum()
+    assert GS.exactness_slack(q, xyz, M, m2)[0] >= -1e-9
+    if not regional:
+        assert m2.mean() > 0.1                      # 24 x 47 tiles over the globe: a fair share is skippable
+    # what is dropped really is below fp32 resolution of the geo softmax
+    G = q @ xyz.T
+    w = np.exp(40.0 * (G - 1)) / lg[:, None]
+    pad = (-N) % 128, (-M) % 128
+    wt = np.pad(w, ((0, pad[0]), (0, pad[1]))).reshape(len(m2), 128, m2.shape[1], 128)
+    dropped = (wt * m2[:, None, :, None]).sum((2, 3))
+    assert dropped.max() < 2.0 ** -24
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("N", [1, 5, 129, 4096, 100_000])
 def test_sort_queries_is_a_deterministic_permutation(N):
@@ -103,6 +135,10 @@ def test_geo_skip_bound_and_equivalence(kind, sh_entries):
     assert bool((mask2 | ~mask).all())                                # never skips less than the statistics-pass mask
     assert mask2.float().mean().item() >= frac
     assert slack[mask2.unsqueeze(1).expand_as(slack)].min().item() >= -1e-5
+    # the kernel's decisions against the numpy restatement (fp32 vs fp64 trigonometry: a handful of borderline tiles)
+    from oracle import geo_skip as GS
+    m_ref = GS.skip_mask(qxyz[:, :3].double().cpu().numpy(), dsort.xyz[: dsort.M, :3].double().cpu().numpy(), M)
+    assert (m_ref != mask.cpu().numpy()).mean() < 2e-3
     a = eng.retrieve("RANGE+", q16, qxyz, 12.0, 40.0, 0.5)
     b = ref.retrieve("RANGE+", q16, qxyz, 12.0, 40.0, 0.5)
     rel = ((a - b).norm(dim=1) / b.norm(dim=1)).max().item()
