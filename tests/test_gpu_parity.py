@@ -380,3 +380,20 @@ def test_other_legendre_degrees(L, sh_entries):
         assert np.abs(Y - Yref)[:, :lo].max() <= 1e-9
         # l >= 20 ('analytic' only): the reference's own fp64 noise on its cancelling 15-digit polynomials
         assert np.abs(Y - Yref).max() <= (1e-3 if flavour == "analytic" else 1e-9)
+
+
+@pytest.mark.parametrize("N,M", [(24_576, 30_011), (13_000, 200_000)])
+def test_producer_consumer_retrieval_is_deterministic(N, M):
+    """a hand-off race in the P' ring (stale slot, early release) would show up as sporadically different rows:
+    repeated launches must be bit-identical (tools/stress_pc.py runs more shapes and repetitions)"""
+    from range_b200.engine import RangeEngine
+    from range_b200.database import DeviceDatabase
+    eng = RangeEngine(DEV, L=40, database=DeviceDatabase.synthetic(M, DEV, seed=N))
+    g = torch.Generator(device="cpu").manual_seed(1)
+    q = torch.randn(N, 256, generator=g); q = (q / q.norm(dim=1, keepdim=True)).half().to(DEV)
+    c = eng.sort_queries(torch.tensor(O.area_uniform(N, np.random.default_rng(1))))[0].cpu()
+    xyz = torch.zeros(N, 4); xyz[:, :3] = torch.tensor(O.rad_to_cart(c.numpy() * np.pi / 180)).float(); xyz = xyz.to(DEV)
+    first = eng.retrieve("RANGE+", q, xyz, 12.0, 40.0, 0.5).clone()
+    assert torch.isfinite(first).all()
+    for _ in range(8):
+        assert torch.equal(eng.retrieve("RANGE+", q, xyz, 12.0, 40.0, 0.5), first)
