@@ -7,17 +7,21 @@
 //
 //   producer pair  (2 CTAs, cta_group::2)  S = Q.K^T -> P' = 2^(a s + cs) + 2^(gam g + cg)  (fp16), ONCE per
 //                                          (query tile, database tile); P' goes to a ring in global memory
-//                                          (it stays in L2: 32 KB per tile, 4 slots per producer CTA)
+//                                          (it stays in L2: 32 KB per tile, 16 slots per producer CTA, tile
+//                                          layout [16 key chunks][128 rows][8 entries])
 //   consumer pairs (2 x 2 CTAs)            O[128 queries x 512 dims] += P' . Vt   (all 512 TMEM columns are
-//                                          accumulators); P' arrives by TMA as the SWIZZLE_128B A operand,
-//                                          Vt halves are shared by the pair as in retrieval.cu
+//                                          accumulators); P' arrives by TMA as a no-swizzle K-major A operand,
+//                                          Vt halves are shared by the pair as in retrieval.cu; the epilogue
+//                                          writes the caller's (N,1280) rows directly (fused concat)
 //
 // One unit = 3 clusters of 2 CTAs = two query tiles x 1024 value dims; 148 SMs = 24 units (+ 2 idle clusters).
-// Producers are MUFU-bound (2 ex2 per pair, 16/clk/SM), consumers tensor-bound (2048 clk per 128x128 tile),
-// both ~2048 clk per tile; nothing is computed twice.  Hand-off through L2 is ordered with
+// Producers are MUFU-bound (1 ex2 per pair + the geo ex2 of the ~40 % unskipped tiles, 16/clk/SM), consumers
+// tensor-bound (2048 clk per 128x128 tile); nothing is computed twice.  Hand-off through L2 is ordered with
 // st.release.gpu / ld.acquire.gpu flags that count tiles (monotonic, zeroed by the host before the launch):
-//   full[p]      tiles producer CTA p has published        (publisher warp, after the softmax warps' stores)
+//   full[p]      tiles producer CTA p has published        (bookkeeping thread, once per 4 tiles, after the softmax
+//                                                           warps' stores)
 //   done[p][c]   tiles consumer pair c has copied to smem  (consumer leader, after the TMA load completed)
+// A window barrier every 64 tiles keeps the 24 units on the same part of the database (L2 reuse).
 // All CTAs must be co-resident: one CTA per SM, capacity checked by the launcher (launch_apply_pc).
 //
 // Measured on B200 at 100 000 x 100 000 (tools/time_apply.py; PROF=1 prints per-role wait cycles):
@@ -29,6 +33,7 @@
 //   + cross-unit window barrier (DRAM reads 33 GB -> 5.5 GB), 4 Vt stages        22.9 ms
 //   + Hilbert-ordered tiles (geo skip 44 % -> 52 %)                              22.6 ms
 //   + three softmax groups over four S buffers                                  21.6 ms
+//   + apply-pass geo mask from the known normalisers (skip 52 % -> 63 %)         20-21 ms (run-to-run +-1 ms: power cap)
 // Dead ends: 64-entry S half tiles with double-buffered groups (UMMA N = 64 is operand-fetch bound: 24.7 ms);
 // every 3rd-6th exponential on the FMA pipe (no gain: the SM is power-capped, not MUFU-issue-bound).
 #include <cstdint>
