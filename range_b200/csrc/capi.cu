@@ -116,7 +116,7 @@ struct RetrievalPlan {
   int mask_rows, mask_words;                // geo-skip mask: [even-padded query tiles][ceil(tiles / 32)]
   bool pc;                                  // apply with the producer/consumer kernel (retrieval_pc.cu)
   bool stats_pc;                            // statistics with the CTA-pair / four-group kernel (retrieval_pc.cu)
-  size_t off_part_sum, off_part_max, off_sums, off_maxs, off_rowc, off_mask, off_ring, off_flags, off_pc_part, off_part_out, off_O, total;
+  size_t off_part_sum, off_part_max, off_sums, off_maxs, off_rowc, off_mask, off_ring, off_flags, off_pc_part, off_pc_scratch, off_part_out, off_O, total;
 };
 
 // 0 = choose by batch size, 1 = always the single-role CTA-pair kernel, 2 = producer/consumer whenever possible
@@ -140,6 +140,9 @@ RetrievalPlan plan_retrieval(const range_ctx* c, int64_t N) {
   int64_t max_splits = tiles / 8 > 0 ? tiles / 8 : 1;      // at least 8 tiles per split
   if (want > max_splits) want = max_splits;
   if (want > 64) want = 64;
+  // the tensor core's fp32 accumulation truncates (retrieval_pc.cu: kAccWindow): at most 256 tiles per accumulator
+  const int64_t for_accuracy = (tiles + 255) / 256 < 256 ? (tiles + 255) / 256 : 256;
+  if (want < for_accuracy) want = for_accuracy;
   p.tiles_per_split = int((tiles + want - 1) / want);
   p.splits = int((tiles + p.tiles_per_split - 1) / p.tiles_per_split);
   // stats kernel: one CTA per (query tile, split).  Its partials are tiny, so choose the split count that
@@ -182,6 +185,7 @@ RetrievalPlan plan_retrieval(const range_ctx* c, int64_t N) {
   p.off_ring = o;     o += p.pc ? align_up(apply_pc_ring_bytes(c->sm_count), 1024) : 0;
   p.off_flags = o;    o += p.pc ? align_up(apply_pc_flag_bytes(c->sm_count, N, c->M), 256) : 0;
   p.off_pc_part = o;  o += p.pc ? align_up(apply_pc_part_bytes(c->sm_count, N, c->M), 256) : 0;
+  p.off_pc_scratch = o; o += p.pc ? align_up(apply_pc_scratch_bytes(c->sm_count), 256) : 0;
   p.off_part_out = o; o += (p.splits > 1 && !p.pc) ? align_up(size_t(p.splits) * N * kDimV * 4, 256) : 0;
   p.off_O = o;        o += p.pc ? 0 : align_up(size_t(N) * kDimV * 4, 256);   // scratch O of range_retrieve_apply_concat (small batches)
   p.total = o;
@@ -588,12 +592,12 @@ static int apply_impl(range_ctx* c, int mode, int64_t N, const void* q16, const 
     if (r) return r;
     if (out) {      // consumers write straight into the (N,1280) result; the location columns follow
       CUDA_TRY(launch_apply_pc(a, tmP, rowc, out, W, out_dtype == RANGE_OUT_F64, perm, ring, ws + p.off_flags,
-                               ws + p.off_pc_part, c->sm_count, s));
+                               ws + p.off_pc_part, ws + p.off_pc_scratch, c->sm_count, s));
       CUDA_TRY(launch_concat_q(q64, int(N), kDimK, perm, out, W, kDimV, out_dtype, s));
       g_launches += 1;
     } else {
       CUDA_TRY(launch_apply_pc(a, tmP, rowc, O, kDimV, 0, nullptr, ring, ws + p.off_flags, ws + p.off_pc_part,
-                               c->sm_count, s));
+                               ws + p.off_pc_scratch, c->sm_count, s));
     }
     g_launches += 2 + (apply_pc_part_bytes(c->sm_count, N, c->M) > 0);
     return RANGE_OK;

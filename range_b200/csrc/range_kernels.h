@@ -99,8 +99,9 @@ size_t apply_pc_part_bytes(int sm_count, int64_t N, int64_t M);
 void apply_pc_describe_plan(int sm_count, int64_t N, int64_t M, int32_t out[7]);   // test hook   // partial outputs of the split tail pairs
 // row n of the result goes to out + (perm ? perm[n] : n) * out_ld (+ column), fp32 or fp64
 cudaError_t launch_apply_pc(const RetrievalArgs& a, const CUtensorMap& tmP, const float* rowc, void* out, int out_ld,
-                            int out_f64, const int* perm, void* ring, void* flags, void* part, int sm_count,
-                            cudaStream_t s);
+                            int out_f64, const int* perm, void* ring, void* flags, void* part, void* scratch,
+                            int sm_count, cudaStream_t s);
+size_t apply_pc_scratch_bytes(int sm_count);   // consumers' accumulation-window scratch
 // statistics pass with the producer's structure (retrieval_pc.cu); same partials as launch_stats
 cudaError_t launch_stats_pc(const RetrievalArgs& a, float* part_sum, float* part_max, cudaStream_t s);
 cudaError_t launch_reduce_out(const float* part, size_t split_stride, int splits, size_t total, float* out,

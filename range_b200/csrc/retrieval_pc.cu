@@ -83,6 +83,14 @@ constexpr int kPolyEvery = RANGE_PC_POLY;
 __device__ __forceinline__ float ex2_mixed(float x, int i) {
   return (kPolyEvery > 0 && (i % (kPolyEvery > 0 ? kPolyEvery : 1)) == kPolyEvery - 1) ? ptx::ex2_poly(x) : ptx::ex2(x);
 }
+// The tensor core adds every K = 16 product block into the fp32 accumulator with truncation, so a sum over the whole
+// database loses ~M/16 * 2^-24 of its mass (measured with V = 1: -4e-4 at M = 100k, -6e-3 at M = 1M).  The consumers
+// therefore accumulate in TMEM over kAccWindow tiles only, add that window into an fp32 scratch with rounded
+// CUDA-core adds and restart from zero: bias <= 1024 * 2^-24 of a window's own contribution (-2e-5 measured).
+#ifndef RANGE_PC_ACC_WINDOW
+#define RANGE_PC_ACC_WINDOW 128
+#endif
+constexpr int kAccWindow = RANGE_PC_ACC_WINDOW;
 // columns of S a softmax warp evaluates per step (one TMEM load in flight while the previous piece is evaluated)
 // Measured: apply 16 (20.2 ms; 32 spills under the 128-register cap: 21.9 ms), statistics 32 (4.56 vs 4.65 ms).
 constexpr int kPieceApply = 16, kPieceStats = 32;
@@ -177,7 +185,8 @@ range_apply_pc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
                       const __grid_constant__ CUtensorMap tmV128, const __grid_constant__ CUtensorMap tmP,
                       const float4* __restrict__ db_xyz, const float4* __restrict__ rowc, int N, int M, float a_sem,
                       void* __restrict__ out, const uint32_t* __restrict__ geo_mask, int mask_words,
-                      float* __restrict__ part, __half* __restrict__ ring, uint32_t* __restrict__ flags,
+                      float* __restrict__ part, float4* __restrict__ acc_scratch, __half* __restrict__ ring,
+                      uint32_t* __restrict__ flags,
                       uint32_t* __restrict__ windows, const PcPlan plan, int dbg, long long* __restrict__ prof) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -594,14 +603,16 @@ range_apply_pc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         uint32_t* done0 = flags + size_t(unit * 2) * kFlagsPerProducer + (1 + cp) * kFlagStride;       // producer rank 0
         uint32_t* done1 = flags + size_t(unit * 2 + 1) * kFlagsPerProducer + (1 + cp) * kFlagStride;   // producer rank 1
         PipeState sv, sp;
-        uint32_t it = 0;
+        uint32_t it = 0, ev = 0;          // ev: accumulation windows handed to the epilogue warps so far
         for (int r = 0; r < rounds; ++r) {
-          if (r > 0) {
-            ptx::mbar_wait_cluster(&bars[L::b_o_empty], (r - 1) & 1);     // both epilogues have read O
-            ptx::tc_fence_after();
-          }
           const PcWork wk = pc_work(plan, unit, r, T);
-          for (int j = 0; j < wk.t1 - wk.t0; ++j, ++it) {
+          const int nt = wk.t1 - wk.t0;
+          for (int j = 0; j < nt; ++j, ++it) {
+            const bool first = j % kAccWindow == 0;                       // first tile of an accumulation window
+            if (first && ev > 0) {
+              ptx::mbar_wait_cluster(&bars[L::b_o_empty], (ev - 1) & 1);  // both epilogues have read the last window
+              ptx::tc_fence_after();
+            }
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
               PC_T0();
@@ -626,7 +637,7 @@ range_apply_pc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
                     if (!(dbg & 4))                          // developer switch: no P.V (producer-bound run)
                     ptx::umma_f16_ss_2sm(tmem_base + nb * 256, ptx::umma_desc_kmajor_nosw(a_base + kk * 4096, 2048, 128),
                                          ptx::umma_desc_kmajor_sw128(b_base + nb * 16384 + kk * 32), idesc_pv,
-                                         (j | half | kk) != 0);
+                                         !(first && half == 0 && kk == 0));
                 ptx::umma_commit_2sm_u32(bars_u + 8 * (L::b_v_empty + sv.idx));
                 ptx::umma_commit_2sm_u32(bars_u + 8 * (L::b_p_empty + sp.idx));
               }
@@ -635,9 +646,12 @@ range_apply_pc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
               sv.advance<L::NV>();
               sp.advance<L::NP>();
             }
+            if ((j + 1) % kAccWindow == 0 || j + 1 == nt) {               // window (or round) complete
+              if (ptx::elect_one()) ptx::umma_commit_2sm_u32(bars_u + 8 * L::b_o_full);
+              __syncwarp();
+              ++ev;
+            }
           }
-          if (ptx::elect_one()) ptx::umma_commit_2sm_u32(bars_u + 8 * L::b_o_full);
-          __syncwarp();
         }
         if (role == 1 && lane == 0) PC_OUT(56);
       }
@@ -646,13 +660,14 @@ range_apply_pc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       const int quarter = warp & 3;
       const int row = quarter * 32 + lane;
       const uint32_t o_empty_leader = ptx::mapa(ptx::smem_u32(&bars[L::b_o_empty]), 0);
+      // this CTA's window scratch: [16 column blocks][8 float4][128 rows] float4 (a warp's access is 512 contiguous bytes)
+      float4* scratch = acc_scratch + size_t((unit * 2 + cp) * 2 + int(rank)) * (128 * 128) + row;
+      uint32_t ev = 0;
       for (int r = 0; r < rounds; ++r) {
         const PcWork wk = pc_work(plan, unit, r, T);
         const int qt = 2 * wk.qp + int(rank);
         const int n = qt * kBlockQ + row;
         const float out_scale = n < N ? rowc[2 * n + 1].y : 0.f;
-        ptx::mbar_wait(&bars[L::b_o_full], r & 1);
-        ptx::tc_fence_after();
         // whole database: the final rows (caller's layout, dtype and row order); one range of a split tail pair: that
         // split's fp32 partial rows (summed and placed by the host's reduce kernel)
         const bool direct = wk.split < 0;
@@ -661,33 +676,55 @@ range_apply_pc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
                                : part + size_t(wk.split) * plan.part_stride + size_t(n - plan.tail_row0) * 1024 + dimbase;
         double* orow64 = reinterpret_cast<double*>(out) + drow + dimbase;
         const bool f64 = direct && plan.out_f64;
+        const int nseg = (wk.t1 - wk.t0 + kAccWindow - 1) / kAccWindow;
+        for (int sg = 0; sg < nseg; ++sg, ++ev) {
+          const bool last = sg == nseg - 1;
+          ptx::mbar_wait(&bars[L::b_o_full], ev & 1);
+          ptx::tc_fence_after();
 #pragma unroll 1
-        for (int cc = 0; cc < 16; ++cc) {
-          uint32_t v[32];
-          ptx::tmem_ld32(tmem_base + (uint32_t(quarter * 32) << 16) + cc * 32, v);
-          ptx::tmem_ld_wait();
-          if (n < N) {
-            if (f64) {
+          for (int cc = 0; cc < 16; ++cc) {
+            uint32_t v[32];
+            ptx::tmem_ld32(tmem_base + (uint32_t(quarter * 32) << 16) + cc * 32, v);
+            ptx::tmem_ld_wait();
+            if (n < N) {
+              float4* sc = scratch + size_t(cc) * 8 * 128;
+              if (sg > 0) {                       // add the windows accumulated so far (rounded fp32 adds)
 #pragma unroll
-              for (int i = 0; i < 32; i += 2)
-                *reinterpret_cast<double2*>(orow64 + cc * 32 + i) =
-                    make_double2(double(__uint_as_float(v[i]) * out_scale), double(__uint_as_float(v[i + 1]) * out_scale));
-            } else {
+                for (int i = 0; i < 8; ++i) {
+                  const float4 a = sc[i * 128];
+                  v[4 * i] = __float_as_uint(__uint_as_float(v[4 * i]) + a.x);
+                  v[4 * i + 1] = __float_as_uint(__uint_as_float(v[4 * i + 1]) + a.y);
+                  v[4 * i + 2] = __float_as_uint(__uint_as_float(v[4 * i + 2]) + a.z);
+                  v[4 * i + 3] = __float_as_uint(__uint_as_float(v[4 * i + 3]) + a.w);
+                }
+              }
+              if (!last) {
 #pragma unroll
-              for (int i = 0; i < 32; i += 4) {
-                float4 o;
-                o.x = __uint_as_float(v[i]) * out_scale;
-                o.y = __uint_as_float(v[i + 1]) * out_scale;
-                o.z = __uint_as_float(v[i + 2]) * out_scale;
-                o.w = __uint_as_float(v[i + 3]) * out_scale;
-                *reinterpret_cast<float4*>(orow32 + cc * 32 + i) = o;
+                for (int i = 0; i < 8; ++i)
+                  sc[i * 128] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                                            __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+              } else if (f64) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 2)
+                  *reinterpret_cast<double2*>(orow64 + cc * 32 + i) =
+                      make_double2(double(__uint_as_float(v[i]) * out_scale), double(__uint_as_float(v[i + 1]) * out_scale));
+              } else {
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                  float4 o;
+                  o.x = __uint_as_float(v[i]) * out_scale;
+                  o.y = __uint_as_float(v[i + 1]) * out_scale;
+                  o.z = __uint_as_float(v[i + 2]) * out_scale;
+                  o.w = __uint_as_float(v[i + 3]) * out_scale;
+                  *reinterpret_cast<float4*>(orow32 + cc * 32 + i) = o;
+                }
               }
             }
           }
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive_cluster(o_empty_leader);
         }
-        ptx::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive_cluster(o_empty_leader);
       }
     }
   }
@@ -984,6 +1021,8 @@ void apply_pc_describe_plan(int sm_count, int64_t N, int64_t M, int32_t out[7]) 
   out[0] = p.n_units; out[1] = p.full_rounds; out[2] = p.tail_pairs; out[3] = p.tail_split; out[4] = p.tail_tiles;
   out[5] = p.tail_row0; out[6] = int32_t(pc_window_count(p, M));
 }
+// window scratch of the consumers: [units * 4 CTAs][128 rows x 512 columns] fp32 (L2-resident, 25 MB on 148 SMs)
+size_t apply_pc_scratch_bytes(int sm_count) { return size_t(apply_pc_units(sm_count)) * 4 * 128 * 512 * 4; }
 // partial outputs of the split tail pairs: [tail_split][tail rows][1024] fp32 (0 when nothing is split)
 size_t apply_pc_part_bytes(int sm_count, int64_t N, int64_t M) {
   const PcPlan p = pc_plan(sm_count, N, M);
@@ -1011,8 +1050,8 @@ __global__ void reduce_tail_kernel(const float4* __restrict__ part, size_t strid
 }
 
 cudaError_t launch_apply_pc(const RetrievalArgs& a, const CUtensorMap& tmP, const float* rowc, void* out, int out_ld,
-                            int out_f64, const int* perm, void* ring, void* flags, void* part, int sm_count,
-                            cudaStream_t stream) {
+                            int out_f64, const int* perm, void* ring, void* flags, void* part, void* scratch,
+                            int sm_count, cudaStream_t stream) {
   PcPlan plan = pc_plan(sm_count, a.N, a.M);
   plan.out_ld = out_ld;
   plan.out_f64 = out_f64;
@@ -1051,7 +1090,7 @@ cudaError_t launch_apply_pc(const RetrievalArgs& a, const CUtensorMap& tmP, cons
   cfg.numAttrs = coop ? 2 : 1;
   e = cudaLaunchKernelEx(&cfg, kern, a.tmQ, a.tmK64, a.tmV128, tmP, a.db_xyz, reinterpret_cast<const float4*>(rowc),
                          a.N, a.M, a.a_sem, out, a.geo_mask, a.mask_words, reinterpret_cast<float*>(part),
-                         reinterpret_cast<__half*>(ring),
+                         reinterpret_cast<float4*>(scratch), reinterpret_cast<__half*>(ring),
                          reinterpret_cast<uint32_t*>(flags),
                          reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(flags) + pc_ring_flag_bytes(sm_count)), plan, dbg,
                          g_prof_buffer);
