@@ -389,6 +389,23 @@ __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.pr
 __device__ __forceinline__ void stg_u4(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
+// L2 residency hints (createpolicy + .L2::cache_hint): data that is re-read soon (the consumers' window scratch) is kept
+// against the streams that pass through the L2 once (database tiles, result rows).
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ float4 ldg_f4_hint(const float4* p, uint64_t pol) {
+  float4 a;
+  asm volatile("ld.global.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "l"(p), "l"(pol) : "memory");
+  return a;
+}
+__device__ __forceinline__ void stg_f4_hint(float4* p, float4 a, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;"
+               ::"l"(p), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "l"(pol) : "memory");
+}
 // Bounded spin on a monotonically increasing counter (never hang the GPU box on a protocol bug)
 __device__ __forceinline__ void wait_flag_ge(const uint32_t* p, uint32_t want) {
   uint32_t spins = 0;

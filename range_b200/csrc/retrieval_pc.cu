@@ -662,6 +662,7 @@ range_apply_pc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       const uint32_t o_empty_leader = ptx::mapa(ptx::smem_u32(&bars[L::b_o_empty]), 0);
       // this CTA's window scratch: [16 column blocks][8 float4][128 rows] float4 (a warp's access is 512 contiguous bytes)
       float4* scratch = acc_scratch + size_t((unit * 2 + cp) * 2 + int(rank)) * (128 * 128) + row;
+      const uint64_t keep = ptx::l2_policy_evict_last();
       uint32_t ev = 0;
       for (int r = 0; r < rounds; ++r) {
         const PcWork wk = pc_work(plan, unit, r, T);
@@ -679,47 +680,63 @@ range_apply_pc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         const int nseg = (wk.t1 - wk.t0 + kAccWindow - 1) / kAccWindow;
         for (int sg = 0; sg < nseg; ++sg, ++ev) {
           const bool last = sg == nseg - 1;
+          // the windows accumulated so far come back from the scratch one column block ahead of the TMEM loads (the
+          // first block before the window's last product has even completed): an L2 round trip per block would
+          // otherwise be exposed sixteen times per flush, with the pair's tensor pipes idle meanwhile
+          const bool acc = sg > 0 && n < N;
+          float4 a0[8], a1[8];
+          auto load_window = [&](int cc, float4 (&a)[8]) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a[i] = ptx::ldg_f4_hint(scratch + size_t(cc) * 8 * 128 + i * 128, keep);
+          };
+          auto flush_block = [&](int cc, uint32_t (&v)[32], const float4 (&a)[8]) {
+            if (n >= N) return;
+            if (acc) {                            // rounded fp32 adds
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                v[4 * i] = __float_as_uint(__uint_as_float(v[4 * i]) + a[i].x);
+                v[4 * i + 1] = __float_as_uint(__uint_as_float(v[4 * i + 1]) + a[i].y);
+                v[4 * i + 2] = __float_as_uint(__uint_as_float(v[4 * i + 2]) + a[i].z);
+                v[4 * i + 3] = __float_as_uint(__uint_as_float(v[4 * i + 3]) + a[i].w);
+              }
+            }
+            if (!last) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                ptx::stg_f4_hint(scratch + size_t(cc) * 8 * 128 + i * 128,
+                                 make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                                             __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3])), keep);
+            } else if (f64) {                     // result rows are written once and never read here: streaming stores
+#pragma unroll
+              for (int i = 0; i < 32; i += 2)
+                __stcs(reinterpret_cast<double2*>(orow64 + cc * 32 + i),
+                       make_double2(double(__uint_as_float(v[i]) * out_scale), double(__uint_as_float(v[i + 1]) * out_scale)));
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) {
+                float4 o;
+                o.x = __uint_as_float(v[i]) * out_scale;
+                o.y = __uint_as_float(v[i + 1]) * out_scale;
+                o.z = __uint_as_float(v[i + 2]) * out_scale;
+                o.w = __uint_as_float(v[i + 3]) * out_scale;
+                __stcs(reinterpret_cast<float4*>(orow32 + cc * 32 + i), o);
+              }
+            }
+          };
+          if (acc) load_window(0, a0);
           ptx::mbar_wait(&bars[L::b_o_full], ev & 1);
           ptx::tc_fence_after();
 #pragma unroll 1
-          for (int cc = 0; cc < 16; ++cc) {
+          for (int cc = 0; cc < 16; cc += 2) {
             uint32_t v[32];
             ptx::tmem_ld32(tmem_base + (uint32_t(quarter * 32) << 16) + cc * 32, v);
+            if (acc) load_window(cc + 1, a1);
             ptx::tmem_ld_wait();
-            if (n < N) {
-              float4* sc = scratch + size_t(cc) * 8 * 128;
-              if (sg > 0) {                       // add the windows accumulated so far (rounded fp32 adds)
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  const float4 a = sc[i * 128];
-                  v[4 * i] = __float_as_uint(__uint_as_float(v[4 * i]) + a.x);
-                  v[4 * i + 1] = __float_as_uint(__uint_as_float(v[4 * i + 1]) + a.y);
-                  v[4 * i + 2] = __float_as_uint(__uint_as_float(v[4 * i + 2]) + a.z);
-                  v[4 * i + 3] = __float_as_uint(__uint_as_float(v[4 * i + 3]) + a.w);
-                }
-              }
-              if (!last) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-                  sc[i * 128] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
-                                            __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
-              } else if (f64) {
-#pragma unroll
-                for (int i = 0; i < 32; i += 2)
-                  *reinterpret_cast<double2*>(orow64 + cc * 32 + i) =
-                      make_double2(double(__uint_as_float(v[i]) * out_scale), double(__uint_as_float(v[i + 1]) * out_scale));
-              } else {
-#pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                  float4 o;
-                  o.x = __uint_as_float(v[i]) * out_scale;
-                  o.y = __uint_as_float(v[i + 1]) * out_scale;
-                  o.z = __uint_as_float(v[i + 2]) * out_scale;
-                  o.w = __uint_as_float(v[i + 3]) * out_scale;
-                  *reinterpret_cast<float4*>(orow32 + cc * 32 + i) = o;
-                }
-              }
-            }
+            flush_block(cc, v, a0);
+            ptx::tmem_ld32(tmem_base + (uint32_t(quarter * 32) << 16) + (cc + 1) * 32, v);
+            if (acc && cc + 2 < 16) load_window(cc + 2, a0);
+            ptx::tmem_ld_wait();
+            flush_block(cc + 1, v, a1);
           }
           ptx::tc_fence_before();
           __syncwarp();
