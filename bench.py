@@ -32,7 +32,7 @@ FLOP_PER_PAIR = 2566.0          # 2*256 + 2*3 + 2*1024 (blended-P 
 METRIC = "RANGE+ embeddings/sec"
 UNIT = "queries/s"
 CPU_SAMPLE_QUERIES = 4000
-DRAM_BYTES_PER_APPLY_LAUNCH = 11.39e9    # measured once with ncu --set full at this workload (profiles/r1m_summary.md)
+DRAM_BYTES_PER_APPLY_LAUNCH = 10.17e9    # measured once with ncu --set full at this workload (profiles/r1n_summary.md)
 
 
 def synthetic_inputs(rank=0):
@@ -257,7 +257,7 @@ def main():
                          "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                          "peak_source": f"{peak_src} bf16 dense sustained",
                          "traffic": DRAM_BYTES_PER_APPLY_LAUNCH,
-                         "traffic_source": "ncu --set full, profiles/r1m_k2_ncu_full_selected.csv (dram read + write)",
+                         "traffic_source": "ncu --set full, profiles/r1n_k2_ncu_full_selected.csv (dram read + write)",
                          "algorithmic_flop_per_launch": FLOP_PER_PAIR * N_QUERIES * M_DB,
                          "launch_ms": seg[2],
                          "stats_plus_apply": {"achieved": achieved_k2, "frac": achieved_k2 / peak_tf,

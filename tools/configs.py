@@ -3,6 +3,7 @@ config; device-resident timing (CUDA events, max over ranks), synthetic data, ra
   C2  RANGE+ beta=0.5, 100k queries x 100k entries                       (bench.py's workload, here for reference)
   C3  RANGE+ beta in {0, .25, .5, .75, 1}, 1M queries, query-sharded
   C4  database scaling M = 100k .. M_MAX, 100k queries; with > 1 rank the database is sharded along M (NCCL merge)
+  ns  one rank's share of the north-star case (1.25 M queries x 1 M entries), CONFIGS=ns
   C5  dense lat/lon raster (visualize_embeddings.py:29-39 coord_grid), RASTER_POINTS points, query-sharded
 """
 import json, os, sys, time
@@ -116,6 +117,27 @@ if "4big" in which:
          pair_rate_per_s=N * Mbig / t, database_build_s=t_build, database_bytes=eng.db.nbytes(),
          finite=bool(torch.isfinite(res).all()), unit_norm=float((res[:, 1024:].double().norm(dim=1) - 1).abs().max()))
     del eng, res
+
+if "ns" in which:
+    # One rank's share of the north-star case (10 M queries x 1 M entries, query-sharded over 8 GPUs: 1.25 M queries per
+    # rank against the whole database, no collective).  NS_QUERIES / NS_M override the sizes.
+    from range_b200.database import DeviceDatabase
+    from range_b200.engine import RangeEngine
+    Mns, Nns = int(os.environ.get("NS_M", 1_000_000)), int(os.environ.get("NS_QUERIES", 1_250_000))
+    eng = RangeEngine(dev, encoder=enc, database=DeviceDatabase.synthetic(Mns, dev))
+    coords = torch.tensor(O.area_uniform(Nns, np.random.default_rng(1 + rank)), device=dev)
+    def share():
+        for lo in range(0, Nns, CHUNK):
+            c, perm = eng.sort_queries(coords[lo:lo + CHUNK])
+            q64, q16, qxyz = eng.encode(c)
+            sums, maxs = eng.retrieve_stats("RANGE+", q16, qxyz, 12.0, 40.0)
+            eng.retrieve_apply_concat("RANGE+", q16, qxyz, 12.0, 40.0, 0.5, sums, maxs, q64, dtype=torch.float32, perm=perm,
+                                      out=out[: c.shape[0]])
+    t = timed(share, reps=1)
+    emit(config="north-star share: 10 M queries x 1 M entries over 8 GPUs = 1.25 M queries per rank", queries_per_rank=Nns,
+         M=Mns, n_gpus=world, seconds=t, queries_per_s=Nns * world / t, pair_rate_per_s=Nns * world * Mns / t,
+         tensor_roofline_frac=2566.0 * Nns * Mns / t / 1364.5e12, parallelism=f"query-sharded x{world}, database replicated")
+    del eng
 
 if "5" in which:
     # coord_grid (visualize_embeddings.py:29-39): lon = linspace(-180, 180, W), lat = linspace(90, -90, H) in float32
