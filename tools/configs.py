@@ -126,17 +126,23 @@ if "ns" in which:
     Mns, Nns = int(os.environ.get("NS_M", 1_000_000)), int(os.environ.get("NS_QUERIES", 1_250_000))
     eng = RangeEngine(dev, encoder=enc, database=DeviceDatabase.synthetic(Mns, dev))
     coords = torch.tensor(O.area_uniform(Nns, np.random.default_rng(1 + rank)), device=dev)
-    def share():
-        for lo in range(0, Nns, CHUNK):
+    def share(n=Nns):
+        for lo in range(0, n, CHUNK):
             c, perm = eng.sort_queries(coords[lo:lo + CHUNK])
             q64, q16, qxyz = eng.encode(c)
             sums, maxs = eng.retrieve_stats("RANGE+", q16, qxyz, 12.0, 40.0)
             eng.retrieve_apply_concat("RANGE+", q16, qxyz, 12.0, 40.0, 0.5, sums, maxs, q64, dtype=torch.float32, perm=perm,
                                       out=out[: c.shape[0]])
-    t = timed(share, reps=1)
+    share(CHUNK); torch.cuda.synchronize()          # warm-up on one chunk (timed() would repeat the whole pass)
+    if world > 1: dist.barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(); share(); b.record(); torch.cuda.synchronize()
+    tt = torch.tensor([a.elapsed_time(b)], device=dev)
+    if world > 1: dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    t = float(tt[0]) * 1e-3
     emit(config="north-star share: 10 M queries x 1 M entries over 8 GPUs = 1.25 M queries per rank", queries_per_rank=Nns,
          M=Mns, n_gpus=world, seconds=t, queries_per_s=Nns * world / t, pair_rate_per_s=Nns * world * Mns / t,
-         tensor_roofline_frac=2566.0 * Nns * Mns / t / 1364.5e12, parallelism=f"query-sharded x{world}, database replicated")
+         tensor_roofline_frac=2566.0 * Nns * Mns / t / 1364.5e12, total_queries=Nns * world, parallelism=f"query-sharded x{world}, database replicated")
     del eng
 
 if "5" in which:
