@@ -119,6 +119,23 @@ size_t range_encode_workspace_bytes(range_ctx* ctx, int64_t N);
 int range_encode(range_ctx* ctx, int64_t N, const double* lonlat, double* q64, void* q16, float* qxyz,
                  void* workspace, size_t workspace_bytes, void* stream);
 
+/* Dense lat/lon rasters (BASELINE config 5; the reference evaluates grids built like
+ * range/evaluation/visualize_embeddings.py:29-45 point by point through spherical_harmonics.py:27-42).  Every analytic
+ * harmonic is (latitude factor) x (longitude factor): range_raster_tables evaluates the latitude factors once per
+ * distinct latitude and the trigonometric factors once per distinct longitude into `tables` (a device buffer of
+ * range_raster_tables_bytes() the caller keeps alive); range_encode_raster then encodes queries given as
+ * ij (N,2) int32 = (latitude index, longitude index) - any subset of the raster in any order, e.g. after
+ * range_sort_queries - and also writes their coordinates lonlat (N,2) fp64 (lon, lat); an index outside the raster
+ * gives a NaN row.  Same outputs, workspace and
+ * bit-identical values as range_encode on those coordinates.  Needs the tensor-core encoder and the analytic
+ * harmonics (RANGE_ERR_UNSUPPORTED otherwise: call range_encode on the coordinates instead). */
+size_t range_raster_tables_bytes(range_ctx* ctx, int64_t n_lat, int64_t n_lon);
+int range_raster_tables(range_ctx* ctx, int64_t n_lat, const double* lat, int64_t n_lon, const double* lon,
+                        void* tables, size_t bytes, void* stream);
+int range_encode_raster(range_ctx* ctx, int64_t n_lat, int64_t n_lon, const void* tables, int64_t N,
+                        const int32_t* ij, double* lonlat, double* q64, void* q16, float* qxyz, void* workspace,
+                        size_t workspace_bytes, void* stream);
+
 /* K2: retrieval, range/range.py:213-217 (RANGE) and :213-238 (RANGE+).
  *   stats: sums (N,2) = {sum_j exp(temp (s_j-1)), sum_j exp(geo_temp (g_j-1))}, maxs (N,2) = {max s, max g}
  *          over THIS ctx's database shard; shards merge with SUM / MAX (M-sharding across GPUs).

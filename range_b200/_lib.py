@@ -37,6 +37,10 @@ PROTOTYPES = {
     "range_encode_workspace_bytes": (c_size_t, [c_void_p, c_int64]),
     "range_encode": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
                              c_void_p]),
+    "range_raster_tables_bytes": (c_size_t, [c_void_p, c_int64, c_int64]),
+    "range_raster_tables": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "range_encode_raster": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
+                                    c_void_p, c_void_p, c_size_t, c_void_p]),
     "range_retrieve_workspace_bytes": (c_size_t, [c_void_p, c_int64]),
     "range_retrieve_stats": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_float, c_float, c_void_p,
                                      c_void_p, c_void_p, c_size_t, c_void_p]),

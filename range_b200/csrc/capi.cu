@@ -458,6 +458,47 @@ size_t range_encode_workspace_bytes(range_ctx* c, int64_t N) {
   return (size_t(c->dims[0]) + 2 * widest) * ld * 8 + size_t(chunk) * kDimK * 8 + 1024;
 }
 
+// Tensor-core encoder over N queries in chunks: features (per-point harmonics from `lonlat`, or - on a raster - the
+// separable evaluation from `rt` / `ij`, which also writes the queries' coordinates to `lonlat_out`), SIREN, normalise.
+static int encode_tc(range_ctx* c, int64_t N, const double* lonlat, const RasterTables* rt, const int32_t* ij,
+                     double* lonlat_out, double* q64, void* q16, float* qxyz, void* workspace, cudaStream_t s) {
+  const int64_t chunk = N < kEncodeChunk ? N : kEncodeChunk;
+  size_t widest = 0;
+  for (int i = 1; i < c->n_layers; ++i) widest = widest > size_t(c->dims[i]) ? widest : size_t(c->dims[i]);
+  char* p = reinterpret_cast<char*>(align_up(reinterpret_cast<size_t>(workspace), 256));
+  const int F = c->dims[0];
+  void* Yh = p; p += align_up(size_t(chunk) * F * 2, 256);
+  void* Yl = p; p += align_up(size_t(chunk) * F * 2, 256);
+  void* hid[2][2];
+  for (int a = 0; a < 2; ++a)
+    for (int b = 0; b < 2; ++b) { hid[a][b] = p; p += align_up(size_t(chunk) * widest * 2, 256); }
+  double* emb = reinterpret_cast<double*>(p);
+  for (int64_t n0 = 0; n0 < N; n0 += chunk) {
+    const int n = int(N - n0 < chunk ? N - n0 : chunk);
+    const double* coords = rt ? lonlat_out + 2 * n0 : lonlat + 2 * n0;
+    if (rt) CUDA_TRY(launch_raster_combine(c->sh, *rt, ij + 2 * n0, n, Yh, Yl, lonlat_out + 2 * n0, s));
+    else CUDA_TRY(launch_sh_rowmajor(c->sh, coords, n, Yh, Yl, s));
+    const void *ah = Yh, *al = Yl;
+    for (int i = 0; i < c->n_layers; ++i) {
+      const bool last = i == c->n_layers - 1;
+      const int K = c->dims[i], H = c->dims[i + 1];
+      CUtensorMap tmAh, tmAl;
+      int r = make_tmap(&tmAh, ah, uint64_t(n), uint64_t(K), 128);
+      if (r) return r;
+      r = make_tmap(&tmAl, al, uint64_t(n), uint64_t(K), 128);
+      if (r) return r;
+      CUDA_TRY(launch_siren_tc(tmAh, tmAl, c->tmWh[i], c->tmWl[i], c->b[i], n, K, H,
+                               last ? 0.0 : (i == 0 ? c->w0_first : c->w0_hidden), last ? nullptr : hid[i & 1][0],
+                               last ? nullptr : hid[i & 1][1], last ? emb : nullptr, s));
+      ah = hid[i & 1][0]; al = hid[i & 1][1];
+    }
+    CUDA_TRY(launch_normalize(emb, coords, n, kDimK, q64 + n0 * kDimK, kDimK,
+                              reinterpret_cast<char*>(q16) + n0 * kDimK * 2, qxyz + n0 * 4, s));
+    g_launches += 2 + c->n_layers;
+  }
+  return RANGE_OK;
+}
+
 int range_encode(range_ctx* c, int64_t N, const double* lonlat, double* q64, void* q16, float* qxyz,
                  void* workspace, size_t workspace_bytes, void* stream) {
   if (!c || !c->sh.pref || !c->n_layers) return fail(RANGE_ERR_INVALID, "encoder not set");
@@ -472,40 +513,8 @@ int range_encode(range_ctx* c, int64_t N, const double* lonlat, double* q64, voi
     return fail(RANGE_ERR_WORKSPACE, "encode workspace too small");
   cudaStream_t s = cudaStream_t(stream);
   const int64_t chunk = N < kEncodeChunk ? N : kEncodeChunk;
-  if (c->enc_precision == RANGE_ENC_F16X3) {
-    size_t widest = 0;
-    for (int i = 1; i < c->n_layers; ++i) widest = widest > size_t(c->dims[i]) ? widest : size_t(c->dims[i]);
-    char* p = reinterpret_cast<char*>(align_up(reinterpret_cast<size_t>(workspace), 256));
-    const int F = c->dims[0];
-    void* Yh = p; p += align_up(size_t(chunk) * F * 2, 256);
-    void* Yl = p; p += align_up(size_t(chunk) * F * 2, 256);
-    void* hid[2][2];
-    for (int a = 0; a < 2; ++a)
-      for (int b = 0; b < 2; ++b) { hid[a][b] = p; p += align_up(size_t(chunk) * widest * 2, 256); }
-    double* emb = reinterpret_cast<double*>(p);
-    for (int64_t n0 = 0; n0 < N; n0 += chunk) {
-      const int n = int(N - n0 < chunk ? N - n0 : chunk);
-      CUDA_TRY(launch_sh_rowmajor(c->sh, lonlat + 2 * n0, n, Yh, Yl, s));
-      const void *ah = Yh, *al = Yl;
-      for (int i = 0; i < c->n_layers; ++i) {
-        const bool last = i == c->n_layers - 1;
-        const int K = c->dims[i], H = c->dims[i + 1];
-        CUtensorMap tmAh, tmAl;
-        int r = make_tmap(&tmAh, ah, uint64_t(n), uint64_t(K), 128);
-        if (r) return r;
-        r = make_tmap(&tmAl, al, uint64_t(n), uint64_t(K), 128);
-        if (r) return r;
-        CUDA_TRY(launch_siren_tc(tmAh, tmAl, c->tmWh[i], c->tmWl[i], c->b[i], n, K, H,
-                                 last ? 0.0 : (i == 0 ? c->w0_first : c->w0_hidden), last ? nullptr : hid[i & 1][0],
-                                 last ? nullptr : hid[i & 1][1], last ? emb : nullptr, s));
-        ah = hid[i & 1][0]; al = hid[i & 1][1];
-      }
-      CUDA_TRY(launch_normalize(emb, lonlat + 2 * n0, n, kDimK, q64 + n0 * kDimK, kDimK,
-                                reinterpret_cast<char*>(q16) + n0 * kDimK * 2, qxyz + n0 * 4, s));
-      g_launches += 2 + c->n_layers;
-    }
-    return RANGE_OK;
-  }
+  if (c->enc_precision == RANGE_ENC_F16X3)
+    return encode_tc(c, N, lonlat, nullptr, nullptr, nullptr, q64, q16, qxyz, workspace, s);
   const size_t ld = align_up(size_t(chunk), 128);
   size_t widest = 0;
   for (int i = 1; i < c->n_layers; ++i) widest = widest > size_t(c->dims[i]) ? widest : size_t(c->dims[i]);
@@ -531,6 +540,48 @@ int range_encode(range_ctx* c, int64_t N, const double* lonlat, double* q64, voi
     g_launches += 2 + c->n_layers;
   }
   return RANGE_OK;
+}
+
+static int raster_supported(const range_ctx* c) {
+  if (!c || !c->sh.pref || !c->n_layers) return fail(RANGE_ERR_INVALID, "encoder not set");
+  if (c->sh.closed_form)
+    return fail(RANGE_ERR_UNSUPPORTED, "raster encoder: closed-form harmonics are not evaluated separably (use range_encode)");
+  if (c->enc_precision != RANGE_ENC_F16X3 || c->dims[0] != c->sh.L * c->sh.L)
+    return fail(RANGE_ERR_UNSUPPORTED, "raster encoder needs the tensor-core encoder (range_ctx_prepare_encoder)");
+  return RANGE_OK;
+}
+
+size_t range_raster_tables_bytes(range_ctx* c, int64_t n_lat, int64_t n_lon) {
+  if (!c || !c->sh.pref || n_lat <= 0 || n_lon <= 0) return 0;
+  return raster_tables_bytes(c->sh.L, int(n_lat), int(n_lon)) + 256;
+}
+
+int range_raster_tables(range_ctx* c, int64_t n_lat, const double* lat, int64_t n_lon, const double* lon, void* tables,
+                        size_t bytes, void* stream) {
+  int r = raster_supported(c);
+  if (r) return r;
+  if (n_lat <= 0 || n_lon <= 0 || n_lat > (1 << 24) || n_lon > (1 << 24) || !lat || !lon || !tables)
+    return fail(RANGE_ERR_INVALID, "bad arguments");
+  if (bytes < range_raster_tables_bytes(c, n_lat, n_lon)) return fail(RANGE_ERR_WORKSPACE, "raster tables buffer too small");
+  void* buf = reinterpret_cast<void*>(align_up(reinterpret_cast<size_t>(tables), 256));
+  const RasterTables t = raster_tables_layout(c->sh.L, int(n_lat), int(n_lon), buf);
+  CUDA_TRY(launch_raster_tables(c->sh, lat, lon, t, cudaStream_t(stream)));
+  g_launches += 3;
+  return RANGE_OK;
+}
+
+int range_encode_raster(range_ctx* c, int64_t n_lat, int64_t n_lon, const void* tables, int64_t N, const int32_t* ij,
+                        double* lonlat, double* q64, void* q16, float* qxyz, void* workspace, size_t workspace_bytes,
+                        void* stream) {
+  int r = raster_supported(c);
+  if (r) return r;
+  if (n_lat <= 0 || n_lon <= 0 || !tables || N <= 0 || !ij || !lonlat || !q64 || !q16 || !qxyz)
+    return fail(RANGE_ERR_INVALID, "bad arguments");
+  if (workspace_bytes < range_encode_workspace_bytes(c, N) || !workspace)
+    return fail(RANGE_ERR_WORKSPACE, "encode workspace too small");
+  void* buf = reinterpret_cast<void*>(align_up(reinterpret_cast<size_t>(const_cast<void*>(tables)), 256));
+  const RasterTables t = raster_tables_layout(c->sh.L, int(n_lat), int(n_lon), buf);
+  return encode_tc(c, N, nullptr, &t, ij, lonlat, q64, q16, qxyz, workspace, cudaStream_t(stream));
 }
 
 size_t range_retrieve_workspace_bytes(range_ctx* c, int64_t N) {

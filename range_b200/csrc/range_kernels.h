@@ -41,6 +41,23 @@ cudaError_t launch_siren_tc(const CUtensorMap& tmAh, const CUtensorMap& tmAl, co
                             const CUtensorMap& tmBl, const double* bias, int N, int K, int H, double act_w0,
                             void* out_hi, void* out_lo, double* out_f64, cudaStream_t s);
 
+// ---- K1 on a lat/lon raster: separable evaluation, bit-identical to launch_sh_rowmajor (encoder_raster.cu) ----
+struct RasterTables {
+  int H = 0, W = 0;               // distinct latitudes / longitudes
+  double* leg = nullptr;          // [H][L(L+1)/2]   latitude factor of every (l, |m|), |m|-major
+  void* trig = nullptr;           // [W][L] double2  (cos |m| phi, sin |m| phi)
+  double* lat = nullptr;          // [H] degrees
+  double* lon = nullptr;          // [W] degrees
+  int* fmap = nullptr;            // [L*L] production-order feature -> entry | |m| << 16 | is_sin << 24
+};
+size_t raster_tables_bytes(int L, int H, int W);
+RasterTables raster_tables_layout(int L, int H, int W, void* buf);     // buf 256-byte aligned
+cudaError_t launch_raster_tables(const ShTable& sh, const double* lat, const double* lon, const RasterTables& t,
+                                 cudaStream_t s);
+// ij (N,2) int32 = (latitude index, longitude index) -> features hi/lo fp16 [N][L*L], lonlat (N,2) fp64
+cudaError_t launch_raster_combine(const ShTable& sh, const RasterTables& t, const int32_t* ij, int N, void* Yh, void* Yl,
+                                  double* lonlat, cudaStream_t s);
+
 // ---- K3: normalise / concat (encoder.cu) ----------------------------------------------------------
 // e [N][D] fp64 row-major -> q64 [N][D] (ld = ldq), q16 [N][D] fp16, qxyz [N][4] fp32 from lonlat
 cudaError_t launch_normalize(const double* e, const double* lonlat, int N, int D, double* q64, size_t ldq,

@@ -168,6 +168,39 @@ class RangeEngine:
                                              ws.numel(), _stream()))
         return q64, q16, qxyz
 
+    def raster_tables(self, lon_axis, lat_axis):
+        """Per-axis tables of a lat/lon raster (encoder_raster.cu): the latitude factor of every harmonic for each
+        distinct latitude, cos/sin(m phi) for each distinct longitude.  Returns an opaque handle for encode_raster."""
+        lon = torch.as_tensor(lon_axis).to(self.device, torch.float64).contiguous()
+        lat = torch.as_tensor(lat_axis).to(self.device, torch.float64).contiguous()
+        H, W = lat.numel(), lon.numel()
+        with torch.cuda.device(self.index):
+            nbytes = self.lib.range_raster_tables_bytes(self.ctx, H, W)
+            buf = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            _lib.check(self.lib.range_raster_tables(self.ctx, H, _ptr(lat), W, _ptr(lon), _ptr(buf), buf.numel(),
+                                                    _stream()))
+        return dict(H=H, W=W, buf=buf, lon=lon, lat=lat)
+
+    def encode_raster(self, tables, ij):
+        """ij (N,2) int32 = (latitude index, longitude index) -> (lonlat (N,2) fp64, q64, q16, qxyz); bit-identical to
+        encode() on those coordinates, without re-evaluating the harmonics' latitude / longitude factors per point."""
+        ij = ij.to(self.device, torch.int32).contiguous()
+        N = ij.shape[0]
+        lonlat = torch.empty(N, 2, dtype=torch.float64, device=self.device)
+        q64 = torch.empty(N, 256, dtype=torch.float64, device=self.device)
+        q16 = torch.empty(N, 256, dtype=torch.float16, device=self.device)
+        qxyz = torch.empty(N, 4, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.index):
+            ws = self._workspace("enc", self.lib.range_encode_workspace_bytes(self.ctx, N))
+            _lib.check(self.lib.range_encode_raster(self.ctx, tables["H"], tables["W"], _ptr(tables["buf"]), N, _ptr(ij),
+                                                    _ptr(lonlat), _ptr(q64), _ptr(q16), _ptr(qxyz), _ptr(ws), ws.numel(),
+                                                    _stream()))
+        return lonlat, q64, q16, qxyz
+
+    def raster_supported(self):
+        """the separable raster encoder needs the analytic harmonics and the tensor-core SIREN"""
+        return self.harmonics == "analytic" and getattr(self, "precision", None) == "f16x3"
+
     def _ret_ws(self, N):
         return self._workspace("ret", self.lib.range_retrieve_workspace_bytes(self.ctx, N))
 

@@ -129,16 +129,77 @@ class LocationEncoder(nn.Module):
         copy stream."""
         if 'RANGE' not in self.location_model_name:
             raise NotImplementedError(f'{self.location_model_name} not implemented')
-        eng = self.engine
         coords = torch.as_tensor(coords)
         if coords.dim() != 2 or coords.shape[1] != 2:
             raise ValueError(f'coords must be (N, 2) (lon, lat) degrees, got {tuple(coords.shape)}')
-        N = coords.shape[0]
+        return self._forward_host(coords.shape[0], coords=coords)
+
+    # ------------------------------------------------------------------ dense lat/lon rasters
+    @staticmethod
+    def coord_grid_axes(grid_size):
+        """(lon_axis (W,), lat_axis (H,)) of the reference's coord_grid(grid_size=(H, W))
+        (evaluation/visualize_embeddings.py:29-39): linspace(-180, 180, W) / linspace(90, -90, H) stored in a float32
+        array and later promoted with .double().  Raster point p = i * W + j is (lon_axis[j], lat_axis[i])."""
+        H, W = grid_size
+        lon = np.linspace(-180, 180, W).astype(np.float32).astype(np.float64)
+        lat = np.linspace(90, -90, H).astype(np.float32).astype(np.float64)
+        return torch.from_numpy(lon), torch.from_numpy(lat)
+
+    def _raster_ij(self, W, p0, p1):
+        p = torch.arange(p0, p1, device=self.engine.device, dtype=torch.int64)
+        return torch.stack((p // W, p % W), dim=1).to(torch.int32)
+
+    @staticmethod
+    def _raster_coords(tables, ij):
+        return torch.stack((tables['lon'][ij[:, 1].long()], tables['lat'][ij[:, 0].long()]), dim=1)
+
+    def raster_tables(self, lon_axis, lat_axis):
+        """per-axis harmonics tables for embed_raster / forward_raster (build once per raster)"""
+        eng = self.engine
+        if eng.raster_supported():
+            return eng.raster_tables(lon_axis, lat_axis)
+        # closed-form harmonics / fp64 encoder: no separable evaluation, the per-point encoder runs on the coordinates
+        lon = torch.as_tensor(lon_axis).to(eng.device, torch.float64).contiguous()
+        lat = torch.as_tensor(lat_axis).to(eng.device, torch.float64).contiguous()
+        return dict(H=lat.numel(), W=lon.numel(), buf=None, lon=lon, lat=lat)
+
+    def _encode_raster(self, tables, ij):
+        eng = self.engine
+        if tables['buf'] is None:
+            return eng.encode(self._raster_coords(tables, ij))
+        return eng.encode_raster(tables, ij)[1:]
+
+    @torch.no_grad()
+    def embed_raster(self, lon_axis, lat_axis, rows=None, out=None, out_dtype=torch.float32, tables=None):
+        """Device-resident dense-grid path (BASELINE config 5): the points [rows[0], rows[1]) of the lat-major raster
+        lat_axis x lon_axis (point p = i * W + j, like coord_grid) -> (n, 1280) device tensor in raster order.  The
+        harmonics are evaluated separably (once per distinct latitude / longitude, csrc/encoder_raster.cu); results
+        are bit-identical to embed() on the same coordinates."""
+        eng = self.engine
+        tables = self.raster_tables(lon_axis, lat_axis) if tables is None else tables
+        p0, p1 = (0, tables['H'] * tables['W']) if rows is None else rows
+        ij = self._raster_ij(tables['W'], p0, p1)
+        perm = None
+        if self._sorts():
+            _, perm = eng.sort_queries(self._raster_coords(tables, ij))
+            ij = ij[perm.long()]
+        q64, q16, qxyz = self._encode_raster(tables, ij)
+        return self._retrieve_concat(q16, qxyz, q64, out, out_dtype, perm)
+
+    @torch.no_grad()
+    def forward_raster(self, lon_axis, lat_axis):
+        """model(coord_grid(...)) without building the coordinate list on the host: numpy float64 (H * W, 1280)."""
+        tables = self.raster_tables(lon_axis, lat_axis)
+        return self._forward_host(tables['H'] * tables['W'], raster=tables)
+
+    def _forward_host(self, N, coords=None, raster=None):
+        eng = self.engine
         host = torch.empty((N, 1280), dtype=torch.float64, pin_memory=True)
         if N == 0:
             return host.numpy()
         with torch.cuda.device(eng.index):
-            dev_coords = coords.to(eng.device, torch.float64, non_blocking=True)
+            if raster is None:
+                dev_coords = coords.to(eng.device, torch.float64, non_blocking=True)
             if self._copy_stream is None:
                 self._copy_stream = torch.cuda.Stream(device=eng.device)
             chunk = min(self.chunk, N)
@@ -150,13 +211,20 @@ class LocationEncoder(nn.Module):
             for s0 in range(0, N, self.super_batch):
                 s1 = min(N, s0 + self.super_batch)
                 cuts = self._chunks(s1 - s0, chunk, self.tail)
-                sub = dev_coords[s0:s1]
+                ij = None
+                if raster is None:
+                    sub = dev_coords[s0:s1]
+                else:
+                    ij = self._raster_ij(raster['W'], s0, s1)
+                    sub = self._raster_coords(raster, ij)
                 perms = None
                 if self._sorts():
                     parts = [eng.sort_queries(sub[lo:hi]) for lo, hi in cuts]
                     sub = torch.cat([p[0] for p in parts]) if len(parts) > 1 else parts[0][0]
                     perms = [p[1] for p in parts]
-                q64, q16, qxyz = eng.encode(sub)
+                    if ij is not None:
+                        ij = torch.cat([ij[lo:hi][p.long()] for (lo, hi), p in zip(cuts, perms)])
+                q64, q16, qxyz = eng.encode(sub) if ij is None else self._encode_raster(raster, ij)
                 for c, (lo, hi) in enumerate(cuts):
                     k = i % len(bufs)
                     i += 1
