@@ -1073,7 +1073,11 @@ cudaError_t launch_apply_pc(const RetrievalArgs& a, const CUtensorMap& tmP, cons
   plan.out_ld = out_ld;
   plan.out_f64 = out_f64;
   plan.perm = perm;
-  static const int dbg = getenv("RANGE_PC_DBG") ? atoi(getenv("RANGE_PC_DBG")) : 0;   // developer switch: decouple the roles
+#ifdef RANGE_DEVELOPER_SWITCHES       // NVCC_EXTRA=-DRANGE_DEVELOPER_SWITCHES: RANGE_PC_DBG decouples the roles (results are then wrong)
+  static const int dbg = getenv("RANGE_PC_DBG") ? atoi(getenv("RANGE_PC_DBG")) : 0;
+#else
+  constexpr int dbg = 0;
+#endif
   cudaError_t e = cudaMemsetAsync(flags, 0, apply_pc_flag_bytes(sm_count, a.N, a.M), stream);
   if (e != cudaSuccess) return e;
   auto kern = a.geo ? range_apply_pc_kernel<true> : range_apply_pc_kernel<false>;
