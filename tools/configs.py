@@ -146,15 +146,25 @@ if "ns" in which:
     del eng
 
 if "5" in which:
-    # coord_grid (visualize_embeddings.py:29-39): lon = linspace(-180, 180, W), lat = linspace(90, -90, H) in float32
+    # coord_grid (visualize_embeddings.py:29-39): lon = linspace(-180, 180, W), lat = linspace(90, -90, H) stored as float32;
+    # raster points sharded over the ranks, the harmonics evaluated separably (embed_raster); RASTER_API=0: the
+    # materialised coordinate list through embed()
     H = int(round((RASTER / 2) ** 0.5)); W = 2 * H
-    lon = torch.linspace(-180, 180, W, dtype=torch.float32); lat = torch.linspace(90, -90, H, dtype=torch.float32)
-    grid = torch.stack(torch.meshgrid(lon, lat, indexing="xy"), dim=-1).reshape(-1, 2).double()
-    lo, hi = shard_rows(grid.shape[0], rank, world)
-    coords = grid[lo:hi].to(dev)
+    lon_axis, lat_axis = LocationEncoder.coord_grid_axes((H, W))
+    lo, hi = shard_rows(H * W, rank, world)
     m = model_for(db, 0.5)
-    t = timed(lambda: run_chunks(m, coords, out), reps=1)
-    emit(config="C5 dense raster", H=H, W=W, queries=grid.shape[0], M=100_000, n_gpus=world, seconds=t,
-         queries_per_s=grid.shape[0] / t, parallelism=f"query-sharded x{world}")
+    use_raster = os.environ.get("RASTER_API", "1") == "1"
+    tables = m.raster_tables(lon_axis, lat_axis)
+    if use_raster:
+        def raster():
+            for p0 in range(lo, hi, CHUNK):
+                p1 = min(hi, p0 + CHUNK)
+                m.embed_raster(lon_axis, lat_axis, rows=(p0, p1), out=out[: p1 - p0], tables=tables)
+        t = timed(raster, reps=1)
+    else:
+        coords = m._raster_coords(tables, m._raster_ij(W, lo, hi))
+        t = timed(lambda: run_chunks(m, coords, out), reps=1)
+    emit(config="C5 dense raster", H=H, W=W, queries=H * W, M=100_000, n_gpus=world, seconds=t,
+         queries_per_s=H * W / t, parallelism=f"query-sharded x{world}", encoder="raster (separable harmonics)" if use_raster else "per point")
 if world > 1:
     dist.destroy_process_group()
