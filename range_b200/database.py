@@ -15,6 +15,8 @@ tiles are then spatially compact, which lets the RANGE+ kernels skip the geograp
 query tile (include/range_b200.h: range_ctx_set_db_caps).
 """
 import math
+import struct
+import zipfile
 
 import numpy as np
 import torch
@@ -32,6 +34,56 @@ def prepare_reference_arrays(db):
     V = np.asarray(db["image_embeddings"]).astype(np.float32)                         # :90
     xyz = rad_to_cart(locs * math.pi / 180)                                           # :93-95 (fp32)
     return K, V, xyz
+
+
+def open_npz(path):
+    """{name: array} of a RANGE database file (range/range.py:78 reads it with np.load).  generate_db.py:209-214 writes
+    it with np.savez, i.e. uncompressed: such members are memory-mapped in place instead of read, so the (M, 1024)
+    float64 value matrix of a 10 M-entry database (82 GB) is never resident at once - DeviceDatabase converts it block
+    by block.  Compressed, object-typed or empty members are read the way np.load reads them."""
+    from numpy.lib import format as npf
+    out, loaded = {}, None
+    with zipfile.ZipFile(path) as zf, open(path, "rb") as f:
+        for info in zf.infolist():
+            name = info.filename[:-4] if info.filename.endswith(".npy") else info.filename
+            arr = None
+            if info.compress_type == zipfile.ZIP_STORED and info.filename.endswith(".npy"):
+                f.seek(info.header_offset)
+                local = f.read(30)                         # local file header: name / extra lengths at bytes 26..30
+                if len(local) == 30 and local[:4] == b"PK\x03\x04":
+                    nlen, elen = struct.unpack("<HH", local[26:30])
+                    f.seek(info.header_offset + 30 + nlen + elen)
+                    try:
+                        version = npf.read_magic(f)
+                        read_header = {(1, 0): npf.read_array_header_1_0, (2, 0): npf.read_array_header_2_0}.get(version)
+                        if read_header is not None:
+                            shape, fortran, dtype = read_header(f)
+                            if not dtype.hasobject and len(shape) > 0 and int(np.prod(shape)) > 0:
+                                arr = np.memmap(path, dtype=dtype, mode="r", offset=f.tell(), shape=shape,
+                                                order="F" if fortran else "C")
+                    except ValueError:
+                        arr = None
+            if arr is None:
+                loaded = np.load(path, allow_pickle=True) if loaded is None else loaded
+                arr = loaded[name]
+            out[name] = arr
+    return out
+
+
+def prepare_keys_and_locations(db):
+    """range/range.py:79-95 without the value matrix: keys fp32 row-normalised, unit vectors fp32"""
+    locs = np.asarray(db["locs"]).astype(np.float32)                                  # :79
+    K = np.asarray(db["satclip_embeddings"]).astype(np.float32)                       # :85
+    K = K / np.linalg.norm(K, ord=2, axis=1, keepdims=True)                           # :89
+    return K, rad_to_cart(locs * math.pi / 180)                                       # :93-95 (fp32)
+
+
+def _abs_max_fp32(V, step=1 << 16):
+    """float(np.abs(V.astype(np.float32)).max()) without materialising the fp32 copy (NaN propagates like there)"""
+    m = np.float32(0.0)
+    for lo in range(0, V.shape[0], step):
+        m = np.maximum(m, np.abs(np.asarray(V[lo:lo + step]).astype(np.float32)).max())
+    return float(m)
 
 
 def _hilbert_index(ix, iy, bits):
@@ -92,7 +144,11 @@ class DeviceDatabase:
         """db: mapping with locs / satclip_embeddings / image_embeddings (an opened .npz works).
         shard=(rank, world): keep rows [rank*M/world, (rank+1)*M/world) of the (sorted) database only (M-sharding).
         spatial_sort: store the rows along a Hilbert curve and build the tile caps (geo-term skipping)."""
-        K, V, xyz = prepare_reference_arrays(db)
+        K, xyz = prepare_keys_and_locations(db)
+        # the value matrix stays what it is (ndarray, or a memory map from open_npz): range.py:90's .astype(float32)
+        # is applied block by block on the way to the device
+        V = db["image_embeddings"]
+        V = V if isinstance(V, np.ndarray) else np.asarray(V)
         self.M_total = K.shape[0]
         self.order = None
         if spatial_sort and self.M_total > 0:
@@ -106,8 +162,8 @@ class DeviceDatabase:
             self.row_range = (lo, hi)
         else:
             self.row_range = (0, self.M_total)
-        if K.shape[1] != 256 or V.shape[1] != 1024:
-            raise ValueError(f"RANGE database must have 256-d keys and 1024-d values, got {K.shape[1]}, {V.shape[1]}")
+        if K.shape[1] != 256 or V.ndim != 2 or V.shape[1] != 1024:
+            raise ValueError(f"RANGE database must have 256-d keys and 1024-d values, got {K.shape[1:]}, {V.shape[1:]}")
         M = K.shape[0]
         if M == 0:
             raise ValueError("empty database (shard)")
@@ -116,14 +172,19 @@ class DeviceDatabase:
         self.M, self.Mpad = M, Mpad
         self.Kh = torch.zeros(Mpad, 256, dtype=torch.float16, device=dev)
         self.Kh[:M] = torch.from_numpy(K).to(dev).half()
-        vmax = float(np.abs(V).max())
+        vmax = _abs_max_fp32(V)
         self.vscale = 1.0 if vmax == 0.0 or not math.isfinite(vmax) else 2.0 ** math.floor(math.log2(256.0 / vmax))
         self.Vt = torch.zeros(1024, Mpad, dtype=torch.float16, device=dev)
         step = 1 << 18
         row0 = self.row_range[0]
         for lo in range(0, M, step):                       # bounded staging memory for 10M-entry databases
             hi = min(M, lo + step)
-            rows = V[lo:hi] if self.order is None else V[self.order[row0 + lo:row0 + hi]]
+            idx = None if self.order is None else np.sort(self.order[row0 + lo:row0 + hi])
+            if idx is None:
+                rows = np.asarray(V[lo:hi]).astype(np.float32)
+            else:                                          # gather in file order (sequential reads of a memory map), then permute
+                blk = np.asarray(V[idx]).astype(np.float32)
+                rows = blk[np.searchsorted(idx, self.order[row0 + lo:row0 + hi])]
             self.Vt[:, lo:hi] = (torch.from_numpy(np.ascontiguousarray(rows)).to(dev) * self.vscale).half().t()
         self.xyz = torch.zeros(Mpad, 4, dtype=torch.float32, device=dev)
         self.xyz[:M, :3] = torch.from_numpy(np.ascontiguousarray(xyz)).to(dev)

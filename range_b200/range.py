@@ -11,7 +11,7 @@ import torch
 import torch.nn as nn
 
 from .checkpoint import load_satclip_location_encoder
-from .database import DeviceDatabase
+from .database import DeviceDatabase, open_npz
 from .engine import RangeEngine
 
 # four rounds of the producer/consumer apply kernel on 148 SMs (24 units x 2 query tiles of 128 per round)
@@ -36,7 +36,7 @@ class LocationEncoder(nn.Module):
         else:
             raise ValueError('Unimplemented RANGE model')                                  # range.py:114
         shard = getattr(args, 'db_shard', None)
-        db = np.load(args.range_db, allow_pickle=True) if isinstance(args.range_db, str) else args.range_db
+        db = open_npz(args.range_db) if isinstance(args.range_db, str) else args.range_db          # range.py:78
         enc = load_satclip_location_encoder(args.pretrained_path) if isinstance(args.pretrained_path, str) \
             else args.pretrained_path
         self.location_feature_dim = 1024 + 256                                             # range.py:86

@@ -73,3 +73,50 @@ def test_forward_chunking_covers_every_row():
     for N, chunk, tail in [(64, 24, 24), (64, 24, 5), (7, 3, 3), (100, 1, 1)]:          # degenerate settings still tile [0, N)
         cuts = LocationEncoder._chunks(N, chunk, tail)
         assert cuts[0][0] == 0 and cuts[-1][1] == N and all(a[1] == b[0] for a, b in zip(cuts, cuts[1:]))
+
+
+def test_open_npz_memory_maps_the_reference_file_format(tmp_path):
+    """generate_db.py:209-214 writes the database with np.savez (float64, uncompressed): open_npz maps the members in
+    place and DeviceDatabase builds bit for bit the layout it builds from np.load's arrays"""
+    from range_b200.database import DeviceDatabase, open_npz
+    db = {k: np.asarray(v, dtype=np.float64) for k, v in _db(700).items()}
+    path = str(tmp_path / "range_db.npz")
+    np.savez(path, locs=db["locs"], image_embeddings=db["image_embeddings"], satclip_embeddings=db["satclip_embeddings"])
+    z = open_npz(path)
+    assert set(z) == {"locs", "image_embeddings", "satclip_embeddings"}
+    assert all(isinstance(v, np.memmap) for v in z.values())               # nothing was read
+    ref = np.load(path)
+    for k in z:
+        assert z[k].dtype == ref[k].dtype and np.array_equal(np.asarray(z[k]), ref[k])
+    for kw in (dict(), dict(shard=(1, 3)), dict(spatial_sort=False), dict(spatial_sort=False, shard=(2, 3))):
+        a, b = DeviceDatabase(z, "cpu", **kw), DeviceDatabase(ref, "cpu", **kw)
+        assert a.vscale == b.vscale and a.row_range == b.row_range
+        for name in ("Kh", "Vt", "xyz"):
+            assert torch.equal(getattr(a, name), getattr(b, name)), (name, kw)
+    # compressed files and odd members take np.load's path
+    cpath = str(tmp_path / "compressed.npz")
+    np.savez_compressed(cpath, locs=db["locs"], image_embeddings=db["image_embeddings"],
+                        satclip_embeddings=db["satclip_embeddings"], note=np.array("x"), empty=np.zeros((0, 3)))
+    c = open_npz(cpath)
+    assert not any(isinstance(v, np.memmap) for v in c.values())
+    assert np.array_equal(c["image_embeddings"], db["image_embeddings"]) and c["empty"].shape == (0, 3)
+    upath = str(tmp_path / "mixed.npz")
+    np.savez(upath, locs=db["locs"], empty=np.zeros((0, 3)), scalar=np.float64(2.5))
+    u = open_npz(upath)
+    assert isinstance(u["locs"], np.memmap) and u["empty"].shape == (0, 3) and float(u["scalar"]) == 2.5
+
+
+def test_block_wise_value_conversion_matches_the_reference_rule():
+    """range.py:90 converts the whole value matrix to fp32 at once; the block-wise conversion gives the same scale and
+    the same fp16 layout, including a NaN value (scale falls back to 1 like before)"""
+    from range_b200.database import DeviceDatabase, _abs_max_fp32, prepare_reference_arrays
+    db = _db(500)
+    _, V, _ = prepare_reference_arrays(db)
+    assert _abs_max_fp32(db["image_embeddings"], step=64) == float(np.abs(V).max())
+    d = DeviceDatabase(db, "cpu")
+    assert torch.equal(d.Vt[:, :500].t().contiguous(), (torch.from_numpy(V[d.order]) * d.vscale).half())
+    bad = dict(db)
+    bad["image_embeddings"] = np.array(db["image_embeddings"], dtype=np.float64)
+    bad["image_embeddings"][17, 5] = np.nan
+    assert math.isnan(_abs_max_fp32(bad["image_embeddings"], step=64))
+    assert DeviceDatabase(bad, "cpu").vscale == 1.0
