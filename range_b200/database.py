@@ -70,14 +70,6 @@ def open_npz(path):
     return out
 
 
-def prepare_keys_and_locations(db):
-    """range/range.py:79-95 without the value matrix: keys fp32 row-normalised, unit vectors fp32"""
-    locs = np.asarray(db["locs"]).astype(np.float32)                                  # :79
-    K = np.asarray(db["satclip_embeddings"]).astype(np.float32)                       # :85
-    K = K / np.linalg.norm(K, ord=2, axis=1, keepdims=True)                           # :89
-    return K, rad_to_cart(locs * math.pi / 180)                                       # :93-95 (fp32)
-
-
 def _abs_max_fp32(V, step=1 << 16):
     """float(np.abs(V.astype(np.float32)).max()) without materialising the fp32 copy (NaN propagates like there)"""
     m = np.float32(0.0)
@@ -140,52 +132,53 @@ def tile_caps(xyz, block=BLOCK):
 
 
 class DeviceDatabase:
+    STAGING_ROWS = 1 << 18          # rows converted / uploaded at a time (1.3 GB of fp32 staging)
+
     def __init__(self, db, device, shard=None, spatial_sort=True):
         """db: mapping with locs / satclip_embeddings / image_embeddings (an opened .npz works).
         shard=(rank, world): keep rows [rank*M/world, (rank+1)*M/world) of the (sorted) database only (M-sharding).
         spatial_sort: store the rows along a Hilbert curve and build the tile caps (geo-term skipping)."""
-        K, xyz = prepare_keys_and_locations(db)
-        # the value matrix stays what it is (ndarray, or a memory map from open_npz): range.py:90's .astype(float32)
-        # is applied block by block on the way to the device
-        V = db["image_embeddings"]
-        V = V if isinstance(V, np.ndarray) else np.asarray(V)
-        self.M_total = K.shape[0]
-        self.order = None
-        if spatial_sort and self.M_total > 0:
-            self.order = hilbert_order(xyz)
-            K, xyz = K[self.order], xyz[self.order]         # V is gathered chunk-wise below (it is the big one)
-        if shard is not None:
-            r, w = shard
-            lo, hi = (self.M_total * r) // w, (self.M_total * (r + 1)) // w
-            K, xyz = K[lo:hi], xyz[lo:hi]
-            V = V[lo:hi] if self.order is None else V
-            self.row_range = (lo, hi)
-        else:
-            self.row_range = (0, self.M_total)
-        if K.shape[1] != 256 or V.ndim != 2 or V.shape[1] != 1024:
-            raise ValueError(f"RANGE database must have 256-d keys and 1024-d values, got {K.shape[1:]}, {V.shape[1:]}")
-        M = K.shape[0]
+        # keys and values stay what they are (ndarrays, or memory maps from open_npz): range.py:85-90's .astype(float32)
+        # and row normalisation are applied block by block on the way to the device, in the reference's arithmetic
+        locs = np.asarray(db["locs"]).astype(np.float32)                                  # range.py:79
+        xyz = rad_to_cart(locs * math.pi / 180)                                           # range.py:93-95 (fp32)
+        Kraw, V = (a if isinstance(a, np.ndarray) else np.asarray(a)
+                   for a in (db["satclip_embeddings"], db["image_embeddings"]))
+        self.M_total = xyz.shape[0]
+        if Kraw.ndim != 2 or Kraw.shape[1] != 256 or V.ndim != 2 or V.shape[1] != 1024:
+            raise ValueError(f"RANGE database must have 256-d keys and 1024-d values, got {Kraw.shape[1:]}, {V.shape[1:]}")
+        if Kraw.shape[0] != self.M_total or V.shape[0] != self.M_total:
+            raise ValueError(f"RANGE database arrays disagree on the number of entries: locs {self.M_total}, "
+                             f"keys {Kraw.shape[0]}, values {V.shape[0]}")
+        self.order = hilbert_order(xyz) if spatial_sort and self.M_total > 0 else None
+        lo, hi = (0, self.M_total) if shard is None else ((self.M_total * shard[0]) // shard[1],
+                                                          (self.M_total * (shard[0] + 1)) // shard[1])
+        self.row_range = (lo, hi)
+        rows_of = np.arange(lo, hi) if self.order is None else self.order[lo:hi]      # file rows of this layout's rows
+        xyz = xyz[rows_of]
+        M = hi - lo
         if M == 0:
             raise ValueError("empty database (shard)")
         Mpad = (M + BLOCK - 1) // BLOCK * BLOCK
         dev = torch.device(device)
         self.M, self.Mpad = M, Mpad
-        self.Kh = torch.zeros(Mpad, 256, dtype=torch.float16, device=dev)
-        self.Kh[:M] = torch.from_numpy(K).to(dev).half()
-        vmax = _abs_max_fp32(V)
+        # the value scale: over this shard's rows when the file order is kept, over the whole file when the rows are
+        # spread by the spatial sort
+        vmax = _abs_max_fp32(V[lo:hi] if self.order is None else V)
         self.vscale = 1.0 if vmax == 0.0 or not math.isfinite(vmax) else 2.0 ** math.floor(math.log2(256.0 / vmax))
+        self.Kh = torch.zeros(Mpad, 256, dtype=torch.float16, device=dev)
         self.Vt = torch.zeros(1024, Mpad, dtype=torch.float16, device=dev)
-        step = 1 << 18
-        row0 = self.row_range[0]
-        for lo in range(0, M, step):                       # bounded staging memory for 10M-entry databases
-            hi = min(M, lo + step)
-            idx = None if self.order is None else np.sort(self.order[row0 + lo:row0 + hi])
-            if idx is None:
-                rows = np.asarray(V[lo:hi]).astype(np.float32)
-            else:                                          # gather in file order (sequential reads of a memory map), then permute
-                blk = np.asarray(V[idx]).astype(np.float32)
-                rows = blk[np.searchsorted(idx, self.order[row0 + lo:row0 + hi])]
-            self.Vt[:, lo:hi] = (torch.from_numpy(np.ascontiguousarray(rows)).to(dev) * self.vscale).half().t()
+        step = self.STAGING_ROWS
+        for b0 in range(0, M, step):                       # bounded staging memory for 10M-entry databases
+            b1 = min(M, b0 + step)
+            want = rows_of[b0:b1]
+            idx = np.sort(want)                            # gather in file order (sequential reads of a memory map) ...
+            back = np.searchsorted(idx, want)              # ... then permute into layout order
+            k = np.asarray(Kraw[idx]).astype(np.float32)                                  # range.py:85
+            k = (k / np.linalg.norm(k, ord=2, axis=1, keepdims=True))[back]               # range.py:89
+            self.Kh[b0:b1] = torch.from_numpy(np.ascontiguousarray(k)).to(dev).half()
+            v = np.asarray(V[idx]).astype(np.float32)[back]                               # range.py:90
+            self.Vt[:, b0:b1] = (torch.from_numpy(np.ascontiguousarray(v)).to(dev) * self.vscale).half().t()
         self.xyz = torch.zeros(Mpad, 4, dtype=torch.float32, device=dev)
         self.xyz[:M, :3] = torch.from_numpy(np.ascontiguousarray(xyz)).to(dev)
         self.caps = torch.from_numpy(tile_caps(xyz)).to(dev) if self.order is not None else None

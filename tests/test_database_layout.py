@@ -120,3 +120,33 @@ def test_block_wise_value_conversion_matches_the_reference_rule():
     bad["image_embeddings"][17, 5] = np.nan
     assert math.isnan(_abs_max_fp32(bad["image_embeddings"], step=64))
     assert DeviceDatabase(bad, "cpu").vscale == 1.0
+
+
+def test_layout_does_not_depend_on_the_staging_block(monkeypatch):
+    """keys and values reach the device in blocks of STAGING_ROWS rows; row-wise arithmetic, so any block size gives
+    the same bits (here: 1000 rows in blocks of 96 against one block)"""
+    from range_b200.database import DeviceDatabase
+    db = _db(1000)
+    one = DeviceDatabase(db, "cpu")
+    monkeypatch.setattr(DeviceDatabase, "STAGING_ROWS", 96)
+    for kw in (dict(), dict(shard=(1, 2)), dict(spatial_sort=False)):
+        monkeypatch.setattr(DeviceDatabase, "STAGING_ROWS", 1 << 18)
+        ref = DeviceDatabase(db, "cpu", **kw)
+        monkeypatch.setattr(DeviceDatabase, "STAGING_ROWS", 96)
+        blk = DeviceDatabase(db, "cpu", **kw)
+        for name in ("Kh", "Vt", "xyz"):
+            assert torch.equal(getattr(ref, name), getattr(blk, name)), (name, kw)
+    assert one.M == 1000
+
+
+def test_inconsistent_database_is_rejected():
+    from range_b200.database import DeviceDatabase
+    import pytest
+    db = dict(_db(50))
+    db["image_embeddings"] = db["image_embeddings"][:40]
+    with pytest.raises(ValueError):
+        DeviceDatabase(db, "cpu")
+    db = dict(_db(50))
+    db["satclip_embeddings"] = db["satclip_embeddings"][:, :128]
+    with pytest.raises(ValueError):
+        DeviceDatabase(db, "cpu")
