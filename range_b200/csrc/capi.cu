@@ -367,7 +367,7 @@ int range_sort_queries(range_ctx* c, int64_t N, const double* lonlat, double* lo
     return fail(RANGE_ERR_INVALID, "bad arguments");
   if (workspace_bytes < sort_workspace_bytes(int(N))) return fail(RANGE_ERR_WORKSPACE, "sort workspace too small");
   CUDA_TRY(launch_sort_queries(lonlat, int(N), lonlat_sorted, perm, workspace, cudaStream_t(stream)));
-  g_launches += 4;
+  g_launches += sort_launches(int(N));
   return RANGE_OK;
 }
 

@@ -71,7 +71,8 @@ cudaError_t launch_concat_q(const double* q64, int N, int DQ, const int* perm, v
 
 // ---- spatial batching of the queries (sort.cu) ----------------------------------------------------
 size_t sort_workspace_bytes(int N);
-// perm[i] = caller's row of sorted row i; lonlat_sorted[i] = lonlat[perm[i]]  (deterministic)
+int sort_launches(int N);     // kernels launch_sort_queries issues
+// perm[i] = caller's row of sorted row i; lonlat_sorted[i] = lonlat[perm[i]]  (stable sort by cell: a pure function of lonlat)
 cudaError_t launch_sort_queries(const double* lonlat, int N, double* lonlat_sorted, int32_t* perm, void* workspace,
                                 cudaStream_t s);
 

@@ -1101,8 +1101,18 @@ cudaError_t launch_apply_pc(const RetrievalArgs& a, const CUtensorMap& tmP, cons
   // SMs for long, the bounded waits in the kernel trap (an error the caller sees) rather than hang.
   static const bool coop = getenv("RANGE_PC_COOP") && atoi(getenv("RANGE_PC_COOP")) == 1;
   cfg.numAttrs = 1;
-  static int resident_clusters = -1;
-  if (resident_clusters < 0 && cudaOccupancyMaxActiveClusters(&resident_clusters, kern, &cfg) != cudaSuccess) resident_clusters = 0;
+  // capacity per (device, kernel instantiation): the answer depends on both
+  static int resident_cache[64][2];
+  static bool resident_known[64][2] = {};
+  int dev = 0;
+  if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+  int resident_clusters = 0;
+  if (dev >= 0 && dev < 64 && resident_known[dev][a.geo ? 1 : 0]) {
+    resident_clusters = resident_cache[dev][a.geo ? 1 : 0];
+  } else {
+    if (cudaOccupancyMaxActiveClusters(&resident_clusters, kern, &cfg) != cudaSuccess) resident_clusters = 0;
+    if (dev >= 0 && dev < 64) { resident_cache[dev][a.geo ? 1 : 0] = resident_clusters; resident_known[dev][a.geo ? 1 : 0] = true; }
+  }
   if (resident_clusters < int(cfg.gridDim.x / 2)) {
     fprintf(stderr, "range_b200: only %d of %u CTA pairs can be resident; producer/consumer kernel not launched\n",
             resident_clusters, cfg.gridDim.x / 2);

@@ -2,13 +2,17 @@
 // range/range.py:213-240 are all row-wise).  The geographic softmax of RANGE+ is local - exp(40 (cos d - 1)) -
 // so when the 128 queries of a tile are close to each other whole database tiles can skip the geo term
 // (retrieval.cu: geo_mask_kernel).  Queries arrive in arbitrary order; this file computes a permutation that
-// groups them by a cube-map Hilbert cell (deterministic counting sort), the encoder and retrieval run on the
-// permuted rows and range_concat scatters the results back to the caller's order.
+// groups them by a cube-map Hilbert cell, the encoder and retrieval run on the permuted rows and range_concat
+// scatters the results back to the caller's order.
 //
-//   cell_hist_kernel    key[i] = face * 4^k + hilbert(u, v);  hist[key]++
-//   cell_scan_kernel    start[c] = exclusive prefix sum (single CTA; <= 6 * 4^7 + 1 cells)
-//   cell_scatter_kernel tmp[cursor[key[i]]++] = i                      (order inside a cell: arbitrary)
-//   cell_rank_kernel    orders each cell's members by original index  (-> deterministic permutation)
+// The permutation is a STABLE least-significant-digit radix sort of (cell key, original index): it is a pure function
+// of the coordinates, whatever the cell occupancy (clustered query sets, raster chunks), so every rank of an
+// M-sharded run derives the same row order and repeated calls are bit-identical.
+//
+//   cell_key_kernel       key[i] = face * 4^k + hilbert(u, v)
+//   per 8-bit digit:      radix_hist_kernel (per-block digit counts, digit-major) -> cell_scan_kernel (single CTA)
+//                         -> radix_scatter_kernel (stable: block order, then warp order, then lane order)
+//   gather_sorted_kernel  perm / sorted coordinates
 #include <cstdint>
 #include <cuda_runtime.h>
 
@@ -17,7 +21,8 @@
 namespace {
 
 constexpr int kMaxBits = 7;            // up to 6 * 4^7 = 98 304 cells
-constexpr int kRankLimit = 64;         // cells larger than this keep the scatter order (still a valid permutation)
+constexpr int kDigitBits = 8, kDigits = 1 << kDigitBits;
+constexpr int kSortThreads = 256, kSortItems = 4, kSortTile = kSortThreads * kSortItems;   // elements per block
 
 // position of grid cell (x, y) of a 2^bits x 2^bits grid along the Hilbert curve (the classic xy2d walk)
 __device__ __forceinline__ uint32_t hilbert_index(uint32_t x, uint32_t y, int bits) {
@@ -57,19 +62,77 @@ __device__ __forceinline__ uint32_t cell_key(double lon_deg, double lat_deg, int
 }
 
 __global__ void __launch_bounds__(256)
-cell_hist_kernel(const double2* __restrict__ lonlat, int N, int bits, uint32_t* __restrict__ key,
-                 uint32_t* __restrict__ hist) {
+cell_key_kernel(const double2* __restrict__ lonlat, int N, int bits, uint32_t* __restrict__ key, uint32_t* __restrict__ idx) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
   const double2 p = lonlat[i];
-  const uint32_t k = cell_key(p.x, p.y, bits);
-  key[i] = k;
-  atomicAdd(&hist[k], 1u);
+  key[i] = cell_key(p.x, p.y, bits);
+  idx[i] = uint32_t(i);
 }
 
-// exclusive scan of hist[0..n) -> start[0..n], start[n] = total; cursor = copy of start.  One CTA of 1024.
+// hist[d * nblocks + block] = elements of this block's tile whose digit is d
+__global__ void __launch_bounds__(kSortThreads)
+radix_hist_kernel(const uint32_t* __restrict__ key, int N, int shift, uint32_t* __restrict__ hist, int nblocks) {
+  __shared__ uint32_t cnt[kDigits];
+  cnt[threadIdx.x] = 0;
+  __syncthreads();
+  const int base = blockIdx.x * kSortTile;
+#pragma unroll
+  for (int r = 0; r < kSortItems; ++r) {
+    const int i = base + r * kSortThreads + threadIdx.x;
+    if (i < N) atomicAdd(&cnt[(key[i] >> shift) & (kDigits - 1)], 1u);
+  }
+  __syncthreads();
+  hist[size_t(threadIdx.x) * nblocks + blockIdx.x] = cnt[threadIdx.x];
+}
+
+// Stable scatter: element i of this block goes to start[digit][block] + (number of earlier elements of the block with
+// the same digit).  "Earlier" = smaller i: rounds in order, warps in order, lanes in order.
+__global__ void __launch_bounds__(kSortThreads)
+radix_scatter_kernel(const uint32_t* __restrict__ key, const uint32_t* __restrict__ idx, int N, int shift,
+                     const uint32_t* __restrict__ start, int nblocks, uint32_t* __restrict__ key_out,
+                     uint32_t* __restrict__ idx_out) {
+  constexpr int kWarps = kSortThreads / 32;
+  __shared__ uint32_t running[kDigits];
+  __shared__ uint32_t wcnt[kWarps][kDigits];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  running[threadIdx.x] = start[size_t(threadIdx.x) * nblocks + blockIdx.x];
+  const int base = blockIdx.x * kSortTile;
+  for (int r = 0; r < kSortItems; ++r) {
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) wcnt[w][threadIdx.x] = 0;
+    __syncthreads();
+    const int i = base + r * kSortThreads + threadIdx.x;
+    const bool valid = i < N;
+    const uint32_t k = valid ? key[i] : 0u;
+    const uint32_t d = valid ? ((k >> shift) & (kDigits - 1)) : uint32_t(kDigits);      // kDigits: matches only other tails
+    const uint32_t peers = __match_any_sync(0xffffffffu, d);
+    const uint32_t before = __popc(peers & ((1u << lane) - 1u));
+    if (valid && before == 0) wcnt[warp][d] = __popc(peers);
+    __syncthreads();
+    {   // thread t owns digit t: exclusive prefix over the warps, then advance the block's running offset
+      uint32_t acc = running[threadIdx.x];
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w) {
+        const uint32_t c = wcnt[w][threadIdx.x];
+        wcnt[w][threadIdx.x] = acc;
+        acc += c;
+      }
+      running[threadIdx.x] = acc;
+    }
+    __syncthreads();
+    if (valid) {
+      const uint32_t dst = wcnt[warp][d] + before;
+      key_out[dst] = k;
+      idx_out[dst] = idx[i];
+    }
+    __syncthreads();
+  }
+}
+
+// exclusive scan of hist[0..n) -> start[0..n], start[n] = total.  One CTA of 1024.
 __global__ void __launch_bounds__(1024)
-cell_scan_kernel(const uint32_t* __restrict__ hist, int n, uint32_t* __restrict__ start, uint32_t* __restrict__ cursor) {
+cell_scan_kernel(const uint32_t* __restrict__ hist, int n, uint32_t* __restrict__ start) {
   __shared__ uint32_t warp_sums[32];
   __shared__ uint32_t carry;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -97,7 +160,7 @@ cell_scan_kernel(const uint32_t* __restrict__ hist, int n, uint32_t* __restrict_
     }
     __syncthreads();
     const uint32_t excl = carry + (warp ? warp_sums[warp - 1] : 0u) + x - v;
-    if (i < n) { start[i] = excl; cursor[i] = excl; }
+    if (i < n) start[i] = excl;
     __syncthreads();
     if (threadIdx.x == 1023) carry = excl + v;
     __syncthreads();
@@ -106,28 +169,13 @@ cell_scan_kernel(const uint32_t* __restrict__ hist, int n, uint32_t* __restrict_
 }
 
 __global__ void __launch_bounds__(256)
-cell_scatter_kernel(const uint32_t* __restrict__ key, int N, uint32_t* __restrict__ cursor, uint32_t* __restrict__ tmp) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= N) return;
-  tmp[atomicAdd(&cursor[key[i]], 1u)] = uint32_t(i);
-}
-
-__global__ void __launch_bounds__(256)
-cell_rank_kernel(const uint32_t* __restrict__ key, const uint32_t* __restrict__ tmp, const uint32_t* __restrict__ start,
-                 const double2* __restrict__ lonlat, int N, int32_t* __restrict__ perm, double2* __restrict__ sorted) {
+gather_sorted_kernel(const uint32_t* __restrict__ idx, const double2* __restrict__ lonlat, int N, int32_t* __restrict__ perm,
+                     double2* __restrict__ sorted) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= N) return;
-  const uint32_t i = tmp[p];
-  const uint32_t c = key[i];
-  const uint32_t lo = start[c], hi = start[c + 1];
-  uint32_t dst = uint32_t(p);
-  if (hi - lo <= uint32_t(kRankLimit)) {
-    uint32_t rank = 0;
-    for (uint32_t r = lo; r < hi; ++r) rank += tmp[r] < i;
-    dst = lo + rank;
-  }
-  perm[dst] = int32_t(i);
-  sorted[dst] = lonlat[i];
+  const uint32_t i = idx[p];
+  perm[p] = int32_t(i);
+  sorted[p] = lonlat[i];
 }
 
 }  // namespace
@@ -141,29 +189,41 @@ int sort_cell_bits(int N) {
   return bits;
 }
 
+static int sort_passes(int bits) { return (3 + 2 * bits + kDigitBits - 1) / kDigitBits; }
+static int sort_blocks(int N) { return (N + kSortTile - 1) / kSortTile; }
+
+int sort_launches(int N) { return N > 0 ? 2 + 3 * sort_passes(sort_cell_bits(N)) : 0; }
+
 size_t sort_workspace_bytes(int N) {
-  const size_t cells = (size_t(6) << (2 * sort_cell_bits(N))) + 1;
-  return (2 * size_t(N) + 3 * cells) * 4 + 1024;
+  // key / index ping-pong buffers, digit-major block histogram and its scan
+  return (4 * size_t(N) + 2 * (size_t(kDigits) * sort_blocks(N) + 1)) * 4 + 1024;
 }
 
 cudaError_t launch_sort_queries(const double* lonlat, int N, double* lonlat_sorted, int32_t* perm, void* workspace,
                                 cudaStream_t s) {
   if (N <= 0) return cudaSuccess;
   const int bits = sort_cell_bits(N);
-  const int cells = 6 << (2 * bits);
-  uint32_t* key = reinterpret_cast<uint32_t*>((reinterpret_cast<size_t>(workspace) + 255) / 256 * 256);
-  uint32_t* tmp = key + N;
-  uint32_t* hist = tmp + N;
-  uint32_t* start = hist + (cells + 1);
-  uint32_t* cursor = start + (cells + 1);
-  cudaError_t e = cudaMemsetAsync(hist, 0, size_t(cells + 1) * 4, s);
-  if (e != cudaSuccess) return e;
+  const int nblocks = sort_blocks(N), nh = kDigits * nblocks;
+  uint32_t* key[2];
+  uint32_t* idx[2];
+  key[0] = reinterpret_cast<uint32_t*>((reinterpret_cast<size_t>(workspace) + 255) / 256 * 256);
+  idx[0] = key[0] + N;
+  key[1] = idx[0] + N;
+  idx[1] = key[1] + N;
+  uint32_t* hist = idx[1] + N;
+  uint32_t* start = hist + (nh + 1);
   const int blocks = (N + 255) / 256;
   const double2* ll = reinterpret_cast<const double2*>(lonlat);
-  cell_hist_kernel<<<blocks, 256, 0, s>>>(ll, N, bits, key, hist);
-  cell_scan_kernel<<<1, 1024, 0, s>>>(hist, cells, start, cursor);
-  cell_scatter_kernel<<<blocks, 256, 0, s>>>(key, N, cursor, tmp);
-  cell_rank_kernel<<<blocks, 256, 0, s>>>(key, tmp, start, ll, N, perm, reinterpret_cast<double2*>(lonlat_sorted));
+  cell_key_kernel<<<blocks, 256, 0, s>>>(ll, N, bits, key[0], idx[0]);
+  int cur = 0;
+  for (int pass = 0; pass < sort_passes(bits); ++pass, cur ^= 1) {
+    const int shift = pass * kDigitBits;
+    radix_hist_kernel<<<nblocks, kSortThreads, 0, s>>>(key[cur], N, shift, hist, nblocks);
+    cell_scan_kernel<<<1, 1024, 0, s>>>(hist, nh, start);
+    radix_scatter_kernel<<<nblocks, kSortThreads, 0, s>>>(key[cur], idx[cur], N, shift, start, nblocks, key[cur ^ 1],
+                                                          idx[cur ^ 1]);
+  }
+  gather_sorted_kernel<<<blocks, 256, 0, s>>>(idx[cur], ll, N, perm, reinterpret_cast<double2*>(lonlat_sorted));
   return cudaGetLastError();
 }
 

@@ -14,7 +14,9 @@ range/range.py:213-238), so the rows are stored sorted along a cube-map Hilbert 
 tiles are then spatially compact, which lets the RANGE+ kernels skip the geographic term for tiles far from a
 query tile (include/range_b200.h: range_ctx_set_db_caps).
 """
+import hashlib
 import math
+import os
 import struct
 import zipfile
 
@@ -154,6 +156,7 @@ class DeviceDatabase:
         lo, hi = (0, self.M_total) if shard is None else ((self.M_total * shard[0]) // shard[1],
                                                           (self.M_total * (shard[0] + 1)) // shard[1])
         self.row_range = (lo, hi)
+        self.shard = None if shard is None else (int(shard[0]), int(shard[1]))
         rows_of = np.arange(lo, hi) if self.order is None else self.order[lo:hi]      # file rows of this layout's rows
         xyz = xyz[rows_of]
         M = hi - lo
@@ -184,40 +187,91 @@ class DeviceDatabase:
         self.caps = torch.from_numpy(tile_caps(xyz)).to(dev) if self.order is not None else None
 
     # ---- device-resident format on disk: skips normalisation / sorting / transposition at start-up
-    CACHE_VERSION = 1
+    CACHE_VERSION = 2
 
-    def save_cache(self, path):
-        """write the prepared layout (fp16 keys / transposed values, xyz, tile caps, row order) as an .npz"""
-        np.savez(path, version=self.CACHE_VERSION, M=self.M, Mpad=self.Mpad, M_total=self.M_total,
-                 row_range=np.asarray(self.row_range), vscale=self.vscale,
-                 Kh=self.Kh.cpu().numpy(), Vt=self.Vt.cpu().numpy(), xyz=self.xyz.cpu().numpy(),
-                 caps=np.zeros((0, 4), np.float32) if self.caps is None else self.caps.cpu().numpy(),
-                 order=np.zeros(0, np.int64) if self.order is None else self.order)
+    @staticmethod
+    def source_fingerprint(source):
+        """identifies the database a cache was built from: (path, size, mtime) of a file, or the entry count and a
+        digest of the locations of an in-memory mapping"""
+        if isinstance(source, (str, os.PathLike)):
+            st = os.stat(source)
+            return f"file:{os.path.abspath(source)}:{st.st_size}:{st.st_mtime_ns}"
+        locs = np.ascontiguousarray(np.asarray(source["locs"]))
+        return f"mem:{locs.shape[0]}:{locs.dtype}:{hashlib.sha1(locs.tobytes()).hexdigest()}"
+
+    @staticmethod
+    def cache_path(path, shard=None):
+        """the file save_cache / from_cache use: always '.npz' (np.savez would append it silently), one file per shard"""
+        path = os.fspath(path)
+        stem = path[:-4] if path.endswith(".npz") else path
+        if shard is not None:
+            stem += f".shard{int(shard[0])}of{int(shard[1])}"
+        return stem + ".npz"
+
+    def save_cache(self, path, fingerprint=""):
+        """write the prepared layout (fp16 keys / transposed values, xyz, tile caps, row order) as an .npz; the file
+        appears atomically (temporary file + rename), so a concurrent reader never sees a partial cache"""
+        path = self.cache_path(path, self.shard)
+        tmp = f"{path}.{os.getpid()}.tmp.npz"
+        shard = (-1, -1) if self.shard is None else self.shard
+        try:
+            with open(tmp, "wb") as f:
+                np.savez(f, version=self.CACHE_VERSION, M=self.M, Mpad=self.Mpad, M_total=self.M_total,
+                         row_range=np.asarray(self.row_range), vscale=self.vscale, shard=np.asarray(shard),
+                         fingerprint=np.asarray(fingerprint),
+                         Kh=self.Kh.cpu().numpy(), Vt=self.Vt.cpu().numpy(), xyz=self.xyz.cpu().numpy(),
+                         caps=np.zeros((0, 4), np.float32) if self.caps is None else self.caps.cpu().numpy(),
+                         order=np.zeros(0, np.int64) if self.order is None else self.order)
+            os.replace(tmp, path)
+        finally:
+            if os.path.exists(tmp):
+                os.remove(tmp)
+        return path
 
     @classmethod
-    def from_cache(cls, path, device):
+    def from_cache(cls, path, device, shard=None, fingerprint=None, spatial_sort=None):
+        """load a cache written by save_cache.  Returns None (the caller rebuilds) when the file is missing or was built
+        for another shard, another source (fingerprint, when given) or another row order; raises on a malformed file."""
+        path = cls.cache_path(path, shard)
+        if not os.path.exists(path):
+            return None
         z = np.load(path)
-        if int(z["version"]) != cls.CACHE_VERSION:
-            raise ValueError(f"{path}: database cache version {int(z['version'])}, expected {cls.CACHE_VERSION}")
+        if "version" not in z or int(z["version"]) != cls.CACHE_VERSION:
+            return None
+        want = (-1, -1) if shard is None else (int(shard[0]), int(shard[1]))
+        if tuple(int(v) for v in z["shard"]) != want:
+            return None
+        if fingerprint is not None and str(z["fingerprint"]) != fingerprint:
+            return None
+        if spatial_sort is not None and bool(z["order"].shape[0]) != bool(spatial_sort):
+            return None
         self = cls.__new__(cls)
         dev = torch.device(device)
         self.M, self.Mpad, self.M_total = int(z["M"]), int(z["Mpad"]), int(z["M_total"])
         self.row_range = tuple(int(v) for v in z["row_range"])
+        self.shard = None if want == (-1, -1) else want
+        if self.shard is not None:
+            lo, hi = (self.M_total * want[0]) // want[1], (self.M_total * (want[0] + 1)) // want[1]
+            if self.row_range != (lo, hi):
+                raise ValueError(f"{path}: rows {self.row_range} do not match shard {want} of {self.M_total} entries")
         self.vscale = float(z["vscale"])
         self.Kh = torch.from_numpy(z["Kh"]).to(dev)
         self.Vt = torch.from_numpy(z["Vt"]).to(dev)
         self.xyz = torch.from_numpy(z["xyz"]).to(dev)
         self.caps = torch.from_numpy(z["caps"]).to(dev) if z["caps"].shape[0] else None
         self.order = z["order"] if z["order"].shape[0] else None
-        if self.Kh.shape != (self.Mpad, 256) or self.Vt.shape != (1024, self.Mpad) or self.Kh.dtype != torch.float16:
+        if self.Kh.shape != (self.Mpad, 256) or self.Vt.shape != (1024, self.Mpad) or self.Kh.dtype != torch.float16 \
+                or self.M != self.row_range[1] - self.row_range[0]:
             raise ValueError(f"{path}: malformed database cache")
         return self
 
     @classmethod
-    def synthetic(cls, M, device, seed=0):
+    def synthetic(cls, M, device, seed=0, shard=None):
         """Benchmark-only: an iid synthetic database (area-uniform locations, N(0,1) keys and values - the worst case
         for the fp16 operands) generated block by block straight into the device layout, so 10 M-entry
-        databases (25.7 GB in fp16) do not need their 51 GB of fp32 source arrays on the host."""
+        databases (25.7 GB in fp16) do not need their 51 GB of fp32 source arrays on the host.
+        shard=(rank, world): rows [rank*M/world, (rank+1)*M/world) of the spatially sorted database only - every rank
+        draws the same M locations (same seed) and sorts them the same way, keys / values are iid per entry."""
         self = cls.__new__(cls)
         dev = torch.device(device)
         rng = np.random.default_rng(seed)
@@ -226,23 +280,26 @@ class DeviceDatabase:
         locs = np.stack([lon, lat], 1).astype(np.float32)
         xyz = rad_to_cart(locs * math.pi / 180)                                       # range.py:93-95 (fp32)
         self.order = hilbert_order(xyz)
-        xyz = xyz[self.order]
-        self.M = self.M_total = M
-        self.Mpad = (M + BLOCK - 1) // BLOCK * BLOCK
-        self.row_range = (0, M)
+        self.M_total = M
+        lo, hi = (0, M) if shard is None else ((M * shard[0]) // shard[1], (M * (shard[0] + 1)) // shard[1])
+        self.shard = None if shard is None else (int(shard[0]), int(shard[1]))
+        self.row_range = (lo, hi)
+        xyz = xyz[self.order[lo:hi]]
+        self.M = m = hi - lo
+        self.Mpad = (m + BLOCK - 1) // BLOCK * BLOCK
         self.vscale = 2.0 ** math.floor(math.log2(256.0 / 6.0))                      # |N(0,1)| < 6
         self.Kh = torch.zeros(self.Mpad, 256, dtype=torch.float16, device=dev)
         self.Vt = torch.zeros(1024, self.Mpad, dtype=torch.float16, device=dev)
-        g = torch.Generator(device=dev).manual_seed(seed)
+        g = torch.Generator(device=dev).manual_seed(seed if shard is None else seed * 1000003 + 1 + int(shard[0]))
         step = 1 << 18
-        for lo in range(0, M, step):
-            hi = min(M, lo + step)
-            k = torch.randn(hi - lo, 256, device=dev, generator=g)
-            self.Kh[lo:hi] = (k / k.norm(dim=1, keepdim=True)).half()                 # range.py:89
-            v = torch.randn(hi - lo, 1024, device=dev, generator=g).clamp_(-6.0, 6.0)
-            self.Vt[:, lo:hi] = (v * self.vscale).half().t()
+        for b0 in range(0, m, step):
+            b1 = min(m, b0 + step)
+            k = torch.randn(b1 - b0, 256, device=dev, generator=g)
+            self.Kh[b0:b1] = (k / k.norm(dim=1, keepdim=True)).half()                 # range.py:89
+            v = torch.randn(b1 - b0, 1024, device=dev, generator=g).clamp_(-6.0, 6.0)
+            self.Vt[:, b0:b1] = (v * self.vscale).half().t()
         self.xyz = torch.zeros(self.Mpad, 4, dtype=torch.float32, device=dev)
-        self.xyz[:M, :3] = torch.from_numpy(np.ascontiguousarray(xyz)).to(dev)
+        self.xyz[:m, :3] = torch.from_numpy(np.ascontiguousarray(xyz)).to(dev)
         self.caps = torch.from_numpy(tile_caps(xyz)).to(dev)
         return self
 

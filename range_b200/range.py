@@ -41,13 +41,15 @@ class LocationEncoder(nn.Module):
             else args.pretrained_path
         self.location_feature_dim = 1024 + 256                                             # range.py:86
         cache = getattr(args, 'db_cache', None)        # optional: prepared device layout on disk (database.py)
-        import os
-        if cache is not None and os.path.exists(cache):
-            ddb = DeviceDatabase.from_cache(cache, args.device)
-        else:
+        ddb = None
+        if cache is not None:
+            # the cache is only used when it was built from this source, for this shard (one file per shard)
+            fp = DeviceDatabase.source_fingerprint(args.range_db)
+            ddb = DeviceDatabase.from_cache(cache, args.device, shard=shard, fingerprint=fp)
+        if ddb is None:
             ddb = DeviceDatabase(db, args.device, shard=shard)
             if cache is not None:
-                ddb.save_cache(cache)
+                ddb.save_cache(cache, fingerprint=fp)
         self.engine = RangeEngine(args.device, encoder=enc, database=ddb)
         self.chunk = int(getattr(args, 'chunk', DEFAULT_CHUNK))
         self.tail = max(1, min(self.chunk, int(getattr(args, 'tail', DEFAULT_TAIL))))

@@ -63,6 +63,50 @@ def test_cache_round_trip(tmp_path):
     assert np.array_equal(d.order, e.order)
 
 
+def test_cache_is_validated(tmp_path):
+    """a cache is used only for the source, shard and row order it was built for (one file per shard, '.npz' or not)"""
+    import os
+    from range_b200.database import DeviceDatabase
+    db, other = _db(300), _db(301)
+    fp = DeviceDatabase.source_fingerprint(db)
+    assert fp == DeviceDatabase.source_fingerprint(db) != DeviceDatabase.source_fingerprint(other)
+    base = str(tmp_path / "layout")                    # no extension: save and lookup must still agree
+    assert DeviceDatabase.from_cache(base, "cpu") is None            # nothing there yet
+    whole = DeviceDatabase(db, "cpu")
+    written = whole.save_cache(base, fingerprint=fp)
+    assert written == base + ".npz" and os.path.exists(written)
+    assert [f for f in os.listdir(tmp_path) if "tmp" in f] == []    # the temporary file is gone
+    assert DeviceDatabase.from_cache(base, "cpu", fingerprint=fp) is not None
+    assert DeviceDatabase.from_cache(base + ".npz", "cpu", fingerprint=fp) is not None
+    assert DeviceDatabase.from_cache(base, "cpu", fingerprint=DeviceDatabase.source_fingerprint(other)) is None   # stale
+    assert DeviceDatabase.from_cache(base, "cpu", fingerprint=fp, spatial_sort=False) is None
+    # shards: their own files, never the whole database's or another rank's
+    assert DeviceDatabase.from_cache(base, "cpu", shard=(1, 2), fingerprint=fp) is None
+    parts = [DeviceDatabase(db, "cpu", shard=(r, 2)) for r in range(2)]
+    files = [p.save_cache(base, fingerprint=fp) for p in parts]
+    assert len(set(files + [written])) == 3
+    for r in range(2):
+        e = DeviceDatabase.from_cache(base, "cpu", shard=(r, 2), fingerprint=fp)
+        assert e.row_range == parts[r].row_range and torch.equal(e.Kh, parts[r].Kh) and e.shard == (r, 2)
+    os.replace(files[0], files[1])                      # rank 1 finds rank 0's rows under its name: refused
+    assert DeviceDatabase.from_cache(base, "cpu", shard=(1, 2), fingerprint=fp) is None
+    # file sources: path + size + mtime
+    f = str(tmp_path / "db.npz")
+    np.savez(f, **db)
+    fp1 = DeviceDatabase.source_fingerprint(f)
+    np.savez(f, **other)
+    assert DeviceDatabase.source_fingerprint(f) != fp1
+
+
+def test_synthetic_shards_tile_the_database():
+    from range_b200.database import DeviceDatabase
+    whole = DeviceDatabase.synthetic(1000, "cpu", seed=3)
+    parts = [DeviceDatabase.synthetic(1000, "cpu", seed=3, shard=(r, 4)) for r in range(4)]
+    assert [p.row_range for p in parts] == [(0, 250), (250, 500), (500, 750), (750, 1000)]
+    assert all(p.M_total == 1000 and p.vscale == whole.vscale for p in parts)
+    assert torch.equal(torch.cat([p.xyz[:p.M] for p in parts]), whole.xyz[:1000])       # same locations, same order
+
+
 def test_forward_chunking_covers_every_row():
     from range_b200.range import LocationEncoder
     for N in (1, 5, 6144, 6145, 12288, 13000, 24576, 24577, 100000, 1 << 20):
