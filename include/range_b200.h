@@ -33,6 +33,9 @@ extern "C" {
 
 #define RANGE_OUT_F64 0
 #define RANGE_OUT_F32 1
+#define RANGE_OUT_PACKED 2 /* rows of 6144 B: 1024 fp32 feature columns, then 256 fp64 location columns - every bit of
+                              information of the reference's float64 row (its feature columns are fp32 values widened,
+                              range/range.py:222,240) in 60 % of the bytes; range_host_unpack widens on the host */
 
 typedef struct range_ctx range_ctx;
 
@@ -161,6 +164,48 @@ int range_retrieve_apply_concat(range_ctx* ctx, int mode, int64_t N, const void*
                                 float geo_temp, float beta, const float* sums, const float* maxs, const double* q64,
                                 const int32_t* perm, void* out, int out_dtype, void* workspace, size_t workspace_bytes,
                                 void* stream);
+
+/* ---- M-sharded database (one process per GPU, rank r holds rows [r M/P, (r+1) M/P) of the database) ----
+ * The softmax-weighted sums of range/range.py:213-217,231-238 are associative in the database axis: with the fixed
+ * offset (|s|,|g| <= 1) the per-shard exp-sums of range_retrieve_stats merge by SUM (one all-reduce of 8 B per query),
+ * the per-shard maxima stay local (they only scale the fp16 weights), and the per-shard outputs of the apply pass,
+ * normalised with the global sums, merge by SUM.  range_retrieve_apply_routed is range_retrieve_apply whose result
+ * rows leave the GPU from the apply kernel's epilogue: row n belongs to rank n / slab_rows and is stored as 1024 fp32
+ * at   route->peer[n / slab_rows] + ((size_t)route->rank * slab_rows + n % slab_rows) * 1024,
+ * peer[r] being rank r's receive buffer [n_ranks][slab_rows][1024] fp32 mapped into this process (range_peer_open;
+ * peer[rank] = the local buffer): the partial rows cross NVLink while the tensor cores work on the next tiles, no
+ * collective moves them.  After a barrier across the ranks, the owner sums its n_ranks slots in rank order
+ * (range_combine_concat: deterministic) and appends the location columns. */
+#define RANGE_MAX_RANKS 8
+typedef struct range_route {
+  int32_t n_ranks, rank;
+  int64_t slab_rows;
+  float* peer[RANGE_MAX_RANKS];
+} range_route;
+int range_retrieve_apply_routed(range_ctx* ctx, int mode, int64_t N, const void* q16, const float* qxyz, float temp,
+                                float geo_temp, float beta, const float* sums, const float* maxs,
+                                const range_route* route, void* workspace, size_t workspace_bytes, void* stream);
+
+/* out row perm[n] (NULL = identity) = [ sum_k weights[k] * parts[k][n][0:1024] | q64[n][0:256] ] in out_dtype.
+ * parts: host array of n_parts (<= 8) device pointers to (N,1024) fp32; weights: host array or NULL (all 1).
+ * Uses: the slots of an M-sharded receive buffer (weights 1); a beta sweep - range/range.py:238 is linear in beta,
+ * so O(beta) = (1-beta) O(0) + beta O(1) serves any number of beta from two apply passes (Readme.md:27-31). */
+int range_combine_concat(range_ctx* ctx, int64_t N, int n_parts, const float* const* parts, const float* weights,
+                         const double* q64, const int32_t* perm, void* out, int out_dtype, void* stream);
+
+/* Receive buffers must be mappable by the other ranks' processes: the one place where the library allocates device
+ * memory itself (cudaMalloc + CUDA IPC handle, 64 opaque bytes to hand to the peers, e.g. with all_gather_object).
+ * range_peer_open maps a peer's buffer into this process (enables peer access over NVLink), range_peer_close unmaps
+ * it, range_peer_free releases an allocation of range_peer_alloc. */
+int range_peer_alloc(size_t bytes, void** dptr, unsigned char* handle64);
+int range_peer_open(const unsigned char* handle64, void** dptr);
+int range_peer_close(void* dptr);
+int range_peer_free(void* dptr);
+
+/* HOST function (no CUDA): widen N packed rows (RANGE_OUT_PACKED, e.g. a pinned staging buffer a device->host copy
+ * just filled) into the caller's (N,1280) float64 array - the array range/range.py:222,240 returns - with a thread
+ * team of n_threads of its own. */
+int range_host_unpack(const void* packed, int64_t N, double* out, int n_threads);
 
 /* K3: out (N,1280) = [O | q64] as fp64 (RANGE_OUT_F64, what the reference returns: range/range.py:222,240)
  * or fp32. */

@@ -10,7 +10,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "librange_b200.so")
 
 RANGE_MODE_RANGE, RANGE_MODE_RANGE_PLUS = 0, 1
-RANGE_OUT_F64, RANGE_OUT_F32 = 0, 1
+RANGE_OUT_F64, RANGE_OUT_F32, RANGE_OUT_PACKED = 0, 1, 2
+RANGE_MAX_RANKS = 8
 RANGE_ENC_F64, RANGE_ENC_F16X3 = 0, 1
 
 # every symbol include/range_b200.h declares: name -> (restype, argtypes)
@@ -51,9 +52,25 @@ PROTOTYPES = {
                                             c_void_p]),
     "range_retrieve": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_float, c_float, c_float, c_void_p,
                                c_void_p, c_size_t, c_void_p]),
+    "range_retrieve_apply_routed": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_float, c_float, c_float,
+                                            c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "range_combine_concat": (c_int, [c_void_p, c_int64, c_int, POINTER(c_void_p), POINTER(c_float), c_void_p, c_void_p,
+                                     c_void_p, c_int, c_void_p]),
+    "range_peer_alloc": (c_int, [c_size_t, POINTER(c_void_p), c_void_p]),
+    "range_peer_open": (c_int, [c_void_p, POINTER(c_void_p)]),
+    "range_peer_close": (c_int, [c_void_p]),
+    "range_peer_free": (c_int, [c_void_p]),
+    "range_host_unpack": (c_int, [c_void_p, c_int64, c_void_p, c_int]),
     "range_concat": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "range_concat_scatter": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
 }
+
+
+
+class Route(ctypes.Structure):
+    """include/range_b200.h: range_route"""
+    _fields_ = [("n_ranks", c_int32), ("rank", c_int32), ("slab_rows", c_int64), ("peer", c_void_p * RANGE_MAX_RANKS)]
+
 
 _lib = None
 

@@ -616,15 +616,39 @@ int range_retrieve_stats(range_ctx* c, int mode, int64_t N, const void* q16, con
 
 // apply pass; the result goes either to O (N,1024) fp32 or, fused with the concat of range/range.py:222,240, to the
 // caller's (N,1280) array `out` (rows through `perm`, fp32 or fp64) together with the location columns q64
+static bool valid_out_dtype(int d) { return d == RANGE_OUT_F64 || d == RANGE_OUT_F32 || d == RANGE_OUT_PACKED; }
+
+static int check_route(const range_route* r, int64_t N, RowRoute* out) {
+  if (!r) return RANGE_OK;
+  if (r->n_ranks < 1 || r->n_ranks > RANGE_MAX_RANKS || r->rank < 0 || r->rank >= r->n_ranks || r->slab_rows < 1)
+    return fail(RANGE_ERR_INVALID, "route: %d ranks (max %d), rank %d, %lld rows per rank", r->n_ranks, RANGE_MAX_RANKS,
+                r->rank, (long long)r->slab_rows);
+  if (N > int64_t(r->n_ranks) * r->slab_rows)
+    return fail(RANGE_ERR_INVALID, "route: %lld rows do not fit %d ranks x %lld rows", (long long)N, r->n_ranks,
+                (long long)r->slab_rows);
+  out->n_ranks = r->n_ranks;
+  out->rank = r->rank;
+  out->slab = r->slab_rows;
+  for (int i = 0; i < r->n_ranks; ++i) {
+    if (!r->peer[i]) return fail(RANGE_ERR_INVALID, "route: receive buffer of rank %d is null", i);
+    out->peer[i] = r->peer[i];
+  }
+  return RANGE_OK;
+}
+
 static int apply_impl(range_ctx* c, int mode, int64_t N, const void* q16, const float* qxyz, float temp, float geo_temp,
                       float beta, const float* sums, const float* maxs, float* O, const double* q64, const int32_t* perm,
-                      void* out, int out_dtype, void* workspace, size_t workspace_bytes, void* stream) {
+                      void* out, int out_dtype, const range_route* route, void* workspace, size_t workspace_bytes,
+                      void* stream) {
   if (!c || !c->Kh) return fail(RANGE_ERR_INVALID, "database not set");
-  if (!q16 || !qxyz || !sums || !maxs || !workspace || (!O && !(out && q64))) return fail(RANGE_ERR_INVALID, "null argument");
+  if (!q16 || !qxyz || !sums || !maxs || !workspace || (!O && !(out && q64) && !route))
+    return fail(RANGE_ERR_INVALID, "null argument");
   if (N <= 0) return fail(RANGE_ERR_INVALID, "N must be positive");
   if (mode == RANGE_MODE_RANGE_PLUS && !(beta >= 0.f && beta <= 1.f))
     return fail(RANGE_ERR_INVALID, "beta must be in [0,1]");
-  if (out && out_dtype != RANGE_OUT_F64 && out_dtype != RANGE_OUT_F32) return fail(RANGE_ERR_INVALID, "unknown out dtype");
+  if (out && !valid_out_dtype(out_dtype)) return fail(RANGE_ERR_INVALID, "unknown out dtype");
+  RowRoute rr;
+  if (int r0 = check_route(route, N, &rr)) return r0;
   const RetrievalPlan p = plan_retrieval(c, N);
   if (workspace_bytes < p.total + 256) return fail(RANGE_ERR_WORKSPACE, "retrieve workspace too small");
   RetrievalArgs a;
@@ -641,13 +665,22 @@ static int apply_impl(range_ctx* c, int mode, int64_t N, const void* q16, const 
     void* ring = ws + p.off_ring;
     r = make_tmap_rows2k(&tmP, ring, uint64_t(apply_pc_ring_rows(c->sm_count)));
     if (r) return r;
-    if (out) {      // consumers write straight into the (N,1280) result; the location columns follow
-      CUDA_TRY(launch_apply_pc(a, tmP, rowc, out, W, out_dtype == RANGE_OUT_F64, perm, ring, ws + p.off_flags,
-                               ws + p.off_pc_part, ws + p.off_pc_scratch, c->sm_count, s));
-      CUDA_TRY(launch_concat_q(q64, int(N), kDimK, perm, out, W, kDimV, out_dtype, s));
+    if (route) {    // M-sharded: consumers store this shard's partial rows into the owner ranks' receive buffers
+      CUDA_TRY(launch_apply_pc(a, tmP, rowc, nullptr, kDimV, 0, nullptr, &rr, ring, ws + p.off_flags, ws + p.off_pc_part,
+                               ws + p.off_pc_scratch, c->sm_count, s));
+    } else if (out) {      // consumers write straight into the (N,1280) result; the location columns follow
+      if (out_dtype == RANGE_OUT_PACKED) {     // rows of 6144 B: 1024 fp32 features, then 256 fp64 location columns
+        CUDA_TRY(launch_apply_pc(a, tmP, rowc, out, 1536, 0, perm, nullptr, ring, ws + p.off_flags, ws + p.off_pc_part,
+                                 ws + p.off_pc_scratch, c->sm_count, s));
+        CUDA_TRY(launch_concat_q(q64, int(N), kDimK, perm, out, 768, 512, RANGE_OUT_F64, s));
+      } else {
+        CUDA_TRY(launch_apply_pc(a, tmP, rowc, out, W, out_dtype == RANGE_OUT_F64, perm, nullptr, ring, ws + p.off_flags,
+                                 ws + p.off_pc_part, ws + p.off_pc_scratch, c->sm_count, s));
+        CUDA_TRY(launch_concat_q(q64, int(N), kDimK, perm, out, W, kDimV, out_dtype, s));
+      }
       g_launches += 1;
     } else {
-      CUDA_TRY(launch_apply_pc(a, tmP, rowc, O, kDimV, 0, nullptr, ring, ws + p.off_flags, ws + p.off_pc_part,
+      CUDA_TRY(launch_apply_pc(a, tmP, rowc, O, kDimV, 0, nullptr, nullptr, ring, ws + p.off_flags, ws + p.off_pc_part,
                                ws + p.off_pc_scratch, c->sm_count, s));
     }
     g_launches += 2 + (apply_pc_part_bytes(c->sm_count, N, c->M) > 0);
@@ -661,8 +694,13 @@ static int apply_impl(range_ctx* c, int mode, int64_t N, const void* q16, const 
     CUDA_TRY(launch_reduce_out(part_out, stride, p.splits, stride, Odst, s));
     g_launches += 1;
   }
-  if (out) {
-    CUDA_TRY(launch_concat(Odst, q64, int(N), kDimV, kDimK, perm, out, out_dtype, s));
+  if (route) {
+    CUDA_TRY(launch_route_rows(Odst, int(N), rr, s));
+    g_launches += 1;
+  } else if (out) {
+    CombineParts one;
+    one.n = 1; one.p[0] = Odst; one.w[0] = 1.f;
+    CUDA_TRY(launch_combine_concat(one, q64, int(N), perm, out, out_dtype, s));
     g_launches += 1;
   }
   return RANGE_OK;
@@ -672,8 +710,8 @@ int range_retrieve_apply(range_ctx* c, int mode, int64_t N, const void* q16, con
                          float geo_temp, float beta, const float* sums, const float* maxs, float* O,
                          void* workspace, size_t workspace_bytes, void* stream) {
   if (!O) return fail(RANGE_ERR_INVALID, "null argument");
-  return apply_impl(c, mode, N, q16, qxyz, temp, geo_temp, beta, sums, maxs, O, nullptr, nullptr, nullptr, 0, workspace,
-                    workspace_bytes, stream);
+  return apply_impl(c, mode, N, q16, qxyz, temp, geo_temp, beta, sums, maxs, O, nullptr, nullptr, nullptr, 0, nullptr,
+                    workspace, workspace_bytes, stream);
 }
 
 int range_retrieve_apply_concat(range_ctx* c, int mode, int64_t N, const void* q16, const float* qxyz, float temp,
@@ -681,8 +719,70 @@ int range_retrieve_apply_concat(range_ctx* c, int mode, int64_t N, const void* q
                                 const int32_t* perm, void* out, int out_dtype, void* workspace, size_t workspace_bytes,
                                 void* stream) {
   if (!out || !q64) return fail(RANGE_ERR_INVALID, "null argument");
-  return apply_impl(c, mode, N, q16, qxyz, temp, geo_temp, beta, sums, maxs, nullptr, q64, perm, out, out_dtype, workspace,
-                    workspace_bytes, stream);
+  return apply_impl(c, mode, N, q16, qxyz, temp, geo_temp, beta, sums, maxs, nullptr, q64, perm, out, out_dtype, nullptr,
+                    workspace, workspace_bytes, stream);
+}
+
+int range_retrieve_apply_routed(range_ctx* c, int mode, int64_t N, const void* q16, const float* qxyz, float temp,
+                                float geo_temp, float beta, const float* sums, const float* maxs, const range_route* route,
+                                void* workspace, size_t workspace_bytes, void* stream) {
+  if (!route) return fail(RANGE_ERR_INVALID, "null route");
+  return apply_impl(c, mode, N, q16, qxyz, temp, geo_temp, beta, sums, maxs, nullptr, nullptr, nullptr, nullptr, 0, route,
+                    workspace, workspace_bytes, stream);
+}
+
+int range_combine_concat(range_ctx* c, int64_t N, int n_parts, const float* const* parts, const float* weights,
+                         const double* q64, const int32_t* perm, void* out, int out_dtype, void* stream) {
+  if (!c || N <= 0 || N > (int64_t(1) << 30) || !parts || !q64 || !out) return fail(RANGE_ERR_INVALID, "bad arguments");
+  if (n_parts < 1 || n_parts > kMaxParts) return fail(RANGE_ERR_INVALID, "n_parts must be in [1, %d]", kMaxParts);
+  if (!valid_out_dtype(out_dtype)) return fail(RANGE_ERR_INVALID, "unknown out dtype");
+  CombineParts cp;
+  cp.n = n_parts;
+  for (int k = 0; k < n_parts; ++k) {
+    if (!parts[k]) return fail(RANGE_ERR_INVALID, "part %d is null", k);
+    cp.p[k] = parts[k];
+    cp.w[k] = weights ? weights[k] : 1.f;
+  }
+  CUDA_TRY(launch_combine_concat(cp, q64, int(N), perm, out, out_dtype, cudaStream_t(stream)));
+  g_launches += 1;
+  return RANGE_OK;
+}
+
+/* ---- peer memory (receive buffers of an M-sharded database) ---- */
+int range_peer_alloc(size_t bytes, void** dptr, unsigned char* handle64) {
+  if (!bytes || !dptr || !handle64) return fail(RANGE_ERR_INVALID, "bad arguments");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  void* p = nullptr;
+  CUDA_TRY(cudaMalloc(&p, bytes));
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) {
+    cudaFree(p);
+    return fail(RANGE_ERR_CUDA, "cudaIpcGetMemHandle: %s", cudaGetErrorString(e));
+  }
+  memcpy(handle64, &h, 64);
+  *dptr = p;
+  return RANGE_OK;
+}
+
+int range_peer_open(const unsigned char* handle64, void** dptr) {
+  if (!handle64 || !dptr) return fail(RANGE_ERR_INVALID, "bad arguments");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  CUDA_TRY(cudaIpcOpenMemHandle(dptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return RANGE_OK;
+}
+
+int range_peer_close(void* dptr) {
+  if (!dptr) return fail(RANGE_ERR_INVALID, "null pointer");
+  CUDA_TRY(cudaIpcCloseMemHandle(dptr));
+  return RANGE_OK;
+}
+
+int range_peer_free(void* dptr) {
+  if (!dptr) return fail(RANGE_ERR_INVALID, "null pointer");
+  CUDA_TRY(cudaFree(dptr));
+  return RANGE_OK;
 }
 
 int range_retrieve(range_ctx* c, int mode, int64_t N, const void* q16, const float* qxyz, float temp,
@@ -704,8 +804,10 @@ int range_retrieve(range_ctx* c, int mode, int64_t N, const void* q16, const flo
 int range_concat_scatter(range_ctx* c, int64_t N, const float* O, const double* q64, const int32_t* perm, void* out,
                          int out_dtype, void* stream) {
   if (!c || N <= 0 || !O || !q64 || !out) return fail(RANGE_ERR_INVALID, "bad arguments");
-  if (out_dtype != RANGE_OUT_F64 && out_dtype != RANGE_OUT_F32) return fail(RANGE_ERR_INVALID, "unknown out dtype");
-  CUDA_TRY(launch_concat(O, q64, int(N), kDimV, kDimK, perm, out, out_dtype, cudaStream_t(stream)));
+  if (!valid_out_dtype(out_dtype)) return fail(RANGE_ERR_INVALID, "unknown out dtype");
+  CombineParts one;
+  one.n = 1; one.p[0] = O; one.w[0] = 1.f;
+  CUDA_TRY(launch_combine_concat(one, q64, int(N), perm, out, out_dtype, cudaStream_t(stream)));
   g_launches += 1;
   return RANGE_OK;
 }

@@ -216,20 +216,6 @@ normalize_kernel(const double* __restrict__ e, const double* __restrict__ lonlat
 }
 
 __global__ void __launch_bounds__(256)
-concat_kernel(const float* __restrict__ O, const double* __restrict__ q64, int N, int DO, int DQ,
-              const int* __restrict__ perm, void* out, int dtype) {
-  const int W = DO + DQ;
-  const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= size_t(N) * W) return;
-  const size_t n = i / W;
-  const int c = int(i - n * W);
-  const double v = c < DO ? double(O[n * DO + c]) : q64[n * DQ + (c - DO)];
-  const size_t o = perm ? size_t(perm[n]) * W + c : i;      // row n was computed for the caller's row perm[n]
-  if (dtype == 0) reinterpret_cast<double*>(out)[o] = v;
-  else reinterpret_cast<float*>(out)[o] = float(v);
-}
-
-__global__ void __launch_bounds__(256)
 concat_q_kernel(const double* __restrict__ q64, int N, int DQ, const int* __restrict__ perm, void* out, int ld, int col0,
                 int dtype) {
   const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -267,14 +253,6 @@ cudaError_t launch_normalize(const double* e, const double* lonlat, int N, int D
   if (N <= 0) return cudaSuccess;
   normalize_kernel<<<(N + 7) / 8, 256, 0, s>>>(e, lonlat, N, D, q64, ldq, reinterpret_cast<__half*>(q16),
                                                reinterpret_cast<float4*>(qxyz));
-  return cudaGetLastError();
-}
-
-cudaError_t launch_concat(const float* O, const double* q64, int N, int DO, int DQ, const int* perm, void* out,
-                          int dtype, cudaStream_t s) {
-  if (N <= 0) return cudaSuccess;
-  const size_t total = size_t(N) * (DO + DQ);
-  concat_kernel<<<unsigned((total + 255) / 256), 256, 0, s>>>(O, q64, N, DO, DQ, perm, out, dtype);
   return cudaGetLastError();
 }
 

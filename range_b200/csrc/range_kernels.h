@@ -62,12 +62,36 @@ cudaError_t launch_raster_combine(const ShTable& sh, const RasterTables& t, cons
 // e [N][D] fp64 row-major -> q64 [N][D] (ld = ldq), q16 [N][D] fp16, qxyz [N][4] fp32 from lonlat
 cudaError_t launch_normalize(const double* e, const double* lonlat, int N, int D, double* q64, size_t ldq,
                              void* q16, float* qxyz, cudaStream_t s);
-// out[perm ? perm[n] : n] = [O[n][0:DO] | q64[n][0:DQ]]  as fp64 (dtype 0) or fp32 (dtype 1)
-cudaError_t launch_concat(const float* O, const double* q64, int N, int DO, int DQ, const int* perm, void* out,
-                          int dtype, cudaStream_t s);
 // only the location columns: out[perm ? perm[n] : n][col0 .. col0 + DQ) = q64[n]  (row length ld)
 cudaError_t launch_concat_q(const double* q64, int N, int DQ, const int* perm, void* out, int ld, int col0, int dtype,
                             cudaStream_t s);
+
+// ---- merging partial retrieved features: M-sharded databases, beta sweeps (merge.cu) ------------------------
+constexpr int kMaxRanks = 8, kMaxParts = 8;
+// Where the rows of an M-sharded apply pass go: row n belongs to rank n / slab and is stored (fp32, 1024 wide) in
+// that rank's receive buffer [n_ranks][slab][1024] at slot `rank` - peer[r] is rank r's buffer as mapped into this
+// process (NVLink peer memory; for r == rank the local buffer).  n_ranks == 0: no routing.
+struct RowRoute {
+  int n_ranks = 0, rank = 0;
+  long long slab = 0;
+  float* peer[kMaxRanks] = {};
+};
+__device__ __forceinline__ float* route_row(const RowRoute& r, int n) {
+  int owner = int(n / r.slab);
+  owner = owner < r.n_ranks ? owner : r.n_ranks - 1;            // padding rows (never stored) must not index past peer[]
+  return r.peer[owner] + (size_t(r.rank) * size_t(r.slab) + size_t(n - owner * r.slab)) * 1024;
+}
+struct CombineParts {
+  int n = 0;
+  const float* p[kMaxParts] = {};
+  float w[kMaxParts] = {};
+};
+// out[perm ? perm[n] : n] = [sum_k w[k] p[k][n][0:1024] | q64[n][0:256]]; dtype 0: fp64 (N,1280), 1: fp32 (N,1280),
+// 2: packed rows of 6144 bytes (1024 fp32 + 256 fp64)
+cudaError_t launch_combine_concat(const CombineParts& parts, const double* q64, int N, const int* perm, void* out,
+                                  int dtype, cudaStream_t s);
+// O (N,1024) fp32 -> the owners' receive buffers
+cudaError_t launch_route_rows(const float* O, int N, const RowRoute& route, cudaStream_t s);
 
 // ---- spatial batching of the queries (sort.cu) ----------------------------------------------------
 size_t sort_workspace_bytes(int N);
@@ -116,9 +140,10 @@ int apply_pc_ring_rows(int sm_count);          // ring as a 2-D tensor [rows][2 
 size_t apply_pc_part_bytes(int sm_count, int64_t N, int64_t M);
 void apply_pc_describe_plan(int sm_count, int64_t N, int64_t M, int32_t out[7]);   // test hook   // partial outputs of the split tail pairs
 // row n of the result goes to out + (perm ? perm[n] : n) * out_ld (+ column), fp32 or fp64
+// (out_ld in elements of the output type); route != null: rows go to the owners' receive buffers instead (fp32)
 cudaError_t launch_apply_pc(const RetrievalArgs& a, const CUtensorMap& tmP, const float* rowc, void* out, int out_ld,
-                            int out_f64, const int* perm, void* ring, void* flags, void* part, void* scratch,
-                            int sm_count, cudaStream_t s);
+                            int out_f64, const int* perm, const RowRoute* route, void* ring, void* flags, void* part,
+                            void* scratch, int sm_count, cudaStream_t s);
 size_t apply_pc_scratch_bytes(int sm_count);   // consumers' accumulation-window scratch
 // statistics pass with the producer's structure (retrieval_pc.cu); same partials as launch_stats
 cudaError_t launch_stats_pc(const RetrievalArgs& a, float* part_sum, float* part_max, cudaStream_t s);

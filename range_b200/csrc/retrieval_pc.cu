@@ -165,6 +165,8 @@ struct PcPlan {
   // the caller's (N, 1280) result, range/range.py:222,240) - or the plain (N, 1024) fp32 O
   int out_ld, out_f64;
   const int* perm;
+  // M-sharded database: finished (partial) rows go to the owner ranks' receive buffers over NVLink instead
+  rangeb200::RowRoute route;
 };
 struct PcWork {
   int qp, t0, t1, split;      // query-tile pair, database tiles [t0, t1), split index or -1 (direct output)
@@ -672,11 +674,13 @@ range_apply_pc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         // whole database: the final rows (caller's layout, dtype and row order); one range of a split tail pair: that
         // split's fp32 partial rows (summed and placed by the host's reduce kernel)
         const bool direct = wk.split < 0;
-        const size_t drow = direct ? size_t(plan.perm && n < N ? plan.perm[n] : n) * plan.out_ld : 0;
-        float* orow32 = direct ? reinterpret_cast<float*>(out) + drow + dimbase
-                               : part + size_t(wk.split) * plan.part_stride + size_t(n - plan.tail_row0) * 1024 + dimbase;
+        const bool routed = plan.route.n_ranks > 0;
+        const size_t drow = direct && !routed ? size_t(plan.perm && n < N ? plan.perm[n] : n) * plan.out_ld : 0;
+        float* orow32 = !direct ? part + size_t(wk.split) * plan.part_stride + size_t(n - plan.tail_row0) * 1024 + dimbase
+                        : routed ? rangeb200::route_row(plan.route, n) + dimbase       // peer memory: stores cross NVLink
+                                 : reinterpret_cast<float*>(out) + drow + dimbase;
         double* orow64 = reinterpret_cast<double*>(out) + drow + dimbase;
-        const bool f64 = direct && plan.out_f64;
+        const bool f64 = direct && !routed && plan.out_f64;
         const int nseg = (wk.t1 - wk.t0 + kAccWindow - 1) / kAccWindow;
         for (int sg = 0; sg < nseg; ++sg, ++ev) {
           const bool last = sg == nseg - 1;
@@ -1048,7 +1052,8 @@ size_t apply_pc_part_bytes(int sm_count, int64_t N, int64_t M) {
 
 // partials [splits][rows][1024] fp32 -> rows row0.. of the caller's output (layout / dtype / row order of PcPlan)
 __global__ void reduce_tail_kernel(const float4* __restrict__ part, size_t stride4, int splits, int rows, int row0,
-                                   const int* __restrict__ perm, void* __restrict__ out, int out_ld, int out_f64) {
+                                   const int* __restrict__ perm, void* __restrict__ out, int out_ld, int out_f64,
+                                   const RowRoute route) {
   const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= size_t(rows) * 256) return;
   float4 a = part[i];
@@ -1057,6 +1062,10 @@ __global__ void reduce_tail_kernel(const float4* __restrict__ part, size_t strid
     a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
   }
   const int n = row0 + int(i / 256), c = int(i % 256) * 4;
+  if (route.n_ranks > 0) {
+    *reinterpret_cast<float4*>(route_row(route, n) + c) = a;
+    return;
+  }
   const size_t o = size_t(perm ? perm[n] : n) * out_ld + c;
   if (out_f64) {
     double* d = reinterpret_cast<double*>(out) + o;
@@ -1067,12 +1076,13 @@ __global__ void reduce_tail_kernel(const float4* __restrict__ part, size_t strid
 }
 
 cudaError_t launch_apply_pc(const RetrievalArgs& a, const CUtensorMap& tmP, const float* rowc, void* out, int out_ld,
-                            int out_f64, const int* perm, void* ring, void* flags, void* part, void* scratch,
-                            int sm_count, cudaStream_t stream) {
+                            int out_f64, const int* perm, const RowRoute* route, void* ring, void* flags, void* part,
+                            void* scratch, int sm_count, cudaStream_t stream) {
   PcPlan plan = pc_plan(sm_count, a.N, a.M);
   plan.out_ld = out_ld;
   plan.out_f64 = out_f64;
   plan.perm = perm;
+  if (route) plan.route = *route;
 #ifdef RANGE_DEVELOPER_SWITCHES       // NVCC_EXTRA=-DRANGE_DEVELOPER_SWITCHES: RANGE_PC_DBG decouples the roles (results are then wrong)
   static const int dbg = getenv("RANGE_PC_DBG") ? atoi(getenv("RANGE_PC_DBG")) : 0;
 #else
@@ -1134,7 +1144,7 @@ cudaError_t launch_apply_pc(const RetrievalArgs& a, const CUtensorMap& tmP, cons
     const int rows = a.N - plan.tail_row0;
     reduce_tail_kernel<<<unsigned((size_t(rows) * 256 + 255) / 256), 256, 0, stream>>>(
         reinterpret_cast<const float4*>(part), plan.part_stride / 4, plan.tail_split, rows, plan.tail_row0, perm, out, out_ld,
-        out_f64);
+        out_f64, plan.route);
     return cudaGetLastError();
   }
   return cudaSuccess;

@@ -22,6 +22,28 @@ def _stream():
     return c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+# result layouts of the concat step: numpy float64 (what the reference returns), float32, or packed rows of 6144 bytes
+# (1024 fp32 + 256 fp64, include/range_b200.h: RANGE_OUT_PACKED) held in a uint8 tensor
+PACKED_ROW_BYTES = 6144
+
+
+def _out_code(t):
+    if t.dtype == torch.float64:
+        return _lib.RANGE_OUT_F64
+    if t.dtype == torch.float32:
+        return _lib.RANGE_OUT_F32
+    if t.dtype == torch.uint8 and t.shape[-1] == PACKED_ROW_BYTES:
+        return _lib.RANGE_OUT_PACKED
+    raise ValueError(f"result tensor must be float64 / float32 (N,1280) or uint8 (N,{PACKED_ROW_BYTES}), got "
+                     f"{t.dtype} {tuple(t.shape)}")
+
+
+def _new_out(N, dtype, device):
+    if dtype == torch.uint8:
+        return torch.empty(N, PACKED_ROW_BYTES, dtype=torch.uint8, device=device)
+    return torch.empty(N, 1280, dtype=dtype, device=device)
+
+
 class RangeEngine:
     def __init__(self, device, encoder=None, database=None, L=None, encoder_precision="auto", harmonics=None):
         """encoder: dict from checkpoint.load_satclip_location_encoder (or None: SH only with `L`);
@@ -238,8 +260,8 @@ class RangeEngine:
                               dtype=torch.float64, perm=None):
         """apply pass + concat in one call: (N,1280) = [retrieved feature | q64], row n at out[perm[n]]"""
         N = q16.shape[0]
-        out = torch.empty(N, 1280, dtype=dtype, device=self.device) if out is None else out
-        code = _lib.RANGE_OUT_F64 if out.dtype == torch.float64 else _lib.RANGE_OUT_F32
+        out = _new_out(N, dtype, self.device) if out is None else out
+        code = _out_code(out)
         with torch.cuda.device(self.index):
             ws = self._ret_ws(N)
             _lib.check(self.lib.range_retrieve_apply_concat(
@@ -251,10 +273,42 @@ class RangeEngine:
     def concat(self, O, q64, out=None, dtype=torch.float64, perm=None):
         """[O | q64] -> (N,1280); with perm (from sort_queries) row n is written to out[perm[n]]"""
         N = O.shape[0]
-        out = torch.empty(N, 1280, dtype=dtype, device=self.device) if out is None else out
-        code = _lib.RANGE_OUT_F64 if out.dtype == torch.float64 else _lib.RANGE_OUT_F32
+        out = _new_out(N, dtype, self.device) if out is None else out
+        code = _out_code(out)
         with torch.cuda.device(self.index):
             _lib.check(self.lib.range_concat_scatter(self.ctx, N, _ptr(O), _ptr(q64),
                                                      c_void_p(None) if perm is None else _ptr(perm), _ptr(out), code,
                                                      _stream()))
+        return out
+
+    def retrieve_apply_routed(self, mode, q16, qxyz, temp, geo_temp, beta, sums, maxs, route):
+        """apply pass of an M-sharded database: this shard's partial rows leave from the kernel's epilogue into the
+        owner ranks' receive buffers (route: _lib.Route with the mapped peer pointers)"""
+        N = q16.shape[0]
+        with torch.cuda.device(self.index):
+            ws = self._ret_ws(N)
+            _lib.check(self.lib.range_retrieve_apply_routed(
+                self.ctx, MODE[mode], N, _ptr(q16), _ptr(qxyz), temp, geo_temp, 0.0 if beta is None else float(beta),
+                _ptr(sums), _ptr(maxs), ctypes.byref(route), _ptr(ws), ws.numel(), _stream()))
+
+    def combine_concat(self, parts, weights, q64, out=None, dtype=torch.float64, perm=None):
+        """out[perm[n]] = [sum_k weights[k] parts[k][n] | q64[n]]: the slots of an M-sharded receive buffer
+        (weights None = 1) or the two ends of a beta sweep, (1 - beta) O(0) + beta O(1)"""
+        N = q64.shape[0]
+        n = len(parts)
+        ptrs = []
+        for p in parts:                       # tensors, or raw device addresses (slots of a peer receive buffer)
+            if isinstance(p, int):
+                ptrs.append(p)
+                continue
+            if p.dtype != torch.float32 or p.shape != (N, 1024) or not p.is_contiguous():
+                raise ValueError(f"parts must be contiguous (N,1024) float32, got {p.dtype} {tuple(p.shape)}")
+            ptrs.append(p.data_ptr())
+        out = _new_out(N, dtype, self.device) if out is None else out
+        P = (c_void_p * n)(*ptrs)
+        W = None if weights is None else (ctypes.c_float * n)(*[float(w) for w in weights])
+        with torch.cuda.device(self.index):
+            _lib.check(self.lib.range_combine_concat(self.ctx, N, n, P, W, _ptr(q64),
+                                                     c_void_p(None) if perm is None else _ptr(perm), _ptr(out),
+                                                     _out_code(out), _stream()))
         return out

@@ -15,8 +15,11 @@ def load_model(model_name='RANGE+', pretrained_path=None, device='cuda', **kwarg
       * names containing 'RANGE' need `db_path`                         (load_model.py:33-35)
       * `beta` defaults to 0.5                                          (load_model.py:37-40)
     Extra, optional keywords (not in the reference): `chunk` (queries per pipelined chunk),
-    `db_shard=(rank, world)` + `db_group` (torch.distributed group) for an M-sharded database, `db_cache` (path
-    of the prepared device layout: written on first use, read afterwards).
+    `db_shard=(rank, world)` + `db_group` (torch.distributed group) for an M-sharded database (model(locs) is then a
+    collective call: every rank passes its own queries; `db_merge='peer'|'reduce_scatter'`), `db_cache` (path of the
+    prepared device layout: written on first use, validated against source and shard, read afterwards), `host_path`
+    ('auto' | 'direct' | 'copy' | 'packed': how the float64 result reaches the host, range.py:_forward_host),
+    `pinned_limit` (bytes), `host_threads`.
     """
     if pretrained_path is None:
         raise ValueError("Please provide the pretrained model path.")
@@ -28,7 +31,8 @@ def load_model(model_name='RANGE+', pretrained_path=None, device='cuda', **kwarg
         raise NotImplementedError(f"{model_name}: range_b200 implements the RANGE and RANGE+ encoders only")
     args = Namespace(location_model_name=model_name, pretrained_path=pretrained_path, device=device,
                      range_db=db_path, beta=beta)
-    for k in ('chunk', 'db_shard', 'db_group', 'db_cache', 'tail', 'super_batch'):
+    for k in ('chunk', 'db_shard', 'db_group', 'db_cache', 'db_merge', 'tail', 'super_batch', 'host_path', 'pinned_limit',
+              'host_threads'):
         if k in kwargs:
             setattr(args, k, kwargs[k])
     model = LocationEncoder(args)

@@ -6,6 +6,8 @@ args.beta), same forward contract: `model(locs)` with locs (N,2) float64 (lon, l
 numpy float64 (N, 1280) array = [retrieved visual feature (1024) | L2-normalised SatCLIP embedding (256)].
 Only the RANGE branches exist here; every other encoder name raises like the reference's final `else`.
 """
+import os
+
 import numpy as np
 import torch
 import torch.nn as nn
@@ -36,17 +38,22 @@ class LocationEncoder(nn.Module):
         else:
             raise ValueError('Unimplemented RANGE model')                                  # range.py:114
         shard = getattr(args, 'db_shard', None)
-        db = open_npz(args.range_db) if isinstance(args.range_db, str) else args.range_db          # range.py:78
         enc = load_satclip_location_encoder(args.pretrained_path) if isinstance(args.pretrained_path, str) \
             else args.pretrained_path
         self.location_feature_dim = 1024 + 256                                             # range.py:86
         cache = getattr(args, 'db_cache', None)        # optional: prepared device layout on disk (database.py)
         ddb = None
-        if cache is not None:
+        if isinstance(args.range_db, DeviceDatabase):   # an already prepared device layout (its own shard, if any)
+            ddb = args.range_db
+            if shard is not None and tuple(shard) != ddb.shard:
+                raise ValueError(f'db_shard={tuple(shard)} but the prepared database holds shard {ddb.shard}')
+            shard = ddb.shard
+        elif cache is not None:
             # the cache is only used when it was built from this source, for this shard (one file per shard)
             fp = DeviceDatabase.source_fingerprint(args.range_db)
             ddb = DeviceDatabase.from_cache(cache, args.device, shard=shard, fingerprint=fp)
         if ddb is None:
+            db = open_npz(args.range_db) if isinstance(args.range_db, str) else args.range_db      # range.py:78
             ddb = DeviceDatabase(db, args.device, shard=shard)
             if cache is not None:
                 ddb.save_cache(cache, fingerprint=fp)
@@ -54,7 +61,18 @@ class LocationEncoder(nn.Module):
         self.chunk = int(getattr(args, 'chunk', DEFAULT_CHUNK))
         self.tail = max(1, min(self.chunk, int(getattr(args, 'tail', DEFAULT_TAIL))))
         self.super_batch = max(self.chunk, int(getattr(args, 'super_batch', 1 << 20)) // self.chunk * self.chunk)
+        # how model(locs) hands the (N,1280) float64 result to the host (see _forward_host)
+        self.host_path = getattr(args, 'host_path', 'auto')
+        if self.host_path not in ('auto', 'copy', 'direct', 'packed'):
+            raise ValueError(f"host_path={self.host_path!r}: expected 'auto', 'copy', 'direct' or 'packed'")
+        self.pinned_limit = int(getattr(args, 'pinned_limit', 8 << 30))       # largest page-locked result, bytes
+        local_ranks = max(1, int(os.environ.get('LOCAL_WORLD_SIZE', '1')))      # torchrun: ranks sharing this host
+        self.host_threads = int(getattr(args, 'host_threads', 0)) or max(1, min(16, (os.cpu_count() or 1) // local_ranks))
         self.group = getattr(args, 'db_group', None)       # torch.distributed group when the DB is M-sharded
+        self.sharded = None
+        if shard is not None and shard[1] > 1:
+            from .distributed import ShardedRetriever
+            self.sharded = ShardedRetriever(self.engine, self.group, merge=getattr(args, 'db_merge', 'peer'))
         self._copy_stream = None
         self.eval()
 
@@ -72,18 +90,20 @@ class LocationEncoder(nn.Module):
         name = self.location_model_name
         beta = getattr(a, 'beta', None)
         geo_temp = float(getattr(a, 'geo_temp', 0.0))
-        if self.group is None:
-            sums, maxs = eng.retrieve_stats(name, q16, qxyz, a.temp, geo_temp)
-            return eng.retrieve_apply_concat(name, q16, qxyz, a.temp, geo_temp, beta, sums, maxs, q64, out=out,
-                                             dtype=out_dtype, perm=perm)
-        from .distributed import sharded_retrieve      # M-sharded: the partial outputs are summed over NCCL first
-        O = sharded_retrieve(eng, name, q16, qxyz, a.temp, geo_temp, beta, self.group)
-        return eng.concat(O, q64, out=out, dtype=out_dtype, perm=perm)
+        sums, maxs = eng.retrieve_stats(name, q16, qxyz, a.temp, geo_temp)
+        return eng.retrieve_apply_concat(name, q16, qxyz, a.temp, geo_temp, beta, sums, maxs, q64, out=out,
+                                         dtype=out_dtype, perm=perm)
 
     @torch.no_grad()
     def embed(self, coords, out=None, out_dtype=torch.float32):
-        """Device-resident path: coords (N,2) fp64 on the device -> (N,1280) device tensor."""
-        eng = self.engine
+        """Device-resident path: coords (N,2) fp64 on the device -> (N,1280) device tensor.
+        With an M-sharded database (db_shard / db_group) this is a COLLECTIVE call: every rank passes its own
+        queries and gets its own rows (distributed.py)."""
+        eng, a = self.engine, self.args
+        if self.sharded is not None:
+            coords = coords.to(eng.device, torch.float64).contiguous()
+            return self.sharded.embed(self.location_model_name, coords, a.temp, float(getattr(a, 'geo_temp', 0.0)),
+                                      getattr(a, 'beta', None), self._sorts(), out=out, out_dtype=out_dtype)
         perm = None
         if self._sorts():
             # spatial batching: the geo softmax is local, tiles of nearby queries skip far database tiles
@@ -93,10 +113,11 @@ class LocationEncoder(nn.Module):
 
     @torch.no_grad()
     def embed_sweep(self, coords, betas, out_dtype=torch.float32):
-        """RANGE+ for several beta on the same queries (multi-resolution use, Readme.md:27-31): the encoder and the
-        statistics pass do not depend on beta and run once; each beta costs one apply pass.  Returns a list of
-        (N,1280) device tensors."""
-        if self.location_model_name != 'RANGE+' or self.group is not None:
+        """RANGE+ for several beta on the same queries (multi-resolution use, Readme.md:27-31).  range/range.py:238 is
+        linear in beta - O(beta) = (1 - beta) O_geo + beta O_sem - so the encoder, the statistics pass and TWO apply
+        passes (the geographic and the semantic end) serve any number of beta; each beta then costs one memory-bound
+        blend + concat kernel.  Returns a list of (N,1280) device tensors."""
+        if self.location_model_name != 'RANGE+' or self.sharded is not None:
             raise NotImplementedError('embed_sweep: RANGE+ with an unsharded database')
         eng, a = self.engine, self.args
         perm = None
@@ -104,8 +125,11 @@ class LocationEncoder(nn.Module):
             coords, perm = eng.sort_queries(coords)
         q64, q16, qxyz = eng.encode(coords)
         sums, maxs = eng.retrieve_stats('RANGE+', q16, qxyz, a.temp, a.geo_temp)
-        return [eng.retrieve_apply_concat('RANGE+', q16, qxyz, a.temp, a.geo_temp, float(b), sums, maxs, q64,
-                                          dtype=out_dtype, perm=perm) for b in betas]
+        O_geo = eng.retrieve_apply('RANGE+', q16, qxyz, a.temp, a.geo_temp, 0.0, sums, maxs)
+        # the semantic end is the one-softmax retrieval at RANGE+'s temperature: no geographic work at all
+        O_sem = eng.retrieve_apply('RANGE', q16, qxyz, a.temp, 0.0, None, sums, maxs)
+        return [eng.combine_concat([O_geo, O_sem], [1.0 - float(b), float(b)], q64, dtype=out_dtype, perm=perm)
+                for b in betas]
 
     @staticmethod
     def _chunks(N, chunk, tail):
@@ -123,6 +147,15 @@ class LocationEncoder(nn.Module):
         cuts.append((lo, N))
         return cuts
 
+    @classmethod
+    def _pieces(cls, N, chunk, tail, super_batch, whole=False):
+        """(super-batches [s0, s1), their pieces [lo, hi) relative to s0, rows of the largest piece).  Buffers are sized
+        for the largest piece of ANY super-batch: a short last super-batch can end in a longer piece than the first."""
+        batches = [(s0, min(N, s0 + super_batch)) for s0 in range(0, N, super_batch)]
+        plan = [[(0, s1 - s0)] if whole else cls._chunks(s1 - s0, chunk, tail) for s0, s1 in batches]
+        rows = max(hi - lo for cuts in plan for lo, hi in cuts)
+        return batches, plan, rows
+
     @torch.no_grad()
     def forward(self, coords):
         """range.py:206-242.  Returns numpy float64 (N, 1280).  Per super-batch (<= 1M queries): every chunk is
@@ -135,6 +168,19 @@ class LocationEncoder(nn.Module):
         if coords.dim() != 2 or coords.shape[1] != 2:
             raise ValueError(f'coords must be (N, 2) (lon, lat) degrees, got {tuple(coords.shape)}')
         return self._forward_host(coords.shape[0], coords=coords)
+
+    @torch.no_grad()
+    def embed_into(self, coords, out):
+        """forward() writing into the caller's float64 (N,1280) array - e.g. rows of a memory-mapped .npy
+        (save.embed_to_npy): the rows cross PCIe packed into small page-locked staging buffers and a host thread team
+        widens them straight into `out` while the GPU works on the next chunks ('packed' path of _forward_host)."""
+        coords = torch.as_tensor(coords)
+        if coords.dim() != 2 or coords.shape[1] != 2:
+            raise ValueError(f'coords must be (N, 2) (lon, lat) degrees, got {tuple(coords.shape)}')
+        if not (isinstance(out, np.ndarray) and out.dtype == np.float64 and out.shape == (coords.shape[0], 1280)
+                and out.flags['C_CONTIGUOUS'] and out.flags['WRITEABLE']):
+            raise ValueError('out must be a writable C-contiguous float64 (N, 1280) array')
+        return self._forward_host(coords.shape[0], coords=coords, result=out)
 
     # ------------------------------------------------------------------ dense lat/lon rasters
     @staticmethod
@@ -194,25 +240,68 @@ class LocationEncoder(nn.Module):
         tables = self.raster_tables(lon_axis, lat_axis)
         return self._forward_host(tables['H'] * tables['W'], raster=tables)
 
-    def _forward_host(self, N, coords=None, raster=None):
+    def _forward_host(self, N, coords=None, raster=None, result=None):
+        """model(locs) -> numpy float64 (N,1280) (range/range.py:222,240).  Three ways to hand the rows to the host:
+
+        'direct'  the apply kernel's epilogue stores the float64 rows straight into the page-locked result (mapped
+                  host memory): they cross PCIe while the tensor cores work on the next tiles, one launch per
+                  super-batch, nothing left to copy at the end.  Result page-locked: N * 10 KB.
+        'copy'    chunk by chunk into device buffers; every chunk's rows travel to the page-locked result on a copy
+                  stream while the next chunk is computed.
+        'packed'  as 'copy', but the rows cross PCIe packed (6 KB: fp32 feature columns + fp64 location columns,
+                  RANGE_OUT_PACKED) into small page-locked staging buffers and are widened into an ordinary (pageable)
+                  numpy array by a host thread team (range_host_unpack): bounded page-locked memory for any N.
+        'auto'    'direct' while the result fits `pinned_limit` (8 GB), else 'packed'."""
         eng = self.engine
-        host = torch.empty((N, 1280), dtype=torch.float64, pin_memory=True)
+        path = self.host_path
+        if result is not None:
+            path = 'packed'
+        elif path == 'auto':
+            path = 'direct' if N * 10240 <= self.pinned_limit else 'packed'
+        if self.sharded is not None:            # collective: distributed.py chunks (every rank must take the same steps)
+            dev = coords.to(eng.device, torch.float64, non_blocking=True)
+            res = self.embed(dev, out_dtype=torch.float64)
+            host = torch.empty((N, 1280), dtype=torch.float64, pin_memory=N * 10240 <= self.pinned_limit)
+            host.copy_(res)
+            if result is None:
+                return host.numpy()
+            result[...] = host.numpy()
+            return result
+        if path == 'packed':
+            result = np.empty((N, 1280), dtype=np.float64) if result is None else result
+        else:
+            host = torch.empty((N, 1280), dtype=torch.float64, pin_memory=True)
+            result = host.numpy()
         if N == 0:
-            return host.numpy()
+            return result
         with torch.cuda.device(eng.index):
             if raster is None:
                 dev_coords = coords.to(eng.device, torch.float64, non_blocking=True)
             if self._copy_stream is None:
                 self._copy_stream = torch.cuda.Stream(device=eng.device)
             chunk = min(self.chunk, N)
-            rows = max(hi - lo for lo, hi in self._chunks(min(N, self.super_batch), chunk, self.tail))
-            bufs = [torch.empty(rows, 1280, dtype=torch.float64, device=eng.device) for _ in range(2 if N > rows else 1)]
-            freed = [None] * len(bufs)
+            batches, plan, rows = self._pieces(N, chunk, self.tail, self.super_batch, whole=path == 'direct')
+            n_pieces = sum(len(cuts) for cuts in plan)
+            if path == 'copy':
+                bufs = [torch.empty(rows, 1280, dtype=torch.float64, device=eng.device) for _ in range(min(2, n_pieces))]
+            elif path == 'packed':
+                depth = min(3, n_pieces)
+                bufs = [torch.empty(rows, 6144, dtype=torch.uint8, device=eng.device) for _ in range(depth)]
+                stage = [torch.empty(rows, 6144, dtype=torch.uint8, pin_memory=True) for _ in range(depth)]
+                landed = [None] * depth          # (event, result rows, staging rows) of the piece in each slot
+            freed = [None] * (len(bufs) if path != 'direct' else 0)
             cur = torch.cuda.current_stream()
+
+            def unpack(slot):
+                ev, r0, r1 = landed[slot]
+                ev.synchronize()
+                _check_unpack(eng.lib.range_host_unpack(stage[slot].data_ptr(), r1 - r0, result[r0:r1].ctypes.data,
+                                                        self.host_threads))
+                landed[slot] = None
+
             i = 0
-            for s0 in range(0, N, self.super_batch):
-                s1 = min(N, s0 + self.super_batch)
-                cuts = self._chunks(s1 - s0, chunk, self.tail)
+            for (s0, s1), cuts in zip(batches, plan):
+                sort_cuts = cuts if path != 'direct' else self._chunks(s1 - s0, chunk, self.tail)
                 ij = None
                 if raster is None:
                     sub = dev_coords[s0:s1]
@@ -221,26 +310,52 @@ class LocationEncoder(nn.Module):
                     sub = self._raster_coords(raster, ij)
                 perms = None
                 if self._sorts():
-                    parts = [eng.sort_queries(sub[lo:hi]) for lo, hi in cuts]
+                    # spatial batching chunk by chunk (a tile's 128 queries should be neighbours; the order of the
+                    # chunks does not matter)
+                    parts = [eng.sort_queries(sub[lo:hi]) for lo, hi in sort_cuts]
                     sub = torch.cat([p[0] for p in parts]) if len(parts) > 1 else parts[0][0]
                     perms = [p[1] for p in parts]
                     if ij is not None:
-                        ij = torch.cat([ij[lo:hi][p.long()] for (lo, hi), p in zip(cuts, perms)])
+                        ij = torch.cat([ij[lo:hi][p.long()] for (lo, hi), p in zip(sort_cuts, perms)])
+                    if path == 'direct' and len(perms) > 1:      # one launch: chunk-local permutations -> one global one
+                        perms = [torch.cat([p + lo for (lo, _), p in zip(sort_cuts, perms)])]
                 q64, q16, qxyz = eng.encode(sub) if ij is None else self._encode_raster(raster, ij)
                 for c, (lo, hi) in enumerate(cuts):
+                    perm = None if perms is None else perms[c]
+                    if path == 'direct':
+                        self._retrieve_concat(q16, qxyz, q64, host[s0:s1], torch.float64, perm)
+                        continue
                     k = i % len(bufs)
                     i += 1
+                    if path == 'packed' and landed[k] is not None:
+                        unpack(k)                              # the slot's previous piece: wait for its copy, widen it
                     if freed[k] is not None:
                         cur.wait_event(freed[k])
                     buf = bufs[k][: hi - lo]
-                    self._retrieve_concat(q16[lo:hi], qxyz[lo:hi], q64[lo:hi], buf, torch.float64,
-                                          None if perms is None else perms[c])
+                    assert buf.shape[0] == hi - lo
+                    self._retrieve_concat(q16[lo:hi], qxyz[lo:hi], q64[lo:hi], buf, buf.dtype, perm)
                     ready = torch.cuda.Event()
                     ready.record(cur)
                     self._copy_stream.wait_event(ready)
                     with torch.cuda.stream(self._copy_stream):
-                        host[s0 + lo:s0 + hi].copy_(buf, non_blocking=True)
+                        if path == 'copy':
+                            host[s0 + lo:s0 + hi].copy_(buf, non_blocking=True)
+                        else:
+                            stage[k][: hi - lo].copy_(buf, non_blocking=True)
                         freed[k] = torch.cuda.Event()
                         freed[k].record(self._copy_stream)
-            self._copy_stream.synchronize()
-        return host.numpy()                                                               # range.py:222,240
+                    if path == 'packed':
+                        landed[k] = (freed[k], s0 + lo, s0 + hi)
+            if path == 'packed':
+                for k in sorted((k for k in range(len(bufs)) if landed[k] is not None), key=lambda k: landed[k][1]):
+                    unpack(k)
+            elif path == 'copy':
+                self._copy_stream.synchronize()
+            else:
+                cur.synchronize()
+        return result                                                                     # range.py:222,240
+
+
+def _check_unpack(code):
+    if code != 0:
+        raise RuntimeError(f'range_host_unpack failed ({code})')

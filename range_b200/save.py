@@ -40,12 +40,22 @@ def save_embeddings(location_model, train_loader, val_loader, embeddings_dir, ta
 
 def embed_to_npy(location_model, coords, path, batch=1 << 20):
     """coords (N,2) (lon, lat) degrees (tensor / array / memmap) -> float64 (N, D) .npy at `path`, written through a
-    memory map `batch` rows at a time; returns the open memmap"""
+    memory map `batch` rows at a time; returns the open memmap.  A range_b200 model fills the map itself
+    (LocationEncoder.embed_into): its chunks cross PCIe packed into page-locked staging buffers and host threads widen
+    them into the mapped pages while the GPU computes the next chunks - no (N, D) array is ever resident."""
     N = len(coords)
     out = None
+    into = getattr(location_model, "embed_into", None)
+    dim = getattr(location_model, "location_feature_dim", None)
+    if into is not None and dim is not None and N > 0:
+        out = np.lib.format.open_memmap(path, mode="w+", dtype=np.float64, shape=(N, dim))
     for lo in range(0, max(N, 1), batch):
         hi = min(N, lo + batch)
-        emb = location_model(torch.as_tensor(np.asarray(coords[lo:hi]), dtype=torch.float64))
+        c = torch.as_tensor(np.asarray(coords[lo:hi]), dtype=torch.float64)
+        if into is not None and out is not None:
+            into(c, out[lo:hi])
+            continue
+        emb = location_model(c)
         if hasattr(emb, "cpu"):
             emb = emb.cpu().numpy()
         if out is None:

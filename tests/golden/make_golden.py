@@ -2,7 +2,7 @@
 
 Runs only in the build container (needs /root/reference and sympy); the output is committed.
 
-What it does:
+What it does (steps 1-3 live in oracle/ref_harness.py, shared with bench.py's reference arm):
   1. regenerates `spherical_harmonics_ylm.py` with the reference's own generator into oracle/_ref/
      (the file is stripped from the mount; .MISSING_LARGE_BLOBS) and pre-registers it under the module
      name the reference imports;
@@ -18,12 +18,10 @@ What it does:
     python tests/golden/make_golden.py --big      # additionally cross-checks N=10000, M=20000, H=512
 """
 import hashlib
-import importlib.util
 import os
 import sys
 import tempfile
 import time
-import types
 
 import numpy as np
 import torch
@@ -32,102 +30,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tools"))
-REF = "/root/reference"
-YLM = os.path.join(ROOT, "oracle", "_ref", "spherical_harmonics_ylm.py")
 BETAS = (0.0, 0.25, 0.5, 0.75, 1.0)
 
 
-def install_stubs():
-    class _Meta(type):
-        def __getattr__(cls, name):
-            if name.startswith("__"):
-                raise AttributeError(name)
-            return _Meta(name, (_Any,), {})
-
-    class _Any(metaclass=_Meta):
-        def __init__(self, *a, **k):
-            pass
-
-        def __call__(self, *a, **k):
-            return _Any()
-
-        def __getattr__(self, name):
-            if name.startswith("__"):
-                raise AttributeError(name)
-            return _Any()
-
-    class LightningModule(torch.nn.Module):
-        def save_hyperparameters(self, *a, **k):
-            pass
-
-        def log(self, *a, **k):
-            pass
-
-    def make(name):
-        mod = types.ModuleType(name)
-        mod.__path__ = []
-
-        def _getattr(attr):
-            if attr.startswith("__"):
-                raise AttributeError(attr)
-            return _Meta(attr, (_Any,), {})
-
-        mod.__getattr__ = _getattr
-        sys.modules[name] = mod
-        if "." in name:
-            parent, child = name.rsplit(".", 1)
-            setattr(sys.modules[parent], child, mod)
-        return mod
-
-    for name in ["lightning", "lightning.pytorch", "lightning.pytorch.callbacks", "lightning.pytorch.cli",
-                 "pytorch_lightning", "timm", "torchgeo", "torchgeo.models", "torchgeo.datasets",
-                 "torchgeo.datasets.geo", "rasterio", "matplotlib", "matplotlib.pyplot", "albumentations",
-                 "albumentations.core", "albumentations.core.transforms_interface", "albumentations.pytorch",
-                 "huggingface_hub", "wandb", "geoclip", "rshf", "rshf.satmae", "cartopy", "skimage", "h5py"]:
-        if name in sys.modules:
-            continue
-        try:
-            importlib.import_module(name)
-        except Exception:
-            make(name)
-    lp = sys.modules["lightning.pytorch"]
-    if not (isinstance(lp.__dict__.get("LightningModule"), type)
-            and issubclass(lp.__dict__["LightningModule"], torch.nn.Module)):
-        lp.LightningModule = LightningModule
-        sys.modules["pytorch_lightning"].LightningModule = LightningModule
-
-
-def import_reference():
-    if not os.path.exists(YLM):
-        from make_sh_table import regenerate
-        regenerate(YLM)
-    name = "range.location_models.satclip.positional_encoding.spherical_harmonics_ylm"
-    spec = importlib.util.spec_from_file_location(name, YLM)
-    mod = importlib.util.module_from_spec(spec)
-    sys.modules[name] = mod
-    spec.loader.exec_module(mod)
-    install_stubs()
-    sys.path.insert(0, REF)
-    from range.load_model import load_model                     # the reference, unmodified
-    from range.location_models.satclip.main_old import SatCLIPLightningModule
-    return load_model, SatCLIPLightningModule
-
-
-def fabricate_ckpt(SatCLIPLightningModule, path, capacity, seed=0):
-    torch.manual_seed(seed)
-    hp = dict(embed_dim=256, image_resolution=64, vision_layers=1, vision_width=64, vision_patch_size=32,
-              in_channels=3, le_type="sphericalharmonics", pe_type="siren", frequency_num=16, max_radius=260,
-              min_radius=1, legendre_polys=40, harmonics_calculation="analytic", sh_embedding_dims=32,
-              learning_rate=1e-4, weight_decay=0.01, num_hidden_layers=2, capacity=capacity)
-    module = SatCLIPLightningModule(**hp)
-    hp.update(eval_downstream=False, air_temp_data_path=None, election_data_path=None)
-    torch.save({"hyper_parameters": hp, "state_dict": module.state_dict()}, path)
-    sd = module.state_dict()
-    pre = "model.location.nnet."
-    weights = [(sd[pre + "layers.0.weight"], sd[pre + "layers.0.bias"]),
-               (sd[pre + "layers.1.weight"], sd[pre + "layers.1.bias"]),
-               (sd[pre + "last_layer.weight"], sd[pre + "last_layer.bias"])]
-    return [(w.double().clone(), b.double().clone()) for w, b in weights]
+from oracle.ref_harness import fabricate_ckpt, import_reference      # noqa: E402  (the unmodified reference)
 
 
 def special_points():

@@ -194,3 +194,21 @@ def test_inconsistent_database_is_rejected():
     db["satclip_embeddings"] = db["satclip_embeddings"][:, :128]
     with pytest.raises(ValueError):
         DeviceDatabase(db, "cpu")
+
+
+def test_forward_buffers_fit_every_piece():
+    """the staging buffers of model(locs) are sized for the largest piece of any super-batch (tail > chunk / 2: a short
+    last super-batch ends in a longer piece than the first one does)"""
+    from range_b200.range import LocationEncoder
+    for N, chunk, tail, sb in [(16384 + 12288, 8192, 6144, 16384), (100000, 24576, 6144, 1 << 20), (5, 24576, 6144, 1 << 20),
+                               (3 * 49152 + 11111, 24576, 20000, 49152), (1000, 64, 60, 128)]:
+        batches, plan, rows = LocationEncoder._pieces(N, min(chunk, N), tail, sb)
+        assert batches[0][0] == 0 and batches[-1][1] == N and all(a[1] == b[0] for a, b in zip(batches, batches[1:]))
+        for (s0, s1), cuts in zip(batches, plan):
+            assert cuts[0][0] == 0 and cuts[-1][1] == s1 - s0 and all(a[1] == b[0] for a, b in zip(cuts, cuts[1:]))
+            assert all(0 < hi - lo <= rows for lo, hi in cuts)
+        whole = LocationEncoder._pieces(N, min(chunk, N), tail, sb, whole=True)
+        assert all(cuts == [(0, s1 - s0)] for (s0, s1), cuts in zip(whole[0], whole[1]))
+    # the case the first-batch-only sizing got wrong: first super-batch's largest piece 10240, the remainder's 12288
+    _, plan, rows = LocationEncoder._pieces(16384 + 12288, 8192, 6144, 16384)
+    assert max(hi - lo for lo, hi in plan[0]) < max(hi - lo for lo, hi in plan[1]) == rows

@@ -89,3 +89,13 @@ def test_closed_form_harmonics_match_reference(golden):
     assert np.allclose(y[:, 3], -np.sqrt(3 / (4 * np.pi)) * np.sin(theta) * np.cos(phi))
     from range_b200.sh_table import closed_form_norms
     assert np.array_equal(closed_form_norms(40), O.closed_form_norms(40))
+
+
+def test_product_side_generators_match_the_oracles():
+    """bench.py / smoke() draw their synthetic inputs from range_b200.synthetic (the product never imports oracle/)"""
+    import torch
+    from range_b200 import synthetic as S
+    a, b = S.area_uniform(1000, np.random.default_rng(4)), O.area_uniform(1000, np.random.default_rng(4))
+    assert np.array_equal(a, b)
+    for (w1, b1), (w2, b2) in zip(S.siren_init(40, 64, 2, 256, seed=3), O.siren_init(40, 64, 2, 256, seed=3)):
+        assert torch.equal(w1, w2) and torch.equal(b1, b2)
