@@ -516,3 +516,19 @@ def test_no_mass_loss_over_a_long_database_axis(N):
     for mode, beta, t in (("RANGE", None, 15.0), ("RANGE+", 0.5, 12.0)):
         dev = eng.retrieve(mode, q, xyz, t, 40.0, beta).double() - 1.0
         assert abs(dev.mean().item()) < 1e-4 and dev.abs().max().item() < 5e-4, (mode, dev.mean().item(), dev.abs().max().item())
+
+
+def test_m_sharded_on_two_gpus():
+    """tools/multi_gpu_check.py under torchrun on 2 GPUs (skipped on a one-GPU box): the M-sharded pipeline with real
+    peer memory and NCCL against the unsharded database, ragged / clustered queries, both merges"""
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29531", os.path.join(root, "tools", "multi_gpu_check.py")],
+                       capture_output=True, text=True, timeout=900, cwd=root, env=dict(os.environ, M="60000", N="9000"))
+    assert p.returncode == 0, (p.stdout[-2000:], p.stderr[-3000:])
+    assert "M-sharded [peer -> ran peer]" in p.stdout, p.stdout[-2000:]

@@ -4,7 +4,8 @@ fp32 accumulation over the database axis."""
 import os, sys
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
-from oracle import range_oracle as O
+from range_b200 import synthetic as O          # seeded input generators
+from range_b200.utils import rad_to_cart
 from range_b200.engine import RangeEngine
 from range_b200.database import DeviceDatabase
 dev = "cuda:0"
@@ -17,7 +18,7 @@ for M in [10_000, 100_000, 1_000_000, 3_000_000]:
     d.Vt.fill_(0); d.Vt[:, :M] = 1.0 * d.vscale                      # V = 1
     eng = RangeEngine(dev, L=40, database=d)
     cs = eng.sort_queries(torch.tensor(c))[0].cpu()
-    xyz = torch.zeros(N, 4); xyz[:, :3] = torch.tensor(O.rad_to_cart(cs.numpy() * np.pi / 180)).float(); xyz = xyz.to(dev)
+    xyz = torch.zeros(N, 4); xyz[:, :3] = torch.tensor(rad_to_cart(cs.numpy() * np.pi / 180)).float(); xyz = xyz.to(dev)
     for mode, beta, t in (("RANGE", None, 15.0), ("RANGE+", 0.5, 12.0)):
         out = eng.retrieve(mode, q, xyz, t, 40.0, beta).double()
         dev_ = out - 1.0

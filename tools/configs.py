@@ -10,7 +10,7 @@ import json, os, sys, time
 import numpy as np, torch, torch.distributed as dist
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
 from argparse import Namespace
-from oracle import range_oracle as O
+from range_b200 import synthetic as O          # seeded input generators (area_uniform, siren_init)
 from range_b200.range import LocationEncoder
 from range_b200.distributed import shard_rows
 
@@ -83,18 +83,28 @@ if "2" in which or "3" in which:
     del m
 
 if "4" in which:
-    N = 100_000
-    coords = torch.tensor(O.area_uniform(N, np.random.default_rng(1)), device=dev)
-    M = 100_000
-    while M <= M_MAX:
-        dbm = make_db(M)
-        kw = dict(db_shard=(rank, world), db_group=dist.group.WORLD) if world > 1 else {}
-        m = model_for(dbm, 0.5, **kw)
-        t = timed(lambda: run_chunks(m, coords, out), reps=1)
-        emit(config="C4 database scaling", queries=N, M=M, n_gpus=world, seconds=t, queries_per_s=N / t,
-             pair_rate_per_s=N * M / t, parallelism=(f"database sharded along M x{world}, NCCL SUM/MAX merge" if world > 1 else "one GPU"))
-        del m, dbm
-        M *= (10 if M * 10 <= M_MAX else 10**9) if os.environ.get("M_DECADES") else 3 if M * 3 <= M_MAX else 10**9
+    # database scaling: with > 1 rank the database is sharded along M (bench.py: run_m_sharded - every rank owns
+    # 100 000 / world of the queries, exp-sums merged by one all-reduce, partial rows stored into the owners' receive
+    # buffers over NVLink), each size next to the replicated-database run; one GPU: the unsharded path
+    import bench
+    sizes = [int(x) for x in os.environ.get("M_SIZES", "").split(",") if x]
+    if not sizes:
+        sizes = [M for M in (100_000, 300_000, 1_000_000, 3_000_000, 10_000_000) if M <= M_MAX]
+    if world > 1:
+        def bar():
+            dist.barrier(); torch.cuda.synchronize()
+        for row in bench.run_m_sharded(world, rank, dev, enc["weights"], 5, 2, bar, sizes):
+            emit(config="C4 database scaling, sharded along M", n_gpus=world, **row)
+    else:
+        from range_b200.database import DeviceDatabase
+        N = 100_000
+        coords = torch.tensor(O.area_uniform(N, np.random.default_rng(1)), device=dev)
+        for M in sizes:
+            m = model_for(DeviceDatabase.synthetic(M, dev), 0.5)
+            t = timed(lambda: run_chunks(m, coords, out), reps=1)
+            emit(config="C4 database scaling", queries=N, M=M, n_gpus=1, seconds=t, queries_per_s=N / t,
+                 pair_rate_per_s=N * M / t, parallelism="one GPU")
+            del m
 
 if "4big" in which:
     # M = 10 M entries on ONE GPU (25.7 GB of fp16 keys / values resident): database generated on the device

@@ -3,7 +3,8 @@ hand-off race in the P' ring (stale slot, early release) would show up as sporad
 import os, sys
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
-from oracle import range_oracle as O
+from range_b200 import synthetic as O          # seeded input generators
+from range_b200.utils import rad_to_cart
 from range_b200.engine import RangeEngine
 from range_b200.database import DeviceDatabase
 dev = "cuda:0"
@@ -13,7 +14,7 @@ for N, M in [(100_000, 100_000), (24_576, 30_011), (6_144, 777), (13_000, 200_00
     g = torch.Generator(device="cpu").manual_seed(1)
     q = torch.randn(N, 256, generator=g); q = (q / q.norm(dim=1, keepdim=True)).half().to(dev)
     c = eng.sort_queries(torch.tensor(O.area_uniform(N, np.random.default_rng(1))))[0].cpu()
-    xyz = torch.zeros(N, 4); xyz[:, :3] = torch.tensor(O.rad_to_cart(c.numpy() * np.pi / 180)).float(); xyz = xyz.to(dev)
+    xyz = torch.zeros(N, 4); xyz[:, :3] = torch.tensor(rad_to_cart(c.numpy() * np.pi / 180)).float(); xyz = xyz.to(dev)
     first, bad = None, 0
     for r in range(reps):
         out = eng.retrieve("RANGE+", q, xyz, 12.0, 40.0, 0.5)

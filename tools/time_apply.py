@@ -2,7 +2,8 @@
 import os, sys
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
-from oracle import range_oracle as O
+from range_b200 import synthetic as O
+from range_b200.utils import rad_to_cart
 from range_b200.engine import RangeEngine
 from range_b200.database import DeviceDatabase
 dev = "cuda:0"
@@ -15,7 +16,7 @@ q = torch.randn(N, 256, device=dev); q = (q / q.norm(dim=1, keepdim=True)).half(
 c = torch.tensor(O.area_uniform(N, np.random.default_rng(1)))
 if os.environ.get("SORT", "1") == "1":      # spatially batched queries (what range.py does for RANGE+)
     c = eng.sort_queries(c)[0].cpu()
-xyz = torch.zeros(N, 4); xyz[:, :3] = torch.tensor(O.rad_to_cart(c.numpy() * np.pi / 180)).float(); xyz = xyz.to(dev)
+xyz = torch.zeros(N, 4); xyz[:, :3] = torch.tensor(rad_to_cart(c.numpy() * np.pi / 180)).float(); xyz = xyz.to(dev)
 def timeit(fn, reps=3):
     fn(); torch.cuda.synchronize(); ts = []
     for _ in range(reps):

@@ -1,4 +1,4 @@
-"""where does model(locs) spend its time? (host-pinned in -> numpy out)"""
+"""where does model(locs) spend its time? (host-pinned in -> numpy float64 out), per host path of range.py:_forward_host"""
 import os, sys, time
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
@@ -7,20 +7,36 @@ from argparse import Namespace
 from range_b200.range import LocationEncoder
 db, weights, coords = bench.synthetic_inputs()
 enc = dict(L=40, dims=[1600, 512, 512, 256], weights=weights)
-model = LocationEncoder(Namespace(location_model_name="RANGE+", pretrained_path=enc, device="cuda:0", range_db=db, beta=0.5))
 h = torch.tensor(coords).pin_memory()
-for _ in range(2): model(h)
-torch.cuda.synchronize()
-for name, fn in [("model(h) full", lambda: model(h)),
-                 ("pinned alloc 1GB", lambda: torch.empty((100000, 1280), dtype=torch.float64, pin_memory=True)),
-                 ("embed device fp64", lambda: model.embed(torch.tensor(coords, device="cuda:0"), out_dtype=torch.float64))]:
+dc = torch.tensor(coords, device="cuda:0")
+
+
+def best(fn, reps=5):
     ts = []
-    for _ in range(4):
+    for _ in range(reps):
         torch.cuda.synchronize(); t = time.perf_counter(); r = fn(); torch.cuda.synchronize(); ts.append(time.perf_counter() - t)
-    print(f"{name}: {min(ts)*1e3:.1f} ms (runs {[round(x*1e3,1) for x in ts]})")
-d = model.embed(torch.tensor(coords, device="cuda:0"), out_dtype=torch.float64)
+    return min(ts), ts
+
+
+model = None
+for path in os.environ.get("PATHS", "direct,copy,packed").split(","):
+    del model
+    model = LocationEncoder(Namespace(location_model_name="RANGE+", pretrained_path=enc, device="cuda:0", range_db=db, beta=0.5,
+                                      host_path=path))
+    for _ in range(3): model(h)
+    t, ts = best(lambda: model(h))
+    print(f"model(h) host_path={path}: {t*1e3:.1f} ms = {len(coords)/t/1e6:.2f} M q/s (runs {[round(x*1e3,1) for x in ts]}; "
+          f"host threads {model.host_threads})")
+t, ts = best(lambda: model.embed(dc, out_dtype=torch.float64))
+print(f"embed device fp64: {t*1e3:.1f} ms")
+t, ts = best(lambda: model.embed(dc, out_dtype=torch.float32))
+print(f"embed device fp32: {t*1e3:.1f} ms")
+d = model.embed(dc, out_dtype=torch.float64)
 hp = torch.empty((100000, 1280), dtype=torch.float64, pin_memory=True)
-ts = []
-for _ in range(4):
-    torch.cuda.synchronize(); t = time.perf_counter(); hp.copy_(d, non_blocking=True); torch.cuda.synchronize(); ts.append(time.perf_counter() - t)
-print(f"D2H 1.02 GB pinned: {min(ts)*1e3:.1f} ms -> {1.024/min(ts):.1f} GB/s")
+t, _ = best(lambda: hp.copy_(d, non_blocking=True))
+print(f"D2H 1.02 GB pinned: {t*1e3:.1f} ms -> {1.024/t:.1f} GB/s")
+pk = torch.empty((100000, 6144), dtype=torch.uint8, pin_memory=True)
+res = np.empty((100000, 1280), np.float64)
+for th in (1, 4, 8, 16):
+    t, _ = best(lambda: model.engine.lib.range_host_unpack(pk.data_ptr(), 100000, res.ctypes.data, th), reps=3)
+    print(f"host unpack 100k rows, {th} threads: {t*1e3:.1f} ms = {0.1/t:.2f} M rows/s")

@@ -4,7 +4,8 @@ import os, sys
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
 from argparse import Namespace
-from oracle import range_oracle as O
+from range_b200 import synthetic as O          # seeded input generators
+from range_b200.utils import rad_to_cart
 from range_b200.range import LocationEncoder
 dev = "cuda:0"
 H = int(os.environ.get("RASTER_H", 384)); W = 2 * H          # 294 912 points = 3 chunks of 98 304
