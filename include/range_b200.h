@@ -135,6 +135,11 @@ int range_encode(range_ctx* ctx, int64_t N, const double* lonlat, double* q64, v
 size_t range_raster_tables_bytes(range_ctx* ctx, int64_t n_lat, int64_t n_lon);
 int range_raster_tables(range_ctx* ctx, int64_t n_lat, const double* lat, int64_t n_lon, const double* lon,
                         void* tables, size_t bytes, void* stream);
+/* index and coordinate rows of the raster points p0 + (perm ? perm[n] : n), n < N (point p = i * n_lon + j, lat-major like
+ * coord_grid): ij (N,2) int32 for range_encode_raster and / or lonlat (N,2) fp64 for range_sort_queries (either may be
+ * NULL) - the host builds neither list.  perm (from range_sort_queries on a chunk's coordinates) is chunk-local. */
+int range_raster_points(range_ctx* ctx, int64_t n_lat, int64_t n_lon, const void* tables, int64_t p0, int64_t N,
+                        const int32_t* perm, int32_t* ij, double* lonlat, void* stream);
 int range_encode_raster(range_ctx* ctx, int64_t n_lat, int64_t n_lon, const void* tables, int64_t N,
                         const int32_t* ij, double* lonlat, double* q64, void* q16, float* qxyz, void* workspace,
                         size_t workspace_bytes, void* stream);

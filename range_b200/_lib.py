@@ -40,6 +40,8 @@ PROTOTYPES = {
                              c_void_p]),
     "range_raster_tables_bytes": (c_size_t, [c_void_p, c_int64, c_int64]),
     "range_raster_tables": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "range_raster_points": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p,
+                                    c_void_p]),
     "range_encode_raster": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
                                     c_void_p, c_void_p, c_size_t, c_void_p]),
     "range_retrieve_workspace_bytes": (c_size_t, [c_void_p, c_int64]),

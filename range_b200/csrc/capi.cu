@@ -570,6 +570,21 @@ int range_raster_tables(range_ctx* c, int64_t n_lat, const double* lat, int64_t 
   return RANGE_OK;
 }
 
+int range_raster_points(range_ctx* c, int64_t n_lat, int64_t n_lon, const void* tables, int64_t p0, int64_t N,
+                        const int32_t* perm, int32_t* ij, double* lonlat, void* stream) {
+  int r = raster_supported(c);
+  if (r) return r;
+  if (n_lat <= 0 || n_lon <= 0 || !tables || N <= 0 || N > (int64_t(1) << 30) || p0 < 0 || (!ij && !lonlat))
+    return fail(RANGE_ERR_INVALID, "bad arguments");
+  if (p0 + N > n_lat * n_lon) return fail(RANGE_ERR_INVALID, "points [%lld, %lld) outside the %lld x %lld raster", (long long)p0,
+                                          (long long)(p0 + N), (long long)n_lat, (long long)n_lon);
+  void* buf = reinterpret_cast<void*>(align_up(reinterpret_cast<size_t>(const_cast<void*>(tables)), 256));
+  const RasterTables t = raster_tables_layout(c->sh.L, int(n_lat), int(n_lon), buf);
+  CUDA_TRY(launch_raster_points(t, p0, int(N), perm, ij, lonlat, cudaStream_t(stream)));
+  g_launches += 1;
+  return RANGE_OK;
+}
+
 int range_encode_raster(range_ctx* c, int64_t n_lat, int64_t n_lon, const void* tables, int64_t N, const int32_t* ij,
                         double* lonlat, double* q64, void* q16, float* qxyz, void* workspace, size_t workspace_bytes,
                         void* stream) {

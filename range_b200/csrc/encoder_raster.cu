@@ -85,6 +85,23 @@ __global__ void raster_feature_map_kernel(int L, int* __restrict__ fmap) {
   }
 }
 
+// raster point p = i * W + j (lat-major, like coord_grid): its (latitude, longitude) indices and its coordinates, for the
+// points p0 + (perm ? perm[n] : n) - the host never builds index or coordinate lists (range_raster_points)
+__global__ void __launch_bounds__(256)
+raster_points_kernel(long long p0, int N, const int* __restrict__ perm, int H, int W, const double* __restrict__ lat,
+                     const double* __restrict__ lon, int2* __restrict__ ij, double2* __restrict__ lonlat) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const long long p = p0 + (perm ? perm[n] : n);
+  const int i = int(p / W), j = int(p - (long long)i * W);
+  if (ij) ij[n] = make_int2(i, j);
+  if (lonlat) {
+    const bool inside = p >= 0 && i < H;
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    lonlat[n] = inside ? make_double2(lon[j], lat[i]) : make_double2(nan, nan);
+  }
+}
+
 constexpr int kCombineWarps = 8;
 __global__ void __launch_bounds__(kCombineWarps * 32)
 raster_combine_kernel(const int2* __restrict__ ij, int N, int L, int H, int W, const double* __restrict__ lat,
@@ -165,6 +182,14 @@ cudaError_t launch_raster_tables(const ShTable& sh, const double* lat, const dou
   raster_lat_kernel<<<(t.H + 63) / 64, 64, 0, s>>>(t.lat, t.H, sh.L, sh.pref, sh.off, sh.coef, sh.par, t.leg);
   raster_lon_kernel<<<(t.W * sh.L + 255) / 256, 256, 0, s>>>(t.lon, t.W, sh.L, reinterpret_cast<double2*>(t.trig));
   raster_feature_map_kernel<<<4, 256, 0, s>>>(sh.L, t.fmap);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_raster_points(const RasterTables& t, long long p0, int N, const int32_t* perm, int32_t* ij,
+                                 double* lonlat, cudaStream_t s) {
+  if (N <= 0) return cudaSuccess;
+  raster_points_kernel<<<(N + 255) / 256, 256, 0, s>>>(p0, N, perm, t.H, t.W, t.lat, t.lon, reinterpret_cast<int2*>(ij),
+                                                      reinterpret_cast<double2*>(lonlat));
   return cudaGetLastError();
 }
 

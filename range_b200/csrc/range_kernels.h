@@ -54,6 +54,9 @@ size_t raster_tables_bytes(int L, int H, int W);
 RasterTables raster_tables_layout(int L, int H, int W, void* buf);     // buf 256-byte aligned
 cudaError_t launch_raster_tables(const ShTable& sh, const double* lat, const double* lon, const RasterTables& t,
                                  cudaStream_t s);
+// raster points p0 + (perm ? perm[n] : n), n < N (point p = i * W + j): ij (N,2) and / or lonlat (N,2), either may be null
+cudaError_t launch_raster_points(const RasterTables& t, long long p0, int N, const int32_t* perm, int32_t* ij,
+                                 double* lonlat, cudaStream_t s);
 // ij (N,2) int32 = (latitude index, longitude index) -> features hi/lo fp16 [N][L*L], lonlat (N,2) fp64
 cudaError_t launch_raster_combine(const ShTable& sh, const RasterTables& t, const int32_t* ij, int N, void* Yh, void* Yl,
                                   double* lonlat, cudaStream_t s);

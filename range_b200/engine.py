@@ -203,6 +203,16 @@ class RangeEngine:
                                                     _stream()))
         return dict(H=H, W=W, buf=buf, lon=lon, lat=lat)
 
+    def raster_points(self, tables, p0, n, perm=None, ij=None, lonlat=None):
+        """rows of the raster points p0 + (perm[k] if perm is given else k), k < n, written into the given tensors:
+        ij (n,2) int32 (latitude index, longitude index) and / or lonlat (n,2) fp64 - built on the device"""
+        with torch.cuda.device(self.index):
+            _lib.check(self.lib.range_raster_points(
+                self.ctx, tables["H"], tables["W"], _ptr(tables["buf"]), int(p0), int(n),
+                c_void_p(None) if perm is None else _ptr(perm), c_void_p(None) if ij is None else _ptr(ij),
+                c_void_p(None) if lonlat is None else _ptr(lonlat), _stream()))
+        return ij, lonlat
+
     def encode_raster(self, tables, ij):
         """ij (N,2) int32 = (latitude index, longitude index) -> (lonlat (N,2) fp64, q64, q16, qxyz); bit-identical to
         encode() on those coordinates, without re-evaluating the harmonics' latitude / longitude factors per point."""

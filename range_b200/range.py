@@ -226,11 +226,20 @@ class LocationEncoder(nn.Module):
         eng = self.engine
         tables = self.raster_tables(lon_axis, lat_axis) if tables is None else tables
         p0, p1 = (0, tables['H'] * tables['W']) if rows is None else rows
-        ij = self._raster_ij(tables['W'], p0, p1)
+        n = p1 - p0
         perm = None
-        if self._sorts():
-            _, perm = eng.sort_queries(self._raster_coords(tables, ij))
-            ij = ij[perm.long()]
+        if tables['buf'] is None:              # no separable evaluation: the per-point encoder on the materialised coordinates
+            ij = self._raster_ij(tables['W'], p0, p1)
+            if self._sorts():
+                _, perm = eng.sort_queries(self._raster_coords(tables, ij))
+                ij = ij[perm.long()]
+        else:                                  # index / coordinate rows come from the device (range_raster_points)
+            if self._sorts():
+                lonlat = torch.empty(n, 2, dtype=torch.float64, device=eng.device)
+                eng.raster_points(tables, p0, n, lonlat=lonlat)
+                _, perm = eng.sort_queries(lonlat)
+            ij = torch.empty(n, 2, dtype=torch.int32, device=eng.device)
+            eng.raster_points(tables, p0, n, perm=perm, ij=ij)
         q64, q16, qxyz = self._encode_raster(tables, ij)
         return self._retrieve_concat(q16, qxyz, q64, out, out_dtype, perm)
 
@@ -302,23 +311,37 @@ class LocationEncoder(nn.Module):
             i = 0
             for (s0, s1), cuts in zip(batches, plan):
                 sort_cuts = cuts if path != 'direct' else self._chunks(s1 - s0, chunk, self.tail)
-                ij = None
-                if raster is None:
-                    sub = dev_coords[s0:s1]
+                ij, perms = None, None
+                if raster is not None and raster['buf'] is not None:
+                    # dense raster: index / coordinate rows are produced on the device, chunk by chunk, straight into
+                    # one (n,2) index array in batched order
+                    n = s1 - s0
+                    ij = torch.empty(n, 2, dtype=torch.int32, device=eng.device)
+                    if self._sorts():
+                        lonlat = torch.empty(n, 2, dtype=torch.float64, device=eng.device)
+                        eng.raster_points(raster, s0, n, lonlat=lonlat)
+                        perms = []
+                        for lo, hi in sort_cuts:
+                            perms.append(eng.sort_queries(lonlat[lo:hi])[1])
+                            eng.raster_points(raster, s0 + lo, hi - lo, perm=perms[-1], ij=ij[lo:hi])
+                    else:
+                        eng.raster_points(raster, s0, n, ij=ij)
                 else:
-                    ij = self._raster_ij(raster['W'], s0, s1)
-                    sub = self._raster_coords(raster, ij)
-                perms = None
-                if self._sorts():
-                    # spatial batching chunk by chunk (a tile's 128 queries should be neighbours; the order of the
-                    # chunks does not matter)
-                    parts = [eng.sort_queries(sub[lo:hi]) for lo, hi in sort_cuts]
-                    sub = torch.cat([p[0] for p in parts]) if len(parts) > 1 else parts[0][0]
-                    perms = [p[1] for p in parts]
-                    if ij is not None:
-                        ij = torch.cat([ij[lo:hi][p.long()] for (lo, hi), p in zip(sort_cuts, perms)])
-                    if path == 'direct' and len(perms) > 1:      # one launch: chunk-local permutations -> one global one
-                        perms = [torch.cat([p + lo for (lo, _), p in zip(sort_cuts, perms)])]
+                    if raster is None:
+                        sub = dev_coords[s0:s1]
+                    else:
+                        ij = self._raster_ij(raster['W'], s0, s1)
+                        sub = self._raster_coords(raster, ij)
+                    if self._sorts():
+                        # spatial batching chunk by chunk (a tile's 128 queries should be neighbours; the order of the
+                        # chunks does not matter)
+                        parts = [eng.sort_queries(sub[lo:hi]) for lo, hi in sort_cuts]
+                        sub = torch.cat([p[0] for p in parts]) if len(parts) > 1 else parts[0][0]
+                        perms = [p[1] for p in parts]
+                        if ij is not None:
+                            ij = torch.cat([ij[lo:hi][p.long()] for (lo, hi), p in zip(sort_cuts, perms)])
+                if perms is not None and path == 'direct' and len(perms) > 1:      # one launch: chunk-local permutations -> one global one
+                    perms = [torch.cat([p + lo for (lo, _), p in zip(sort_cuts, perms)])]
                 q64, q16, qxyz = eng.encode(sub) if ij is None else self._encode_raster(raster, ij)
                 for c, (lo, hi) in enumerate(cuts):
                     perm = None if perms is None else perms[c]

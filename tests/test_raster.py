@@ -58,6 +58,15 @@ def test_raster_encoder_is_bit_identical():
     r64, r16, rxyz = eng.encode(coords)
     assert torch.isfinite(q64).all()
     assert torch.equal(q64, r64) and torch.equal(q16, r16) and torch.equal(qxyz, rxyz)
+    # index / coordinate rows built on the device (range_raster_points), whole raster and a permuted window of it
+    ij2 = torch.empty(H * W, 2, dtype=torch.int32, device=DEV)
+    ll2 = torch.empty(H * W, 2, dtype=torch.float64, device=DEV)
+    eng.raster_points(tables, 0, H * W, ij=ij2, lonlat=ll2)
+    assert torch.equal(ij2, ij) and torch.equal(ll2.cpu(), coords)
+    pw = torch.randperm(1500, generator=torch.Generator().manual_seed(1)).to(torch.int32).to(DEV)
+    ijw = torch.empty(1500, 2, dtype=torch.int32, device=DEV)
+    eng.raster_points(tables, 1000, 1500, perm=pw, ij=ijw)
+    assert torch.equal(ijw, ij[1000:2500][pw.long()])
     sel = torch.randperm(H * W, generator=torch.Generator().manual_seed(0))[:1000].to(DEV)      # any subset, any order
     s64 = eng.encode_raster(tables, ij[sel])[1]
     assert torch.equal(s64, r64[sel])
