@@ -1105,11 +1105,13 @@ cudaError_t launch_apply_pc(const RetrievalArgs& a, const CUtensorMap& tmP, cons
   attr[1].id = cudaLaunchAttributeCooperative;
   attr[1].val.cooperative = 1;
   cfg.attrs = attr;
-  // Every CTA must be resident (the roles wait on each other).  The grid is one CTA per SM and the capacity is checked
-  // here once; a plain cluster launch is used because the cooperative launch path measured 6 % slower (21.3 vs 20.0 ms)
-  // and profilers cannot replay it.  RANGE_PC_COOP=1 asks for the cooperative launch anyway.  If another kernel holds
-  // SMs for long, the bounded waits in the kernel trap (an error the caller sees) rather than hang.
-  static const bool coop = getenv("RANGE_PC_COOP") && atoi(getenv("RANGE_PC_COOP")) == 1;
+  // Every CTA must be resident (the roles wait on each other): the kernel is launched COOPERATIVELY, which either
+  // guarantees co-residency or fails with a clean launch error the caller sees (no spinning CTAs, no poisoned context).
+  // Round 1 measured the cooperative path 6 % slower; re-measured on the r2a build it is not (21.5 vs 22.1 ms, inside the
+  // +-1 ms run-to-run spread of this power-capped kernel).  RANGE_PC_COOP=0 selects the plain cluster launch (capacity
+  // checked below) for profilers that cannot replay cooperative launches; the kernel's bounded waits still trap rather
+  // than hang if another kernel then holds SMs for long.
+  static const bool coop = !(getenv("RANGE_PC_COOP") && atoi(getenv("RANGE_PC_COOP")) == 0);
   cfg.numAttrs = 1;
   // capacity per (device, kernel instantiation): the answer depends on both
   static int resident_cache[64][2];
@@ -1129,12 +1131,45 @@ cudaError_t launch_apply_pc(const RetrievalArgs& a, const CUtensorMap& tmP, cons
     return cudaErrorCooperativeLaunchTooLarge;
   }
   cfg.numAttrs = coop ? 2 : 1;
+  // The consumers' window scratch (25 MB, read and rewritten every 128 tiles) competes for the L2 with the database
+  // stream, the P' ring and the result rows; evict_last hints alone left 4.8 GB per launch going to DRAM (r1n profile).
+  // A persisting-L2 access window over the scratch keeps it resident for this launch (device limit raised once per
+  // device; the stream attribute is restored afterwards).  RANGE_PC_PERSIST=0 disables.
+  static const bool persist = !(getenv("RANGE_PC_PERSIST") && atoi(getenv("RANGE_PC_PERSIST")) == 0);
+  bool window_set = false;
+  if (persist && scratch) {
+    static bool limit_set[64] = {};
+    if (dev >= 0 && dev < 64 && !limit_set[dev]) {
+      size_t cur = 0;
+      const size_t want = apply_pc_scratch_bytes(sm_count) + (size_t(2) << 20);
+      if (cudaDeviceGetLimit(&cur, cudaLimitPersistingL2CacheSize) == cudaSuccess && cur < want)
+        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+      limit_set[dev] = true;
+      (void)cudaGetLastError();
+    }
+    cudaStreamAttrValue av{};
+    av.accessPolicyWindow.base_ptr = scratch;
+    av.accessPolicyWindow.num_bytes = apply_pc_scratch_bytes(sm_count);
+    av.accessPolicyWindow.hitRatio = 1.0f;
+    av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    window_set = cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &av) == cudaSuccess;
+    (void)cudaGetLastError();
+  }
+  auto clear_window = [&]() {
+    if (!window_set) return;
+    cudaStreamAttrValue av{};
+    av.accessPolicyWindow.num_bytes = 0;
+    cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &av);
+    (void)cudaGetLastError();
+  };
   e = cudaLaunchKernelEx(&cfg, kern, a.tmQ, a.tmK64, a.tmV128, tmP, a.db_xyz, reinterpret_cast<const float4*>(rowc),
                          a.N, a.M, a.a_sem, out, a.geo_mask, a.mask_words, reinterpret_cast<float*>(part),
                          reinterpret_cast<float4*>(scratch), reinterpret_cast<__half*>(ring),
                          reinterpret_cast<uint32_t*>(flags),
                          reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(flags) + pc_ring_flag_bytes(sm_count)), plan, dbg,
                          g_prof_buffer);
+  clear_window();
   if (e != cudaSuccess) {
     fprintf(stderr, "range_b200: producer/consumer apply launch failed (%s); grid %u smem %d\n", cudaGetErrorString(e),
             cfg.gridDim.x, kDynamicSmem);

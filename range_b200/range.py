@@ -16,9 +16,11 @@ from .checkpoint import load_satclip_location_encoder
 from .database import DeviceDatabase, open_npz
 from .engine import RangeEngine
 
-# four rounds of the producer/consumer apply kernel on 148 SMs (24 units x 2 query tiles of 128 per round)
-DEFAULT_CHUNK = 4 * 24 * 256
-DEFAULT_TAIL = 24 * 256          # one round: the unoverlapped last copy is 63 MB instead of 252 MB
+# one round of the producer/consumer apply kernel on 148 SMs: 24 units x 2 query tiles of 128
+ROUND_ROWS = 24 * 256
+DEFAULT_CHUNK = 8 * ROUND_ROWS   # largest piece of model(locs)'s pipeline (two device buffers of chunk x 10 KB)
+DEFAULT_TAIL = 2048              # the last piece: its device->host copy (20 MB) is the only one not overlapped
+DEFAULT_TAPER = 0.5
 
 
 class LocationEncoder(nn.Module):
@@ -61,10 +63,11 @@ class LocationEncoder(nn.Module):
         self.chunk = int(getattr(args, 'chunk', DEFAULT_CHUNK))
         self.tail = max(1, min(self.chunk, int(getattr(args, 'tail', DEFAULT_TAIL))))
         self.super_batch = max(self.chunk, int(getattr(args, 'super_batch', 1 << 20)) // self.chunk * self.chunk)
+        self.taper = float(getattr(args, 'taper', DEFAULT_TAPER))
         # how model(locs) hands the (N,1280) float64 result to the host (see _forward_host)
         self.host_path = getattr(args, 'host_path', 'auto')
-        if self.host_path not in ('auto', 'copy', 'direct', 'packed'):
-            raise ValueError(f"host_path={self.host_path!r}: expected 'auto', 'copy', 'direct' or 'packed'")
+        if self.host_path not in ('auto', 'copy', 'packed'):
+            raise ValueError(f"host_path={self.host_path!r}: expected 'auto', 'copy' or 'packed'")
         self.pinned_limit = int(getattr(args, 'pinned_limit', 8 << 30))       # largest page-locked result, bytes
         local_ranks = max(1, int(os.environ.get('LOCAL_WORLD_SIZE', '1')))      # torchrun: ranks sharing this host
         self.host_threads = int(getattr(args, 'host_threads', 0)) or max(1, min(16, (os.cpu_count() or 1) // local_ranks))
@@ -132,27 +135,37 @@ class LocationEncoder(nn.Module):
                 for b in betas]
 
     @staticmethod
-    def _chunks(N, chunk, tail):
-        """[lo, hi) slices: full chunks, half chunks over the last two chunks' worth of rows, and a short last piece.
-        Every chunk's device->host copy overlaps the next chunk's computation except the last one, so the pieces get
-        smaller towards the end (half a chunk is still two full rounds of the producer/consumer apply kernel)."""
+    def _chunks(N, chunk, tail, taper=DEFAULT_TAPER):
+        """[lo, hi) pieces of one super-batch.  Every piece's device->host copy overlaps the computation of the pieces
+        after it, except the last one's: full chunks while more than two chunks' worth of rows remain, then every piece
+        takes the fraction `taper` of what is left (whole rounds of the producer/consumer apply kernel - 24 units x 256
+        rows on 148 SMs - while it is at least one round, else whole 128-row tiles), down to a last piece of about
+        `tail` rows.  taper <= 0.64 keeps a piece's copy (5.6 M rows/s over PCIe) shorter than the computation that
+        follows it (3.2 M rows/s)."""
         cuts, lo = [], 0
-        half = max(tail, chunk // 2)
+        tail = max(1, tail)
         while N - lo > 2 * chunk:
             cuts.append((lo, lo + chunk)); lo += chunk
-        while N - lo > half + tail:
-            cuts.append((lo, lo + half)); lo += half
-        if N - lo > 2 * tail:
-            cuts.append((lo, N - tail)); lo = N - tail
+        while N - lo > tail + tail // 2:
+            rem = N - lo
+            piece = int(rem * taper)
+            if piece >= ROUND_ROWS:
+                piece = piece // ROUND_ROWS * ROUND_ROWS
+            elif piece >= 128:
+                piece = piece // 128 * 128
+            piece = min(chunk, max(piece, min(tail, rem)))
+            if rem - piece < max(1, tail // 2):          # do not leave a sliver behind
+                break
+            cuts.append((lo, lo + piece)); lo += piece
         cuts.append((lo, N))
         return cuts
 
     @classmethod
-    def _pieces(cls, N, chunk, tail, super_batch, whole=False):
+    def _pieces(cls, N, chunk, tail, super_batch, taper=DEFAULT_TAPER):
         """(super-batches [s0, s1), their pieces [lo, hi) relative to s0, rows of the largest piece).  Buffers are sized
         for the largest piece of ANY super-batch: a short last super-batch can end in a longer piece than the first."""
         batches = [(s0, min(N, s0 + super_batch)) for s0 in range(0, N, super_batch)]
-        plan = [[(0, s1 - s0)] if whole else cls._chunks(s1 - s0, chunk, tail) for s0, s1 in batches]
+        plan = [cls._chunks(s1 - s0, chunk, tail, taper) for s0, s1 in batches]
         rows = max(hi - lo for cuts in plan for lo, hi in cuts)
         return batches, plan, rows
 
@@ -250,23 +263,25 @@ class LocationEncoder(nn.Module):
         return self._forward_host(tables['H'] * tables['W'], raster=tables)
 
     def _forward_host(self, N, coords=None, raster=None, result=None):
-        """model(locs) -> numpy float64 (N,1280) (range/range.py:222,240).  Three ways to hand the rows to the host:
+        """model(locs) -> numpy float64 (N,1280) (range/range.py:222,240).  Two ways to hand the rows to the host:
 
-        'direct'  the apply kernel's epilogue stores the float64 rows straight into the page-locked result (mapped
-                  host memory): they cross PCIe while the tensor cores work on the next tiles, one launch per
-                  super-batch, nothing left to copy at the end.  Result page-locked: N * 10 KB.
-        'copy'    chunk by chunk into device buffers; every chunk's rows travel to the page-locked result on a copy
-                  stream while the next chunk is computed.
-        'packed'  as 'copy', but the rows cross PCIe packed (6 KB: fp32 feature columns + fp64 location columns,
-                  RANGE_OUT_PACKED) into small page-locked staging buffers and are widened into an ordinary (pageable)
-                  numpy array by a host thread team (range_host_unpack): bounded page-locked memory for any N.
-        'auto'    'direct' while the result fits `pinned_limit` (8 GB), else 'packed'."""
+        'copy'    chunk by chunk into device buffers; every chunk's float64 rows travel to the page-locked result on a
+                  copy stream while the next chunk is computed (pieces get smaller towards the end: only the last
+                  piece's copy is exposed).  Result page-locked: N * 10 KB.
+        'packed'  the rows cross PCIe packed (6 KB: fp32 feature columns + fp64 location columns, RANGE_OUT_PACKED)
+                  into small page-locked staging buffers and are widened into an ordinary (pageable) numpy array - or
+                  the caller's array, embed_into - by a host thread team (range_host_unpack): bounded page-locked
+                  memory for any N, 40 % fewer PCIe bytes, but the host cores must keep up (measured on the 16-core
+                  1-GPU box: 6.3 M rows/s with 16 threads, 2.2 M queries/s end to end against 2.9 M for 'copy').
+        'auto'    'copy' while the result fits `pinned_limit` (8 GB), else 'packed'.
+        (Measured and dropped: letting the apply kernel's epilogue store straight into the mapped page-locked result -
+        stores from the SMs to host memory run at ~6 GB/s and stall the consumers: 170 ms per 100 000 queries.)"""
         eng = self.engine
         path = self.host_path
         if result is not None:
             path = 'packed'
         elif path == 'auto':
-            path = 'direct' if N * 10240 <= self.pinned_limit else 'packed'
+            path = 'copy' if N * 10240 <= self.pinned_limit else 'packed'
         if self.sharded is not None:            # collective: distributed.py chunks (every rank must take the same steps)
             dev = coords.to(eng.device, torch.float64, non_blocking=True)
             res = self.embed(dev, out_dtype=torch.float64)
@@ -289,7 +304,7 @@ class LocationEncoder(nn.Module):
             if self._copy_stream is None:
                 self._copy_stream = torch.cuda.Stream(device=eng.device)
             chunk = min(self.chunk, N)
-            batches, plan, rows = self._pieces(N, chunk, self.tail, self.super_batch, whole=path == 'direct')
+            batches, plan, rows = self._pieces(N, chunk, self.tail, self.super_batch, self.taper)
             n_pieces = sum(len(cuts) for cuts in plan)
             if path == 'copy':
                 bufs = [torch.empty(rows, 1280, dtype=torch.float64, device=eng.device) for _ in range(min(2, n_pieces))]
@@ -298,7 +313,7 @@ class LocationEncoder(nn.Module):
                 bufs = [torch.empty(rows, 6144, dtype=torch.uint8, device=eng.device) for _ in range(depth)]
                 stage = [torch.empty(rows, 6144, dtype=torch.uint8, pin_memory=True) for _ in range(depth)]
                 landed = [None] * depth          # (event, result rows, staging rows) of the piece in each slot
-            freed = [None] * (len(bufs) if path != 'direct' else 0)
+            freed = [None] * len(bufs)
             cur = torch.cuda.current_stream()
 
             def unpack(slot):
@@ -310,7 +325,7 @@ class LocationEncoder(nn.Module):
 
             i = 0
             for (s0, s1), cuts in zip(batches, plan):
-                sort_cuts = cuts if path != 'direct' else self._chunks(s1 - s0, chunk, self.tail)
+                sort_cuts = cuts
                 ij, perms = None, None
                 if raster is not None and raster['buf'] is not None:
                     # dense raster: index / coordinate rows are produced on the device, chunk by chunk, straight into
@@ -340,14 +355,9 @@ class LocationEncoder(nn.Module):
                         perms = [p[1] for p in parts]
                         if ij is not None:
                             ij = torch.cat([ij[lo:hi][p.long()] for (lo, hi), p in zip(sort_cuts, perms)])
-                if perms is not None and path == 'direct' and len(perms) > 1:      # one launch: chunk-local permutations -> one global one
-                    perms = [torch.cat([p + lo for (lo, _), p in zip(sort_cuts, perms)])]
                 q64, q16, qxyz = eng.encode(sub) if ij is None else self._encode_raster(raster, ij)
                 for c, (lo, hi) in enumerate(cuts):
                     perm = None if perms is None else perms[c]
-                    if path == 'direct':
-                        self._retrieve_concat(q16, qxyz, q64, host[s0:s1], torch.float64, perm)
-                        continue
                     k = i % len(bufs)
                     i += 1
                     if path == 'packed' and landed[k] is not None:
@@ -372,10 +382,8 @@ class LocationEncoder(nn.Module):
             if path == 'packed':
                 for k in sorted((k for k in range(len(bufs)) if landed[k] is not None), key=lambda k: landed[k][1]):
                     unpack(k)
-            elif path == 'copy':
-                self._copy_stream.synchronize()
             else:
-                cur.synchronize()
+                self._copy_stream.synchronize()
         return result                                                                     # range.py:222,240
 
 

@@ -110,13 +110,19 @@ def test_synthetic_shards_tile_the_database():
 def test_forward_chunking_covers_every_row():
     from range_b200.range import LocationEncoder
     for N in (1, 5, 6144, 6145, 12288, 13000, 24576, 24577, 100000, 1 << 20):
-        cuts = LocationEncoder._chunks(N, 24576, 6144)
-        assert cuts[0][0] == 0 and cuts[-1][1] == N and all(a[1] == b[0] for a, b in zip(cuts, cuts[1:]))
-        assert all(0 < hi - lo <= 24576 for lo, hi in cuts)
-        assert cuts[-1][1] - cuts[-1][0] <= 12288            # the unoverlapped last copy stays short
+        for taper in (0.5, 0.6):
+            cuts = LocationEncoder._chunks(N, 24576, 6144, taper)
+            assert cuts[0][0] == 0 and cuts[-1][1] == N and all(a[1] == b[0] for a, b in zip(cuts, cuts[1:]))
+            assert all(0 < hi - lo <= 24576 for lo, hi in cuts)
+            assert cuts[-1][1] - cuts[-1][0] <= 6144 + 3072          # the unoverlapped last copy stays short
+            sizes = [hi - lo for lo, hi in cuts]
+            assert all(a >= b or b <= 6144 + 3072 for a, b in zip(sizes, sizes[1:]))     # pieces shrink towards the end
+    cuts = LocationEncoder._chunks(100_000, 49152, 2048)
+    assert [hi - lo for lo, hi in cuts] == [49152, 24576, 12288, 6144, 3840, 2048, 1952]
     for N, chunk, tail in [(64, 24, 24), (64, 24, 5), (7, 3, 3), (100, 1, 1)]:          # degenerate settings still tile [0, N)
         cuts = LocationEncoder._chunks(N, chunk, tail)
         assert cuts[0][0] == 0 and cuts[-1][1] == N and all(a[1] == b[0] for a, b in zip(cuts, cuts[1:]))
+        assert all(0 < hi - lo <= max(chunk, tail + tail // 2) for lo, hi in cuts)
 
 
 def test_open_npz_memory_maps_the_reference_file_format(tmp_path):
@@ -207,8 +213,12 @@ def test_forward_buffers_fit_every_piece():
         for (s0, s1), cuts in zip(batches, plan):
             assert cuts[0][0] == 0 and cuts[-1][1] == s1 - s0 and all(a[1] == b[0] for a, b in zip(cuts, cuts[1:]))
             assert all(0 < hi - lo <= rows for lo, hi in cuts)
-        whole = LocationEncoder._pieces(N, min(chunk, N), tail, sb, whole=True)
-        assert all(cuts == [(0, s1 - s0)] for (s0, s1), cuts in zip(whole[0], whole[1]))
-    # the case the first-batch-only sizing got wrong: first super-batch's largest piece 10240, the remainder's 12288
-    _, plan, rows = LocationEncoder._pieces(16384 + 12288, 8192, 6144, 16384)
-    assert max(hi - lo for lo, hi in plan[0]) < max(hi - lo for lo, hi in plan[1]) == rows
+    # buffers must cover the largest piece of ANY super-batch, not of the first one: search the small settings for a
+    # case where a later (shorter) super-batch ends in a longer piece than the first, and check it is covered
+    found = 0
+    for N in range(200, 1200, 7):
+        for chunk, tail, sb in [(64, 60, 128), (96, 90, 192), (50, 45, 100)]:
+            _, plan, rows = LocationEncoder._pieces(N, chunk, tail, sb)
+            assert rows == max(hi - lo for cuts in plan for lo, hi in cuts)
+            found += max(hi - lo for lo, hi in plan[0]) < rows
+    assert found > 0

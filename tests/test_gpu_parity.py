@@ -329,7 +329,9 @@ def test_beta_sweep_and_database_cache(tmp_path, sh_entries):
         assert torch.equal(got[:, 1024:], one[:, 1024:]), beta
         assert rel_rows(got[:, :1024].cpu().numpy(), one[:, :1024].cpu().numpy()).max() <= 5e-4, beta
         ref = O.RangeOracle("RANGE+", ws, sh_entries, db, beta=beta, exact=True)(c.cpu().numpy())
-        assert rel_rows(got[:, :1024].cpu().numpy(), ref[:, :1024]).max() <= 1e-3, beta
+        # the iid database is the worst case of the purely semantic softmax (flat weights over zero-mean values: the
+        # fp16 rounding of q and K shows undamped): 2e-3 there, 1e-3 as soon as the geographic term takes part
+        assert rel_rows(got[:, :1024].cpu().numpy(), ref[:, :1024]).max() <= (2e-3 if beta == 1.0 else 1e-3), beta
     fresh = mk(0.25).embed(c)
     assert torch.equal(fresh, mk(0.25, db_cache=cache).embed(c))
 
@@ -406,8 +408,9 @@ def test_m_sharded_routed_merge_emulated(slab, sh_entries):
 
 
 def test_host_paths_agree(sh_entries):
-    """model(locs) hands the rows to the host in three ways (range.py:_forward_host): stored straight into the
-    page-locked result by the kernels, copied chunk by chunk, or packed (fp32 features) + widened on the host"""
+    """model(locs) hands the rows to the host in two ways (range.py:_forward_host): float64 rows copied chunk by chunk
+    into the page-locked result, or packed rows (fp32 features) widened on the host - also into the caller's own array
+    (embed_into, what save.embed_to_npy uses on a memory-mapped .npy)"""
     from argparse import Namespace
     from range_b200.range import LocationEncoder
     db = O.synthetic_db(3000, seed=6, kind="iid")
@@ -415,17 +418,24 @@ def test_host_paths_agree(sh_entries):
     enc = dict(L=40, dims=[1600, 64, 64, 256], weights=ws)
     c = torch.tensor(O.area_uniform(30_000, np.random.default_rng(7)))
     outs = {}
-    for path in ("copy", "packed", "direct"):
+    for path in ("copy", "packed"):
         m = LocationEncoder(Namespace(location_model_name="RANGE+", pretrained_path=enc, device=DEV, range_db=db, beta=0.5,
                                       host_path=path, chunk=12288, tail=6144, super_batch=24576))
         outs[path] = m(c)
         assert outs[path].dtype == np.float64 and outs[path].shape == (30_000, 1280)
     assert np.array_equal(outs["copy"], outs["packed"])              # same kernels; the widening is exact
-    assert np.array_equal(outs["copy"][:, 1024:], outs["direct"][:, 1024:])
-    assert rel_rows(outs["direct"][:, :1024], outs["copy"][:, :1024]).max() <= 5e-4
     sub = np.linspace(0, 29_999, 100).astype(np.int64)
     ref = O.RangeOracle("RANGE+", ws, sh_entries, db, beta=0.5, exact=True)(c.numpy()[sub])
-    assert rel_rows(outs["direct"][sub, :1024], ref[:, :1024]).max() <= 1e-3
+    assert rel_rows(outs["copy"][sub, :1024], ref[:, :1024]).max() <= 1e-3
+    # the streaming writer of save.py on the real model: rows land in a memory-mapped .npy
+    import os
+    import tempfile
+    from range_b200.save import embed_to_npy
+    with tempfile.TemporaryDirectory() as d:
+        mm = embed_to_npy(m, c.numpy(), os.path.join(d, "emb.npy"), batch=20_000)
+        assert mm.shape == (30_000, 1280) and np.array_equal(np.asarray(mm), outs["copy"])
+        del mm
+        assert np.array_equal(np.load(os.path.join(d, "emb.npy"), mmap_mode="r")[:100], outs["copy"][:100])
 
 
 def test_closed_form_harmonics_vs_reference(golden):

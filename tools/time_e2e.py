@@ -1,4 +1,5 @@
-"""where does model(locs) spend its time? (host-pinned in -> numpy float64 out), per host path of range.py:_forward_host"""
+"""where does model(locs) spend its time? (host-pinned in -> numpy float64 out), per host path and piece plan of
+range.py:_forward_host"""
 import os, sys, time
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
@@ -19,14 +20,18 @@ def best(fn, reps=5):
 
 
 model = None
-for path in os.environ.get("PATHS", "direct,copy,packed").split(","):
+# host path x (chunk, tail, taper) of the pipelined pieces
+settings = [("copy", 49152, 2048, 0.5), ("copy", 49152, 2048, 0.6), ("copy", 24576, 6144, 0.5), ("copy", 61440, 2048, 0.6),
+            ("copy", 49152, 1024, 0.5), ("copy", 49152, 4096, 0.5), ("packed", 49152, 2048, 0.5)]
+for path, chunk, tail, taper in settings:
     del model
     model = LocationEncoder(Namespace(location_model_name="RANGE+", pretrained_path=enc, device="cuda:0", range_db=db, beta=0.5,
-                                      host_path=path))
+                                      host_path=path, chunk=chunk, tail=tail, taper=taper))
     for _ in range(3): model(h)
     t, ts = best(lambda: model(h))
-    print(f"model(h) host_path={path}: {t*1e3:.1f} ms = {len(coords)/t/1e6:.2f} M q/s (runs {[round(x*1e3,1) for x in ts]}; "
-          f"host threads {model.host_threads})")
+    pieces = [hi - lo for lo, hi in model._chunks(len(coords), chunk, tail, taper)]
+    print(f"model(h) host_path={path} chunk={chunk} tail={tail} taper={taper}: {t*1e3:.1f} ms = {len(coords)/t/1e6:.2f} M q/s "
+          f"(runs {[round(x*1e3,1) for x in ts]}; pieces {pieces}; host threads {model.host_threads})")
 t, ts = best(lambda: model.embed(dc, out_dtype=torch.float64))
 print(f"embed device fp64: {t*1e3:.1f} ms")
 t, ts = best(lambda: model.embed(dc, out_dtype=torch.float32))
