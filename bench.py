@@ -287,7 +287,7 @@ def run_m_sharded(world, rank, dev, weights, steps, warmup, barrier, sizes):
                 ns = Namespace(location_model_name="RANGE+", pretrained_path=enc, device=dev, range_db=ddb, beta=BETA)
                 if shard is not None:
                     ns.db_shard, ns.db_group = shard, None
-                model = LocationEncoder(ns, device_database=ddb)
+                model = LocationEncoder(ns)
             res = torch.empty(n_rank, 1280, dtype=torch.float32, device=dev)
             ms = time_steps(lambda: model.embed(coords, out=res), k, min(warmup, 2), barrier)
             t = torch.tensor([ms], device=dev, dtype=torch.float64)
