@@ -433,9 +433,12 @@ def test_host_paths_agree(sh_entries):
     from range_b200.save import embed_to_npy
     with tempfile.TemporaryDirectory() as d:
         mm = embed_to_npy(m, c.numpy(), os.path.join(d, "emb.npy"), batch=20_000)
-        assert mm.shape == (30_000, 1280) and np.array_equal(np.asarray(mm), outs["copy"])
+        got = np.asarray(mm)
+        # other batch boundaries -> other query tiles: the fp16 rounding of the weights differs in the last bit
+        assert mm.shape == (30_000, 1280) and np.array_equal(got[:, 1024:], outs["copy"][:, 1024:])
+        assert rel_rows(got[:, :1024], outs["copy"][:, :1024]).max() <= 5e-4
         del mm
-        assert np.array_equal(np.load(os.path.join(d, "emb.npy"), mmap_mode="r")[:100], outs["copy"][:100])
+        assert np.array_equal(np.load(os.path.join(d, "emb.npy"), mmap_mode="r")[:100], got[:100])
 
 
 def test_closed_form_harmonics_vs_reference(golden):
