@@ -407,9 +407,12 @@ def main():
     for _ in range(3):
         res = model(h_coords)          # held across iterations like the timed loop (two pinned result buffers)
     barrier()
+    e2e_steps = []
     w0 = time.perf_counter()
     for _ in range(args.steps):
+        w1 = time.perf_counter()
         res = model(h_coords)
+        e2e_steps.append((time.perf_counter() - w1) * 1e3)
     barrier()
     e2e_s = (time.perf_counter() - w0)
     assert res.shape == (N_QUERIES, 1280) and res.dtype == np.float64
@@ -458,7 +461,7 @@ def main():
                                               "launch_ms": seg[1] + seg[2]}},
             "e2e": {"value": world * N_QUERIES * args.steps / (e2e_ms * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": N_QUERIES * 16, "d2h_bytes_per_step": N_QUERIES * 1280 * 8,
-                    "host_path": host_path,
+                    "host_path": host_path, "ms_per_call_rank0": [round(x, 2) for x in e2e_steps],
                     "api": "range_b200.load_model(...)(locs) -> numpy float64 (N,1280)"},
             "gpu_launches": int(launches), "clocks": clocks.summary()}
         if sharded is not None:
