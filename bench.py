@@ -96,6 +96,8 @@ class ClockSampler:
         self.t1 = time.time()
 
     def __enter__(self):
+        if os.environ.get("RANGE_BENCH_NO_SMI") == "1":      # developer switch: run without the sampler process
+            return self
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "50"],
