@@ -18,8 +18,8 @@ from .engine import RangeEngine
 
 # one round of the producer/consumer apply kernel on 148 SMs: 24 units x 2 query tiles of 128
 ROUND_ROWS = 24 * 256
-DEFAULT_CHUNK = 8 * ROUND_ROWS   # largest piece of model(locs)'s pipeline (two device buffers of chunk x 10 KB)
-DEFAULT_TAIL = 2048              # the last piece: its device->host copy (20 MB) is the only one not overlapped
+DEFAULT_CHUNK = 4 * ROUND_ROWS   # largest piece of model(locs)'s pipeline (two device buffers of chunk x 10 KB)
+DEFAULT_TAIL = ROUND_ROWS        # the last piece: its device->host copy (63-94 MB) is the only one not overlapped
 DEFAULT_TAPER = 0.5
 
 

@@ -21,17 +21,19 @@ def best(fn, reps=5):
 
 model = None
 # host path x (chunk, tail, taper) of the pipelined pieces
-settings = [("copy", 49152, 2048, 0.5), ("copy", 49152, 2048, 0.6), ("copy", 24576, 6144, 0.5), ("copy", 61440, 2048, 0.6),
-            ("copy", 49152, 1024, 0.5), ("copy", 49152, 4096, 0.5), ("packed", 49152, 2048, 0.5)]
+settings = [("copy", 24576, 6144, 0.5), ("copy", 24576, 2048, 0.5), ("copy", 24576, 3072, 0.5), ("copy", 36864, 3072, 0.5),
+            ("copy", 24576, 3072, 0.6), ("copy", 18432, 3072, 0.5), ("copy", 24576, 6144, 0.5), ("packed", 24576, 6144, 0.5)]
+if os.environ.get("SETTINGS"):       # "path:chunk:tail:taper,..."
+    settings = [(a, int(b), int(c), float(d)) for a, b, c, d in (x.split(":") for x in os.environ["SETTINGS"].split(","))]
 for path, chunk, tail, taper in settings:
     del model
     model = LocationEncoder(Namespace(location_model_name="RANGE+", pretrained_path=enc, device="cuda:0", range_db=db, beta=0.5,
                                       host_path=path, chunk=chunk, tail=tail, taper=taper))
     for _ in range(3): model(h)
-    t, ts = best(lambda: model(h))
+    t, ts = best(lambda: model(h), reps=10)
     pieces = [hi - lo for lo, hi in model._chunks(len(coords), chunk, tail, taper)]
     print(f"model(h) host_path={path} chunk={chunk} tail={tail} taper={taper}: {t*1e3:.1f} ms = {len(coords)/t/1e6:.2f} M q/s "
-          f"(runs {[round(x*1e3,1) for x in ts]}; pieces {pieces}; host threads {model.host_threads})")
+          f"(mean {sum(ts)/len(ts)*1e3:.1f}; runs {[round(x*1e3,1) for x in ts]}; pieces {pieces}; host threads {model.host_threads})")
 t, ts = best(lambda: model.embed(dc, out_dtype=torch.float64))
 print(f"embed device fp64: {t*1e3:.1f} ms")
 t, ts = best(lambda: model.embed(dc, out_dtype=torch.float32))
