@@ -77,6 +77,7 @@ class LocationEncoder(nn.Module):
             from .distributed import ShardedRetriever
             self.sharded = ShardedRetriever(self.engine, self.group, merge=getattr(args, 'db_merge', 'peer'))
         self._copy_stream = None
+        self.trace = None           # developer timeline of _forward_host: a list collects (rows, computed, copied) events
         self.eval()
 
     # the reference calls model.to(device) after construction (load_model.py:50); tensors live in the engine
@@ -315,6 +316,10 @@ class LocationEncoder(nn.Module):
                 landed = [None] * depth          # (event, result rows, staging rows) of the piece in each slot
             freed = [None] * len(bufs)
             cur = torch.cuda.current_stream()
+            if self.trace is not None:
+                t0 = torch.cuda.Event(enable_timing=True)
+                t0.record(cur)
+                self.trace.append((0, t0, t0))
 
             def unpack(slot):
                 ev, r0, r1 = landed[slot]
@@ -367,7 +372,8 @@ class LocationEncoder(nn.Module):
                     buf = bufs[k][: hi - lo]
                     assert buf.shape[0] == hi - lo
                     self._retrieve_concat(q16[lo:hi], qxyz[lo:hi], q64[lo:hi], buf, buf.dtype, perm)
-                    ready = torch.cuda.Event()
+                    timed = self.trace is not None            # developer timeline (tools/time_e2e.py)
+                    ready = torch.cuda.Event(enable_timing=timed)
                     ready.record(cur)
                     self._copy_stream.wait_event(ready)
                     with torch.cuda.stream(self._copy_stream):
@@ -375,8 +381,10 @@ class LocationEncoder(nn.Module):
                             host[s0 + lo:s0 + hi].copy_(buf, non_blocking=True)
                         else:
                             stage[k][: hi - lo].copy_(buf, non_blocking=True)
-                        freed[k] = torch.cuda.Event()
+                        freed[k] = torch.cuda.Event(enable_timing=timed)
                         freed[k].record(self._copy_stream)
+                    if timed:
+                        self.trace.append((hi - lo, ready, freed[k]))
                     if path == 'packed':
                         landed[k] = (freed[k], s0 + lo, s0 + hi)
             if path == 'packed':

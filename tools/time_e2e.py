@@ -34,6 +34,16 @@ for path, chunk, tail, taper in settings:
     pieces = [hi - lo for lo, hi in model._chunks(len(coords), chunk, tail, taper)]
     print(f"model(h) host_path={path} chunk={chunk} tail={tail} taper={taper}: {t*1e3:.1f} ms = {len(coords)/t/1e6:.2f} M q/s "
           f"(mean {sum(ts)/len(ts)*1e3:.1f}; runs {[round(x*1e3,1) for x in ts]}; pieces {pieces}; host threads {model.host_threads})")
+if os.environ.get("TRACE", "1") == "1":       # timeline of one call with the last setting's model: when each piece is computed / copied
+    model = LocationEncoder(Namespace(location_model_name="RANGE+", pretrained_path=enc, device="cuda:0", range_db=db, beta=0.5))
+    for _ in range(3): model(h)
+    for rep in range(2):
+        model.trace = []
+        torch.cuda.synchronize(); w = time.perf_counter(); model(h); wall = time.perf_counter() - w
+        t0 = model.trace[0][1]
+        print(f"timeline (wall {wall*1e3:.1f} ms): " + " | ".join(
+            f"{rows}: computed {t0.elapsed_time(a):.1f} copied {t0.elapsed_time(b):.1f}" for rows, a, b in model.trace[1:]))
+    model.trace = None
 t, ts = best(lambda: model.embed(dc, out_dtype=torch.float64))
 print(f"embed device fp64: {t*1e3:.1f} ms")
 t, ts = best(lambda: model.embed(dc, out_dtype=torch.float32))
