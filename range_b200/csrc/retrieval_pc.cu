@@ -1131,11 +1131,11 @@ cudaError_t launch_apply_pc(const RetrievalArgs& a, const CUtensorMap& tmP, cons
     return cudaErrorCooperativeLaunchTooLarge;
   }
   cfg.numAttrs = coop ? 2 : 1;
-  // The consumers' window scratch (25 MB, read and rewritten every 128 tiles) competes for the L2 with the database
-  // stream, the P' ring and the result rows; evict_last hints alone left 4.8 GB per launch going to DRAM (r1n profile).
-  // A persisting-L2 access window over the scratch keeps it resident for this launch (device limit raised once per
-  // device; the stream attribute is restored afterwards).  RANGE_PC_PERSIST=0 disables.
-  static const bool persist = !(getenv("RANGE_PC_PERSIST") && atoi(getenv("RANGE_PC_PERSIST")) == 0);
+  // Optional (RANGE_PC_PERSIST=1): a persisting-L2 access window over the consumers' window scratch (25 MB, read and
+  // rewritten every 128 tiles; with evict_last hints alone part of it still goes to DRAM between flushes).  Measured on
+  // the r2f build: no gain (apply 22.2 ms with the window, 21.8 ms without - inside the run-to-run spread), so it is
+  // off by default; the device limit is raised once per device and the stream attribute restored after the launch.
+  static const bool persist = getenv("RANGE_PC_PERSIST") && atoi(getenv("RANGE_PC_PERSIST")) == 1;
   bool window_set = false;
   if (persist && scratch) {
     static bool limit_set[64] = {};
