@@ -177,6 +177,7 @@ int range_retrieve_apply_concat(range_ctx* ctx, int mode, int64_t N, const void*
  * normalised with the global sums, merge by SUM.  range_retrieve_apply_routed is range_retrieve_apply whose result
  * rows leave the GPU from the apply kernel's epilogue: row n belongs to rank n / slab_rows and is stored as 1024 fp32
  * at   route->peer[n / slab_rows] + ((size_t)route->rank * slab_rows + n % slab_rows) * 1024,
+ * (slab_rows a multiple of 128: a 128-query tile has one owner; the stores are warp-transposed into full 128-byte lines)
  * peer[r] being rank r's receive buffer [n_ranks][slab_rows][1024] fp32 mapped into this process (range_peer_open;
  * peer[rank] = the local buffer): the partial rows cross NVLink while the tensor cores work on the next tiles, no
  * collective moves them.  After a barrier across the ranks, the owner sums its n_ranks slots in rank order

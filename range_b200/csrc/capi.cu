@@ -638,6 +638,9 @@ static int check_route(const range_route* r, int64_t N, RowRoute* out) {
   if (r->n_ranks < 1 || r->n_ranks > RANGE_MAX_RANKS || r->rank < 0 || r->rank >= r->n_ranks || r->slab_rows < 1)
     return fail(RANGE_ERR_INVALID, "route: %d ranks (max %d), rank %d, %lld rows per rank", r->n_ranks, RANGE_MAX_RANKS,
                 r->rank, (long long)r->slab_rows);
+  if (r->slab_rows % kBlockQ)
+    return fail(RANGE_ERR_INVALID, "route: slab_rows (%lld) must be a multiple of %d (a query tile has one owner)",
+                (long long)r->slab_rows, kBlockQ);
   if (N > int64_t(r->n_ranks) * r->slab_rows)
     return fail(RANGE_ERR_INVALID, "route: %lld rows do not fit %d ranks x %lld rows", (long long)N, r->n_ranks,
                 (long long)r->slab_rows);

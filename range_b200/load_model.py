@@ -19,7 +19,8 @@ def load_model(model_name='RANGE+', pretrained_path=None, device='cuda', **kwarg
     collective call: every rank passes its own queries; `db_merge='peer'|'reduce_scatter'`), `db_cache` (path of the
     prepared device layout: written on first use, validated against source and shard, read afterwards), `host_path`
     ('auto' | 'copy' | 'packed': how the float64 result reaches the host, range.py:_forward_host),
-    `pinned_limit` (bytes), `host_threads`.
+    `out_dtype` (np.float64 like the reference, or np.float32: half the device->host bytes), `pinned_limit` (bytes),
+    `host_threads`.
     """
     if pretrained_path is None:
         raise ValueError("Please provide the pretrained model path.")
@@ -31,7 +32,7 @@ def load_model(model_name='RANGE+', pretrained_path=None, device='cuda', **kwarg
         raise NotImplementedError(f"{model_name}: range_b200 implements the RANGE and RANGE+ encoders only")
     args = Namespace(location_model_name=model_name, pretrained_path=pretrained_path, device=device,
                      range_db=db_path, beta=beta)
-    for k in ('chunk', 'db_shard', 'db_group', 'db_cache', 'db_merge', 'tail', 'taper', 'super_batch', 'host_path', 'pinned_limit',
+    for k in ('chunk', 'db_shard', 'db_group', 'db_cache', 'db_merge', 'tail', 'taper', 'super_batch', 'host_path', 'out_dtype', 'pinned_limit',
               'host_threads'):
         if k in kwargs:
             setattr(args, k, kwargs[k])

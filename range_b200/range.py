@@ -64,6 +64,12 @@ class LocationEncoder(nn.Module):
         self.tail = max(1, min(self.chunk, int(getattr(args, 'tail', DEFAULT_TAIL))))
         self.super_batch = max(self.chunk, int(getattr(args, 'super_batch', 1 << 20)) // self.chunk * self.chunk)
         self.taper = float(getattr(args, 'taper', DEFAULT_TAPER))
+        # numpy dtype of model(locs)'s result: float64 is what the reference returns (range.py:222,240 - its feature
+        # columns are fp32 values widened by np.concatenate); 'float32' is an opt-in that halves the bytes crossing PCIe
+        # and landing in host memory - the e2e ceiling when several GPUs share one host (profiles/r2_d2h_wall.md)
+        self.out_dtype = np.dtype(getattr(args, 'out_dtype', np.float64))
+        if self.out_dtype not in (np.dtype(np.float64), np.dtype(np.float32)):
+            raise ValueError(f'out_dtype={self.out_dtype}: expected float64 (the reference\'s) or float32')
         # how model(locs) hands the (N,1280) float64 result to the host (see _forward_host)
         self.host_path = getattr(args, 'host_path', 'auto')
         if self.host_path not in ('auto', 'copy', 'packed'):
@@ -279,14 +285,18 @@ class LocationEncoder(nn.Module):
         stores from the SMs to host memory run at ~6 GB/s and stall the consumers: 170 ms per 100 000 queries.)"""
         eng = self.engine
         path = self.host_path
+        tdtype = torch.float32 if self.out_dtype == np.dtype(np.float32) and result is None else torch.float64
+        row_bytes = 1280 * (4 if tdtype == torch.float32 else 8)
         if result is not None:
             path = 'packed'
+        elif tdtype == torch.float32:
+            path = 'copy'                          # nothing to widen: the rows are copied as they are
         elif path == 'auto':
-            path = 'copy' if N * 10240 <= self.pinned_limit else 'packed'
+            path = 'copy' if N * row_bytes <= self.pinned_limit else 'packed'
         if self.sharded is not None:            # collective: distributed.py chunks (every rank must take the same steps)
             dev = coords.to(eng.device, torch.float64, non_blocking=True)
-            res = self.embed(dev, out_dtype=torch.float64)
-            host = torch.empty((N, 1280), dtype=torch.float64, pin_memory=N * 10240 <= self.pinned_limit)
+            res = self.embed(dev, out_dtype=tdtype)
+            host = torch.empty((N, 1280), dtype=tdtype, pin_memory=N * row_bytes <= self.pinned_limit)
             host.copy_(res)
             if result is None:
                 return host.numpy()
@@ -295,7 +305,7 @@ class LocationEncoder(nn.Module):
         if path == 'packed':
             result = np.empty((N, 1280), dtype=np.float64) if result is None else result
         else:
-            host = torch.empty((N, 1280), dtype=torch.float64, pin_memory=True)
+            host = torch.empty((N, 1280), dtype=tdtype, pin_memory=True)
             result = host.numpy()
         if N == 0:
             return result
@@ -310,7 +320,7 @@ class LocationEncoder(nn.Module):
             if path == 'copy':
                 # three buffers: with two, piece i + 2 waits for the copy of piece i, which is still running when the
                 # pieces shrink faster than their copies (measured: 0.9 ms stall before the fifth piece of 100 000 rows)
-                bufs = [torch.empty(rows, 1280, dtype=torch.float64, device=eng.device) for _ in range(min(3, n_pieces))]
+                bufs = [torch.empty(rows, 1280, dtype=tdtype, device=eng.device) for _ in range(min(3, n_pieces))]
             elif path == 'packed':
                 depth = min(3, n_pieces)
                 bufs = [torch.empty(rows, 6144, dtype=torch.uint8, device=eng.device) for _ in range(depth)]

@@ -424,6 +424,11 @@ def test_host_paths_agree(sh_entries):
         outs[path] = m(c)
         assert outs[path].dtype == np.float64 and outs[path].shape == (30_000, 1280)
     assert np.array_equal(outs["copy"], outs["packed"])              # same kernels; the widening is exact
+    m32 = LocationEncoder(Namespace(location_model_name="RANGE+", pretrained_path=enc, device=DEV, range_db=db, beta=0.5,
+                                    out_dtype=np.float32, chunk=12288, tail=6144, super_batch=24576))
+    o32 = m32(c)                                                      # opt-in: float32 rows (not the reference's dtype)
+    assert o32.dtype == np.float32 and np.array_equal(o32[:, :1024], outs["copy"][:, :1024].astype(np.float32))
+    assert np.array_equal(o32[:, 1024:], outs["copy"][:, 1024:].astype(np.float32))
     sub = np.linspace(0, 29_999, 100).astype(np.int64)
     ref = O.RangeOracle("RANGE+", ws, sh_entries, db, beta=0.5, exact=True)(c.numpy()[sub])
     assert rel_rows(outs["copy"][sub, :1024], ref[:, :1024]).max() <= 1e-3
