@@ -10,10 +10,11 @@ tail -15 ${o}_pytest.log
 timeout 600 python bench.py --steps 10 --warmup 3 > ${o}_bench.json 2> ${o}_bench.err; echo "bench exit $?"
 cat ${o}_bench.json
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > ${o}_smoke.log 2>&1; echo "smoke exit $?"; tail -2 ${o}_smoke.log
-timeout 400 python tools/time_e2e.py > ${o}_time_e2e.log 2>&1; echo "time_e2e exit $?"; grep -v "Using RANGE" ${o}_time_e2e.log | tail -14
+SETTINGS=copy:24576:6144:0.5,packed:24576:6144:0.5 timeout 400 python tools/time_e2e.py > ${o}_time_e2e.log 2>&1; echo "time_e2e exit $?"; grep -v "Using RANGE" ${o}_time_e2e.log | tail -14
 timeout 300 python tools/time_apply.py > ${o}_time_apply.log 2>&1; tail -2 ${o}_time_apply.log
 RANGE_PC_COOP=0 timeout 300 python tools/time_apply.py 2>&1 | tail -1 | sed 's/^/plain cluster launch (RANGE_PC_COOP=0): /' | tee -a ${o}_time_apply.log
 RANGE_PC_PERSIST=1 timeout 300 python tools/time_apply.py 2>&1 | tail -1 | sed 's/^/persisting-L2 window over the scratch (RANGE_PC_PERSIST=1): /' | tee -a ${o}_time_apply.log
+PROF=1 RANGE_APPLY_KERNEL=pc timeout 300 python tools/time_apply.py 2>&1 | tail -9 > ${o}_apply_roles.log; cat ${o}_apply_roles.log
 CONFIGS=3 timeout 600 python tools/configs.py > ${o}_config3_1gpu.jsonl 2> ${o}_config3.err; echo "config3 exit $?"; cat ${o}_config3_1gpu.jsonl
 [ -x build/probe_ex2 ] && build/probe_ex2 | tee ${o}_probe_ex2.log
 if [ "${NCU:-1}" = "1" ]; then
