@@ -98,7 +98,7 @@ sh_rowmajor_kernel(const double* __restrict__ lonlat, int N, int L, const double
       }
       continue;
     }
-    // Horner chains of consecutive degrees l = am + 2k, am + 2k + 1 have the same length (k + 1 terms): two
+    // Horner chains of consecutive degrees l = am + 2k, am + 2k + 1 have the same length (k + 1 terms): several
     // independent chains per iteration hide the fp64 FMA and table-load latency (a thread owns a whole query)
     auto finish = [&](double acc, int ee) {
       if (__ldg(par + ee)) acc *= c;
@@ -111,6 +111,27 @@ sh_rowmajor_kernel(const double* __restrict__ lonlat, int N, int L, const double
       }
     };
     int l = am;
+    // four chains per iteration (degrees l .. l + 3: lengths n, n, n + 1, n + 1), then the two-chain step for a remainder
+    for (; l + 3 < L; l += 4, e += 4) {
+      const int k0 = __ldg(off + e), k1 = __ldg(off + e + 1), k2 = __ldg(off + e + 2), k3 = __ldg(off + e + 3);
+      const int n0 = k1 - k0, n1 = k2 - k1, n2 = k3 - k2, n3 = __ldg(off + e + 4) - k3;
+      double a0 = __ldg(coef + k0), a1 = __ldg(coef + k1), a2 = __ldg(coef + k2), a3 = __ldg(coef + k3);
+      const int nmin = min(min(n0, n1), min(n2, n3));
+      for (int t = 1; t < nmin; ++t) {
+        a0 = fma(a0, c2, __ldg(coef + k0 + t));
+        a1 = fma(a1, c2, __ldg(coef + k1 + t));
+        a2 = fma(a2, c2, __ldg(coef + k2 + t));
+        a3 = fma(a3, c2, __ldg(coef + k3 + t));
+      }
+      for (int t = nmin; t < n0; ++t) a0 = fma(a0, c2, __ldg(coef + k0 + t));
+      for (int t = nmin; t < n1; ++t) a1 = fma(a1, c2, __ldg(coef + k1 + t));
+      for (int t = nmin; t < n2; ++t) a2 = fma(a2, c2, __ldg(coef + k2 + t));
+      for (int t = nmin; t < n3; ++t) a3 = fma(a3, c2, __ldg(coef + k3 + t));
+      finish(a0, e);
+      finish(a1, e + 1);
+      finish(a2, e + 2);
+      finish(a3, e + 3);
+    }
     for (; l + 1 < L; l += 2, e += 2) {
       int k0 = __ldg(off + e);
       int k1 = __ldg(off + e + 1);
@@ -168,7 +189,8 @@ siren_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kTcStages * kTcStageBytes);   // full[S] | empty[S] | done
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kTcStages + 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row0 = blockIdx.x * 128, col0 = blockIdx.y * 256;
+  // blockIdx.x = column block: the CTAs that share a row tile's A operand are adjacent in launch order (second read from L2)
+  const int row0 = blockIdx.y * 128, col0 = blockIdx.x * 256;
   const int KB = K / 64;                  // K blocks of 64 fp16 = one 128-byte swizzle row
 
   if (threadIdx.x == 0) {
@@ -306,7 +328,7 @@ cudaError_t launch_siren_tc(const CUtensorMap& tmAh, const CUtensorMap& tmAl, co
   if (K % 64 || H % 256) return cudaErrorInvalidValue;
   cudaError_t e = cudaFuncSetAttribute(siren_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem);
   if (e != cudaSuccess) return e;
-  dim3 grid((N + 127) / 128, H / 256);
+  dim3 grid(H / 256, (N + 127) / 128);
   siren_tc_kernel<<<grid, kTcThreads, kTcSmem, s>>>(tmAh, tmAl, tmBh, tmBl, bias, N, K, H, act_w0,
                                                     reinterpret_cast<__half*>(out_hi), reinterpret_cast<__half*>(out_lo), out_f64);
   return cudaGetLastError();
