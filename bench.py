@@ -461,9 +461,10 @@ def main():
                        + ("; m_sharded: DB sharded along M" if world > 1 else ""),
                        "l2": "inputs larger than L2 (DB 257 MB fp16 streamed every step; 512 MB output)",
                        "segments_ms": {"sort_queries": seg[4], "encode": seg[0], "retrieve_stats": seg[1], "retrieve_apply_concat": seg[2]},
-                       "parity_tolerance": "retrieved columns: relative row error <= 1e-3 (RANGE on the iid worst-case DB: 2e-3), "
-                                           "cosine >= 0.99999; location columns: max-abs <= 5e-5 (|lat| < 60 deg) / 2e-3 (polar) "
-                                           "= the reference's own fp64 polynomial noise (tests/test_gpu_parity.py)"},
+                       "parity_tolerance": "retrieved columns: relative row error <= 1e-3, 2e-4 on the structured DB (named exception: purely "
+                                           "semantic softmax on the iid worst-case DB 2e-3), cosine >= 0.99999; location columns: "
+                                           "max-abs <= 3e-5 (|lat| < 60 deg) / 1e-3 (polar) = the reference's own fp64 polynomial "
+                                           "noise (tests/test_gpu_parity.py)"},
             # dominant kernel = the apply pass (all 2566 algorithmic flop per pair live there); the stats pass that
             # precedes it is algorithmically redundant work, so the stricter figure over both kernels is given too
             "roofline": {"bound": "tensor", "kernel": "range_apply_pc_kernel (K2b: Q.K^T + softmax blend + P.V)",

@@ -1,15 +1,19 @@
 """Parity of the CUDA path (through the C ABI) against the CPU oracle and the reference's golden vectors.
 
-Tolerances (measured noise floors in DESIGN.md):
-  * location columns q (fp64 path): max-abs <= 5e-5 for |lat| < 60 deg, <= 2e-3 elsewhere = 5x the reference's
-    own fp64 rounding noise on its 15-digit polynomials (1e-5 / 4e-4 there): "equal up
-    to the reference's irreproducible noise", not a looser implementation.  Features with l < 20 (no
-    cancellation) must agree to 1e-9.
-  * retrieved columns O (fp16 operands, fp32 accumulate): on the iid worst-case DB (outputs are averages of
-    zero-mean noise, so fp16 rounding of q and K shows undamped: logit error = temperature x 2.5e-5) relative
-    row error mean <= 6e-4, max <= 2e-3; on the structured DB (non-zero-mean values, like real SatMAE
-    features) max <= 2e-4; cosine >= 0.99999 everywhere - against the reference's CPU fp32 output and the fp64-exact restatement.
-    (The reference itself runs these matmuls in TF32 on CUDA: 5.9e-3, SURVEY.md Appendix B.)
+Tolerances (SURVEY.md section 8c recommends: retrieved columns relative row error <= 1e-3 and cosine >= 0.99999,
+location columns max-abs <= 1e-5 for |lat| < 60 deg / <= 1e-3 elsewhere; measured noise floors in DESIGN.md section 2):
+  * retrieved columns O (fp16 operands, fp32 accumulate), against the reference's CPU fp32 output and the fp64-exact
+    restatement: relative row error <= 1e-3 (TOL_O) whenever the geographic softmax takes part (RANGE+ with beta < 1;
+    measured 3.4e-4 max at the bench shape) and <= 2e-4 on the structured database (non-zero-mean values, like real
+    SatMAE features; measured 1.5e-4) - also at full size; cosine >= 0.99999 everywhere.
+    NAMED EXCEPTION (TOL_O_IID_SEM = 2e-3): the purely semantic softmax (RANGE, or RANGE+ at beta = 1) on the iid
+    database - flat weights over zero-mean values, so the fp16 rounding of q and K shows undamped (logit error =
+    temperature x 2.5e-5): measured 1.2e-3 max, mean <= 6e-4.  (The reference itself runs these matmuls in TF32 on
+    CUDA: 5.9e-3, SURVEY.md Appendix B.)
+  * location columns q: max-abs <= 3e-5 for |lat| < 60 deg, <= 1e-3 elsewhere.  Section 8c's 1e-5 is the reference's OWN
+    fp64 rounding noise on its 15-digit polynomials there (1e-5 / 4e-4; measured here 1.2e-5 /
+    2.9e-4): "equal up to the reference's irreproducible noise", not a looser implementation.  Features with l < 20
+    (no cancellation) must agree to 1e-9.
 """
 import numpy as np
 import pytest
@@ -19,6 +23,13 @@ from oracle import range_oracle as O
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
+TOL_O, TOL_O_IID_SEM, TOL_O_STRUCTURED = 1e-3, 2e-3, 2e-4
+TOL_Q, TOL_Q_POLAR = 3e-5, 1e-3
+
+
+def tol_o(name, beta):
+    """iid database: the named exception applies to the purely semantic softmax only"""
+    return TOL_O_IID_SEM if (name == "RANGE" or beta == 1.0) else TOL_O
 
 
 def rel_rows(a, b):
@@ -85,8 +96,8 @@ def test_encoder_vs_reference(gold_setup):
     q = q64.cpu().numpy()
     lat = np.abs(g["coords"][:, 1])
     d = np.abs(q - g["q"]).max(1)
-    assert d[lat < 60].max() <= 5e-5
-    assert d.max() <= 2e-3
+    assert d[lat < 60].max() <= TOL_Q
+    assert d.max() <= TOL_Q_POLAR
     assert np.allclose(np.linalg.norm(q, axis=1), 1.0, atol=1e-14)
     assert (q16.double() - q64).abs().max().item() < 1e-3
     xyz = O.rad_to_cart(g["coords"] * np.pi / 180).astype(np.float32)
@@ -112,7 +123,7 @@ def test_encoder_split_vs_fp64(sh_entries):
     qr = helper.encode(torch.tensor(c)).numpy()
     lat = np.abs(c[:, 1])
     d = np.abs(b.cpu().numpy() - qr).max(1)
-    assert d[lat < 60].max() <= 5e-5 and d.max() <= 2e-3
+    assert d[lat < 60].max() <= TOL_Q and d.max() <= TOL_Q_POLAR
     with pytest.raises(Exception):
         RangeEngine(DEV, encoder=dict(L=40, dims=[1600, 64, 64, 256], weights=O.siren_init(40, 64, 2, 256)),
                     encoder_precision="f16x3")
@@ -122,12 +133,12 @@ def test_retrieval_vs_reference_golden(gold_setup):
     g, _, _, eng = gold_setup
     q64, q16, qxyz = eng.encode(torch.tensor(g["coords"]))
     Ot = eng.retrieve("RANGE", q16, qxyz, 15.0, 0.0, None).cpu().numpy()
-    assert rel_rows(Ot, g["O_range"]).max() <= 2e-3 and cos_rows(Ot, g["O_range"]).min() >= 0.99999
+    assert rel_rows(Ot, g["O_range"]).max() <= TOL_O_IID_SEM and cos_rows(Ot, g["O_range"]).min() >= 0.99999
     for beta in g["betas"]:
         Ot = eng.retrieve("RANGE+", q16, qxyz, 12.0, 40.0, float(beta)).cpu().numpy()
         ref = g[f"O_plus_{beta}"]
         assert np.isfinite(Ot).all()
-        assert rel_rows(Ot, ref).max() <= 2e-3 and rel_rows(Ot, ref).mean() <= 6e-4, beta
+        assert rel_rows(Ot, ref).max() <= tol_o("RANGE+", float(beta)) and rel_rows(Ot, ref).mean() <= 6e-4, beta
         assert cos_rows(Ot, ref).min() >= 0.99999, beta
 
 
@@ -148,7 +159,7 @@ def test_retrieval_ragged_vs_exact_oracle(N, M, sh_entries):
         Ot = eng.retrieve(name, q16, qxyz, orc.temp, 40.0, beta).cpu().numpy()
         assert np.isfinite(Ot).all()
         r = rel_rows(Ot, ref)
-        assert r.max() <= 2e-3 and r.mean() <= 6e-4, (name, beta, r.max(), r.mean())
+        assert r.max() <= tol_o(name, beta) and r.mean() <= 6e-4, (name, beta, r.max(), r.mean())
         assert cos_rows(Ot, ref).min() >= 0.99999, (name, beta)
 
 
@@ -167,7 +178,7 @@ def test_structured_db_and_properties(sh_entries):
     q64, q16, qxyz = eng.encode(torch.tensor(c))
     ref = O.RangeOracle("RANGE+", ws, sh_entries, db, beta=0.5, exact=True)(c)[:, :1024]
     full = eng.retrieve("RANGE+", q16, qxyz, 12.0, 40.0, 0.5).cpu().numpy()
-    assert rel_rows(full, ref).max() <= 2e-4
+    assert rel_rows(full, ref).max() <= TOL_O_STRUCTURED
     # beta = 1 is the semantic softmax alone at temperature 12, beta = 0 the geographic one
     sem = eng.retrieve("RANGE+", q16, qxyz, 12.0, 40.0, 1.0).cpu().numpy()
     geo = eng.retrieve("RANGE+", q16, qxyz, 12.0, 40.0, 0.0).cpu().numpy()
@@ -215,11 +226,11 @@ def test_load_model_api(tmp_path, golden, sh_entries):
     assert model.location_feature_dim == 1280 and model.args.temp == 12.0 and model.args.geo_temp == 40.0
     out = model(torch.tensor(g["coords"]).to("cuda"))          # chunk=24 -> exercises the pipelined path
     assert isinstance(out, np.ndarray) and out.dtype == np.float64 and out.shape == (64, 1280)
-    assert rel_rows(out[:, :1024], g["O_plus_0.5"]).max() <= 2e-3
-    assert np.abs(out[:, 1024:] - g["q"]).max() <= 2e-3
+    assert rel_rows(out[:, :1024], g["O_plus_0.5"]).max() <= TOL_O
+    assert np.abs(out[:, 1024:] - g["q"]).max() <= TOL_Q_POLAR
     m2 = load_model("RANGE", str(ckpt), device="cuda", db_path=str(dbfile))
     out2 = m2(torch.tensor(g["coords"]))
-    assert m2.args.temp == 15.0 and rel_rows(out2[:, :1024], g["O_range"]).max() <= 2e-3
+    assert m2.args.temp == 15.0 and rel_rows(out2[:, :1024], g["O_range"]).max() <= TOL_O_IID_SEM
     with pytest.raises(ValueError):
         load_model("RANGE++", str(ckpt), device="cuda", db_path=str(dbfile))
 
@@ -244,7 +255,7 @@ def test_large_batch_producer_consumer_apply(sh_entries):
         assert np.isfinite(Ot).all()
         ref = orc(c[p[sub]])[:, :1024]
         r = rel_rows(Ot[sub], ref)
-        assert r.max() <= 2e-3 and r.mean() <= 6e-4, (name, beta, r.max(), r.mean())
+        assert r.max() <= tol_o(name, beta) and r.mean() <= 6e-4, (name, beta, r.max(), r.mean())
     # and the same rows through the single-role kernel (small batch): same arithmetic, same P' rounding
     small = eng.retrieve("RANGE+", q16[:1000], qxyz[:1000], 12.0, 40.0, 0.5)
     big = eng.retrieve("RANGE+", q16, qxyz, 12.0, 40.0, 0.5)[:1000]
@@ -280,11 +291,27 @@ def test_full_size_properties(sh_entries):
     ref = O.RangeOracle("RANGE+", ws, sh_entries, db, beta=0.5, exact=True)(c[sub])
     got = outs[0.5][torch.tensor(sub, device=DEV)].cpu().numpy()
     r = rel_rows(got[:, :1024], ref[:, :1024])
-    assert r.max() <= 2e-3 and r.mean() <= 6e-4, (r.max(), r.mean())
+    assert r.max() <= TOL_O and r.mean() <= 6e-4, (r.max(), r.mean())
     assert cos_rows(got[:, :1024], ref[:, :1024]).min() >= 0.99999
     lat = np.abs(c[sub, 1])
     dq = np.abs(got[:, 1024:] - ref[:, 1024:])
-    assert dq[lat < 60].max() <= 5e-5 and dq.max() <= 2e-3
+    assert dq[lat < 60].max() <= TOL_Q and dq.max() <= TOL_Q_POLAR
+    # the structured database (peaky softmax over non-zero-mean values, like real SatMAE features) at the same size:
+    # keys = the encoder's own embedding of the entry location + noise
+    rng = np.random.default_rng(3)
+    eng = LocationEncoder(Namespace(location_model_name="RANGE+", pretrained_path=enc, device=DEV, range_db=db, beta=0.5)).engine
+    E = eng.encode(torch.tensor(db["locs"], device=DEV))[0].cpu().numpy()
+    K = E + 0.1 * rng.standard_normal((M, 256))
+    V = (K @ rng.standard_normal((256, 1024)) / 16 + 0.5 + 0.2 * rng.standard_normal((M, 1024))).astype(np.float32)
+    sdb = dict(locs=db["locs"], satclip_embeddings=K.astype(np.float32), image_embeddings=V)
+    del eng
+    for name, beta in (("RANGE+", 0.5), ("RANGE", None)):
+        m = LocationEncoder(Namespace(location_model_name=name, pretrained_path=enc, device=DEV, range_db=sdb, beta=beta))
+        got = m.embed(dc, out_dtype=torch.float64)[torch.tensor(sub, device=DEV)].cpu().numpy()
+        ref = O.RangeOracle(name, ws, sh_entries, sdb, beta=beta, exact=True)(c[sub])
+        r = rel_rows(got[:, :1024], ref[:, :1024])
+        assert r.max() <= TOL_O_STRUCTURED, (name, r.max())
+        del m
 
 
 @pytest.mark.parametrize("N,M", [(13_000, 77), (12_288, 128), (20_000, 129)])
@@ -304,7 +331,7 @@ def test_large_batch_tiny_database(N, M, sh_entries):
     P = 0.25 * torch.softmax((q.float() @ K.t()) * 12.0, dim=1) + 0.75 * torch.softmax((xyz[:, :3] @ X.t()) * 40.0, dim=1)
     ref = P @ V
     rel = ((out - ref).norm(dim=1) / ref.norm(dim=1))
-    assert torch.isfinite(out).all() and rel.max().item() <= 2e-3, rel.max().item()
+    assert torch.isfinite(out).all() and rel.max().item() <= TOL_O, rel.max().item()
 
 
 def test_beta_sweep_and_database_cache(tmp_path, sh_entries):
@@ -331,7 +358,7 @@ def test_beta_sweep_and_database_cache(tmp_path, sh_entries):
         ref = O.RangeOracle("RANGE+", ws, sh_entries, db, beta=beta, exact=True)(c.cpu().numpy())
         # the iid database is the worst case of the purely semantic softmax (flat weights over zero-mean values: the
         # fp16 rounding of q and K shows undamped): 2e-3 there, 1e-3 as soon as the geographic term takes part
-        assert rel_rows(got[:, :1024].cpu().numpy(), ref[:, :1024]).max() <= (2e-3 if beta == 1.0 else 1e-3), beta
+        assert rel_rows(got[:, :1024].cpu().numpy(), ref[:, :1024]).max() <= tol_o("RANGE+", beta), beta
     fresh = mk(0.25).embed(c)
     assert torch.equal(fresh, mk(0.25, db_cache=cache).embed(c))
 
