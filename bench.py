@@ -170,7 +170,7 @@ class ReferenceCpu:
 
             def run(coords, m=m):
                 with torch.no_grad():
-                    return m(torch.tensor(coords))
+                    return m(torch.tensor(coords).to(device))       # the reference expects the locations on its device
         else:
             from oracle import range_oracle as O
             from range_b200.sh_table import load_entries
