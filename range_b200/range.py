@@ -264,12 +264,18 @@ class LocationEncoder(nn.Module):
         return self._retrieve_concat(q16, qxyz, q64, out, out_dtype, perm)
 
     @torch.no_grad()
-    def forward_raster(self, lon_axis, lat_axis):
-        """model(coord_grid(...)) without building the coordinate list on the host: numpy float64 (H * W, 1280)."""
+    def forward_raster(self, lon_axis, lat_axis, rows=None, out=None):
+        """model(coord_grid(...)) without building the coordinate list on the host: numpy float64 (H * W, 1280).
+        rows=(p0, p1): only those raster points (a rank's slab); out: the caller's float64 (p1 - p0, 1280) array, e.g.
+        rows of a memory-mapped .npy (filled through the packed path with bounded page-locked memory)."""
         tables = self.raster_tables(lon_axis, lat_axis)
-        return self._forward_host(tables['H'] * tables['W'], raster=tables)
+        p0, p1 = (0, tables['H'] * tables['W']) if rows is None else rows
+        if out is not None and not (isinstance(out, np.ndarray) and out.dtype == np.float64 and out.shape == (p1 - p0, 1280)
+                                    and out.flags['C_CONTIGUOUS'] and out.flags['WRITEABLE']):
+            raise ValueError('out must be a writable C-contiguous float64 (rows, 1280) array')
+        return self._forward_host(p1 - p0, raster=tables, result=out, raster_p0=p0)
 
-    def _forward_host(self, N, coords=None, raster=None, result=None):
+    def _forward_host(self, N, coords=None, raster=None, result=None, raster_p0=0):
         """model(locs) -> numpy float64 (N,1280) (range/range.py:222,240).  Two ways to hand the rows to the host:
 
         'copy'    chunk by chunk into device buffers; every chunk's float64 rows travel to the page-locked result on a
@@ -351,18 +357,18 @@ class LocationEncoder(nn.Module):
                     ij = torch.empty(n, 2, dtype=torch.int32, device=eng.device)
                     if self._sorts():
                         lonlat = torch.empty(n, 2, dtype=torch.float64, device=eng.device)
-                        eng.raster_points(raster, s0, n, lonlat=lonlat)
+                        eng.raster_points(raster, raster_p0 + s0, n, lonlat=lonlat)
                         perms = []
                         for lo, hi in sort_cuts:
                             perms.append(eng.sort_queries(lonlat[lo:hi])[1])
-                            eng.raster_points(raster, s0 + lo, hi - lo, perm=perms[-1], ij=ij[lo:hi])
+                            eng.raster_points(raster, raster_p0 + s0 + lo, hi - lo, perm=perms[-1], ij=ij[lo:hi])
                     else:
-                        eng.raster_points(raster, s0, n, ij=ij)
+                        eng.raster_points(raster, raster_p0 + s0, n, ij=ij)
                 else:
                     if raster is None:
                         sub = dev_coords[s0:s1]
                     else:
-                        ij = self._raster_ij(raster['W'], s0, s1)
+                        ij = self._raster_ij(raster['W'], raster_p0 + s0, raster_p0 + s1)
                         sub = self._raster_coords(raster, ij)
                     if self._sorts():
                         # spatial batching chunk by chunk (a tile's 128 queries should be neighbours; the order of the

@@ -130,3 +130,28 @@ def test_apply_work_plan_covers_every_query_tile_pair_once():
             assert ranges[0][0] == 0 and ranges[-1][1] == T and all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
         longest = full * T + (0 if tail_pairs == 0 else (tail_tiles if split > 1 else T))
         assert windows >= -(-longest // 64)
+
+
+def test_host_unpack_widens_packed_rows_exactly():
+    """range_host_unpack is a HOST entry point (no GPU needed): packed rows (1024 fp32 + 256 fp64 = 6144 B) -> the
+    float64 (N,1280) rows of range/range.py:222,240; exact, any thread count, aligned or not, ragged row counts"""
+    import numpy as np
+    from range_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(0)
+    for N in (0, 1, 255, 256, 1000, 5000):
+        f = rng.standard_normal((N, 1024)).astype(np.float32)
+        q = rng.standard_normal((N, 256))
+        if N:
+            f[0, :4] = [0.0, -0.0, np.float32(1e-45), np.float32(3.4e38)]          # zero, signed zero, subnormal, near max
+        packed = np.empty((N, 6144), np.uint8)
+        packed[:, :4096] = f.view(np.uint8).reshape(N, 4096)
+        packed[:, 4096:] = q.view(np.uint8).reshape(N, 2048)
+        want = np.concatenate([f.astype(np.float64), q], axis=1)
+        for threads in (1, 3, 16):
+            for off in (0, 1):                                   # off = 1: result not 32-byte aligned (scalar path)
+                buf = np.full(N * 1280 + 1, np.nan)
+                out = buf[off:off + N * 1280].reshape(N, 1280)
+                assert lib.range_host_unpack(packed.ctypes.data if N else None, N, out.ctypes.data if N else None, threads) == 0
+                assert np.array_equal(out, want) and np.array_equal(np.signbit(out), np.signbit(want))
+    assert lib.range_host_unpack(None, 5, None, 1) == -1

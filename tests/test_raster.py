@@ -79,6 +79,10 @@ def test_raster_encoder_is_bit_identical():
         out = m.forward_raster(lon, lat)
         assert isinstance(out, np.ndarray) and out.dtype == np.float64 and out.shape == (H * W, 1280)
         assert np.array_equal(out, m(coords))
+        # a slab of the raster into the caller's array (packed rows widened on the host), e.g. a memory-mapped file
+        mine = np.full((1500, 1280), np.nan)
+        assert m.forward_raster(lon, lat, rows=(1000, 2500), out=mine) is mine
+        assert np.array_equal(mine, m(coords[1000:2500]))
     bad = ij.clone()                                  # an index outside the raster gives a NaN row, nothing else changes
     bad[5, 0] = H
     b64 = eng.encode_raster(tables, bad)[1]

@@ -176,5 +176,32 @@ if "5" in which:
         t = timed(lambda: run_chunks(m, coords, out), reps=1)
     emit(config="C5 dense raster", H=H, W=W, queries=H * W, M=100_000, n_gpus=world, seconds=t,
          queries_per_s=H * W / t, parallelism=f"query-sharded x{world}", encoder="raster (separable harmonics)" if use_raster else "per point")
+if "5file" in which:
+    # config 5 end to end TO A FILE: every rank streams its slab of the raster into its own memory-mapped .npy
+    # (forward_raster(rows=, out=): packed rows over PCIe, widened by host threads into the mapped pages).
+    # RASTER_FILE_POINTS points in total (default 2 M = 20 GB of float64 rows), files under RASTER_DIR (default /dev/shm).
+    import tempfile
+    total = int(os.environ.get("RASTER_FILE_POINTS", 2_000_000))
+    H = int(round((total / 2) ** 0.5)); W = 2 * H
+    lon_axis, lat_axis = LocationEncoder.coord_grid_axes((H, W))
+    lo, hi = shard_rows(H * W, rank, world)
+    m = model_for(db, 0.5)
+    d = tempfile.mkdtemp(prefix="range_raster_", dir=os.environ.get("RASTER_DIR", "/dev/shm"))
+    path = os.path.join(d, f"emb_rank{rank}.npy")
+    m.forward_raster(lon_axis, lat_axis, rows=(lo, min(hi, lo + 30_000)), out=np.empty((min(hi, lo + 30_000) - lo, 1280)))   # warm-up
+    mm = np.lib.format.open_memmap(path, mode="w+", dtype=np.float64, shape=(hi - lo, 1280))
+    torch.cuda.synchronize()
+    if world > 1: dist.barrier()
+    t0 = time.perf_counter()
+    m.forward_raster(lon_axis, lat_axis, rows=(lo, hi), out=mm)
+    mm.flush()
+    dt = torch.tensor([time.perf_counter() - t0], device=dev)
+    if world > 1: dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    ok = bool(np.isfinite(mm[:: max(1, (hi - lo) // 1000)]).all())
+    del mm
+    os.remove(path); os.rmdir(d)
+    emit(config="C5 dense raster, end to end into memory-mapped .npy files (one per rank)", H=H, W=W, queries=H * W, M=100_000,
+         n_gpus=world, seconds=float(dt[0]), queries_per_s=H * W / float(dt[0]), bytes_written=H * W * 10240, finite=ok,
+         host_threads_per_rank=m.host_threads, parallelism=f"query-sharded x{world}")
 if world > 1:
     dist.destroy_process_group()
