@@ -7,7 +7,8 @@ import os
 from ctypes import (POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_size_t, c_void_p)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librange_b200.so")
+# RANGE_B200_LIB: developer switch (tools/variants.sh builds the library with other tuning macros for A/B timing)
+LIB_PATH = os.environ.get("RANGE_B200_LIB") or os.path.join(_HERE, "librange_b200.so")
 
 RANGE_MODE_RANGE, RANGE_MODE_RANGE_PLUS = 0, 1
 RANGE_OUT_F64, RANGE_OUT_F32, RANGE_OUT_PACKED = 0, 1, 2

@@ -17,7 +17,7 @@ c = torch.tensor(O.area_uniform(N, np.random.default_rng(1)))
 if os.environ.get("SORT", "1") == "1":      # spatially batched queries (what range.py does for RANGE+)
     c = eng.sort_queries(c)[0].cpu()
 xyz = torch.zeros(N, 4); xyz[:, :3] = torch.tensor(rad_to_cart(c.numpy() * np.pi / 180)).float(); xyz = xyz.to(dev)
-def timeit(fn, reps=3):
+def timeit(fn, reps=int(os.environ.get("REPS", 3))):
     fn(); torch.cuda.synchronize(); ts = []
     for _ in range(reps):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
