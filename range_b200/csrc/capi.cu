@@ -182,9 +182,15 @@ RetrievalPlan plan_retrieval(const range_ctx* c, int64_t N) {
   const int64_t qpairs = (qtiles + 1) / 2;
   const int ov = apply_kernel_override();
   p.pc = units > 0 && ov != 1 && (ov == 2 || qpairs >= units);
-  p.off_ring = o;     o += p.pc ? align_up(apply_pc_ring_bytes(c->sm_count), 1024) : 0;
-  p.off_flags = o;    o += p.pc ? align_up(apply_pc_flag_bytes(c->sm_count, N, c->M), 256) : 0;
-  p.off_pc_part = o;  o += p.pc ? align_up(apply_pc_part_bytes(c->sm_count, N, c->M), 256) : 0;
+  const size_t ring_b = apply_pc_ring_bytes(c->sm_count) > fold_pc_ring_bytes(c->sm_count) ? apply_pc_ring_bytes(c->sm_count)
+                                                                                             : fold_pc_ring_bytes(c->sm_count);
+  const size_t flag_b = apply_pc_flag_bytes(c->sm_count, N, c->M) > fold_pc_flag_bytes(c->sm_count, N, c->M)
+                            ? apply_pc_flag_bytes(c->sm_count, N, c->M) : fold_pc_flag_bytes(c->sm_count, N, c->M);
+  const size_t part_b = apply_pc_part_bytes(c->sm_count, N, c->M) > fold_pc_part_bytes(c->sm_count, N, c->M)
+                            ? apply_pc_part_bytes(c->sm_count, N, c->M) : fold_pc_part_bytes(c->sm_count, N, c->M);
+  p.off_ring = o;     o += p.pc ? align_up(ring_b, 1024) : 0;
+  p.off_flags = o;    o += p.pc ? align_up(flag_b, 256) : 0;
+  p.off_pc_part = o;  o += p.pc ? align_up(part_b, 256) : 0;
   p.off_pc_scratch = o; o += p.pc ? align_up(apply_pc_scratch_bytes(c->sm_count), 256) : 0;
   p.off_part_out = o; o += (p.splits > 1 && !p.pc) ? align_up(size_t(p.splits) * N * kDimV * 4, 256) : 0;
   p.off_O = o;        o += p.pc ? 0 : align_up(size_t(N) * kDimV * 4, 256);   // scratch O of range_retrieve_apply_concat (small batches)
@@ -739,6 +745,58 @@ int range_retrieve_apply_concat(range_ctx* c, int mode, int64_t N, const void* q
   if (!out || !q64) return fail(RANGE_ERR_INVALID, "null argument");
   return apply_impl(c, mode, N, q16, qxyz, temp, geo_temp, beta, sums, maxs, nullptr, q64, perm, out, out_dtype, nullptr,
                     workspace, workspace_bytes, stream);
+}
+
+// 0 = default (fold whenever the producer/consumer kernel applies), RANGE_FOLD=0: always statistics pass + apply pass
+static bool fold_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("RANGE_FOLD");
+    v = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  return v == 1;
+}
+
+int range_retrieve_concat(range_ctx* c, int mode, int64_t N, const void* q16, const float* qxyz, float temp, float geo_temp,
+                          float beta, const double* q64, const int32_t* perm, void* out, int out_dtype, void* workspace,
+                          size_t workspace_bytes, void* stream) {
+  if (!c || !c->Kh) return fail(RANGE_ERR_INVALID, "database not set");
+  if (!q16 || !qxyz || !q64 || !out || !workspace) return fail(RANGE_ERR_INVALID, "null argument");
+  if (N <= 0) return fail(RANGE_ERR_INVALID, "N must be positive");
+  if (mode == RANGE_MODE_RANGE_PLUS && !(beta >= 0.f && beta <= 1.f)) return fail(RANGE_ERR_INVALID, "beta must be in [0,1]");
+  if (!valid_out_dtype(out_dtype)) return fail(RANGE_ERR_INVALID, "unknown out dtype");
+  const RetrievalPlan p = plan_retrieval(c, N);
+  if (workspace_bytes < p.total + 256) return fail(RANGE_ERR_WORKSPACE, "retrieve workspace too small");
+  char* ws = reinterpret_cast<char*>(align_up(reinterpret_cast<size_t>(workspace), 256));
+  if (!p.pc || !fold_enabled()) {      // small batches (single-role kernels) or the two-pass path on request
+    float* sums = reinterpret_cast<float*>(ws + p.off_sums);
+    float* maxs = reinterpret_cast<float*>(ws + p.off_maxs);
+    int r = range_retrieve_stats(c, mode, N, q16, qxyz, temp, geo_temp, sums, maxs, workspace, workspace_bytes, stream);
+    if (r) return r;
+    return range_retrieve_apply_concat(c, mode, N, q16, qxyz, temp, geo_temp, beta, sums, maxs, q64, perm, out, out_dtype,
+                                       workspace, workspace_bytes, stream);
+  }
+  RetrievalArgs a;
+  cudaStream_t s = cudaStream_t(stream);
+  int r = fill_args(c, mode, N, q16, qxyz, temp, geo_temp, p, ws, s, &a);      // geo mask from the tile caps (no sums yet)
+  if (r) return r;
+  CUtensorMap tmP;
+  void* ring = ws + p.off_ring;
+  r = make_tmap_rows2k(&tmP, ring, uint64_t(fold_pc_ring_rows(c->sm_count)));
+  if (r) return r;
+  float* rowc = reinterpret_cast<float*>(ws + p.off_rowc);
+  const int W = kDimV + kDimK;
+  if (out_dtype == RANGE_OUT_PACKED) {
+    CUDA_TRY(launch_fold_pc(a, tmP, beta, 1.f / c->vscale, rowc, out, 1536, 0, perm, ring, ws + p.off_flags, ws + p.off_pc_part,
+                            ws + p.off_pc_scratch, c->sm_count, s));
+    CUDA_TRY(launch_concat_q(q64, int(N), kDimK, perm, out, 768, 512, RANGE_OUT_F64, s));
+  } else {
+    CUDA_TRY(launch_fold_pc(a, tmP, beta, 1.f / c->vscale, rowc, out, W, out_dtype == RANGE_OUT_F64, perm, ring,
+                            ws + p.off_flags, ws + p.off_pc_part, ws + p.off_pc_scratch, c->sm_count, s));
+    CUDA_TRY(launch_concat_q(q64, int(N), kDimK, perm, out, W, kDimV, out_dtype, s));
+  }
+  g_launches += 3 + (fold_pc_part_bytes(c->sm_count, N, c->M) > 0);
+  return RANGE_OK;
 }
 
 int range_retrieve_apply_routed(range_ctx* c, int mode, int64_t N, const void* q16, const float* qxyz, float temp,

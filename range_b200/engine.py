@@ -280,6 +280,19 @@ class RangeEngine:
                 _ptr(ws), ws.numel(), _stream()))
         return out
 
+    def retrieve_concat(self, mode, q16, qxyz, temp, geo_temp, beta, q64, out=None, dtype=torch.float64, perm=None):
+        """statistics + apply + concat in one call (unsharded database): (N,1280) = [retrieved feature | q64], row n at
+        out[perm[n]]; large batches run the single fused retrieval kernel (csrc/retrieval_fold.cu)"""
+        N = q16.shape[0]
+        out = _new_out(N, dtype, self.device) if out is None else out
+        with torch.cuda.device(self.index):
+            ws = self._ret_ws(N)
+            _lib.check(self.lib.range_retrieve_concat(
+                self.ctx, MODE[mode], N, _ptr(q16), _ptr(qxyz), temp, geo_temp, 0.0 if beta is None else float(beta),
+                _ptr(q64), c_void_p(None) if perm is None else _ptr(perm), _ptr(out), _out_code(out), _ptr(ws), ws.numel(),
+                _stream()))
+        return out
+
     def concat(self, O, q64, out=None, dtype=torch.float64, perm=None):
         """[O | q64] -> (N,1280); with perm (from sort_queries) row n is written to out[perm[n]]"""
         N = O.shape[0]
