@@ -489,7 +489,11 @@ range_fold_pc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           const uint32_t ix = uint32_t(p) * uint32_t(T) + uint32_t(j);
           const int x = ix & (L::NX - 1);
           const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + 256 + bb * kKeys;
+#ifdef RANGE_FOLD_NOGEOSTATS          // timing experiment only (wrong results): no geographic work in the statistics group
+          const bool with_geo = false;
+#else
           const bool with_geo = kGeo && !mask_bit(mask_row, j);
+#endif
           ptx::mbar_wait(&bars[L::b_sb_full + bb], (ib >> 1) & 1);
           if (with_geo) ptx::mbar_wait(&bars[L::b_xyz_full + x], (ix / L::NX) & 1);
           ptx::tc_fence_after();
