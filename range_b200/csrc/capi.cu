@@ -116,6 +116,8 @@ struct RetrievalPlan {
   int mask_rows, mask_words;                // geo-skip mask: [even-padded query tiles][ceil(tiles / 32)]
   bool pc;                                  // apply with the producer/consumer kernel (retrieval_pc.cu)
   bool stats_pc;                            // statistics with the CTA-pair / four-group kernel (retrieval_pc.cu)
+  int geo_splits, geo_tiles_per_split;      // geographic statistics of the fused retrieval kernel (retrieval_fold.cu)
+  size_t off_gpart_sum, off_gpart_max;
   size_t off_part_sum, off_part_max, off_sums, off_maxs, off_rowc, off_mask, off_ring, off_flags, off_pc_part, off_pc_scratch, off_part_out, off_O, total;
 };
 
@@ -171,6 +173,16 @@ RetrievalPlan plan_retrieval(const range_ctx* c, int64_t N) {
   size_t o = 0;
   p.off_part_sum = o; o += align_up(size_t(p.stats_splits) * N * 8, 256);
   p.off_part_max = o; o += align_up(size_t(p.stats_splits) * N * 8, 256);
+  {   // geo statistics kernel: about two waves of 128-thread blocks (16 per SM), at least 8 tiles per split
+    int64_t gs = (int64_t(2) * 16 * c->sm_count + qtiles - 1) / qtiles;
+    if (gs > tiles / 8) gs = tiles / 8;
+    if (gs > 32) gs = 32;
+    if (gs < 1) gs = 1;
+    p.geo_tiles_per_split = int((tiles + gs - 1) / gs);
+    p.geo_splits = int((tiles + p.geo_tiles_per_split - 1) / p.geo_tiles_per_split);
+  }
+  p.off_gpart_sum = o; o += align_up(size_t(p.geo_splits) * N * 8, 256);
+  p.off_gpart_max = o; o += align_up(size_t(p.geo_splits) * N * 8, 256);
   p.off_sums = o;     o += align_up(size_t(N) * 8, 256);
   p.off_maxs = o;     o += align_up(size_t(N) * 8, 256);
   p.off_rowc = o;     o += align_up(size_t(N) * 32, 256);
@@ -780,6 +792,24 @@ int range_retrieve_concat(range_ctx* c, int mode, int64_t N, const void* q16, co
   cudaStream_t s = cudaStream_t(stream);
   int r = fill_args(c, mode, N, q16, qxyz, temp, geo_temp, p, ws, s, &a);      // geo mask from the tile caps (no sums yet)
   if (r) return r;
+  float* gsums = nullptr;
+  float* gmaxs = nullptr;
+  if (a.geo) {
+    // the geographic normaliser needs no tensor core: a CUDA-core pass over the unskipped tiles, then the tighter mask
+    // the known normalisers allow (fill_args with sums) for the apply side of the fused kernel
+    gsums = reinterpret_cast<float*>(ws + p.off_sums);
+    gmaxs = reinterpret_cast<float*>(ws + p.off_maxs);
+    float* ps = p.geo_splits > 1 ? reinterpret_cast<float*>(ws + p.off_gpart_sum) : gsums;
+    float* pm = p.geo_splits > 1 ? reinterpret_cast<float*>(ws + p.off_gpart_max) : gmaxs;
+    CUDA_TRY(launch_geo_stats(a, p.geo_splits, p.geo_tiles_per_split, ps, pm, s));
+    g_launches += 1;
+    if (p.geo_splits > 1) {
+      CUDA_TRY(launch_reduce_stats(ps, pm, int(N), p.geo_splits, gsums, gmaxs, s));
+      g_launches += 1;
+    }
+    r = fill_args(c, mode, N, q16, qxyz, temp, geo_temp, p, ws, s, &a, gsums);
+    if (r) return r;
+  }
   CUtensorMap tmP;
   void* ring = ws + p.off_ring;
   r = make_tmap_rows2k(&tmP, ring, uint64_t(fold_pc_ring_rows(c->sm_count)));
@@ -787,11 +817,11 @@ int range_retrieve_concat(range_ctx* c, int mode, int64_t N, const void* q16, co
   float* rowc = reinterpret_cast<float*>(ws + p.off_rowc);
   const int W = kDimV + kDimK;
   if (out_dtype == RANGE_OUT_PACKED) {
-    CUDA_TRY(launch_fold_pc(a, tmP, beta, 1.f / c->vscale, rowc, out, 1536, 0, perm, ring, ws + p.off_flags, ws + p.off_pc_part,
+    CUDA_TRY(launch_fold_pc(a, tmP, beta, 1.f / c->vscale, gsums, gmaxs, rowc, out, 1536, 0, perm, ring, ws + p.off_flags, ws + p.off_pc_part,
                             ws + p.off_pc_scratch, c->sm_count, s));
     CUDA_TRY(launch_concat_q(q64, int(N), kDimK, perm, out, 768, 512, RANGE_OUT_F64, s));
   } else {
-    CUDA_TRY(launch_fold_pc(a, tmP, beta, 1.f / c->vscale, rowc, out, W, out_dtype == RANGE_OUT_F64, perm, ring,
+    CUDA_TRY(launch_fold_pc(a, tmP, beta, 1.f / c->vscale, gsums, gmaxs, rowc, out, W, out_dtype == RANGE_OUT_F64, perm, ring,
                             ws + p.off_flags, ws + p.off_pc_part, ws + p.off_pc_scratch, c->sm_count, s));
     CUDA_TRY(launch_concat_q(q64, int(N), kDimK, perm, out, W, kDimV, out_dtype, s));
   }

@@ -10,13 +10,16 @@
 //   pass p = 0 .. rounds     apply of the unit's work item p - 1   S  = Q(p-1) . K^T -> P' -> ring -> consumers   (p >= 1)
 //                            statistics of its work item p         S' = Q(p)   . K^T -> row sums / maxima          (p < rounds)
 //
-// Both products read the same K stage; two softmax groups of four warps turn S into P' (tiles alternate between them,
-// each owns one TMEM buffer), a third group of four warps reduces S' (two buffers).  At the end of pass p the statistics
-// group turns its sums into the per-row constants of work item p (the arithmetic of row_constants_kernel) for the apply
-// groups of pass p + 1 (shared memory) and the output scale for the consumers (global memory + a release flag).  Pass 0
-// is a statistics-only prologue (the consumers wait for the first P' tile), the last pass is apply-only.  Every 4th
-// semantic exponential runs on the FMA pipe (ptx::ex2_poly, 2.7e-6): the producers would otherwise be MUFU-bound
-// (two exponential sets per tile) and set the pace instead of the consumers' tensor pipes.
+// Both products read the same K stage.  Three softmax groups of four warps (as in retrieval_pc.cu: pass tile ix belongs to
+// group ix mod 3) handle a tile's two products one after the other: S -> P' -> ring first (the consumers wait for it), then
+// S' -> running row sum / maximum of the SEMANTIC softmax.  Two TMEM buffers per product (a dedicated statistics group of
+// four warps - one warp per SM sub-partition working through every tile serially - could not keep the consumers' pace:
+// 28.5 ms against 23 ms).  The GEOGRAPHIC normaliser needs no tensor core and no Q.K^T: a CUDA-core kernel over the
+// unskipped tiles (range_geo_stats_kernel, ~1.3 ms) computes it beforehand, which also restores the tighter geo-skip mask
+// of the apply side (known normalisers).  At the end of pass p the groups combine their partial sums and group 0 turns
+// them into the per-row constants of work item p (the arithmetic of row_constants_kernel) for the apply side of pass
+// p + 1 (shared memory) and the output scale for the consumers (global memory + a release flag).  Pass 0 is a
+// statistics-only prologue (the consumers wait for the first P' tile), the last pass is apply-only.
 //
 // Consumers, ring, flags, accumulation windows and the cross-unit window barrier are those of retrieval_pc.cu (the
 // consumer role is the same code; it only reads its output scale late, once the producer has published it).  An
@@ -34,8 +37,8 @@
 namespace {
 
 constexpr int kBlockQ = 128, kKeys = 128, kXyzBytes = kKeys * 16;
-constexpr int kApplyGroups = 2;                              // softmax groups S -> P' (warps 0..7), one TMEM buffer each
-constexpr int kSoftmaxWarps = 12;                            // + one statistics group (warps 8..11)
+constexpr int kGroups = 3;                                   // softmax groups of 4 warps; pass tile ix belongs to group ix % 3
+constexpr int kSoftmaxWarps = 4 * kGroups;
 constexpr int kWarpTma = kSoftmaxWarps, kWarpMma = kSoftmaxWarps + 1, kWarpPublish = kSoftmaxWarps + 2,
               kWarpXyz = kSoftmaxWarps + 3;
 constexpr int kThreads = (kSoftmaxWarps + 4) * 32;
@@ -43,9 +46,9 @@ constexpr int kRing = 16;                                    // P' slots per pro
 constexpr int kPublishBatch = 4;                             // tiles per release of the `full` counter
 constexpr int kWindow = 64;                                  // tiles per cross-unit synchronisation window
 constexpr int kAccWindow = 128;                              // tiles per TMEM accumulation window (retrieval_pc.cu)
-constexpr int kPieceApply = 16, kPieceStats = 32;
+constexpr int kPiece = 16;                                   // S columns per TMEM load (both products share the registers)
 #ifndef RANGE_FOLD_POLY
-#define RANGE_FOLD_POLY 4
+#define RANGE_FOLD_POLY 0
 #endif
 constexpr int kPolyEvery = RANGE_FOLD_POLY;                  // every kPolyEvery-th semantic exponential on the FMA pipe (0: never)
 __device__ __forceinline__ float ex2_mixed(float x, int i) {
@@ -66,7 +69,8 @@ struct ProdSmem {
   static constexpr int stages = q + 2 * 65536;
   static constexpr int xyz = stages + NS * 32768;
   static constexpr int rowc = xyz + NX * kXyzBytes;          // [2][128 rows][2 float4] per-row constants of a work item
-  static constexpr int bars = rowc + 2 * kBlockQ * 32;
+  static constexpr int red = rowc + 2 * kBlockQ * 32;        // [2][groups][128 rows] float2 partial (sum, max) of a pass
+  static constexpr int bars = red + 2 * kGroups * kBlockQ * 8;
   static constexpr int b_q_full = 0, b_q_pair = 1, b_q_empty = 2;
   static constexpr int b_stage_full = 3;
   static constexpr int b_stage_empty = b_stage_full + NS;
@@ -140,7 +144,8 @@ template <bool kGeo>
 __global__ void __launch_bounds__(kThreads, 1)
 range_fold_pc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK64,
                      const __grid_constant__ CUtensorMap tmV128, const __grid_constant__ CUtensorMap tmP,
-                     const float4* __restrict__ db_xyz, const float4* __restrict__ q_xyz, float4* rowc_out, int N, int M,
+                     const float4* __restrict__ db_xyz, const float4* __restrict__ q_xyz, const float2* __restrict__ geo_sums,
+                     const float2* __restrict__ geo_maxs, float4* rowc_out, int N, int M,
                      float a_sem, void* __restrict__ out, const uint32_t* __restrict__ geo_mask, int mask_words,
                      float* __restrict__ part, float4* __restrict__ acc_scratch, __half* __restrict__ ring,
                      uint32_t* __restrict__ flags, uint32_t* __restrict__ windows, const FoldPlan plan) {
@@ -188,11 +193,11 @@ range_fold_pc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         ptx::mbar_init(&bars[L::b_sa_empty + i], 2 * 4);                 // the owning group's 4 warps in both CTAs
         ptx::mbar_init(&bars[L::b_sb_full + i], 1);
         ptx::mbar_init(&bars[L::b_sb_empty + i], 2 * 4);
-        ptx::mbar_init(&bars[L::b_rowc_ready + i], 4);                   // the statistics group's 4 warps
+        ptx::mbar_init(&bars[L::b_rowc_ready + i], 4);                   // group 0's 4 warps, once the groups' partials are combined
       }
       for (int i = 0; i < L::NX; ++i) {
         ptx::mbar_init(&bars[L::b_xyz_full + i], 1);
-        ptx::mbar_init(&bars[L::b_xyz_empty + i], 8);                    // 4 apply + 4 statistics warps (or the loader for an absent side)
+        ptx::mbar_init(&bars[L::b_xyz_empty + i], 4);                    // the 4 warps of the group that owns the tile
       }
       for (int i = 0; i < kRing; ++i) {
         ptx::mbar_init(&bars[L::b_slot_free + i], 1);
@@ -269,25 +274,20 @@ range_fold_pc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           for (uint32_t w = (ix + kWindow - 1) / kWindow; w < uint32_t(n_windows); ++w) atomicAdd(&windows[w], 1u);
       }
     } else if (warp == kWarpXyz) {
-      // ----- entry unit vectors of pass tile ix -> slot ix & 3; the slot frees when both sides are done with tile ix - 4 -----
+      // ----- entry unit vectors of apply tile ia -> slot ia & 3 (only the apply side has geographic work) -----
       if (kGeo && lane == 0) {
-        uint32_t ix = 0;
-        for (int p = 0; p < passes; ++p) {
-          const bool apply_on = p >= 1, stats_on = p < rounds;
-          const uint32_t* rowA = apply_on ? mask_row_of(pc_work(plan, unit, p - 1, T).qp) : nullptr;
-          const uint32_t* rowS = stats_on ? mask_row_of(pc_work(plan, unit, p, T).qp) : nullptr;
-          for (int j = pass_lo(p); j < pass_hi(p); ++j, ++ix) {
-            const int x = ix & (L::NX - 1);
-            ptx::mbar_wait(&bars[L::b_xyz_empty + x], ((ix / L::NX) & 1) ^ 1);
-            const bool need = (apply_on && !mask_bit(rowA, j)) || (stats_on && !mask_bit(rowS, j));
-            if (need) {
+        uint32_t ia = 0;
+        for (int p = 1; p < passes; ++p) {
+          const uint32_t* rowA = mask_row_of(pc_work(plan, unit, p - 1, T).qp);
+          for (int j = pass_lo(p); j < pass_hi(p); ++j, ++ia) {
+            const int x = ia & (L::NX - 1);
+            ptx::mbar_wait(&bars[L::b_xyz_empty + x], ((ia / L::NX) & 1) ^ 1);
+            if (!mask_bit(rowA, j)) {
               ptx::mbar_expect_tx(&bars[L::b_xyz_full + x], kXyzBytes);
               ptx::bulk_load_1d(smem + L::xyz + x * kXyzBytes, db_xyz + j * kKeys, kXyzBytes, &bars[L::b_xyz_full + x]);
             } else {
               ptx::mbar_arrive(&bars[L::b_xyz_full + x]);
             }
-            if (!apply_on || !stats_on)                                   // the absent side's four arrivals on this tile's slot
-              for (int k = 0; k < 4; ++k) ptx::mbar_arrive(&bars[L::b_xyz_empty + x]);
           }
         }
       }
@@ -373,209 +373,193 @@ range_fold_pc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           }
         }
       }
-    } else if (warp < 4 * kApplyGroups) {
-      // ----- apply groups: S (TMEM fp32) -> P' (fp16) -> ring.  Apply tile ia belongs to group ia & 1 = its S buffer. -----
+    } else {
+      // ----- softmax groups (warps 0..11): pass tile ix belongs to group ix % 3; apply product first, then the statistics -----
       const int grp = warp >> 2, quarter = warp & 3;
       const int row = quarter * 32 + lane;
-      const uint32_t sa_empty_leader = ptx::mapa(ptx::smem_u32(&bars[L::b_sa_empty + grp]), 0);
+      const uint32_t sa_empty_leader0 = ptx::mapa(ptx::smem_u32(&bars[L::b_sa_empty]), 0);
+      const uint32_t sb_empty_leader0 = ptx::mapa(ptx::smem_u32(&bars[L::b_sb_empty]), 0);
       __half* ring_row = ring + size_t(prod_id) * kRing * 128 * 128 + row * 8;
-      const uint32_t total = my_tiles, base_tail = uint32_t(plan.full_rounds) * uint32_t(T);
-      const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + grp * kKeys;
-      int cur_r = -1, n = 0, tail_t0 = 0;
-      const uint32_t* mask_row = nullptr;
-      float cs = -INFINITY, cg = -INFINITY, gx = 0.f, gy = 0.f, gz = 0.f;
-      uint32_t bufA[kPieceApply], bufB[kPieceApply];
-      for (uint32_t ia = uint32_t(grp); ia < total; ia += kApplyGroups) {
-        const int r = ia < base_tail ? int(ia / uint32_t(T)) : plan.full_rounds;
-        if (r != cur_r) {
-          cur_r = r;
-          const PcWork wk = pc_work(plan, unit, r, T);
-          tail_t0 = wk.t0;
-          n = (2 * wk.qp + int(rank)) * kBlockQ + row;
-          mask_row = mask_row_of(wk.qp);
-          // constants of work item r: written by the statistics group at the end of pass r
+      const uint32_t lane_base = tmem_base + (uint32_t(quarter * 32) << 16);
+      uint32_t bufA[kPiece], bufB[kPiece];
+      constexpr int kPairs = 128 / (2 * kPiece);
+      for (int p = 0; p < passes; ++p) {
+        const bool apply_on = p >= 1, stats_on = p < rounds;
+        const int lo = pass_lo(p), len = pass_hi(p) - lo;
+        const uint32_t base_ix = uint32_t(p) * uint32_t(T);
+        // apply side: work item p - 1, constants written by group 0 at the end of pass p - 1
+        const uint32_t* mask_row = nullptr;
+        float cs = -INFINITY, cg = -INFINITY, gx = 0.f, gy = 0.f, gz = 0.f;
+        if (apply_on) {
+          const int r = p - 1;
+          mask_row = mask_row_of(pc_work(plan, unit, r, T).qp);
           ptx::mbar_wait(&bars[L::b_rowc_ready + (r & 1)], (r >> 1) & 1);
           const float4* rc = reinterpret_cast<const float4*>(smem + L::rowc + (r & 1) * kBlockQ * 32) + 2 * row;
           const float4 c0 = rc[0], c1 = rc[1];
           cs = c0.x; cg = c0.y; gx = c0.z; gy = c0.w; gz = c1.x;
         }
-        const int j = ia < base_tail ? int(ia - uint32_t(r) * uint32_t(T)) : tail_t0 + int(ia - base_tail);   // database tile
-        const uint32_t ix = uint32_t(r + 1) * uint32_t(T) + uint32_t(j - (r == rounds - 1 ? pass_lo(rounds) : 0));
-        const int x = ix & (L::NX - 1);
-        const int slot = ia % kRing;
-        const bool with_geo = kGeo && !mask_bit(mask_row, j);
-        __half* dst = ring_row + size_t(slot) * 128 * 128;
-        ptx::mbar_wait(&bars[L::b_sa_full + grp], (ia >> 1) & 1);
-        if (with_geo) ptx::mbar_wait(&bars[L::b_xyz_full + x], (ix / L::NX) & 1);
-        ptx::tc_fence_after();
-        tmem_ld_piece(taddr, bufA);
-        auto piece = [&](const uint32_t (&cur)[kPieceApply], int h) {
-          const uint32_t kxyz = smem_u + L::xyz + x * kXyzBytes + h * kPieceApply * 16;
-          const int nvalid = M - (j * kKeys + h * kPieceApply);
-          uint32_t packed[kPieceApply / 2];
-          auto body = [&](auto masked, auto geo) {
-            constexpr bool kM = decltype(masked)::value, kG = decltype(geo)::value;
+        float sum_s = 0.f, max_s = -2.f;                                  // statistics side: work item p
+        for (int k = int((uint32_t(grp) + 3u - base_ix % 3u) % 3u); k < len; k += kGroups) {
+          const int j = lo + k;
+          const uint32_t ix = base_ix + uint32_t(k);
+          if (apply_on) {
+            // ======== S (TMEM fp32) -> P' (fp16) -> ring ========
+            const uint32_t ia = ix - uint32_t(T);
+            const int ba = ia & 1, x = ia & (L::NX - 1), slot = ia % kRing;
+            const uint32_t taddr = lane_base + ba * kKeys;
+            const bool with_geo = kGeo && !mask_bit(mask_row, j);
+            __half* dst = ring_row + size_t(slot) * 128 * 128;
+            ptx::mbar_wait(&bars[L::b_sa_full + ba], (ia >> 1) & 1);
+            if (with_geo) ptx::mbar_wait(&bars[L::b_xyz_full + x], (ia / L::NX) & 1);
+            ptx::tc_fence_after();
+            tmem_ld_piece(taddr, bufA);
+            auto piece = [&](const uint32_t (&cur)[kPiece], int h) {
+              const uint32_t kxyz = smem_u + L::xyz + x * kXyzBytes + h * kPiece * 16;
+              const int nvalid = M - (j * kKeys + h * kPiece);
+              uint32_t packed[kPiece / 2];
+              auto body = [&](auto masked, auto geo) {
+                constexpr bool kM = decltype(masked)::value, kG = decltype(geo)::value;
 #pragma unroll
-            for (int w = 0; w < kPieceApply / 2; ++w) {
-              float pv[2];
+                for (int w = 0; w < kPiece / 2; ++w) {
+                  float pv[2];
 #pragma unroll
-              for (int u = 0; u < 2; ++u) {
-                const int i = 2 * w + u;
-                float pr = ex2_mixed(fmaf(__uint_as_float(cur[i]), a_sem, cs), i);
-                if (kG) {
-                  const float4 k = ptx::lds_f4(kxyz + i * 16);
-                  pr += ptx::ex2(fmaf(gx, k.x, fmaf(gy, k.y, fmaf(gz, k.z, cg))));
+                  for (int u = 0; u < 2; ++u) {
+                    const int i = 2 * w + u;
+                    float pr = ex2_mixed(fmaf(__uint_as_float(cur[i]), a_sem, cs), i);
+                    if (kG) {
+                      const float4 kk = ptx::lds_f4(kxyz + i * 16);
+                      pr += ptx::ex2(fmaf(gx, kk.x, fmaf(gy, kk.y, fmaf(gz, kk.z, cg))));
+                    }
+                    if (kM && i >= nvalid) pr = 0.f;
+                    pv[u] = pr;
+                  }
+                  packed[w] = ptx::pack_half2(pv[0], pv[1]);
                 }
-                if (kM && i >= nvalid) pr = 0.f;
-                pv[u] = pr;
+              };
+              if (nvalid >= kPiece) {
+                if (with_geo) body(std::false_type{}, std::true_type{}); else body(std::false_type{}, std::false_type{});
+              } else {
+                if (with_geo) body(std::true_type{}, std::true_type{}); else body(std::true_type{}, std::false_type{});
               }
-              packed[w] = ptx::pack_half2(pv[0], pv[1]);
-            }
-          };
-          if (nvalid >= kPieceApply) {
-            if (with_geo) body(std::false_type{}, std::true_type{}); else body(std::false_type{}, std::false_type{});
-          } else {
-            if (with_geo) body(std::true_type{}, std::true_type{}); else body(std::true_type{}, std::false_type{});
-          }
-          if (h == 0) ptx::mbar_wait(&bars[L::b_slot_free + slot], (ia / kRing) & 1);   // both consumers copied tile ia - kRing
+              if (h == 0) ptx::mbar_wait(&bars[L::b_slot_free + slot], (ia / kRing) & 1);   // both consumers copied tile ia - kRing
 #pragma unroll
-          for (int e = 0; e < kPieceApply / 8; ++e)
-            ptx::stg_u4(dst + ((h * (kPieceApply / 8) + e) * 128) * 8, packed[4 * e], packed[4 * e + 1], packed[4 * e + 2],
-                        packed[4 * e + 3]);
-        };
-        constexpr int kPairs = 128 / (2 * kPieceApply);
+              for (int e = 0; e < kPiece / 8; ++e)
+                ptx::stg_u4(dst + ((h * (kPiece / 8) + e) * 128) * 8, packed[4 * e], packed[4 * e + 1], packed[4 * e + 2],
+                            packed[4 * e + 3]);
+            };
 #pragma unroll 1
-        for (int hp = 0; hp < kPairs; ++hp) {
-          ptx::tmem_ld_wait();
-          tmem_ld_piece(taddr + (2 * hp + 1) * kPieceApply, bufB);
-          piece(bufA, 2 * hp);
-          ptx::tmem_ld_wait();
-          if (hp < kPairs - 1) {
-            tmem_ld_piece(taddr + (2 * hp + 2) * kPieceApply, bufA);
-          } else {                              // the whole S tile is in registers: the MMA warp may overwrite the buffer
-            ptx::tc_fence_before();
+            for (int hp = 0; hp < kPairs; ++hp) {
+              ptx::tmem_ld_wait();
+              tmem_ld_piece(taddr + (2 * hp + 1) * kPiece, bufB);
+              piece(bufA, 2 * hp);
+              ptx::tmem_ld_wait();
+              if (hp < kPairs - 1) {
+                tmem_ld_piece(taddr + (2 * hp + 2) * kPiece, bufA);
+              } else {                          // the whole S tile is in registers: the MMA warp may overwrite the buffer
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                  if (leader) ptx::mbar_arrive(&bars[L::b_sa_empty + ba]);
+                  else ptx::mbar_arrive_cluster_relaxed(sa_empty_leader0 + 8 * ba);
+                }
+              }
+              piece(bufB, 2 * hp + 1);
+            }
             __syncwarp();
             if (lane == 0) {
-              if (leader) ptx::mbar_arrive(&bars[L::b_sa_empty + grp]);
-              else ptx::mbar_arrive_cluster_relaxed(sa_empty_leader);
+              ptx::mbar_arrive(&bars[L::b_p_written + slot]);
+              if (kGeo) ptx::mbar_arrive(&bars[L::b_xyz_empty + x]);
             }
           }
-          piece(bufB, 2 * hp + 1);
-        }
-        __syncwarp();
-        if (lane == 0) {
-          ptx::mbar_arrive(&bars[L::b_p_written + slot]);
-          if (kGeo) ptx::mbar_arrive(&bars[L::b_xyz_empty + x]);
-        }
-      }
-    } else {
-      // ----- statistics group (warps 8..11): S' of work item p -> row sums / maxima -> constants of work item p -----
-      const int quarter = warp & 3;
-      const int row = quarter * 32 + lane;
-      const uint32_t sb_empty_leader0 = ptx::mapa(ptx::smem_u32(&bars[L::b_sb_empty]), 0);
-      uint32_t ib = 0;
-      uint32_t bufA[kPieceStats], bufB[kPieceStats];
-      for (int p = 0; p < rounds; ++p) {
-        const PcWork wk = pc_work(plan, unit, p, T);
-        const int n = (2 * wk.qp + int(rank)) * kBlockQ + row;
-        const uint32_t* mask_row = mask_row_of(wk.qp);
-        float4 qx = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (kGeo && n < N) qx = q_xyz[n];
-        const float a_geo = plan.a_geo;
-        const float gx = qx.x * a_geo, gy = qx.y * a_geo, gz = qx.z * a_geo;
-        float sum_s = 0.f, sum_g = 0.f, max_s = -2.f, max_g = -3.0e38f;
-        for (int j = 0; j < T; ++j, ++ib) {
-          const int bb = ib & 1;
-          const uint32_t ix = uint32_t(p) * uint32_t(T) + uint32_t(j);
-          const int x = ix & (L::NX - 1);
-          const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + 256 + bb * kKeys;
-#ifdef RANGE_FOLD_NOGEOSTATS          // timing experiment only (wrong results): no geographic work in the statistics group
-          const bool with_geo = false;
-#else
-          const bool with_geo = kGeo && !mask_bit(mask_row, j);
-#endif
-          ptx::mbar_wait(&bars[L::b_sb_full + bb], (ib >> 1) & 1);
-          if (with_geo) ptx::mbar_wait(&bars[L::b_xyz_full + x], (ix / L::NX) & 1);
-          ptx::tc_fence_after();
-          tmem_ld_piece(taddr, bufA);
-          auto piece = [&](const uint32_t (&cur)[kPieceStats], int h) {
-            const uint32_t kxyz = smem_u + L::xyz + x * kXyzBytes + h * kPieceStats * 16;
-            const int nvalid = M - (j * kKeys + h * kPieceStats);
-            auto body = [&](auto masked, auto geo) {
-              constexpr bool kM = decltype(masked)::value, kG = decltype(geo)::value;
+          if (stats_on) {
+            // ======== S' (TMEM fp32) -> running sum 2^(a (s - 1)) and maximum of the semantic softmax ========
+            const uint32_t ib = ix;
+            const int bb = ib & 1;
+            const uint32_t taddr = lane_base + 256 + bb * kKeys;
+            ptx::mbar_wait(&bars[L::b_sb_full + bb], (ib >> 1) & 1);
+            ptx::tc_fence_after();
+            tmem_ld_piece(taddr, bufA);
+            auto piece = [&](const uint32_t (&cur)[kPiece], int h) {
+              const int nvalid = M - (j * kKeys + h * kPiece);
+              auto body = [&](auto masked) {
+                constexpr bool kM = decltype(masked)::value;
 #pragma unroll
-              for (int i = 0; i < kPieceStats; i += 2) {
-                float sv[2], gv[2];
+                for (int i = 0; i < kPiece; i += 2) {
+                  float sv[2];
 #pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                  const float s = __uint_as_float(cur[i + u]);
-                  const bool valid = !kM || (i + u < nvalid);
-                  float es = ex2_mixed(fmaf(s, a_sem, -a_sem), i + u);
-                  if (!valid) es = 0.f;
-                  sum_s += es;
-                  sv[u] = valid ? s : -2.f;
-                  if (kG) {
-                    const float4 k = ptx::lds_f4(kxyz + (i + u) * 16);
-                    const float g = fmaf(gx, k.x, fmaf(gy, k.y, fmaf(gz, k.z, -a_geo)));   // a_geo (g - 1)
-                    float eg = ptx::ex2(g);
-                    if (!valid) eg = 0.f;
-                    sum_g += eg;
-                    gv[u] = valid ? g : -3.0e38f;
+                  for (int u = 0; u < 2; ++u) {
+                    const float sc = __uint_as_float(cur[i + u]);
+                    const bool valid = !kM || (i + u < nvalid);
+                    float es = ex2_mixed(fmaf(sc, a_sem, -a_sem), i + u);
+                    if (!valid) es = 0.f;
+                    sum_s += es;
+                    sv[u] = valid ? sc : -2.f;
                   }
+                  max_s = ptx::max3(max_s, sv[0], sv[1]);
                 }
-                max_s = ptx::max3(max_s, sv[0], sv[1]);
-                if (kG) max_g = ptx::max3(max_g, gv[0], gv[1]);
-              }
+              };
+              if (nvalid >= kPiece) body(std::false_type{}); else body(std::true_type{});
             };
-            if (nvalid >= kPieceStats) {
-              if (with_geo) body(std::false_type{}, std::true_type{}); else body(std::false_type{}, std::false_type{});
-            } else {
-              if (with_geo) body(std::true_type{}, std::true_type{}); else body(std::true_type{}, std::false_type{});
-            }
-          };
-          constexpr int kPairs = 128 / (2 * kPieceStats);
 #pragma unroll 1
-          for (int hp = 0; hp < kPairs; ++hp) {
-            ptx::tmem_ld_wait();
-            tmem_ld_piece(taddr + (2 * hp + 1) * kPieceStats, bufB);
-            piece(bufA, 2 * hp);
-            ptx::tmem_ld_wait();
-            if (hp < kPairs - 1) {
-              tmem_ld_piece(taddr + (2 * hp + 2) * kPieceStats, bufA);
-            } else {
-              ptx::tc_fence_before();
-              __syncwarp();
-              if (lane == 0) {
-                if (leader) ptx::mbar_arrive(&bars[L::b_sb_empty + bb]);
-                else ptx::mbar_arrive_cluster_relaxed(sb_empty_leader0 + 8 * bb);
+            for (int hp = 0; hp < kPairs; ++hp) {
+              ptx::tmem_ld_wait();
+              tmem_ld_piece(taddr + (2 * hp + 1) * kPiece, bufB);
+              piece(bufA, 2 * hp);
+              ptx::tmem_ld_wait();
+              if (hp < kPairs - 1) {
+                tmem_ld_piece(taddr + (2 * hp + 2) * kPiece, bufA);
+              } else {
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                  if (leader) ptx::mbar_arrive(&bars[L::b_sb_empty + bb]);
+                  else ptx::mbar_arrive_cluster_relaxed(sb_empty_leader0 + 8 * bb);
+                }
               }
+              piece(bufB, 2 * hp + 1);
             }
-            piece(bufB, 2 * hp + 1);
-          }
-          if (kGeo) {
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&bars[L::b_xyz_empty + x]);
           }
         }
-        // constants of work item p (retrieval.cu: row_constants_kernel; max_g holds a_geo (g_max - 1) already)
-        {
-          const float top_s = plan.w_sem * ptx::ex2(a_sem * (max_s - 1.f)) / sum_s;
-          const float top_g = kGeo ? plan.w_geo * ptx::ex2(max_g) / sum_g : 0.f;
-          const float B = top_s + top_g;
-          const float C = 8192.f;
-          float cs = (plan.w_sem > 0.f) ? -a_sem + log2f(plan.w_sem * C / (B * sum_s)) : -INFINITY;
-          float cg = (kGeo && plan.w_geo > 0.f) ? -a_geo + log2f(plan.w_geo * C / (B * sum_g)) : -INFINITY;
-          float scale = B / C * plan.inv_vscale;
-          if (n >= N) { cs = -INFINITY; cg = -INFINITY; scale = 0.f; }
-          float4* rc = reinterpret_cast<float4*>(smem + L::rowc + (p & 1) * kBlockQ * 32) + 2 * row;
-          rc[0] = make_float4(cs, cg, gx, gy);
-          rc[1] = make_float4(gz, scale, 0.f, 0.f);
-          if (n < N) rowc_out[2 * n + 1] = make_float4(gz, scale, sum_s, sum_g);     // the consumers' output scale (+ the sums, for inspection)
-          __threadfence();
-          asm volatile("bar.sync 2, 128;" ::: "memory");                             // the group's four warps
-          if (warp == 8 && lane == 0) ptx::st_release_gpu(scale_flag, uint32_t(p + 1));
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(&bars[L::b_rowc_ready + (p & 1)]);
+        if (stats_on) {
+          // ---- end of pass p: combine the groups' partials; group 0 forms the constants of work item p ----
+          float2* red = reinterpret_cast<float2*>(smem + L::red) + (p & 1) * kGroups * kBlockQ;
+          red[grp * kBlockQ + row] = make_float2(sum_s, max_s);
+          asm volatile("bar.sync 2, %0;" ::"n"(kSoftmaxWarps * 32) : "memory");
+          if (grp == 0) {
+            const int n = (2 * pc_work(plan, unit, p, T).qp + int(rank)) * kBlockQ + row;
+            float l_s = 0.f, m_s = -2.f;
+#pragma unroll
+            for (int g2 = 0; g2 < kGroups; ++g2) {                        // fixed order: repeatable
+              const float2 o = red[g2 * kBlockQ + row];
+              l_s += o.x;
+              m_s = fmaxf(m_s, o.y);
+            }
+            float l_g = 1.f, top_g = 0.f, qgx = 0.f, qgy = 0.f, qgz = 0.f;
+            const float a_geo = plan.a_geo;
+            if (kGeo && n < N) {
+              l_g = geo_sums[n].y;                                       // range_geo_stats_kernel
+              top_g = plan.w_geo * ptx::ex2(a_geo * (geo_maxs[n].y - 1.f)) / l_g;
+              const float4 qx = q_xyz[n];
+              qgx = qx.x * a_geo; qgy = qx.y * a_geo; qgz = qx.z * a_geo;
+            }
+            // (retrieval.cu: row_constants_kernel)
+            const float top_s = plan.w_sem * ptx::ex2(a_sem * (m_s - 1.f)) / l_s;
+            const float B = top_s + top_g;
+            const float C = 8192.f;
+            float c_s = (plan.w_sem > 0.f) ? -a_sem + log2f(plan.w_sem * C / (B * l_s)) : -INFINITY;
+            float c_g = (kGeo && plan.w_geo > 0.f) ? -a_geo + log2f(plan.w_geo * C / (B * l_g)) : -INFINITY;
+            float scale = B / C * plan.inv_vscale;
+            if (n >= N) { c_s = -INFINITY; c_g = -INFINITY; scale = 0.f; }
+            float4* rc = reinterpret_cast<float4*>(smem + L::rowc + (p & 1) * kBlockQ * 32) + 2 * row;
+            rc[0] = make_float4(c_s, c_g, qgx, qgy);
+            rc[1] = make_float4(qgz, scale, 0.f, 0.f);
+            if (n < N) rowc_out[2 * n + 1] = make_float4(qgz, scale, l_s, l_g);      // the consumers' output scale (+ the sums, for inspection)
+            __threadfence();
+            asm volatile("bar.sync 3, 128;" ::: "memory");                           // group 0's four warps
+            if (warp == 0 && lane == 0) ptx::st_release_gpu(scale_flag, uint32_t(p + 1));
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&bars[L::b_rowc_ready + (p & 1)]);
+          }
         }
       }
     }
@@ -781,6 +765,60 @@ range_fold_pc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   if (active && warp == kWarpMma) ptx::tmem_dealloc_2sm<512>(tmem_base);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Geographic row statistics on the CUDA cores (no Q.K^T, no tensor core): per row  sum_j 2^(a_g (g_j - 1))  and  max_j g_j
+// over the tiles of one split that the bounding-cap mask does not skip (reference: the denominator of the geographic
+// softmax, range/range.py:231-234).  Block = one 128-query tile, thread = one query; the entry unit vectors of a tile go
+// through shared memory (broadcast LDS.128).  Partials [split][N] float2 = (0, sum) / (-2, max cos) in the layout of the
+// statistics kernels, so reduce_stats_kernel merges them.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+range_geo_stats_kernel(const float4* __restrict__ db_xyz, const float4* __restrict__ q_xyz, int N, int M, int tiles_per_split,
+                       float a_geo, float2* __restrict__ part_sum, float2* __restrict__ part_max,
+                       const uint32_t* __restrict__ geo_mask, int mask_words) {
+  __shared__ float4 xs[2][kKeys];
+  const int qt = blockIdx.x, split = blockIdx.y;
+  const int n = qt * kBlockQ + threadIdx.x;
+  const int total_tiles = (M + kKeys - 1) / kKeys;
+  const int t_begin = split * tiles_per_split, t_end = min(total_tiles, t_begin + tiles_per_split);
+  const uint32_t* mask_row = geo_mask ? geo_mask + size_t(qt) * mask_words : nullptr;
+  float4 qx = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (n < N) qx = q_xyz[n];
+  const float gx = qx.x * a_geo, gy = qx.y * a_geo, gz = qx.z * a_geo;
+  float sum0 = 0.f, sum1 = 0.f, mx = -3.0e38f;
+  int buf = 0;
+  for (int t = t_begin; t < t_end; ++t) {
+    if (mask_row != nullptr && ((__ldg(mask_row + (t >> 5)) >> (t & 31)) & 1u)) continue;     // block-uniform
+    xs[buf][threadIdx.x] = db_xyz[size_t(t) * kKeys + threadIdx.x];
+    __syncthreads();             // (two buffers: a thread can only overwrite buffer b after everyone passed the next barrier)
+    const int nvalid = min(kKeys, M - t * kKeys);
+    const uint32_t base = ptx::smem_u32(&xs[buf][0]);
+    if (nvalid == kKeys) {
+#pragma unroll 8
+      for (int i = 0; i < kKeys; i += 2) {
+        const float4 k0 = ptx::lds_f4(base + i * 16), k1 = ptx::lds_f4(base + i * 16 + 16);
+        const float g0 = fmaf(gx, k0.x, fmaf(gy, k0.y, fmaf(gz, k0.z, -a_geo)));
+        const float g1 = fmaf(gx, k1.x, fmaf(gy, k1.y, fmaf(gz, k1.z, -a_geo)));
+        sum0 += ptx::ex2(g0);
+        sum1 += ptx::ex2(g1);
+        mx = ptx::max3(mx, g0, g1);
+      }
+    } else {
+      for (int i = 0; i < nvalid; ++i) {
+        const float4 k0 = ptx::lds_f4(base + i * 16);
+        const float g0 = fmaf(gx, k0.x, fmaf(gy, k0.y, fmaf(gz, k0.z, -a_geo)));
+        sum0 += ptx::ex2(g0);
+        mx = fmaxf(mx, g0);
+      }
+    }
+    buf ^= 1;
+  }
+  if (n < N) {
+    part_sum[size_t(split) * N + n] = make_float2(0.f, sum0 + sum1);
+    part_max[size_t(split) * N + n] = make_float2(-2.f, mx / a_geo + 1.f);      // mx holds a_geo (g - 1): store the raw cosine
+  }
+}
+
 // partials [splits][rows][1024] fp32 -> rows row0.. of the caller's output
 __global__ void fold_reduce_tail_kernel(const float4* __restrict__ part, size_t stride4, int splits, int rows, int row0,
                                         const int* __restrict__ perm, void* __restrict__ out, int out_ld, int out_f64) {
@@ -842,7 +880,18 @@ size_t fold_pc_part_bytes(int sm_count, int64_t N, int64_t M) {
 size_t fold_pc_ring_bytes(int sm_count) { return size_t(apply_pc_units(sm_count)) * 2 * kRing * 128 * 128 * 2; }
 int fold_pc_ring_rows(int sm_count) { return apply_pc_units(sm_count) * 2 * kRing * 16; }
 
-cudaError_t launch_fold_pc(const RetrievalArgs& a, const CUtensorMap& tmP, float beta, float inv_vscale, float* rowc, void* out,
+// grid (query tiles, splits); partials in the statistics kernels' layout
+cudaError_t launch_geo_stats(const RetrievalArgs& a, int splits, int tiles_per_split, float* part_sum, float* part_max,
+                             cudaStream_t stream) {
+  const int qtiles = (a.N + kBlockQ - 1) / kBlockQ;
+  range_geo_stats_kernel<<<dim3(unsigned(qtiles), unsigned(splits)), 128, 0, stream>>>(
+      a.db_xyz, a.q_xyz, a.N, a.M, tiles_per_split, a.a_geo, reinterpret_cast<float2*>(part_sum),
+      reinterpret_cast<float2*>(part_max), a.geo_mask, a.mask_words);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_fold_pc(const RetrievalArgs& a, const CUtensorMap& tmP, float beta, float inv_vscale, const float* geo_sums,
+                           const float* geo_maxs, float* rowc, void* out,
                            int out_ld, int out_f64, const int* perm, void* ring, void* flags, void* part, void* scratch,
                            int sm_count, cudaStream_t stream) {
   FoldPlan plan = fold_plan(sm_count, a.N, a.M);
@@ -882,7 +931,8 @@ cudaError_t launch_fold_pc(const RetrievalArgs& a, const CUtensorMap& tmP, float
     return cudaErrorCooperativeLaunchTooLarge;
   }
   cfg.numAttrs = coop ? 2 : 1;
-  e = cudaLaunchKernelEx(&cfg, kern, a.tmQ, a.tmK64, a.tmV128, tmP, a.db_xyz, a.q_xyz, reinterpret_cast<float4*>(rowc), a.N, a.M,
+  e = cudaLaunchKernelEx(&cfg, kern, a.tmQ, a.tmK64, a.tmV128, tmP, a.db_xyz, a.q_xyz, reinterpret_cast<const float2*>(geo_sums),
+                         reinterpret_cast<const float2*>(geo_maxs), reinterpret_cast<float4*>(rowc), a.N, a.M,
                          a.a_sem, out, a.geo_mask, a.mask_words, reinterpret_cast<float*>(part),
                          reinterpret_cast<float4*>(scratch), reinterpret_cast<__half*>(ring), reinterpret_cast<uint32_t*>(flags),
                          reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(flags) + fold_ring_flag_bytes(sm_count)), plan);

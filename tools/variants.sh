@@ -5,9 +5,7 @@
 set -e
 cd "$(dirname "$0")/.."
 SRC=${SRC:-retrieval_fold}
-VARIANTS=("base:" "poly0:-DRANGE_FOLD_POLY=0" "poly2:-DRANGE_FOLD_POLY=2" "nogeo:-DRANGE_FOLD_NOGEOSTATS" \
-          "nogeo_poly0:-DRANGE_FOLD_NOGEOSTATS -DRANGE_FOLD_POLY=0" "nogeo_poly2:-DRANGE_FOLD_NOGEOSTATS -DRANGE_FOLD_POLY=2" \
-          "nogeo_poly8:-DRANGE_FOLD_NOGEOSTATS -DRANGE_FOLD_POLY=8")
+VARIANTS=("base:" "poly4:-DRANGE_FOLD_POLY=4" "poly8:-DRANGE_FOLD_POLY=8")
 if [ "${1:-build}" = "build" ]; then
   mkdir -p build/variants
   FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC --use_fast_math -diag-suppress 177"
