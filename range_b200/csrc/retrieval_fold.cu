@@ -74,12 +74,16 @@ struct ProdSmem {
   static constexpr int b_q_full = 0, b_q_pair = 1, b_q_empty = 2;
   static constexpr int b_stage_full = 3;
   static constexpr int b_stage_empty = b_stage_full + NS;
-  static constexpr int b_sa_full = b_stage_empty + NS;       // apply S buffers (one per apply group)
-  static constexpr int b_sa_empty = b_sa_full + 2;
-  static constexpr int b_sb_full = b_sa_empty + 2;           // statistics S' buffers
-  static constexpr int b_sb_empty = b_sb_full + 2;
-  static constexpr int b_xyz_full = b_sb_empty + 2;
-  static constexpr int b_xyz_empty = b_xyz_full + NX;
+  // "full" barriers are indexed by the tile number modulo lcm(buffers, groups): a barrier's consecutive phases then belong
+  // to the SAME softmax group, which waits for them in order.  (Indexed by buffer, a group that runs two fills ahead of
+  // the tensor core would take the completed phase before last for its own: mbarrier waits only know a parity.)
+  static constexpr int NF = 6, NXF = 12;
+  static constexpr int b_sa_full = b_stage_empty + NS;       // apply S: 2 buffers (tile ia & 1), NF full barriers (ia % 6)
+  static constexpr int b_sa_empty = b_sa_full + NF;
+  static constexpr int b_sb_full = b_sa_empty + 2;           // statistics S': 2 buffers, NF full barriers
+  static constexpr int b_sb_empty = b_sb_full + NF;
+  static constexpr int b_xyz_full = b_sb_empty + 2;          // xyz: NX slots (ia & 3), NXF full barriers (ia % 12)
+  static constexpr int b_xyz_empty = b_xyz_full + NXF;
   static constexpr int b_rowc_ready = b_xyz_empty + NX;      // [2]
   static constexpr int b_slot_free = b_rowc_ready + 2;
   static constexpr int b_p_written = b_slot_free + kRing;
@@ -188,17 +192,17 @@ range_fold_pc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         ptx::mbar_init(&bars[L::b_stage_full + i], 1);
         ptx::mbar_init(&bars[L::b_stage_empty + i], 1);
       }
-      for (int i = 0; i < 2; ++i) {
+      for (int i = 0; i < L::NF; ++i) {
         ptx::mbar_init(&bars[L::b_sa_full + i], 1);                      // MMA commit
-        ptx::mbar_init(&bars[L::b_sa_empty + i], 2 * 4);                 // the owning group's 4 warps in both CTAs
         ptx::mbar_init(&bars[L::b_sb_full + i], 1);
+      }
+      for (int i = 0; i < 2; ++i) {
+        ptx::mbar_init(&bars[L::b_sa_empty + i], 2 * 4);                 // the 4 warps of the tile's group in both CTAs
         ptx::mbar_init(&bars[L::b_sb_empty + i], 2 * 4);
         ptx::mbar_init(&bars[L::b_rowc_ready + i], 4);                   // group 0's 4 warps, once the groups' partials are combined
       }
-      for (int i = 0; i < L::NX; ++i) {
-        ptx::mbar_init(&bars[L::b_xyz_full + i], 1);
-        ptx::mbar_init(&bars[L::b_xyz_empty + i], 4);                    // the 4 warps of the group that owns the tile
-      }
+      for (int i = 0; i < L::NXF; ++i) ptx::mbar_init(&bars[L::b_xyz_full + i], 1);
+      for (int i = 0; i < L::NX; ++i) ptx::mbar_init(&bars[L::b_xyz_empty + i], 4);     // the 4 warps of the tile's group
       for (int i = 0; i < kRing; ++i) {
         ptx::mbar_init(&bars[L::b_slot_free + i], 1);
         ptx::mbar_init(&bars[L::b_p_written + i], 4);
@@ -282,11 +286,12 @@ range_fold_pc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           for (int j = pass_lo(p); j < pass_hi(p); ++j, ++ia) {
             const int x = ia & (L::NX - 1);
             ptx::mbar_wait(&bars[L::b_xyz_empty + x], ((ia / L::NX) & 1) ^ 1);
+            uint64_t* full = &bars[L::b_xyz_full + ia % L::NXF];
             if (!mask_bit(rowA, j)) {
-              ptx::mbar_expect_tx(&bars[L::b_xyz_full + x], kXyzBytes);
-              ptx::bulk_load_1d(smem + L::xyz + x * kXyzBytes, db_xyz + j * kKeys, kXyzBytes, &bars[L::b_xyz_full + x]);
+              ptx::mbar_expect_tx(full, kXyzBytes);
+              ptx::bulk_load_1d(smem + L::xyz + x * kXyzBytes, db_xyz + j * kKeys, kXyzBytes, full);
             } else {
-              ptx::mbar_arrive(&bars[L::b_xyz_full + x]);
+              ptx::mbar_arrive(full);
             }
           }
         }
@@ -320,7 +325,7 @@ range_fold_pc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                 for (int kk = 0; kk < 4; ++kk)
                   ptx::umma_f16_ss_2sm(tmem_base + ba * kKeys, ptx::umma_desc_kmajor_sw128(a_base + c * 16384 + kk * 32),
                                        ptx::umma_desc_kmajor_sw128(b_base + c * 8192 + kk * 32), idesc_qk, (c | kk) != 0);
-              ptx::umma_commit_2sm_u32(bars_u + 8 * (L::b_sa_full + ba));
+              ptx::umma_commit_2sm_u32(bars_u + 8 * (L::b_sa_full + ia % L::NF));
             }
             if (stats_on) {
               const uint32_t a_base = smem_u + L::q + (p & 1) * 65536;
@@ -330,7 +335,7 @@ range_fold_pc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                 for (int kk = 0; kk < 4; ++kk)
                   ptx::umma_f16_ss_2sm(tmem_base + 256 + bb * kKeys, ptx::umma_desc_kmajor_sw128(a_base + c * 16384 + kk * 32),
                                        ptx::umma_desc_kmajor_sw128(b_base + c * 8192 + kk * 32), idesc_qk, (c | kk) != 0);
-              ptx::umma_commit_2sm_u32(bars_u + 8 * (L::b_sb_full + bb));
+              ptx::umma_commit_2sm_u32(bars_u + 8 * (L::b_sb_full + ib % L::NF));
             }
             ptx::umma_commit_2sm_u32(bars_u + 8 * (L::b_stage_empty + st.idx));
           }
@@ -409,8 +414,8 @@ range_fold_pc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             const uint32_t taddr = lane_base + ba * kKeys;
             const bool with_geo = kGeo && !mask_bit(mask_row, j);
             __half* dst = ring_row + size_t(slot) * 128 * 128;
-            ptx::mbar_wait(&bars[L::b_sa_full + ba], (ia >> 1) & 1);
-            if (with_geo) ptx::mbar_wait(&bars[L::b_xyz_full + x], (ia / L::NX) & 1);
+            ptx::mbar_wait(&bars[L::b_sa_full + ia % L::NF], (ia / L::NF) & 1);
+            if (with_geo) ptx::mbar_wait(&bars[L::b_xyz_full + ia % L::NXF], (ia / L::NXF) & 1);
             ptx::tc_fence_after();
             tmem_ld_piece(taddr, bufA);
             auto piece = [&](const uint32_t (&cur)[kPiece], int h) {
@@ -476,7 +481,7 @@ range_fold_pc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             const uint32_t ib = ix;
             const int bb = ib & 1;
             const uint32_t taddr = lane_base + 256 + bb * kKeys;
-            ptx::mbar_wait(&bars[L::b_sb_full + bb], (ib >> 1) & 1);
+            ptx::mbar_wait(&bars[L::b_sb_full + ib % L::NF], (ib / L::NF) & 1);
             ptx::tc_fence_after();
             tmem_ld_piece(taddr, bufA);
             auto piece = [&](const uint32_t (&cur)[kPiece], int h) {
