@@ -65,15 +65,12 @@ def peaks():
 
 def apply_kernel_traffic():
     """DRAM bytes per launch of the apply kernel from the newest `ncu --set full` summary under profiles/
-    (dram__bytes_read.sum + dram__bytes_write.sum of the retrieval kernel's column), or (None, None)"""
+    (dram__bytes_read.sum + dram__bytes_write.sum of the range_apply_pc_kernel column), or (None, None)"""
     import csv
     for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_k2_ncu_full_selected.csv")), reverse=True):
         try:
             rows = {r[0]: r for r in csv.reader(open(path)) if r}
-            names = rows["Kernel Name"]
-            col = next((i for i, v in enumerate(names) if "range_fold_pc_kernel" in v), None)
-            if col is None:
-                col = next(i for i, v in enumerate(names) if "range_apply_pc_kernel" in v)
+            col = next(i for i, v in enumerate(rows["Kernel Name"]) if "range_apply_pc_kernel" in v)
             scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
             total = sum(float(rows[k][col]) * scale[rows[k][1]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
             return total, os.path.relpath(path, ROOT)
@@ -374,7 +371,6 @@ def main():
     qxyz = torch.empty(N_QUERIES, 4, dtype=torch.float32, device=dev)
 
     marks = []
-    two_pass = os.environ.get("RANGE_FOLD") == "0"       # the separate statistics + apply kernels (A/B switch of the library)
 
     def step(record=False):
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)] if record else None
@@ -383,15 +379,10 @@ def main():
         if record: ev[0].record()
         eng.encode(s_coords, q64, q16, qxyz)
         if record: ev[1].record()
-        if two_pass:
-            sums, maxs = eng.retrieve_stats("RANGE+", q16, qxyz, 12.0, 40.0)
-            if record: ev[2].record()
-            # apply pass: its epilogue writes the (N,1280) result (rows back in the caller's order); then the location columns
-            eng.retrieve_apply_concat("RANGE+", q16, qxyz, 12.0, 40.0, BETA, sums, maxs, q64, out=out, perm=perm)
-        else:
-            if record: ev[2].record()
-            # ONE retrieval kernel: row statistics (folded into the producers), softmax blend, P.V and the concat epilogue
-            eng.retrieve_concat("RANGE+", q16, qxyz, 12.0, 40.0, BETA, q64, out=out, perm=perm)
+        sums, maxs = eng.retrieve_stats("RANGE+", q16, qxyz, 12.0, 40.0)
+        if record: ev[2].record()
+        # apply pass: its epilogue writes the (N,1280) result (rows back in the caller's order); then the location columns
+        eng.retrieve_apply_concat("RANGE+", q16, qxyz, 12.0, 40.0, BETA, sums, maxs, q64, out=out, perm=perm)
         if record:
             ev[3].record()
             marks.append(ev)
@@ -458,7 +449,7 @@ def main():
     if rank == 0:
         peak_tf, _, peak_src = peaks()
         t_k2 = (seg[1] + seg[2]) * 1e-3
-        achieved_k2 = FLOP_PER_PAIR * N_QUERIES * M_DB / t_k2 / 1e12            # the whole retrieval (stats + apply when two-pass)
+        achieved_k2 = FLOP_PER_PAIR * N_QUERIES * M_DB / t_k2 / 1e12            # stats + apply
         achieved = FLOP_PER_PAIR * N_QUERIES * M_DB / (seg[2] * 1e-3) / 1e12    # dominant kernel alone
         traffic, traffic_src = apply_kernel_traffic()
         line = {
@@ -469,20 +460,18 @@ def main():
             "config": {"workload": f"{WORKLOAD}, {N_QUERIES} queries/GPU", "parallelism": f"query-sharded x{world}, DB replicated"
                        + ("; m_sharded: DB sharded along M" if world > 1 else ""),
                        "l2": "inputs larger than L2 (DB 257 MB fp16 streamed every step; 512 MB output)",
-                       "segments_ms": ({"sort_queries": seg[4], "encode": seg[0], "retrieve_stats": seg[1], "retrieve_apply_concat": seg[2]}
-                                       if two_pass else {"sort_queries": seg[4], "encode": seg[0], "retrieve_concat (fused)": seg[2]}),
+                       "segments_ms": {"sort_queries": seg[4], "encode": seg[0], "retrieve_stats": seg[1], "retrieve_apply_concat": seg[2]},
                        "parity_tolerance": "retrieved columns: relative row error <= 1e-3, 2e-4 on the structured DB (named exception: purely "
                                            "semantic softmax on the iid worst-case DB 2e-3), cosine >= 0.99999; location columns: "
                                            "max-abs <= 3e-5 (|lat| < 60 deg) / 1e-3 (polar) = the reference's own fp64 polynomial "
                                            "noise (tests/test_gpu_parity.py)"},
             # dominant kernel = the apply pass (all 2566 algorithmic flop per pair live there); the stats pass that
             # precedes it is algorithmically redundant work, so the stricter figure over both kernels is given too
-            "roofline": {"bound": "tensor", "kernel": ("range_apply_pc_kernel (K2b: Q.K^T + softmax blend + P.V)" if two_pass else
-                                                       "range_fold_pc_kernel (K2: row statistics + Q.K^T + softmax blend + P.V + concat, one kernel)"),
+            "roofline": {"bound": "tensor", "kernel": "range_apply_pc_kernel (K2b: Q.K^T + softmax blend + P.V)",
                          "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                          "peak_source": f"{peak_src} bf16 dense sustained",
                          "traffic": traffic,
-                         "traffic_source": f"ncu --set full, {traffic_src} (dram read + write of the retrieval kernel)",
+                         "traffic_source": f"ncu --set full, {traffic_src} (dram read + write of the apply kernel)",
                          "algorithmic_flop_per_launch": FLOP_PER_PAIR * N_QUERIES * M_DB,
                          "launch_ms": seg[2],
                          "stats_plus_apply": {"achieved": achieved_k2, "frac": achieved_k2 / peak_tf,

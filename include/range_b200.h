@@ -170,11 +170,8 @@ int range_retrieve_apply_concat(range_ctx* ctx, int mode, int64_t N, const void*
                                 const int32_t* perm, void* out, int out_dtype, void* workspace, size_t workspace_bytes,
                                 void* stream);
 
-/* K2 + K3 in ONE call without precomputed statistics (unsharded database): row statistics, apply pass and concat.  For
- * large batches a single retrieval kernel runs in which the producer CTAs compute the statistics of their next work
- * item alongside the apply pass of the current one (csrc/retrieval_fold.cu) - no separate statistics pass; small
- * batches run range_retrieve_stats + range_retrieve_apply_concat internally.  Same result layout as
- * range_retrieve_apply_concat. */
+/* K2 + K3 in ONE call for an unsharded database: range_retrieve_stats + range_retrieve_apply_concat with the statistics
+ * kept in the workspace.  Same result layout as range_retrieve_apply_concat. */
 int range_retrieve_concat(range_ctx* ctx, int mode, int64_t N, const void* q16, const float* qxyz, float temp,
                           float geo_temp, float beta, const double* q64, const int32_t* perm, void* out, int out_dtype,
                           void* workspace, size_t workspace_bytes, void* stream);

@@ -116,8 +116,6 @@ struct RetrievalPlan {
   int mask_rows, mask_words;                // geo-skip mask: [even-padded query tiles][ceil(tiles / 32)]
   bool pc;                                  // apply with the producer/consumer kernel (retrieval_pc.cu)
   bool stats_pc;                            // statistics with the CTA-pair / four-group kernel (retrieval_pc.cu)
-  int geo_splits, geo_tiles_per_split;      // geographic statistics of the fused retrieval kernel (retrieval_fold.cu)
-  size_t off_gpart_sum, off_gpart_max;
   size_t off_part_sum, off_part_max, off_sums, off_maxs, off_rowc, off_mask, off_ring, off_flags, off_pc_part, off_pc_scratch, off_part_out, off_O, total;
 };
 
@@ -173,16 +171,6 @@ RetrievalPlan plan_retrieval(const range_ctx* c, int64_t N) {
   size_t o = 0;
   p.off_part_sum = o; o += align_up(size_t(p.stats_splits) * N * 8, 256);
   p.off_part_max = o; o += align_up(size_t(p.stats_splits) * N * 8, 256);
-  {   // geo statistics kernel: about two waves of 128-thread blocks (16 per SM), at least 8 tiles per split
-    int64_t gs = (int64_t(2) * 16 * c->sm_count + qtiles - 1) / qtiles;
-    if (gs > tiles / 8) gs = tiles / 8;
-    if (gs > 32) gs = 32;
-    if (gs < 1) gs = 1;
-    p.geo_tiles_per_split = int((tiles + gs - 1) / gs);
-    p.geo_splits = int((tiles + p.geo_tiles_per_split - 1) / p.geo_tiles_per_split);
-  }
-  p.off_gpart_sum = o; o += align_up(size_t(p.geo_splits) * N * 8, 256);
-  p.off_gpart_max = o; o += align_up(size_t(p.geo_splits) * N * 8, 256);
   p.off_sums = o;     o += align_up(size_t(N) * 8, 256);
   p.off_maxs = o;     o += align_up(size_t(N) * 8, 256);
   p.off_rowc = o;     o += align_up(size_t(N) * 32, 256);
@@ -194,15 +182,9 @@ RetrievalPlan plan_retrieval(const range_ctx* c, int64_t N) {
   const int64_t qpairs = (qtiles + 1) / 2;
   const int ov = apply_kernel_override();
   p.pc = units > 0 && ov != 1 && (ov == 2 || qpairs >= units);
-  const size_t ring_b = apply_pc_ring_bytes(c->sm_count) > fold_pc_ring_bytes(c->sm_count) ? apply_pc_ring_bytes(c->sm_count)
-                                                                                             : fold_pc_ring_bytes(c->sm_count);
-  const size_t flag_b = apply_pc_flag_bytes(c->sm_count, N, c->M) > fold_pc_flag_bytes(c->sm_count, N, c->M)
-                            ? apply_pc_flag_bytes(c->sm_count, N, c->M) : fold_pc_flag_bytes(c->sm_count, N, c->M);
-  const size_t part_b = apply_pc_part_bytes(c->sm_count, N, c->M) > fold_pc_part_bytes(c->sm_count, N, c->M)
-                            ? apply_pc_part_bytes(c->sm_count, N, c->M) : fold_pc_part_bytes(c->sm_count, N, c->M);
-  p.off_ring = o;     o += p.pc ? align_up(ring_b, 1024) : 0;
-  p.off_flags = o;    o += p.pc ? align_up(flag_b, 256) : 0;
-  p.off_pc_part = o;  o += p.pc ? align_up(part_b, 256) : 0;
+  p.off_ring = o;     o += p.pc ? align_up(apply_pc_ring_bytes(c->sm_count), 1024) : 0;
+  p.off_flags = o;    o += p.pc ? align_up(apply_pc_flag_bytes(c->sm_count, N, c->M), 256) : 0;
+  p.off_pc_part = o;  o += p.pc ? align_up(apply_pc_part_bytes(c->sm_count, N, c->M), 256) : 0;
   p.off_pc_scratch = o; o += p.pc ? align_up(apply_pc_scratch_bytes(c->sm_count), 256) : 0;
   p.off_part_out = o; o += (p.splits > 1 && !p.pc) ? align_up(size_t(p.splits) * N * kDimV * 4, 256) : 0;
   p.off_O = o;        o += p.pc ? 0 : align_up(size_t(N) * kDimV * 4, 256);   // scratch O of range_retrieve_apply_concat (small batches)
@@ -759,74 +741,21 @@ int range_retrieve_apply_concat(range_ctx* c, int mode, int64_t N, const void* q
                     workspace, workspace_bytes, stream);
 }
 
-// 0 = default (fold whenever the producer/consumer kernel applies), RANGE_FOLD=0: always statistics pass + apply pass
-static bool fold_enabled() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("RANGE_FOLD");
-    v = (e && atoi(e) == 0) ? 0 : 1;
-  }
-  return v == 1;
-}
-
 int range_retrieve_concat(range_ctx* c, int mode, int64_t N, const void* q16, const float* qxyz, float temp, float geo_temp,
                           float beta, const double* q64, const int32_t* perm, void* out, int out_dtype, void* workspace,
                           size_t workspace_bytes, void* stream) {
   if (!c || !c->Kh) return fail(RANGE_ERR_INVALID, "database not set");
-  if (!q16 || !qxyz || !q64 || !out || !workspace) return fail(RANGE_ERR_INVALID, "null argument");
+  if (!workspace) return fail(RANGE_ERR_INVALID, "null workspace");
   if (N <= 0) return fail(RANGE_ERR_INVALID, "N must be positive");
-  if (mode == RANGE_MODE_RANGE_PLUS && !(beta >= 0.f && beta <= 1.f)) return fail(RANGE_ERR_INVALID, "beta must be in [0,1]");
-  if (!valid_out_dtype(out_dtype)) return fail(RANGE_ERR_INVALID, "unknown out dtype");
   const RetrievalPlan p = plan_retrieval(c, N);
   if (workspace_bytes < p.total + 256) return fail(RANGE_ERR_WORKSPACE, "retrieve workspace too small");
   char* ws = reinterpret_cast<char*>(align_up(reinterpret_cast<size_t>(workspace), 256));
-  if (!p.pc || !fold_enabled()) {      // small batches (single-role kernels) or the two-pass path on request
-    float* sums = reinterpret_cast<float*>(ws + p.off_sums);
-    float* maxs = reinterpret_cast<float*>(ws + p.off_maxs);
-    int r = range_retrieve_stats(c, mode, N, q16, qxyz, temp, geo_temp, sums, maxs, workspace, workspace_bytes, stream);
-    if (r) return r;
-    return range_retrieve_apply_concat(c, mode, N, q16, qxyz, temp, geo_temp, beta, sums, maxs, q64, perm, out, out_dtype,
-                                       workspace, workspace_bytes, stream);
-  }
-  RetrievalArgs a;
-  cudaStream_t s = cudaStream_t(stream);
-  int r = fill_args(c, mode, N, q16, qxyz, temp, geo_temp, p, ws, s, &a);      // geo mask from the tile caps (no sums yet)
+  float* sums = reinterpret_cast<float*>(ws + p.off_sums);
+  float* maxs = reinterpret_cast<float*>(ws + p.off_maxs);
+  int r = range_retrieve_stats(c, mode, N, q16, qxyz, temp, geo_temp, sums, maxs, workspace, workspace_bytes, stream);
   if (r) return r;
-  float* gsums = nullptr;
-  float* gmaxs = nullptr;
-  if (a.geo) {
-    // the geographic normaliser needs no tensor core: a CUDA-core pass over the unskipped tiles, then the tighter mask
-    // the known normalisers allow (fill_args with sums) for the apply side of the fused kernel
-    gsums = reinterpret_cast<float*>(ws + p.off_sums);
-    gmaxs = reinterpret_cast<float*>(ws + p.off_maxs);
-    float* ps = p.geo_splits > 1 ? reinterpret_cast<float*>(ws + p.off_gpart_sum) : gsums;
-    float* pm = p.geo_splits > 1 ? reinterpret_cast<float*>(ws + p.off_gpart_max) : gmaxs;
-    CUDA_TRY(launch_geo_stats(a, p.geo_splits, p.geo_tiles_per_split, ps, pm, s));
-    g_launches += 1;
-    if (p.geo_splits > 1) {
-      CUDA_TRY(launch_reduce_stats(ps, pm, int(N), p.geo_splits, gsums, gmaxs, s));
-      g_launches += 1;
-    }
-    r = fill_args(c, mode, N, q16, qxyz, temp, geo_temp, p, ws, s, &a, gsums);
-    if (r) return r;
-  }
-  CUtensorMap tmP;
-  void* ring = ws + p.off_ring;
-  r = make_tmap_rows2k(&tmP, ring, uint64_t(fold_pc_ring_rows(c->sm_count)));
-  if (r) return r;
-  float* rowc = reinterpret_cast<float*>(ws + p.off_rowc);
-  const int W = kDimV + kDimK;
-  if (out_dtype == RANGE_OUT_PACKED) {
-    CUDA_TRY(launch_fold_pc(a, tmP, beta, 1.f / c->vscale, gsums, gmaxs, rowc, out, 1536, 0, perm, ring, ws + p.off_flags, ws + p.off_pc_part,
-                            ws + p.off_pc_scratch, c->sm_count, s));
-    CUDA_TRY(launch_concat_q(q64, int(N), kDimK, perm, out, 768, 512, RANGE_OUT_F64, s));
-  } else {
-    CUDA_TRY(launch_fold_pc(a, tmP, beta, 1.f / c->vscale, gsums, gmaxs, rowc, out, W, out_dtype == RANGE_OUT_F64, perm, ring,
-                            ws + p.off_flags, ws + p.off_pc_part, ws + p.off_pc_scratch, c->sm_count, s));
-    CUDA_TRY(launch_concat_q(q64, int(N), kDimK, perm, out, W, kDimV, out_dtype, s));
-  }
-  g_launches += 3 + (fold_pc_part_bytes(c->sm_count, N, c->M) > 0);
-  return RANGE_OK;
+  return range_retrieve_apply_concat(c, mode, N, q16, qxyz, temp, geo_temp, beta, sums, maxs, q64, perm, out, out_dtype,
+                                     workspace, workspace_bytes, stream);
 }
 
 int range_retrieve_apply_routed(range_ctx* c, int mode, int64_t N, const void* q16, const float* qxyz, float temp,

@@ -148,20 +148,6 @@ cudaError_t launch_apply_pc(const RetrievalArgs& a, const CUtensorMap& tmP, cons
                             int out_f64, const int* perm, const RowRoute* route, void* ring, void* flags, void* part,
                             void* scratch, int sm_count, cudaStream_t s);
 size_t apply_pc_scratch_bytes(int sm_count);   // consumers' accumulation-window scratch
-// ONE retrieval kernel for large batches of an unsharded database (retrieval_fold.cu): the statistics of a unit's next
-// work item are folded into its current apply round; rowc (N x 2 float4) is written by the kernel
-size_t fold_pc_flag_bytes(int sm_count, int64_t N, int64_t M);
-size_t fold_pc_part_bytes(int sm_count, int64_t N, int64_t M);
-size_t fold_pc_ring_bytes(int sm_count);
-int fold_pc_ring_rows(int sm_count);
-// geographic row statistics on the CUDA cores over the unskipped tiles (a.geo_mask); partials [split][N] float2
-cudaError_t launch_geo_stats(const RetrievalArgs& a, int splits, int tiles_per_split, float* part_sum, float* part_max,
-                             cudaStream_t s);
-// geo_sums / geo_maxs: (N,2) float, [n][1] = the geographic normaliser / largest cosine (launch_geo_stats + reduce; null for RANGE)
-cudaError_t launch_fold_pc(const RetrievalArgs& a, const CUtensorMap& tmP, float beta, float inv_vscale, const float* geo_sums,
-                           const float* geo_maxs, float* rowc, void* out,
-                           int out_ld, int out_f64, const int* perm, void* ring, void* flags, void* part, void* scratch,
-                           int sm_count, cudaStream_t s);
 // statistics pass with the producer's structure (retrieval_pc.cu); same partials as launch_stats
 cudaError_t launch_stats_pc(const RetrievalArgs& a, float* part_sum, float* part_max, cudaStream_t s);
 cudaError_t launch_reduce_out(const float* part, size_t split_stride, int splits, size_t total, float* out,

@@ -282,7 +282,7 @@ class RangeEngine:
 
     def retrieve_concat(self, mode, q16, qxyz, temp, geo_temp, beta, q64, out=None, dtype=torch.float64, perm=None):
         """statistics + apply + concat in one call (unsharded database): (N,1280) = [retrieved feature | q64], row n at
-        out[perm[n]]; large batches run the single fused retrieval kernel (csrc/retrieval_fold.cu)"""
+        out[perm[n]]"""
         N = q16.shape[0]
         out = _new_out(N, dtype, self.device) if out is None else out
         with torch.cuda.device(self.index):

@@ -100,7 +100,6 @@ class LocationEncoder(nn.Module):
         name = self.location_model_name
         beta = getattr(a, 'beta', None)
         geo_temp = float(getattr(a, 'geo_temp', 0.0))
-        # one call: large batches run the single fused retrieval kernel (statistics folded into the apply pass)
         return eng.retrieve_concat(name, q16, qxyz, a.temp, geo_temp, beta, q64, out=out, dtype=out_dtype, perm=perm)
 
     @torch.no_grad()

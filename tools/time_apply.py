@@ -33,13 +33,6 @@ t_ap = timeit(lambda: eng.retrieve_apply("RANGE+", q, xyz, 12.0, 40.0, 0.5, sums
 s2, m2 = eng.retrieve_stats("RANGE", q, xyz, 15.0, 0.0)
 t_st_r = timeit(lambda: eng.retrieve_stats("RANGE", q, xyz, 15.0, 0.0))
 t_ap_r = timeit(lambda: eng.retrieve_apply("RANGE", q, xyz, 15.0, 0.0, None, s2, m2))
-q64 = q.double()
-outb = torch.empty(N, 1280, dtype=torch.float32, device=dev)
-t_two = timeit(lambda: eng.retrieve_apply_concat("RANGE+", q, xyz, 12.0, 40.0, 0.5, *eng.retrieve_stats("RANGE+", q, xyz, 12.0, 40.0), q64, out=outb))
-t_one = timeit(lambda: eng.retrieve_concat("RANGE+", q, xyz, 12.0, 40.0, 0.5, q64, out=outb))
-t_one_r = timeit(lambda: eng.retrieve_concat("RANGE", q, xyz, 15.0, 0.0, None, q64, out=outb))
-print(f"whole retrieval + concat, RANGE+: statistics pass + apply pass {t_two:.2f} ms | one fused kernel {t_one:.2f} ms "
-      f"({2566.0 * N * M / (t_one * 1e-3) / 1364.5e12:.3f} of peak) | RANGE fused {t_one_r:.2f} ms")
 fl = 2566.0 * N * M
 print(f"DBG={os.environ.get('RANGE_DBG','0')} N={N} M={M}: RANGE+ stats {t_st:.2f} apply {t_ap:.2f} ms ({fl/((t_st+t_ap)*1e-3)/1364.5e12:.3f} of peak) | RANGE stats {t_st_r:.2f} apply {t_ap_r:.2f} ms")
 if os.environ.get("PROF"):
