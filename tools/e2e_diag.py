@@ -1,7 +1,6 @@
-"""Where does model(locs) lose time when several ranks share a host?  Run plain (1 process) or under torchrun.
-Per call: wall time until the last launch is enqueued (host side), until the device has finished, until the copies have
-landed; GPU time per piece from CUDA events.  NO_DIST=1 skips process-group creation (independent processes)."""
-import os, sys, time
+"""model(locs) when several ranks share a host: aggregate queries/s per host path.  Run plain (1 process) or under torchrun.
+SETTINGS="copy,hybrid:0.3,hybrid:0.45,packed" (host_path[:packed_share]); NO_DIST=1 skips process-group creation."""
+import contextlib, os, sys, time
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
 import bench
@@ -16,30 +15,41 @@ if use_dist:
     dist.init_process_group("nccl", device_id=dev)
 db, weights, coords = bench.synthetic_inputs(rank)
 enc = dict(L=40, dims=[1600, 512, 512, 256], weights=weights)
-import contextlib
-with contextlib.redirect_stdout(sys.stderr):
-    model = LocationEncoder(Namespace(location_model_name="RANGE+", pretrained_path=enc, device=dev, range_db=db, beta=0.5))
 h = torch.tensor(coords).pin_memory()
-for _ in range(3): model(h)
-torch.cuda.synchronize()
-if use_dist: dist.barrier()
-ts = []
-for _ in range(8):
-    t = time.perf_counter(); r = model(h); ts.append(time.perf_counter() - t)
-d = torch.tensor(coords, device=dev)
-torch.cuda.synchronize()
-te = []
-for _ in range(4):
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record(); model.embed(d, out_dtype=torch.float32); b.record(); torch.cuda.synchronize(); te.append(a.elapsed_time(b))
-# host-side enqueue time alone: same call with the copy stream idle (device work still queued)
-big = torch.empty(100000, 1280, dtype=torch.float64, pin_memory=True)
-dd = torch.empty(100000, 1280, dtype=torch.float64, device=dev)
-tc = []
-for _ in range(4):
-    torch.cuda.synchronize(); t = time.perf_counter(); big.copy_(dd, non_blocking=True); torch.cuda.synchronize(); tc.append(time.perf_counter() - t)
-print(f"rank {rank}/{world} dist={use_dist} OMP={os.environ.get('OMP_NUM_THREADS')} cpus={os.cpu_count()} affinity={len(os.sched_getaffinity(0))}: "
-      f"model(h) {min(ts)*1e3:.1f} ms (runs {[round(x*1e3,1) for x in ts]}); embed device {min(te):.1f} ms; "
-      f"D2H 1 GB {min(tc)*1e3:.1f} ms", flush=True)
+K = int(os.environ.get("CALLS", 8))
+
+
+def barrier():
+    torch.cuda.synchronize()
+    if use_dist:
+        dist.barrier()
+
+
+ddb = None
+for setting in os.environ.get("SETTINGS", "copy,hybrid:0.3,hybrid:0.45,hybrid:0.6").split(","):
+    path, _, share = setting.partition(":")
+    with contextlib.redirect_stdout(sys.stderr):
+        ns = Namespace(location_model_name="RANGE+", pretrained_path=enc, device=dev, range_db=db if ddb is None else ddb, beta=0.5,
+                       host_path=path)
+        if share:
+            ns.packed_share = float(share)
+        model = LocationEncoder(ns)
+        ddb = model.engine.db                       # the prepared device layout is reused by the next setting
+    for _ in range(3):
+        r = model(h)
+    barrier()
+    ts = []
+    t0 = time.perf_counter()
+    for _ in range(K):
+        t = time.perf_counter(); r = model(h); ts.append(time.perf_counter() - t)
+    barrier()
+    total = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    if use_dist:
+        dist.all_reduce(total, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        print(f"{setting:12s} world {world}: {world * len(coords) * K / float(total[0]) / 1e6:.2f} M queries/s aggregate "
+              f"(rank 0 calls: min {min(ts)*1e3:.1f} mean {sum(ts)/K*1e3:.1f} max {max(ts)*1e3:.1f} ms; host threads {model.host_threads})",
+              flush=True)
+    del model, r
 if use_dist:
     dist.barrier(); dist.destroy_process_group()
