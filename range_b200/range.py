@@ -72,9 +72,8 @@ class LocationEncoder(nn.Module):
             raise ValueError(f'out_dtype={self.out_dtype}: expected float64 (the reference\'s) or float32')
         # how model(locs) hands the (N,1280) float64 result to the host (see _forward_host)
         self.host_path = getattr(args, 'host_path', 'auto')
-        if self.host_path not in ('auto', 'copy', 'packed', 'hybrid'):
-            raise ValueError(f"host_path={self.host_path!r}: expected 'auto', 'copy', 'packed' or 'hybrid'")
-        self.packed_share = min(1.0, max(0.0, float(getattr(args, 'packed_share', 0.45))))
+        if self.host_path not in ('auto', 'copy', 'packed'):
+            raise ValueError(f"host_path={self.host_path!r}: expected 'auto', 'copy' or 'packed'")
         self.pinned_limit = int(getattr(args, 'pinned_limit', 8 << 30))       # largest page-locked result, bytes
         local_ranks = max(1, int(os.environ.get('LOCAL_WORLD_SIZE', '1')))      # torchrun: ranks sharing this host
         self.host_threads = int(getattr(args, 'host_threads', 0)) or max(1, min(16, (os.cpu_count() or 1) // local_ranks))
@@ -165,21 +164,6 @@ class LocationEncoder(nn.Module):
             cuts.append((lo, lo + piece)); lo += piece
         cuts.append((lo, N))
         return cuts
-
-    @staticmethod
-    def _assign_packed(sizes, share):
-        """which pieces (rows per piece, in order) take the packed route so that about `share` of the rows do: greedy on
-        the running row counts; the last two pieces stay on the copy route (nothing left to widen when the device is
-        done) unless every piece is packed"""
-        if share >= 1.0:
-            return [True] * len(sizes)
-        out, packed, seen = [], 0, 0
-        for i, n in enumerate(sizes):
-            take = share > 0.0 and i < len(sizes) - 2 and packed + n <= share * (seen + n) + 0.5 * n
-            out.append(bool(take))
-            packed += n if take else 0
-            seen += n
-        return out
 
     @classmethod
     def _pieces(cls, N, chunk, tail, super_batch, taper=DEFAULT_TAPER):
@@ -300,9 +284,6 @@ class LocationEncoder(nn.Module):
                   the caller's array, embed_into - by a host thread team (range_host_unpack): bounded page-locked
                   memory for any N, 40 % fewer PCIe bytes, but the host cores must keep up (measured on the 16-core
                   1-GPU box: 6.3 M rows/s with 16 threads, 2.2 M queries/s end to end against 2.9 M for 'copy').
-        'hybrid'  the share `packed_share` of the rows (whole pieces) takes the packed route, the rest the copy route: on a
-                  host whose page-locked ingest is the ceiling (8 GPUs: 92.6 GB/s) the two routes use different
-                  resources - DMA bytes vs host cores.
         'auto'    'copy' while the result fits `pinned_limit` (8 GB), else 'packed'.
         (Measured and dropped: letting the apply kernel's epilogue store straight into the mapped page-locked result -
         stores from the SMs to host memory run at ~6 GB/s and stall the consumers: 170 ms per 100 000 queries.)"""
@@ -325,9 +306,7 @@ class LocationEncoder(nn.Module):
                 return host.numpy()
             result[...] = host.numpy()
             return result
-        # share of the rows that cross PCIe packed and are widened by the host cores; the rest travels as float64 copies
-        share = {'copy': 0.0, 'packed': 1.0, 'hybrid': self.packed_share}[path]
-        if share >= 1.0:
+        if path == 'packed':
             result = np.empty((N, 1280), dtype=np.float64) if result is None else result
         else:
             host = torch.empty((N, 1280), dtype=tdtype, pin_memory=True)
@@ -342,18 +321,16 @@ class LocationEncoder(nn.Module):
             chunk = min(self.chunk, N)
             batches, plan, rows = self._pieces(N, chunk, self.tail, self.super_batch, self.taper)
             n_pieces = sum(len(cuts) for cuts in plan)
-            packed_piece = self._assign_packed([hi - lo for cuts in plan for lo, hi in cuts], share)
-            n_packed = sum(packed_piece)
-            # copy lane - three device buffers: with two, piece i + 2 waits for the copy of piece i, which is still running
-            # when the pieces shrink faster than their copies (measured: 0.9 ms stall before the fifth piece of 100 000 rows)
-            bufs = [torch.empty(rows, 1280, dtype=tdtype, device=eng.device) for _ in range(min(3, n_pieces - n_packed))]
+            if path == 'copy':
+                # three buffers: with two, piece i + 2 waits for the copy of piece i, which is still running when the
+                # pieces shrink faster than their copies (measured: 0.9 ms stall before the fifth piece of 100 000 rows)
+                bufs = [torch.empty(rows, 1280, dtype=tdtype, device=eng.device) for _ in range(min(3, n_pieces))]
+            elif path == 'packed':
+                depth = min(3, n_pieces)
+                bufs = [torch.empty(rows, 6144, dtype=torch.uint8, device=eng.device) for _ in range(depth)]
+                stage = [torch.empty(rows, 6144, dtype=torch.uint8, pin_memory=True) for _ in range(depth)]
+                landed = [None] * depth          # (event, result rows, staging rows) of the piece in each slot
             freed = [None] * len(bufs)
-            # packed lane: device buffers + page-locked staging; a slot's rows are widened when the slot comes round again
-            depth = min(3, n_packed)
-            pbufs = [torch.empty(rows, 6144, dtype=torch.uint8, device=eng.device) for _ in range(depth)]
-            stage = [torch.empty(rows, 6144, dtype=torch.uint8, pin_memory=True) for _ in range(depth)]
-            pfreed = [None] * depth
-            landed = [None] * depth              # (event, first result row, end row) of the piece in each slot
             cur = torch.cuda.current_stream()
             if self.trace is not None:
                 t0 = torch.cuda.Event(enable_timing=True)
@@ -367,7 +344,7 @@ class LocationEncoder(nn.Module):
                                                         self.host_threads))
                 landed[slot] = None
 
-            i = ic = ip = 0
+            i = 0
             for (s0, s1), cuts in zip(batches, plan):
                 sort_cuts = cuts
                 ij, perms = None, None
@@ -402,22 +379,13 @@ class LocationEncoder(nn.Module):
                 q64, q16, qxyz = eng.encode(sub) if ij is None else self._encode_raster(raster, ij)
                 for c, (lo, hi) in enumerate(cuts):
                     perm = None if perms is None else perms[c]
-                    packed = packed_piece[i]
+                    k = i % len(bufs)
                     i += 1
-                    if packed:
-                        k = ip % depth
-                        ip += 1
-                        if landed[k] is not None:
-                            unpack(k)                          # the slot's previous piece: wait for its copy, widen it
-                        if pfreed[k] is not None:
-                            cur.wait_event(pfreed[k])
-                        buf = pbufs[k][: hi - lo]
-                    else:
-                        k = ic % len(bufs)
-                        ic += 1
-                        if freed[k] is not None:
-                            cur.wait_event(freed[k])
-                        buf = bufs[k][: hi - lo]
+                    if path == 'packed' and landed[k] is not None:
+                        unpack(k)                              # the slot's previous piece: wait for its copy, widen it
+                    if freed[k] is not None:
+                        cur.wait_event(freed[k])
+                    buf = bufs[k][: hi - lo]
                     assert buf.shape[0] == hi - lo
                     self._retrieve_concat(q16[lo:hi], qxyz[lo:hi], q64[lo:hi], buf, buf.dtype, perm)
                     timed = self.trace is not None            # developer timeline (tools/time_e2e.py)
@@ -425,21 +393,21 @@ class LocationEncoder(nn.Module):
                     ready.record(cur)
                     self._copy_stream.wait_event(ready)
                     with torch.cuda.stream(self._copy_stream):
-                        done = torch.cuda.Event(enable_timing=timed)
-                        if packed:
-                            stage[k][: hi - lo].copy_(buf, non_blocking=True)
-                            done.record(self._copy_stream)
-                            pfreed[k] = done
-                            landed[k] = (done, s0 + lo, s0 + hi)
-                        else:
+                        if path == 'copy':
                             host[s0 + lo:s0 + hi].copy_(buf, non_blocking=True)
-                            done.record(self._copy_stream)
-                            freed[k] = done
+                        else:
+                            stage[k][: hi - lo].copy_(buf, non_blocking=True)
+                        freed[k] = torch.cuda.Event(enable_timing=timed)
+                        freed[k].record(self._copy_stream)
                     if timed:
-                        self.trace.append((hi - lo, ready, done))
-            for k in sorted((k for k in range(depth) if landed[k] is not None), key=lambda k: landed[k][1]):
-                unpack(k)
-            self._copy_stream.synchronize()
+                        self.trace.append((hi - lo, ready, freed[k]))
+                    if path == 'packed':
+                        landed[k] = (freed[k], s0 + lo, s0 + hi)
+            if path == 'packed':
+                for k in sorted((k for k in range(len(bufs)) if landed[k] is not None), key=lambda k: landed[k][1]):
+                    unpack(k)
+            else:
+                self._copy_stream.synchronize()
         return result                                                                     # range.py:222,240
 
 

@@ -445,19 +445,14 @@ def test_host_paths_agree(sh_entries):
     enc = dict(L=40, dims=[1600, 64, 64, 256], weights=ws)
     c = torch.tensor(O.area_uniform(30_000, np.random.default_rng(7)))
     outs = {}
-    for path in ("copy", "packed", "hybrid"):
+    for path in ("copy", "packed"):
         m = LocationEncoder(Namespace(location_model_name="RANGE+", pretrained_path=enc, device=DEV, range_db=db, beta=0.5,
-                                      host_path=path, chunk=6144, tail=2048, super_batch=24576, packed_share=0.5))
+                                      host_path=path, chunk=12288, tail=6144, super_batch=24576))
         outs[path] = m(c)
         assert outs[path].dtype == np.float64 and outs[path].shape == (30_000, 1280)
     assert np.array_equal(outs["copy"], outs["packed"])              # same kernels; the widening is exact
-    assert np.array_equal(outs["copy"], outs["hybrid"])              # some pieces copied as float64, some packed + widened
-    from range_b200.range import LocationEncoder as LE
-    assert LE._assign_packed([6144] * 6, 0.5) == [True, False, True, False, False, False]
-    m = LocationEncoder(Namespace(location_model_name="RANGE+", pretrained_path=enc, device=DEV, range_db=db, beta=0.5,
-                                  host_path="packed", chunk=12288, tail=6144, super_batch=24576))
     m32 = LocationEncoder(Namespace(location_model_name="RANGE+", pretrained_path=enc, device=DEV, range_db=db, beta=0.5,
-                                    out_dtype=np.float32, chunk=6144, tail=2048, super_batch=24576))
+                                    out_dtype=np.float32, chunk=12288, tail=6144, super_batch=24576))
     o32 = m32(c)                                                      # opt-in: float32 rows (not the reference's dtype)
     assert o32.dtype == np.float32 and np.array_equal(o32[:, :1024], outs["copy"][:, :1024].astype(np.float32))
     assert np.array_equal(o32[:, 1024:], outs["copy"][:, 1024:].astype(np.float32))

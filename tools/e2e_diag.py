@@ -1,5 +1,5 @@
 """model(locs) when several ranks share a host: aggregate queries/s per host path.  Run plain (1 process) or under torchrun.
-SETTINGS="copy,hybrid:0.3,hybrid:0.45,packed" (host_path[:packed_share]); NO_DIST=1 skips process-group creation."""
+SETTINGS="copy,packed" (host_path); NO_DIST=1 skips process-group creation."""
 import contextlib, os, sys, time
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
@@ -26,7 +26,7 @@ def barrier():
 
 
 ddb = None
-for setting in os.environ.get("SETTINGS", "copy,hybrid:0.3,hybrid:0.45,hybrid:0.6").split(","):
+for setting in os.environ.get("SETTINGS", "copy,packed").split(","):
     path, _, share = setting.partition(":")
     with contextlib.redirect_stdout(sys.stderr):
         ns = Namespace(location_model_name="RANGE+", pretrained_path=enc, device=dev, range_db=db if ddb is None else ddb, beta=0.5,
