@@ -86,6 +86,11 @@ class LocationEncoder(nn.Module):
         self.trace = None           # developer timeline of _forward_host: a list collects (rows, computed, copied) events
         self.eval()
 
+    def close(self):
+        """release the peer receive buffers of an M-sharded model (a collective call: every rank closes)"""
+        if self.sharded is not None:
+            self.sharded.close()
+
     # the reference calls model.to(device) after construction (load_model.py:50); tensors live in the engine
     def _apply(self, fn, recurse=True):
         return self
