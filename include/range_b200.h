@@ -225,7 +225,8 @@ int range_host_unpack(const void* packed, int64_t N, double* out, int n_threads)
  * q16 / qxyz arrays (i.e. before `perm`); *full_rounds = 0 when the batch is too small for that kernel.  With counters set
  * (device-accessible memory the host can read, e.g. page-locked; range_progress_words() uint32, zeroed by the caller before
  * each call) every epilogue warp of range_retrieve_apply_concat / range_retrieve_concat stores the number of full rounds
- * whose rows it has completely written - location columns included - after a system-wide fence: round r is finished
+ * whose rows it has completely written to device memory - location columns included -, ordered by a device-scope fence
+ * (the copy engines read device memory through the L2): round r is finished
  * when every counter is > r.  Rows beyond the last full round are complete when the stream has drained.  NULL disables. */
 int range_progress_words(range_ctx* ctx);
 int range_ctx_set_progress(range_ctx* ctx, uint32_t* counters);
