@@ -219,19 +219,6 @@ int range_peer_free(void* dptr);
  * team of n_threads of its own. */
 int range_host_unpack(const void* packed, int64_t N, double* out, int n_threads);
 
-/* Progress of the large-batch apply pass, for callers that move finished rows off the device while the kernel is still
- * running (range_b200/range.py: model(locs) copies them to the host round by round).  The kernel processes the rows in
- * rounds of *rows_per_round (24 units x 256 rows on 148 SMs): round r = rows [r, r+1) * rows_per_round in the order of the
- * q16 / qxyz arrays (i.e. before `perm`); *full_rounds = 0 when the batch is too small for that kernel.  With counters set
- * (device-accessible memory the host can read, e.g. page-locked; range_progress_words() uint32, zeroed by the caller before
- * each call) every epilogue warp of range_retrieve_apply_concat / range_retrieve_concat stores the number of full rounds
- * whose rows it has completely written to device memory - location columns included -, ordered by a device-scope fence
- * (the copy engines read device memory through the L2): round r is finished
- * when every counter is > r.  Rows beyond the last full round are complete when the stream has drained.  NULL disables. */
-int range_progress_words(range_ctx* ctx);
-int range_ctx_set_progress(range_ctx* ctx, uint32_t* counters);
-int range_progress_rows(range_ctx* ctx, int64_t N, int64_t* rows_per_round, int64_t* full_rounds);
-
 /* K3: out (N,1280) = [O | q64] as fp64 (RANGE_OUT_F64, what the reference returns: range/range.py:222,240)
  * or fp32. */
 int range_concat(range_ctx* ctx, int64_t N, const float* O, const double* q64, void* out, int out_dtype,

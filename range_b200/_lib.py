@@ -66,9 +66,6 @@ PROTOTYPES = {
     "range_peer_close": (c_int, [c_void_p]),
     "range_peer_free": (c_int, [c_void_p]),
     "range_host_unpack": (c_int, [c_void_p, c_int64, c_void_p, c_int]),
-    "range_progress_words": (c_int, [c_void_p]),
-    "range_ctx_set_progress": (c_int, [c_void_p, c_void_p]),
-    "range_progress_rows": (c_int, [c_void_p, c_int64, POINTER(c_int64), POINTER(c_int64)]),
     "range_concat": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "range_concat_scatter": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
 }

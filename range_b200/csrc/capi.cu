@@ -106,7 +106,6 @@ struct range_ctx {
   bool enc_prepared = false;
   const int* perm = nullptr;
   std::vector<CUtensorMap> tmWh, tmWl;
-  uint32_t* progress = nullptr;    // optional progress counters of the large-batch apply kernel (range_ctx_set_progress)
 };
 
 namespace {
@@ -334,23 +333,6 @@ int range_ctx_set_db_caps(range_ctx* c, int64_t n_tiles, const float* caps, int6
                 (long long)c->Mpad, (long long)M_total);
   c->caps = caps;
   c->M_total = M_total;
-  return RANGE_OK;
-}
-
-int range_progress_words(range_ctx* c) { return c ? apply_pc_progress_words(c->sm_count) : 0; }
-
-int range_ctx_set_progress(range_ctx* c, uint32_t* counters) {
-  if (!c) return fail(RANGE_ERR_INVALID, "null ctx");
-  c->progress = counters;
-  return RANGE_OK;
-}
-
-int range_progress_rows(range_ctx* c, int64_t N, int64_t* rows_per_round, int64_t* full_rounds) {
-  if (!c || !c->Kh || N <= 0 || !rows_per_round || !full_rounds) return fail(RANGE_ERR_INVALID, "bad arguments");
-  const RetrievalPlan p = plan_retrieval(c, N);
-  const int64_t per_round = int64_t(apply_pc_units(c->sm_count)) * 2 * kBlockQ;
-  *rows_per_round = per_round;
-  *full_rounds = p.pc ? N / per_round : 0;
   return RANGE_OK;
 }
 
@@ -702,23 +684,21 @@ static int apply_impl(range_ctx* c, int mode, int64_t N, const void* q16, const 
     r = make_tmap_rows2k(&tmP, ring, uint64_t(apply_pc_ring_rows(c->sm_count)));
     if (r) return r;
     if (route) {    // M-sharded: consumers store this shard's partial rows into the owner ranks' receive buffers
-      CUDA_TRY(launch_apply_pc(a, tmP, rowc, nullptr, kDimV, 0, nullptr, &rr, nullptr, ring, ws + p.off_flags, ws + p.off_pc_part,
+      CUDA_TRY(launch_apply_pc(a, tmP, rowc, nullptr, kDimV, 0, nullptr, &rr, ring, ws + p.off_flags, ws + p.off_pc_part,
                                ws + p.off_pc_scratch, c->sm_count, s));
     } else if (out) {      // consumers write straight into the (N,1280) result; the location columns follow
-      // (the location columns first: a row is then complete the moment the apply kernel has written its feature columns,
-      //  which is what the progress counters announce)
       if (out_dtype == RANGE_OUT_PACKED) {     // rows of 6144 B: 1024 fp32 features, then 256 fp64 location columns
-        CUDA_TRY(launch_concat_q(q64, int(N), kDimK, perm, out, 768, 512, RANGE_OUT_F64, s));
-        CUDA_TRY(launch_apply_pc(a, tmP, rowc, out, 1536, 0, perm, nullptr, c->progress, ring, ws + p.off_flags, ws + p.off_pc_part,
+        CUDA_TRY(launch_apply_pc(a, tmP, rowc, out, 1536, 0, perm, nullptr, ring, ws + p.off_flags, ws + p.off_pc_part,
                                  ws + p.off_pc_scratch, c->sm_count, s));
+        CUDA_TRY(launch_concat_q(q64, int(N), kDimK, perm, out, 768, 512, RANGE_OUT_F64, s));
       } else {
-        CUDA_TRY(launch_concat_q(q64, int(N), kDimK, perm, out, W, kDimV, out_dtype, s));
-        CUDA_TRY(launch_apply_pc(a, tmP, rowc, out, W, out_dtype == RANGE_OUT_F64, perm, nullptr, c->progress, ring, ws + p.off_flags,
+        CUDA_TRY(launch_apply_pc(a, tmP, rowc, out, W, out_dtype == RANGE_OUT_F64, perm, nullptr, ring, ws + p.off_flags,
                                  ws + p.off_pc_part, ws + p.off_pc_scratch, c->sm_count, s));
+        CUDA_TRY(launch_concat_q(q64, int(N), kDimK, perm, out, W, kDimV, out_dtype, s));
       }
       g_launches += 1;
     } else {
-      CUDA_TRY(launch_apply_pc(a, tmP, rowc, O, kDimV, 0, nullptr, nullptr, nullptr, ring, ws + p.off_flags, ws + p.off_pc_part,
+      CUDA_TRY(launch_apply_pc(a, tmP, rowc, O, kDimV, 0, nullptr, nullptr, ring, ws + p.off_flags, ws + p.off_pc_part,
                                ws + p.off_pc_scratch, c->sm_count, s));
     }
     g_launches += 2 + (apply_pc_part_bytes(c->sm_count, N, c->M) > 0);

@@ -145,9 +145,8 @@ void apply_pc_describe_plan(int sm_count, int64_t N, int64_t M, int32_t out[7]);
 // row n of the result goes to out + (perm ? perm[n] : n) * out_ld (+ column), fp32 or fp64
 // (out_ld in elements of the output type); route != null: rows go to the owners' receive buffers instead (fp32)
 cudaError_t launch_apply_pc(const RetrievalArgs& a, const CUtensorMap& tmP, const float* rowc, void* out, int out_ld,
-                            int out_f64, const int* perm, const RowRoute* route, uint32_t* progress, void* ring, void* flags,
-                            void* part, void* scratch, int sm_count, cudaStream_t s);
-int apply_pc_progress_words(int sm_count);     // progress counters the apply kernel writes (4 per consumer CTA)
+                            int out_f64, const int* perm, const RowRoute* route, void* ring, void* flags, void* part,
+                            void* scratch, int sm_count, cudaStream_t s);
 size_t apply_pc_scratch_bytes(int sm_count);   // consumers' accumulation-window scratch
 // statistics pass with the producer's structure (retrieval_pc.cu); same partials as launch_stats
 cudaError_t launch_stats_pc(const RetrievalArgs& a, float* part_sum, float* part_max, cudaStream_t s);

@@ -167,9 +167,6 @@ struct PcPlan {
   const int* perm;
   // M-sharded database: finished (partial) rows go to the owner ranks' receive buffers over NVLink instead
   rangeb200::RowRoute route;
-  // optional progress counters (host-mapped memory, zeroed by the caller): epilogue warp w of consumer CTA c stores the
-  // number of full rounds it has written out to progress[4 c + w] - the host copies finished rows while the kernel runs
-  uint32_t* progress;
 };
 struct PcWork {
   int qp, t0, t1, split;      // query-tile pair, database tiles [t0, t1), split index or -1 (direct output)
@@ -774,15 +771,6 @@ range_apply_pc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive_cluster(o_empty_leader);
         }
-        if (plan.progress != nullptr && direct && !routed) {
-          // rows of round r are written: order them before the counter at GPU scope - the copy engine reads device
-          // memory through the L2, the point of coherence (a system-scope fence here cost 110 us per round: 1.9 ms per
-          // 100 000 queries, measured) - then publish the count
-          __threadfence();
-          __syncwarp();
-          if (lane == 0)
-            *reinterpret_cast<volatile uint32_t*>(plan.progress + ((size_t(unit) * 2 + cp) * 2 + rank) * 4 + quarter) = uint32_t(r + 1);
-        }
       }
     }
   }
@@ -1043,7 +1031,6 @@ extern long long* g_prof_buffer;      // retrieval.cu (developer instrumentation
 
 int apply_pc_units(int sm_count) { return (sm_count / 2) / 3; }
 size_t apply_pc_ring_bytes(int sm_count) { return size_t(apply_pc_units(sm_count)) * 2 * kRing * 128 * 128 * 2; }
-int apply_pc_progress_words(int sm_count) { return apply_pc_units(sm_count) * 2 * 2 * 4; }
 int apply_pc_ring_rows(int sm_count) { return apply_pc_units(sm_count) * 2 * kRing * 16; }   // rows of 2 KB
 
 static PcPlan pc_plan(int sm_count, int64_t N, int64_t M) {
@@ -1114,13 +1101,12 @@ __global__ void reduce_tail_kernel(const float4* __restrict__ part, size_t strid
 }
 
 cudaError_t launch_apply_pc(const RetrievalArgs& a, const CUtensorMap& tmP, const float* rowc, void* out, int out_ld,
-                            int out_f64, const int* perm, const RowRoute* route, uint32_t* progress, void* ring, void* flags,
-                            void* part, void* scratch, int sm_count, cudaStream_t stream) {
+                            int out_f64, const int* perm, const RowRoute* route, void* ring, void* flags, void* part,
+                            void* scratch, int sm_count, cudaStream_t stream) {
   PcPlan plan = pc_plan(sm_count, a.N, a.M);
   plan.out_ld = out_ld;
   plan.out_f64 = out_f64;
   plan.perm = perm;
-  plan.progress = progress;
   if (route) plan.route = *route;
 #ifdef RANGE_DEVELOPER_SWITCHES       // NVCC_EXTRA=-DRANGE_DEVELOPER_SWITCHES: RANGE_PC_DBG decouples the roles (results are then wrong)
   static const int dbg = getenv("RANGE_PC_DBG") ? atoi(getenv("RANGE_PC_DBG")) : 0;

@@ -233,20 +233,6 @@ class RangeEngine:
         """the separable raster encoder needs the analytic harmonics and the tensor-core SIREN"""
         return self.harmonics == "analytic" and getattr(self, "precision", None) == "f16x3"
 
-    # ------------------------------------------------------------------ progress of the large-batch apply pass
-    def progress_words(self):
-        return int(self.lib.range_progress_words(self.ctx))
-
-    def set_progress(self, counters):
-        """counters: page-locked int32 tensor of progress_words() elements (zeroed by the caller) or None"""
-        _lib.check(self.lib.range_ctx_set_progress(self.ctx, c_void_p(None) if counters is None else _ptr(counters)))
-
-    def progress_rows(self, N):
-        """(rows per round, full rounds) of a retrieve_concat / retrieve_apply_concat call on N rows; (_, 0): no counters"""
-        per, full = ctypes.c_int64(), ctypes.c_int64()
-        _lib.check(self.lib.range_progress_rows(self.ctx, int(N), ctypes.byref(per), ctypes.byref(full)))
-        return per.value, full.value
-
     def _ret_ws(self, N):
         return self._workspace("ret", self.lib.range_retrieve_workspace_bytes(self.ctx, N))
 

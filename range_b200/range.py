@@ -72,8 +72,8 @@ class LocationEncoder(nn.Module):
             raise ValueError(f'out_dtype={self.out_dtype}: expected float64 (the reference\'s) or float32')
         # how model(locs) hands the (N,1280) float64 result to the host (see _forward_host)
         self.host_path = getattr(args, 'host_path', 'auto')
-        if self.host_path not in ('auto', 'copy', 'packed', 'stream'):
-            raise ValueError(f"host_path={self.host_path!r}: expected 'auto', 'copy', 'packed' or 'stream'")
+        if self.host_path not in ('auto', 'copy', 'packed'):
+            raise ValueError(f"host_path={self.host_path!r}: expected 'auto', 'copy' or 'packed'")
         self.pinned_limit = int(getattr(args, 'pinned_limit', 8 << 30))       # largest page-locked result, bytes
         local_ranks = max(1, int(os.environ.get('LOCAL_WORLD_SIZE', '1')))      # torchrun: ranks sharing this host
         self.host_threads = int(getattr(args, 'host_threads', 0)) or max(1, min(16, (os.cpu_count() or 1) // local_ranks))
@@ -83,8 +83,6 @@ class LocationEncoder(nn.Module):
             from .distributed import ShardedRetriever
             self.sharded = ShardedRetriever(self.engine, self.group, merge=getattr(args, 'db_merge', 'peer'))
         self._copy_stream = None
-        self._progress = None       # page-locked progress counters of the 'stream' path
-        self._dev_result = None     # its device-resident result buffer (grow-only)
         self.trace = None           # developer timeline of _forward_host: a list collects (rows, computed, copied) events
         self.eval()
 
@@ -280,99 +278,6 @@ class LocationEncoder(nn.Module):
             raise ValueError('out must be a writable C-contiguous float64 (rows, 1280) array')
         return self._forward_host(p1 - p0, raster=tables, result=out, raster_p0=p0)
 
-    @staticmethod
-    def _stream_pieces(n, per_round, full_rounds, chunk_rounds):
-        """[lo, hi) pieces of a super-batch for the 'stream' path: whole rounds of the apply kernel, `chunk_rounds` at a
-        time while more than two chunks remain, then halving down to single rounds (the copy of a piece starts when
-        its last round is announced), and the rows after the last full round as the last piece"""
-        counts, rem = [], full_rounds
-        while rem > 2 * chunk_rounds:
-            counts.append(chunk_rounds); rem -= chunk_rounds
-        while rem > 0:
-            take = max(1, min(chunk_rounds, rem // 2))
-            counts.append(take); rem -= take
-        cuts, lo = [], 0
-        for c in counts:
-            cuts.append((lo, lo + c * per_round)); lo += c * per_round
-        if lo < n:
-            cuts.append((lo, n))
-        return cuts
-
-    def _forward_stream(self, N, coords, raster, raster_p0, tdtype):
-        """'stream' path of _forward_host; returns None when the batch is too small for the progress counters"""
-        eng = self.engine
-        per_round, _ = eng.progress_rows(N)
-        cap = max(per_round, min(self.super_batch, 1 << 18) // per_round * per_round)      # rows per launch (device result <= 2.7 GB)
-        if eng.progress_rows(min(N, cap))[1] < 2:
-            return None
-        host = torch.empty((N, 1280), dtype=tdtype, pin_memory=True)
-        with torch.cuda.device(eng.index):
-            if raster is None:
-                dev_coords = coords.to(eng.device, torch.float64, non_blocking=True)
-            if self._copy_stream is None:
-                self._copy_stream = torch.cuda.Stream(device=eng.device)
-            if self._progress is None:
-                self._progress = torch.zeros(eng.progress_words(), dtype=torch.int32, pin_memory=True)
-            flags = self._progress.numpy()
-            rows_cap = min(N, cap)
-            if self._dev_result is None or self._dev_result.numel() < rows_cap * 1280 * 8:
-                self._dev_result = torch.empty(rows_cap * 1280 * 8, dtype=torch.uint8, device=eng.device)
-            dev_out = self._dev_result[: rows_cap * 1280 * host.element_size()].view(tdtype).view(rows_cap, 1280)
-            cur = torch.cuda.current_stream()
-            chunk_rounds = max(1, self.chunk // per_round)
-            for s0 in range(0, N, cap):
-                s1 = min(N, s0 + cap)
-                n = s1 - s0
-                full_rounds = eng.progress_rows(n)[1]
-                cuts = self._stream_pieces(n, per_round, full_rounds, chunk_rounds) if full_rounds > 0 else [(0, n)]
-                # spatial batching piece by piece; one permutation for the whole launch (piece-local ones shifted)
-                ij, perm = None, None
-                if raster is not None and raster['buf'] is not None:
-                    ij = torch.empty(n, 2, dtype=torch.int32, device=eng.device)
-                    if self._sorts():
-                        lonlat = torch.empty(n, 2, dtype=torch.float64, device=eng.device)
-                        eng.raster_points(raster, raster_p0 + s0, n, lonlat=lonlat)
-                        perms = []
-                        for lo, hi in cuts:
-                            perms.append(eng.sort_queries(lonlat[lo:hi])[1])
-                            eng.raster_points(raster, raster_p0 + s0 + lo, hi - lo, perm=perms[-1], ij=ij[lo:hi])
-                        perm = torch.cat([p + lo for (lo, _), p in zip(cuts, perms)]) if len(perms) > 1 else perms[0]
-                    else:
-                        eng.raster_points(raster, raster_p0 + s0, n, ij=ij)
-                else:
-                    if raster is None:
-                        sub = dev_coords[s0:s1]
-                    else:
-                        ij = self._raster_ij(raster['W'], raster_p0 + s0, raster_p0 + s1)
-                        sub = self._raster_coords(raster, ij)
-                    if self._sorts():
-                        parts = [eng.sort_queries(sub[lo:hi]) for lo, hi in cuts]
-                        sub = torch.cat([p[0] for p in parts]) if len(parts) > 1 else parts[0][0]
-                        perm = torch.cat([p[1] + lo for (lo, _), p in zip(cuts, parts)]) if len(parts) > 1 else parts[0][1]
-                        if ij is not None:
-                            ij = torch.cat([ij[lo:hi][p[1].long()] for (lo, hi), p in zip(cuts, parts)])
-                q64, q16, qxyz = eng.encode(sub) if ij is None else self._encode_raster(raster, ij)
-                self._copy_stream.synchronize()              # the previous super-batch's copies still read dev_out
-                flags[:] = 0
-                eng.set_progress(self._progress)
-                try:
-                    self._retrieve_concat(q16, qxyz, q64, dev_out[:n], tdtype, perm)
-                finally:
-                    eng.set_progress(None)
-                drained = torch.cuda.Event()
-                drained.record(cur)
-                for lo, hi in cuts:
-                    need = hi // per_round if (hi % per_round == 0 and hi // per_round <= full_rounds) else None
-                    if need is None:
-                        drained.synchronize()                # rows after the last full round: complete when the stream has drained
-                    else:
-                        while int(flags.min()) < need and not drained.query():
-                            pass
-                    with torch.cuda.stream(self._copy_stream):
-                        host[s0 + lo:s0 + hi].copy_(dev_out[lo:hi], non_blocking=True)
-            self._copy_stream.synchronize()
-        return host.numpy()
-
     def _forward_host(self, N, coords=None, raster=None, result=None, raster_p0=0):
         """model(locs) -> numpy float64 (N,1280) (range/range.py:222,240).  Two ways to hand the rows to the host:
 
@@ -384,12 +289,7 @@ class LocationEncoder(nn.Module):
                   the caller's array, embed_into - by a host thread team (range_host_unpack): bounded page-locked
                   memory for any N, 40 % fewer PCIe bytes, but the host cores must keep up (measured on the 16-core
                   1-GPU box: 6.3 M rows/s with 16 threads, 2.2 M queries/s end to end against 2.9 M for 'copy').
-        'stream'  ONE statistics + apply launch per super-batch (<= 262 144 rows) into a device-resident result; the apply
-                  kernel announces every finished round of 6 144 rows through progress counters in page-locked memory
-                  (range_ctx_set_progress) and the host copies finished pieces while the kernel is still running: no
-                  per-piece launches, only the rows after the last full round wait for the end of the kernel.
-        'auto'    'stream' for unsharded float64 / float32 results of at least two rounds that fit `pinned_limit` (8 GB),
-                  'copy' for smaller ones, 'packed' beyond the limit.
+        'auto'    'copy' while the result fits `pinned_limit` (8 GB), else 'packed'.
         (Measured and dropped: letting the apply kernel's epilogue store straight into the mapped page-locked result -
         stores from the SMs to host memory run at ~6 GB/s and stall the consumers: 170 ms per 100 000 queries.)"""
         eng = self.engine
@@ -398,18 +298,10 @@ class LocationEncoder(nn.Module):
         row_bytes = 1280 * (4 if tdtype == torch.float32 else 8)
         if result is not None:
             path = 'packed'
-        else:
-            if tdtype == torch.float32 and path == 'packed':
-                path = 'copy'                      # nothing to widen: float32 rows are copied as they are
-            if path == 'auto':
-                path = 'copy' if (N * row_bytes <= self.pinned_limit or tdtype == torch.float32) else 'packed'
-                if path == 'copy' and self.sharded is None and N >= 2 * ROUND_ROWS:
-                    path = 'stream'
-        if path == 'stream' and self.sharded is None and N > 0:
-            out = self._forward_stream(N, coords, raster, raster_p0, tdtype)
-            if out is not None:
-                return out
-            path = 'copy'                          # batch too small for the progress counters
+        elif tdtype == torch.float32:
+            path = 'copy'                          # nothing to widen: the rows are copied as they are
+        elif path == 'auto':
+            path = 'copy' if N * row_bytes <= self.pinned_limit else 'packed'
         if self.sharded is not None:            # collective: distributed.py chunks (every rank must take the same steps)
             dev = coords.to(eng.device, torch.float64, non_blocking=True)
             res = self.embed(dev, out_dtype=tdtype)

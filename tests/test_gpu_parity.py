@@ -451,17 +451,6 @@ def test_host_paths_agree(sh_entries):
         outs[path] = m(c)
         assert outs[path].dtype == np.float64 and outs[path].shape == (30_000, 1280)
     assert np.array_equal(outs["copy"], outs["packed"])              # same kernels; the widening is exact
-    # 'stream': one launch per super-batch, finished rounds copied while the kernel runs (other piece boundaries)
-    ms = LocationEncoder(Namespace(location_model_name="RANGE+", pretrained_path=enc, device=DEV, range_db=db, beta=0.5,
-                                   host_path="stream", chunk=12288, super_batch=24576))
-    for _ in range(2):
-        st = ms(c)
-        assert st.dtype == np.float64 and np.array_equal(st[:, 1024:], outs["copy"][:, 1024:])
-        assert rel_rows(st[:, :1024], outs["copy"][:, :1024]).max() <= 5e-4
-    assert np.array_equal(st, ms(c))                                  # repeatable
-    auto = LocationEncoder(Namespace(location_model_name="RANGE+", pretrained_path=enc, device=DEV, range_db=db, beta=0.5))
-    assert np.array_equal(auto(c[:5000]), LocationEncoder(Namespace(location_model_name="RANGE+", pretrained_path=enc, device=DEV,
-                                                                    range_db=db, beta=0.5, host_path="copy"))(c[:5000]))
     m32 = LocationEncoder(Namespace(location_model_name="RANGE+", pretrained_path=enc, device=DEV, range_db=db, beta=0.5,
                                     out_dtype=np.float32, chunk=12288, tail=6144, super_batch=24576))
     o32 = m32(c)                                                      # opt-in: float32 rows (not the reference's dtype)

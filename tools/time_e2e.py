@@ -21,7 +21,7 @@ def best(fn, reps=5):
 
 model = None
 # host path x (chunk, tail, taper) of the pipelined pieces
-settings = [("stream", 24576, 6144, 0.5), ("copy", 24576, 6144, 0.5), ("copy", 24576, 2048, 0.5), ("copy", 24576, 3072, 0.5), ("copy", 36864, 3072, 0.5),
+settings = [("copy", 24576, 6144, 0.5), ("copy", 24576, 2048, 0.5), ("copy", 24576, 3072, 0.5), ("copy", 36864, 3072, 0.5),
             ("copy", 24576, 3072, 0.6), ("copy", 18432, 3072, 0.5), ("copy", 24576, 6144, 0.5), ("packed", 24576, 6144, 0.5)]
 if os.environ.get("SETTINGS"):       # "path:chunk:tail:taper,..."
     settings = [(a, int(b), int(c), float(d)) for a, b, c, d in (x.split(":") for x in os.environ["SETTINGS"].split(","))]
