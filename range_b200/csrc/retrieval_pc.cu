@@ -196,13 +196,20 @@ range_apply_pc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   const uint32_t rank = ptx::cluster_ctarank();
   // developer instrumentation (tools/time_apply.py): wait-cycle accounting of unit 1's leader CTAs
   long long pacc[6] = {0, 0, 0, 0, 0, 0};
-  const bool prof_on = prof != nullptr && (blockIdx.x >> 1) / 3 == 1 && rank == 0;
+#ifndef RANGE_PC_ROLEMAP
+#define RANGE_PC_ROLEMAP 0
+#endif
+  // cluster -> (unit, role).  0: a unit's producer pair and two consumer pairs are consecutive clusters; 1 (experiment):
+  // all producer pairs first, then the consumer pairs (a unit's clusters n_units apart)
+  const int cid_ = blockIdx.x >> 1;
+  const int unit_ = RANGE_PC_ROLEMAP == 0 ? cid_ / 3 : (cid_ < 3 * plan.n_units ? cid_ % plan.n_units : plan.n_units);
+  const int role_ = RANGE_PC_ROLEMAP == 0 ? cid_ % 3 : (cid_ < 3 * plan.n_units ? cid_ / plan.n_units : 0);
+  const bool prof_on = prof != nullptr && unit_ == 1 && rank == 0;
 #define PC_T0() long long _t0 = prof_on ? clock64() : 0
 #define PC_ADD(k) do { if (prof_on) { long long _t1 = clock64(); pacc[k] += _t1 - _t0; _t0 = _t1; } } while (0)
 #define PC_OUT(base) do { if (prof_on) { for (int _k = 0; _k < 6; ++_k) prof[(base) + _k] = pacc[_k]; } } while (0)
   const bool leader = rank == 0;
-  const int cid = blockIdx.x >> 1;
-  const int unit = cid / 3, role = cid % 3;                 // role 0: producer pair; 1, 2: consumer pairs
+  const int unit = unit_, role = role_;                     // role 0: producer pair; 1, 2: consumer pairs
   const int n_units = plan.n_units;
   const bool active = unit < n_units;
   const bool producer = role == 0;
@@ -655,7 +662,7 @@ range_apply_pc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
             }
           }
         }
-        if (role == 1 && lane == 0) PC_OUT(56);
+        if (lane == 0) PC_OUT(role == 1 ? 56 : 24);
       }
     } else if (warp >= 2 && warp < 6) {
       // ----- epilogue warps: O (TMEM, 128 lanes x 512 columns) -> global fp32, scaled -----

@@ -52,7 +52,7 @@ if os.environ.get("PROF"):
         print(f" producer softmax  wait_s_full | tmem_ld | compute | wait_slot_free | store+arrive : {f(32, 5)}")
         print(f" consumer Vt load  wait_v_empty (per tile = 2 stages)            : {f(40, 1)}")
         print(f" consumer P load   wait_full flag | proxy fence | wait_p_empty   : {f(48, 3)}")
-        print(f" consumer mma      wait_p_full | issue | wait_v_full (per tile)   : {f(56, 3)}")
+        print(f" consumer mma      wait_p_full | issue | wait_v_full (per tile)   : {f(56, 3)}   (second consumer pair: {f(24, 3)})")
         sys.exit(0)
     T = max(1, b[22])
     print(f"tiles {T}; per-tile cycles:")
