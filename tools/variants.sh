@@ -5,7 +5,8 @@
 set -e
 cd "$(dirname "$0")/.."
 SRC=${SRC:-retrieval_pc}
-VARIANTS=("relaxed:" "acquire:-DRANGE_PC_GATE_ACQUIRE" "relaxed_batch2:-DRANGE_PC_BATCH=2" "acquire_batch2:-DRANGE_PC_GATE_ACQUIRE -DRANGE_PC_BATCH=2")
+VARIANTS=("base:" "batch2:-DRANGE_PC_BATCH=2" "batch8:-DRANGE_PC_BATCH=8" "ring32:-DRANGE_PC_RING=32" "acc256:-DRANGE_PC_ACC_WINDOW=256" \
+          "win128:-DRANGE_PC_WINDOW=128" "win32:-DRANGE_PC_WINDOW=32")
 if [ "${1:-build}" = "build" ]; then
   mkdir -p build/variants
   FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC --use_fast_math -diag-suppress 177"
