@@ -385,14 +385,7 @@ range_apply_pc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           if (gate < total) {
             const uint32_t need = gate >= uint32_t(kRing) && !(dbg & 2) ? gate - kRing + 1 : 0u;
             if (seen < need) {
-#ifdef RANGE_PC_GATE_ACQUIRE
               const uint32_t d0 = ptx::ld_acquire_gpu(full_flag + kFlagStride), d1 = ptx::ld_acquire_gpu(full_flag + 2 * kFlagStride);
-#else
-              // Two relaxed loads in flight together (one L2 round trip instead of two serialised acquire loads): this one
-              // thread also publishes, and every clock it spends polling delays both hand-offs.  Relaxed is enough for the
-              // slot's write-after-read hazard: the consumers' TMA reads of the slot completed before they stored `done`.
-              const uint32_t d0 = ptx::ld_relaxed_gpu(full_flag + kFlagStride), d1 = ptx::ld_relaxed_gpu(full_flag + 2 * kFlagStride);
-#endif
               seen = d0 < d1 ? d0 : d1;
             }
             if (seen >= need) {
