@@ -44,14 +44,10 @@ constexpr int kShWarps = 4;
 __global__ void __launch_bounds__(kShWarps * 32)
 sh_rowmajor_kernel(const double* __restrict__ lonlat, int N, int L, const double* __restrict__ pref,
                    const int* __restrict__ off, const double* __restrict__ coef, const int* __restrict__ par,
-                   int closed_form, const double* __restrict__ norm, __half* __restrict__ Yh, __half* __restrict__ Yl,
-                   int am_split, int f_split, int e_split) {
+                   int closed_form, const double* __restrict__ norm, __half* __restrict__ Yh, __half* __restrict__ Yl) {
   __shared__ __half tile[kShWarps][2][32][34];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // am_split > 0: two warps share 32 queries - orders |m| < am_split (features [0, f_split)) and >= am_split (the rest):
-  // the kernel is bound by the latency of its dependent Horner steps, twice the warps hide twice as much of it
-  const int part = am_split > 0 ? (warp & 1) : 0;
-  const int n0 = am_split > 0 ? (blockIdx.x * (kShWarps / 2) + (warp >> 1)) * 32 : (blockIdx.x * kShWarps + warp) * 32;
+  const int n0 = (blockIdx.x * kShWarps + warp) * 32;
   if (n0 >= N) return;
   const int n = n0 + lane;
   const int F = L * L;
@@ -63,8 +59,7 @@ sh_rowmajor_kernel(const double* __restrict__ lonlat, int N, int L, const double
   const double c2 = c * c;
   const double s = sqrt(1.0 - c2);
   double spow = 1.0;
-  int e = part ? e_split : 0, cnt = 0, f0 = part ? f_split : 0;
-  const int am_begin = part ? am_split : 0, am_end = (am_split > 0 && part == 0) ? am_split : L;
+  int e = 0, cnt = 0, f0 = 0;
   auto emit = [&](double v) {
     __half hi, lo;
     split_f16(v, hi, lo);
@@ -84,11 +79,7 @@ sh_rowmajor_kernel(const double* __restrict__ lonlat, int N, int L, const double
   };
   rangeb200::ClosedFormLegendre cf;
   cf.init(c);
-  for (int am = 0; am < am_begin; ++am) {         // the second part replays the per-order state of the orders it skips
-    if (am > 0) spow *= s;
-    if (closed_form) cf.start_order(am);
-  }
-  for (int am = am_begin; am < am_end; ++am) {
+  for (int am = 0; am < L; ++am) {
     double cm = 1.0, sm = 0.0;
     if (am > 0) {
       spow *= s;
@@ -316,24 +307,10 @@ namespace rangeb200 {
 
 cudaError_t launch_sh_rowmajor(const ShTable& t, const double* lonlat, int N, void* Yh, void* Yl, cudaStream_t s) {
   if (N <= 0) return cudaSuccess;
-  // split the orders |m| between two warps per 32 queries where the cost (sum of (L - am)^2 Horner steps) is about halved
-  // and the first part's feature count is a multiple of the 32-feature store chunk (L = 40: am < 8, 544 features)
-  const int L = t.L;
-  long long total = 0;
-  for (int am = 0; am < L; ++am) total += (long long)(L - am) * (L - am);
-  int am_split = 0, f_split = 0, e_split = 0;
-  long long cost = 0, best = total;
-  for (int am = 0, f = 0, e = 0; am < L; ++am) {
-    if (am > 0 && f % 32 == 0 && llabs(2 * cost - total) < best) { best = llabs(2 * cost - total); am_split = am; f_split = f; e_split = e; }
-    cost += (long long)(L - am) * (L - am);
-    f += (am == 0 ? 1 : 2) * (L - am);
-    e += L - am;
-  }
-  if (best * 4 > total) am_split = 0;                     // no balanced split on a chunk boundary: one warp per 32 queries
-  const int per_block = (am_split > 0 ? kShWarps / 2 : kShWarps) * 32;      // queries per block
-  sh_rowmajor_kernel<<<(N + per_block - 1) / per_block, kShWarps * 32, 0, s>>>(
-      lonlat, N, t.L, t.pref, t.off, t.coef, t.par, t.closed_form, t.norm, reinterpret_cast<__half*>(Yh),
-      reinterpret_cast<__half*>(Yl), am_split, f_split, e_split);
+  const int per_block = kShWarps * 32;
+  sh_rowmajor_kernel<<<(N + per_block - 1) / per_block, per_block, 0, s>>>(lonlat, N, t.L, t.pref, t.off, t.coef,
+                                                                           t.par, t.closed_form, t.norm, reinterpret_cast<__half*>(Yh),
+                                                                           reinterpret_cast<__half*>(Yl));
   return cudaGetLastError();
 }
 
