@@ -486,6 +486,23 @@ def main():
             "gpu_launches": int(launches), "clocks": clocks.summary()}
         if sharded is not None:
             line["m_sharded"] = sharded
+        if world == 1:
+            # BASELINE.json configs[0] on this implementation: RANGE, range_db_med shape, 10 000 queries in one model(locs) call
+            with contextlib.redirect_stdout(sys.stderr):
+                db1, _, c1 = synthetic_inputs(M=M_MED, n=10_000)
+                m1 = LocationEncoder(Namespace(location_model_name="RANGE", pretrained_path=enc, device=dev, range_db=db1))
+            h1 = torch.tensor(c1).pin_memory()
+            for _ in range(3):
+                m1(h1)
+            torch.cuda.synchronize()
+            w1 = time.perf_counter()
+            for _ in range(10):
+                r1 = m1(h1)
+            t1 = (time.perf_counter() - w1) / 10
+            assert r1.shape == (10_000, 1280) and r1.dtype == np.float64
+            line["config1_RANGE_Mmed_N10000"] = {"value": 10_000 / t1, "unit": UNIT, "ms_per_call": t1 * 1e3, "M": M_MED,
+                                                 "api": "model(locs): pinned host in, numpy float64 out"}
+            del m1, r1
         if world == 1 and not args.no_cpu_baseline:
             torch.set_num_threads(os.cpu_count() or 1)
             ref = ReferenceCpu()
