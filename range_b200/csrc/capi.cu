@@ -1,4 +1,5 @@
 // C-ABI layer: argument checking, workspace carving, tensor-map construction, kernel sequencing.
+#include <algorithm>
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
@@ -106,9 +107,92 @@ struct range_ctx {
   bool enc_prepared = false;
   const int* perm = nullptr;
   std::vector<CUtensorMap> tmWh, tmWl;
+  std::vector<int> sh_off, sh_par;     // host copies of the harmonics table's chain offsets / parities (layout planning)
 };
 
 namespace {
+
+// ---- feature layout of the tensor-core encoder's first layer (ShTable::K0 / fmap, range_kernels.h) --------------------
+// Rounds layout: the (l, |m|) Horner chains sorted by length (longest first; ties by |m|, then l), 32 per round.
+struct ShLayout {
+  int rounds = 0, K0 = 0;
+  std::vector<int> order;              // rounds layout: slot (32 r + lane) -> entry, -1 for an unused slot
+  std::vector<int> roff;               // [rounds + 1] offsets (doubles) into the round table
+  std::vector<int> perm, fmap;         // [K0]: column -> reference feature index l*l + l +- |m| (-1: zero column) / entry map
+};
+
+void entry_lm(int L, std::vector<int>& el, std::vector<int>& em) {
+  for (int am = 0; am < L; ++am)
+    for (int l = am; l < L; ++l) { el.push_back(l); em.push_back(am); }
+}
+
+// want_rounds == false: production order (for am: for l >= am: cos, then sin when am > 0), K0 = L*L
+ShLayout plan_sh_layout(int L, const std::vector<int>& off, bool want_rounds) {
+  ShLayout y;
+  const int E = L * (L + 1) / 2;
+  std::vector<int> el, em;
+  entry_lm(L, el, em);
+  if (!want_rounds) {
+    y.K0 = L * L;
+    for (int e = 0; e < E; ++e) {
+      y.perm.push_back(el[e] * el[e] + el[e] + em[e]);
+      y.fmap.push_back(em[e] == 0 ? e : (e | em[e] << 16));
+      if (em[e]) {
+        y.perm.push_back(el[e] * el[e] + el[e] - em[e]);
+        y.fmap.push_back(e | em[e] << 16 | 1 << 24);
+      }
+    }
+    return y;
+  }
+  std::vector<int> idx(E);
+  for (int e = 0; e < E; ++e) idx[e] = e;
+  std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) {
+    const int la = off[a + 1] - off[a], lb = off[b + 1] - off[b];
+    return la != lb ? la > lb : a < b;             // entries are already ordered by |m|, then l
+  });
+  y.rounds = (E + 31) / 32;
+  y.K0 = 64 * y.rounds;
+  y.order.assign(size_t(y.rounds) * 32, -1);
+  for (int i = 0; i < E; ++i) y.order[i] = idx[i];
+  y.roff.push_back(0);
+  for (int r = 0; r < y.rounds; ++r) {
+    int nst = 1;
+    for (int i = 0; i < 32; ++i) {
+      const int e = y.order[r * 32 + i];
+      if (e >= 0) nst = std::max(nst, off[e + 1] - off[e]);
+      if (e < 0) {
+        y.perm.push_back(-1); y.perm.push_back(-1);
+        y.fmap.push_back(kShZeroSlot); y.fmap.push_back(kShZeroSlot);
+      } else {
+        y.perm.push_back(el[e] * el[e] + el[e] + em[e]);
+        y.fmap.push_back(em[e] == 0 ? e : (e | em[e] << 16));
+        y.perm.push_back(em[e] ? el[e] * el[e] + el[e] - em[e] : -1);
+        y.fmap.push_back(em[e] ? (e | em[e] << 16 | 1 << 24) : kShZeroSlot);
+      }
+    }
+    y.roff.push_back(y.roff.back() + 32 * (1 + nst));
+  }
+  return y;
+}
+
+// rounds layout only when its table and the kernel's scratch fit in shared memory
+bool sh_rounds_fit(int L, const ShLayout& y) {
+  return y.rounds > 0 && sh_rounds_smem_bytes(L, y.rounds, y.roff.back()) <= size_t(200) * 1024;
+}
+
+ShLayout choose_sh_layout(const range_ctx* c) {
+  if (!c->sh.closed_form && !c->sh_off.empty()) {
+    ShLayout y = plan_sh_layout(c->sh.L, c->sh_off, true);
+    if (sh_rounds_fit(c->sh.L, y)) return y;
+  }
+  return plan_sh_layout(c->sh.L, c->sh_off, false);
+}
+
+size_t sh_layout_bytes(const ShLayout& y) {      // perm + fmap (+ round table, meta, offsets) inside the prepared buffer
+  size_t b = 2 * align_up(size_t(y.K0) * 4, 256);
+  if (y.rounds) b += align_up(size_t(y.roff.back()) * 8, 256) + align_up(size_t(y.rounds) * 128, 256) + align_up(size_t(y.rounds + 1) * 4, 256);
+  return b;
+}
 
 struct RetrievalPlan {
   int splits, tiles_per_split;              // apply kernel
@@ -271,6 +355,16 @@ int range_ctx_set_sh_table(range_ctx* c, int L, int n_entries, const double* pre
   if (!c || L <= 0 || n_entries != L * (L + 1) / 2 || !pref || !off || !coef || !par)
     return fail(RANGE_ERR_INVALID, "bad spherical-harmonics table (L=%d, entries=%d)", L, n_entries);
   c->sh = ShTable{L, n_entries, pref, off, coef, par};
+  c->sh_off.assign(size_t(n_entries) + 1, 0);
+  c->sh_par.assign(size_t(n_entries), 0);
+  CUDA_TRY(cudaMemcpy(c->sh_off.data(), off, c->sh_off.size() * 4, cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(c->sh_par.data(), par, c->sh_par.size() * 4, cudaMemcpyDeviceToHost));
+  for (int e = 0; e < n_entries; ++e)
+    if (c->sh_off[e + 1] <= c->sh_off[e] || c->sh_off[e + 1] - c->sh_off[e] > 255) {
+      c->sh = ShTable{};
+      return fail(RANGE_ERR_INVALID, "spherical-harmonics table: entry %d has %d coefficients", e, c->sh_off[e + 1] - c->sh_off[e]);
+    }
+  c->enc_prepared = false;
   return RANGE_OK;
 }
 
@@ -283,6 +377,8 @@ int range_ctx_set_sh_closed_form(range_ctx* c, int L, int n_entries, const doubl
   c->sh.pref = norm;              // "a table is set" marker for the entry checks; unused by the closed-form kernels
   c->sh.closed_form = 1;
   c->sh.norm = norm;
+  c->sh_off.clear(); c->sh_par.clear();
+  c->enc_prepared = false;
   return RANGE_OK;
 }
 
@@ -387,9 +483,11 @@ static bool tc_supported(const range_ctx* c) {
 }
 
 size_t range_encoder_prepared_bytes(range_ctx* c) {
-  if (!tc_supported(c)) return 0;
-  size_t b = align_up(size_t(c->dims[0]) * 4, 256);
-  for (int i = 0; i < c->n_layers; ++i) b += 2 * align_up(size_t(c->dims[i]) * c->dims[i + 1] * 2, 256);   // hi + lo fp16
+  if (!tc_supported(c) || !c->sh.pref || c->dims[0] != c->sh.L * c->sh.L) return 0;
+  const ShLayout y = choose_sh_layout(c);
+  size_t b = sh_layout_bytes(y);
+  for (int i = 0; i < c->n_layers; ++i)
+    b += 2 * align_up(size_t(i == 0 ? y.K0 : c->dims[i]) * c->dims[i + 1] * 2, 256);   // hi + lo fp16
   return b + 256;
 }
 
@@ -400,26 +498,55 @@ int range_ctx_prepare_encoder(range_ctx* c, void* buf, size_t bytes, void* strea
   const int L = c->sh.L, F = L * L;
   if (c->dims[0] != F) return fail(RANGE_ERR_INVALID, "encoder input dim %d != L*L", c->dims[0]);
   cudaStream_t s = cudaStream_t(stream);
-  // production order of sh_rowmajor_kernel -> reference feature index l*l + l +- am
-  std::vector<int> perm;
-  perm.reserve(F);
-  for (int am = 0; am < L; ++am)
-    for (int l = am; l < L; ++l) {
-      perm.push_back(l * l + l + am);
-      if (am) perm.push_back(l * l + l - am);
-    }
+  // feature layout of the first layer's input: column -> reference feature index l*l + l +- am (the weight columns
+  // are permuted / zero-padded to match), column -> harmonics entry (raster combine), round table (sh_rounds_kernel)
+  const ShLayout y = choose_sh_layout(c);
   char* p = reinterpret_cast<char*>(align_up(reinterpret_cast<size_t>(buf), 256));
-  int* dperm = reinterpret_cast<int*>(p);
-  CUDA_TRY(cudaMemcpyAsync(dperm, perm.data(), size_t(F) * 4, cudaMemcpyHostToDevice, s));
-  CUDA_TRY(cudaStreamSynchronize(s));          // perm is a stack-lifetime host vector
-  p += align_up(size_t(F) * 4, 256);
+  int* dperm = reinterpret_cast<int*>(p); p += align_up(size_t(y.K0) * 4, 256);
+  int* dfmap = reinterpret_cast<int*>(p); p += align_up(size_t(y.K0) * 4, 256);
+  CUDA_TRY(cudaMemcpyAsync(dperm, y.perm.data(), size_t(y.K0) * 4, cudaMemcpyHostToDevice, s));
+  CUDA_TRY(cudaMemcpyAsync(dfmap, y.fmap.data(), size_t(y.K0) * 4, cudaMemcpyHostToDevice, s));
+  c->sh.K0 = y.K0; c->sh.fmap = dfmap;
+  c->sh.rounds = 0; c->sh.rtab = nullptr; c->sh.rtab_doubles = 0; c->sh.rmeta = nullptr; c->sh.rroff = nullptr;
+  std::vector<double> tab;
+  std::vector<int> meta;
+  if (y.rounds) {
+    const int E = c->sh.n_entries;
+    std::vector<double> pref(E), coef(size_t(c->sh_off[E]));
+    CUDA_TRY(cudaMemcpy(pref.data(), c->sh.pref, pref.size() * 8, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(coef.data(), c->sh.coef, coef.size() * 8, cudaMemcpyDeviceToHost));
+    std::vector<int> el, em;
+    entry_lm(L, el, em);
+    tab.assign(size_t(y.roff.back()), 0.0);
+    meta.assign(size_t(y.rounds) * 32, 0);
+    for (int r = 0; r < y.rounds; ++r) {
+      const int nst = (y.roff[r + 1] - y.roff[r]) / 32 - 1;
+      double* t = tab.data() + y.roff[r];
+      for (int i = 0; i < 32; ++i) {
+        const int e = y.order[r * 32 + i];
+        if (e < 0) continue;                                   // unused slot: pref = 0, zero coefficients -> zero columns
+        t[i] = em[e] == 0 ? 1.0 : pref[e];                     // |m| = 0: the per-query kernels emit the chain value itself
+        const int len = c->sh_off[e + 1] - c->sh_off[e], pad = nst - len;
+        for (int k = 0; k < len; ++k) t[32 * (1 + pad + k) + i] = coef[size_t(c->sh_off[e]) + k];
+        meta[r * 32 + i] = em[e] | (c->sh_par[e] ? 0x100 : 0);
+      }
+    }
+    double* dtab = reinterpret_cast<double*>(p); p += align_up(tab.size() * 8, 256);
+    int* dmeta = reinterpret_cast<int*>(p); p += align_up(meta.size() * 4, 256);
+    int* droff = reinterpret_cast<int*>(p); p += align_up(y.roff.size() * 4, 256);
+    CUDA_TRY(cudaMemcpyAsync(dtab, tab.data(), tab.size() * 8, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(dmeta, meta.data(), meta.size() * 4, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(droff, y.roff.data(), y.roff.size() * 4, cudaMemcpyHostToDevice, s));
+    c->sh.rounds = y.rounds; c->sh.rtab = dtab; c->sh.rtab_doubles = int(tab.size()); c->sh.rmeta = dmeta; c->sh.rroff = droff;
+  }
+  CUDA_TRY(cudaStreamSynchronize(s));          // the sources above are stack-lifetime host vectors
   c->perm = dperm;
   c->tmWh.assign(c->n_layers, CUtensorMap{}); c->tmWl.assign(c->n_layers, CUtensorMap{});
   for (int i = 0; i < c->n_layers; ++i) {
-    const int K = c->dims[i], H = c->dims[i + 1];
+    const int K_in = c->dims[i], K = i == 0 ? y.K0 : K_in, H = c->dims[i + 1];
     void* wh = p; p += align_up(size_t(K) * H * 2, 256);
     void* wl = p; p += align_up(size_t(K) * H * 2, 256);
-    CUDA_TRY(launch_split_weights(c->W[i], H, K, i == 0 ? dperm : nullptr, wh, wl, s));
+    CUDA_TRY(launch_split_weights(c->W[i], H, K_in, K, i == 0 ? dperm : nullptr, wh, wl, s));
     g_launches += 1;
     int r = make_tmap(&c->tmWh[i], wh, uint64_t(H), uint64_t(K), 256);
     if (r) return r;
@@ -443,7 +570,7 @@ static size_t encode_ws_tc(const range_ctx* c, int64_t chunk) {
   size_t widest = 0;
   for (int i = 1; i < c->n_layers; ++i) widest = widest > size_t(c->dims[i]) ? widest : size_t(c->dims[i]);
   // features hi + lo, two ping-pong hidden buffers hi + lo (all fp16), row-major fp64 embedding
-  return 2 * align_up(size_t(chunk) * c->dims[0] * 2, 256) + 4 * align_up(size_t(chunk) * widest * 2, 256) +
+  return 2 * align_up(size_t(chunk) * c->sh.K0 * 2, 256) + 4 * align_up(size_t(chunk) * widest * 2, 256) +
          size_t(chunk) * kDimK * 8 + 1024;
 }
 
@@ -466,7 +593,7 @@ static int encode_tc(range_ctx* c, int64_t N, const double* lonlat, const Raster
   size_t widest = 0;
   for (int i = 1; i < c->n_layers; ++i) widest = widest > size_t(c->dims[i]) ? widest : size_t(c->dims[i]);
   char* p = reinterpret_cast<char*>(align_up(reinterpret_cast<size_t>(workspace), 256));
-  const int F = c->dims[0];
+  const int F = c->sh.K0;              // columns of the feature rows (ShTable::K0: L*L, or 64 per round)
   void* Yh = p; p += align_up(size_t(chunk) * F * 2, 256);
   void* Yl = p; p += align_up(size_t(chunk) * F * 2, 256);
   void* hid[2][2];
@@ -477,11 +604,11 @@ static int encode_tc(range_ctx* c, int64_t N, const double* lonlat, const Raster
     const int n = int(N - n0 < chunk ? N - n0 : chunk);
     const double* coords = rt ? lonlat_out + 2 * n0 : lonlat + 2 * n0;
     if (rt) CUDA_TRY(launch_raster_combine(c->sh, *rt, ij + 2 * n0, n, Yh, Yl, lonlat_out + 2 * n0, s));
-    else CUDA_TRY(launch_sh_rowmajor(c->sh, coords, n, Yh, Yl, s));
+    else CUDA_TRY(launch_sh_rowmajor(c->sh, coords, n, Yh, Yl, c->sm_count, s));
     const void *ah = Yh, *al = Yl;
     for (int i = 0; i < c->n_layers; ++i) {
       const bool last = i == c->n_layers - 1;
-      const int K = c->dims[i], H = c->dims[i + 1];
+      const int K = i == 0 ? F : c->dims[i], H = c->dims[i + 1];
       CUtensorMap tmAh, tmAl;
       int r = make_tmap(&tmAh, ah, uint64_t(n), uint64_t(K), 128);
       if (r) return r;
@@ -566,7 +693,7 @@ int range_raster_tables(range_ctx* c, int64_t n_lat, const double* lat, int64_t 
   void* buf = reinterpret_cast<void*>(align_up(reinterpret_cast<size_t>(tables), 256));
   const RasterTables t = raster_tables_layout(c->sh.L, int(n_lat), int(n_lon), buf);
   CUDA_TRY(launch_raster_tables(c->sh, lat, lon, t, cudaStream_t(stream)));
-  g_launches += 3;
+  g_launches += 2;
   return RANGE_OK;
 }
 

@@ -8,7 +8,8 @@
 // takes only H distinct values per (l,am) and the trigonometric factor only W per am, so
 //   raster_lat_kernel      one thread per DISTINCT latitude: the 820 Horner chains (5950 fp64 FMAs) -> leg[H][E]
 //   raster_lon_kernel      one thread per (distinct longitude, am): sincos -> trig[W][L]
-//   raster_combine_kernel  one warp per query: 1600 fp64 multiplies, hi/lo fp16 split, coalesced row-major stores
+//   raster_combine_kernel  one warp per query: 1600 fp64 multiplies, hi/lo fp16 split, coalesced row-major stores in the
+//                          encoder's feature layout (ShTable::fmap: column -> entry, |m|, cos / sin, or always zero)
 // replace 5950 FMAs + 40 sincos per query.  Each operation is the one the per-point kernel performs, in the same order,
 // so the features are bit-identical to it (tests/test_gpu_parity.py::test_raster_encoder_is_bit_identical).
 // The combine kernel also materialises the queries' (lon, lat) rows for the normalise kernel's unit vectors.
@@ -17,6 +18,7 @@
 #include <cuda_runtime.h>
 
 #include "range_kernels.h"
+#include "split_f16.cuh"
 
 namespace {
 
@@ -24,10 +26,7 @@ constexpr double kDeg2Rad = 0.017453292519943295769236907684886;
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-__device__ __forceinline__ void split_f16(double x, __half& hi, __half& lo) {
-  hi = __float2half_rn(float(x));
-  lo = __float2half_rn(float(__dsub_rn(x, double(__half2float(hi)))));       // never contracted with the product before it
-}
+using rangeb200::split_f16;
 
 // leg[i * E + e], entries e in the table's |m|-major order (for am: for l >= am)
 __global__ void __launch_bounds__(64)
@@ -68,23 +67,6 @@ __global__ void raster_lon_kernel(const double* __restrict__ lon, int W, int L, 
   trig[t] = make_double2(cm, sm);
 }
 
-// fmap[f] = e | am << 16 | is_sin << 24 for production-order feature f (for am: for l >= am: cos, then sin if am > 0)
-__global__ void raster_feature_map_kernel(int L, int* __restrict__ fmap) {
-  const int F = L * L;
-  for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < F; f += gridDim.x * blockDim.x) {
-    int am = 0, f0 = 0, e0 = 0;               // f0 / e0: first feature / entry of order am
-    while (true) {
-      const int nf = (am == 0 ? 1 : 2) * (L - am);
-      if (f < f0 + nf) break;
-      f0 += nf;
-      e0 += L - am;
-      ++am;
-    }
-    const int t = f - f0;
-    fmap[f] = am == 0 ? (e0 + t) : ((e0 + (t >> 1)) | am << 16 | (t & 1) << 24);
-  }
-}
-
 // raster point p = i * W + j (lat-major, like coord_grid): its (latitude, longitude) indices and its coordinates, for the
 // points p0 + (perm ? perm[n] : n) - the host never builds index or coordinate lists (range_raster_points)
 __global__ void __launch_bounds__(256)
@@ -104,14 +86,14 @@ raster_points_kernel(long long p0, int N, const int* __restrict__ perm, int H, i
 
 constexpr int kCombineWarps = 8;
 __global__ void __launch_bounds__(kCombineWarps * 32)
-raster_combine_kernel(const int2* __restrict__ ij, int N, int L, int H, int W, const double* __restrict__ lat,
+raster_combine_kernel(const int2* __restrict__ ij, int N, int L, int F, int H, int W, const double* __restrict__ lat,
                       const double* __restrict__ lon, const double* __restrict__ leg, const double2* __restrict__ trig,
                       const int* __restrict__ fmap, __half* __restrict__ Yh, __half* __restrict__ Yl,
                       double* __restrict__ lonlat) {
   const int n = blockIdx.x * kCombineWarps + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (n >= N) return;
   const int2 idx = ij[n];                      // (latitude index, longitude index)
-  const int F = L * L, E = L * (L + 1) / 2;
+  const int E = L * (L + 1) / 2;               // F = columns per row in the encoder's feature layout (ShTable::K0, fmap)
   if (idx.x < 0 || idx.x >= H || idx.y < 0 || idx.y >= W) {     // not a raster point: a NaN row, visible in the result
     const double nan = __longlong_as_double(0x7ff8000000000000LL);
     if (lane == 0) reinterpret_cast<double2*>(lonlat)[n] = make_double2(nan, nan);
@@ -127,13 +109,14 @@ raster_combine_kernel(const int2* __restrict__ ij, int N, int L, int H, int W, c
   if (lane == 0) reinterpret_cast<double2*>(lonlat)[n] = make_double2(lon[idx.y], lat[idx.x]);
   __half2* yh = reinterpret_cast<__half2*>(Yh + size_t(n) * F);
   __half2* yl = reinterpret_cast<__half2*>(Yl + size_t(n) * F);
-  for (int p = lane; 2 * p < F; p += 32) {     // features 2p, 2p + 1 (F is even: the tensor-core encoder needs F % 64 == 0)
+  for (int p = lane; 2 * p < F; p += 32) {     // columns 2p, 2p + 1 (F % 64 == 0)
     const int2 m = reinterpret_cast<const int2*>(fmap)[p];
     double v[2];
     const int mm[2] = {m.x, m.y};
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
       const int am = (mm[u] >> 16) & 0xff;
+      if (mm[u] & rangeb200::kShZeroSlot) { v[u] = 0.0; continue; }
       const double a = __ldg(lrow + (mm[u] & 0xffff));
       if (am == 0) {
         v[u] = a;
@@ -157,7 +140,7 @@ namespace rangeb200 {
 size_t raster_tables_bytes(int L, int H, int W) {
   const size_t E = size_t(L) * (L + 1) / 2;
   return align_up(size_t(H) * E * 8, 256) + align_up(size_t(W) * L * 16, 256) + align_up(size_t(H) * 8, 256) +
-         align_up(size_t(W) * 8, 256) + align_up(size_t(L) * L * 4, 256);
+         align_up(size_t(W) * 8, 256);
 }
 
 RasterTables raster_tables_layout(int L, int H, int W, void* buf) {
@@ -168,8 +151,7 @@ RasterTables raster_tables_layout(int L, int H, int W, void* buf) {
   t.leg = reinterpret_cast<double*>(p); p += align_up(size_t(H) * E * 8, 256);
   t.trig = p; p += align_up(size_t(W) * L * 16, 256);
   t.lat = reinterpret_cast<double*>(p); p += align_up(size_t(H) * 8, 256);
-  t.lon = reinterpret_cast<double*>(p); p += align_up(size_t(W) * 8, 256);
-  t.fmap = reinterpret_cast<int*>(p);
+  t.lon = reinterpret_cast<double*>(p);
   return t;
 }
 
@@ -181,7 +163,6 @@ cudaError_t launch_raster_tables(const ShTable& sh, const double* lat, const dou
   if (e != cudaSuccess) return e;
   raster_lat_kernel<<<(t.H + 63) / 64, 64, 0, s>>>(t.lat, t.H, sh.L, sh.pref, sh.off, sh.coef, sh.par, t.leg);
   raster_lon_kernel<<<(t.W * sh.L + 255) / 256, 256, 0, s>>>(t.lon, t.W, sh.L, reinterpret_cast<double2*>(t.trig));
-  raster_feature_map_kernel<<<4, 256, 0, s>>>(sh.L, t.fmap);
   return cudaGetLastError();
 }
 
@@ -197,8 +178,8 @@ cudaError_t launch_raster_combine(const ShTable& sh, const RasterTables& t, cons
                                   double* lonlat, cudaStream_t s) {
   if (N <= 0) return cudaSuccess;
   raster_combine_kernel<<<(N + kCombineWarps - 1) / kCombineWarps, kCombineWarps * 32, 0, s>>>(
-      reinterpret_cast<const int2*>(ij), N, sh.L, t.H, t.W, t.lat, t.lon, t.leg, reinterpret_cast<const double2*>(t.trig),
-      t.fmap, reinterpret_cast<__half*>(Yh), reinterpret_cast<__half*>(Yl), lonlat);
+      reinterpret_cast<const int2*>(ij), N, sh.L, sh.K0, t.H, t.W, t.lat, t.lon, t.leg,
+      reinterpret_cast<const double2*>(t.trig), sh.fmap, reinterpret_cast<__half*>(Yh), reinterpret_cast<__half*>(Yl), lonlat);
   return cudaGetLastError();
 }
 

@@ -10,9 +10,14 @@
 // their low parts stay in fp16's normal range (|W| <= 1/1600 in the first layer); the epilogue scales back.  Bias add
 // and the sine's argument reduction are done in fp64 in the epilogue.
 //
-//   sh_rowmajor_kernel   features in PRODUCTION order (|m|-major; the first layer's columns are permuted to
-//                        match) as hi/lo fp16, row-major [N][L*L], through a per-warp 32x32 smem transpose
-//                        so global writes are coalesced although a thread owns a whole query.
+//   sh_rounds_kernel     the analytic harmonics, lanes over Horner chains: the 820 (l,|m|) chains are sorted by length and
+//                        cut into rounds of 32; a warp evaluates one round for four queries at a time (one coefficient
+//                        load feeds four DFMAs), multiplies by the queries' cos / sin(|m| phi) and writes each round's 64
+//                        columns (cos, sin per chain) as one coalesced 128-byte store per query: K0 = 64 * rounds columns,
+//                        the first layer's columns are permuted (and zero-padded) to match.
+//   sh_rowmajor_kernel   thread per query (closed-form harmonics, or tables too large for shared memory): features in
+//                        PRODUCTION order (|m|-major) as hi/lo fp16, row-major [N][L*L], through a per-warp 32x32 smem
+//                        transpose so global writes are coalesced although a thread owns a whole query.
 //   split_weights_kernel W fp64 [H][K] -> hi, lo fp16 of 2^10 W, [H][K] (optionally with the column permutation)
 //   siren_tc_kernel      CTA = 128 queries x 256 outputs, K-blocks of 64: TMA (SWIZZLE_128B) -> smem ring ->
 //                        12 x tcgen05.mma kind::f16 (128x256x16) per block -> TMEM -> epilogue warps.
@@ -25,6 +30,7 @@
 #include "ptx.cuh"
 #include "range_kernels.h"
 #include "sh_closed_form.cuh"
+#include "split_f16.cuh"
 
 namespace {
 
@@ -32,10 +38,8 @@ constexpr double kDeg2Rad = 0.017453292519943295769236907684886;
 
 constexpr float kWScale = 1024.f;        // weights are stored as 2^10 W (hi + lo fp16)
 
-__device__ __forceinline__ void split_f16(double x, __half& hi, __half& lo) {
-  hi = __float2half_rn(float(x));
-  lo = __float2half_rn(float(x - double(__half2float(hi))));
-}
+using rangeb200::split_f16;
+using rangeb200::split_f16x2;
 
 // ---------------------------------------------------------------------------------------------------
 // SH features, row-major hi/lo fp32, production order:  for am: for l >= am: [cos] then [sin] (am > 0)
@@ -158,14 +162,126 @@ sh_rowmajor_kernel(const double* __restrict__ lonlat, int N, int L, const double
   }
 }
 
-// W fp64 [H][K] -> hi/lo fp16 of 2^10 W, [H][K]; column f of the output reads column perm[f] of the input (perm may be null)
-__global__ void split_weights_kernel(const double* __restrict__ W, int H, int K, const int* __restrict__ perm,
+// ---------------------------------------------------------------------------------------------------
+// SH features by rounds (ShTable::rounds): lane = Horner chain, kRoundQ queries per warp pass
+// ---------------------------------------------------------------------------------------------------
+// Same operations per feature as sh_rowmajor_kernel / the raster kernels, in the same association:
+//   acc = Horner in c^2 (a chain shorter than its round starts with fma(0, c2, 0) = 0 steps: exact), acc *= c for odd
+//   parity, leg = (pref * s^|m|) * acc, feature = leg * cos(|m| phi) | leg * sin(|m| phi);  |m| = 0 has pref = 1 in the
+//   round table (1 * 1 * acc * 1 = acc exactly; its sin column is 0 and the first layer's weight column there is zero).
+// A thread-per-query kernel executes ~3 400 warp instructions per query (coefficient loads, loop overhead and the
+// transposing stores around 5 950 DFMAs) and waits on the coefficient loads (L1 hit rate 57 %); here the round table sits
+// in shared memory, a coefficient load feeds kRoundQ DFMAs and nothing is transposed: ~1 100 warp instructions per query.
+constexpr int kRoundWarps = 24;
+constexpr int kRoundQ = 4;
+
+__host__ __device__ constexpr size_t round_scratch_doubles(int L) { return size_t(kRoundQ) * 4 + size_t(3) * kRoundQ * L; }
+
+__global__ void __launch_bounds__(kRoundWarps * 32, 1)
+sh_rounds_kernel(const double* __restrict__ lonlat, int N, int L, int R, const double* __restrict__ g_tab, int tab_doubles,
+                 const int* __restrict__ g_meta, const int* __restrict__ g_roff, int K0, uint32_t* __restrict__ Yh,
+                 uint32_t* __restrict__ Yl) {
+  extern __shared__ __align__(16) uint8_t sh_smem[];
+  double* tab = reinterpret_cast<double*>(sh_smem);
+  int* meta = reinterpret_cast<int*>(tab + tab_doubles);
+  int* roff = meta + R * 32;
+  const size_t scratch0 = (size_t(tab_doubles) * 8 + size_t(R) * 128 + size_t(R + 1) * 4 + 15) & ~size_t(15);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* qv = reinterpret_cast<double*>(sh_smem + scratch0) + size_t(warp) * round_scratch_doubles(L);   // [Q][4]: c, c2, s, phi
+  double* cmw = qv + kRoundQ * 4;          // [Q][L] cos(am phi)
+  double* smw = cmw + kRoundQ * L;         // [Q][L] sin(am phi)
+  double* spw = smw + kRoundQ * L;         // [Q][L] s^am (sequential products, like the per-query kernels)
+  {
+    const double2* src = reinterpret_cast<const double2*>(g_tab);
+    double2* dst = reinterpret_cast<double2*>(tab);
+    for (int i = threadIdx.x; i < tab_doubles / 2; i += blockDim.x) dst[i] = __ldg(src + i);
+    for (int i = threadIdx.x; i < R * 32; i += blockDim.x) meta[i] = __ldg(g_meta + i);
+    for (int i = threadIdx.x; i <= R; i += blockDim.x) roff[i] = __ldg(g_roff + i);
+  }
+  __syncthreads();
+  const int nb = (N + kRoundQ - 1) / kRoundQ;
+  const uint32_t row_words = uint32_t(K0) / 2;
+  for (int b = blockIdx.x * kRoundWarps + warp; b < nb; b += gridDim.x * kRoundWarps) {
+    __syncwarp();
+    if (lane < kRoundQ) {
+      const int n = b * kRoundQ + lane;
+      double lon = 0.0, lat = 0.0;
+      if (n < N) { lon = lonlat[2 * n]; lat = lonlat[2 * n + 1]; }
+      const double phi = __dmul_rn(__dadd_rn(lon, 180.0), kDeg2Rad);
+      const double theta = __dmul_rn(__dadd_rn(lat, 90.0), kDeg2Rad);
+      const double c = cos(theta);
+      const double c2 = __dmul_rn(c, c);
+      const double s = sqrt(__dsub_rn(1.0, c2));
+      qv[lane * 4 + 0] = c; qv[lane * 4 + 1] = c2; qv[lane * 4 + 2] = s; qv[lane * 4 + 3] = phi;
+      double sp = 1.0;
+      spw[lane * L] = 1.0;
+      for (int am = 1; am < L; ++am) {
+        sp = __dmul_rn(sp, s);
+        spw[lane * L + am] = sp;
+      }
+    }
+    __syncwarp();
+    for (int it = lane; it < kRoundQ * L; it += 32) {
+      const int q = it / L, am = it - q * L;
+      double sv, cv;
+      sincos(__dmul_rn(double(am), qv[q * 4 + 3]), &sv, &cv);      // am = 0: (0, 1) exactly
+      cmw[it] = cv;
+      smw[it] = sv;
+    }
+    __syncwarp();
+    double c[kRoundQ], c2[kRoundQ];
+    uint32_t row[kRoundQ];
+#pragma unroll
+    for (int q = 0; q < kRoundQ; ++q) {
+      c[q] = qv[q * 4];
+      c2[q] = qv[q * 4 + 1];
+      row[q] = uint32_t(b * kRoundQ + q) * row_words + lane;
+    }
+    const int nvalid = min(kRoundQ, N - b * kRoundQ);
+#pragma unroll 1
+    for (int r = 0; r < R; ++r) {
+      const int o = roff[r];
+      const int nst = ((roff[r + 1] - o) >> 5) - 1;
+      const double* t = tab + o + lane;
+      const double pref = t[0];
+      const int m = meta[r * 32 + lane];
+      const int am = m & 0xff;
+      double a[kRoundQ];
+#pragma unroll
+      for (int q = 0; q < kRoundQ; ++q) a[q] = 0.0;
+#pragma unroll 2
+      for (int st = 1; st <= nst; ++st) {
+        const double cf = t[st * 32];
+#pragma unroll
+        for (int q = 0; q < kRoundQ; ++q) a[q] = fma(a[q], c2[q], cf);
+      }
+#pragma unroll
+      for (int q = 0; q < kRoundQ; ++q) {
+        double x = a[q];
+        if (m & 0x100) x = __dmul_rn(x, c[q]);
+        const double leg = __dmul_rn(__dmul_rn(pref, spw[q * L + am]), x);
+        const double vc = __dmul_rn(leg, cmw[q * L + am]), vs = __dmul_rn(leg, smw[q * L + am]);
+        uint32_t h, l;
+        split_f16x2(vc, vs, h, l);
+        if (q < nvalid) {
+          Yh[row[q] + r * 32] = h;
+          Yl[row[q] + r * 32] = l;
+        }
+      }
+    }
+  }
+}
+
+// W fp64 [H][K_in] -> hi/lo fp16 of 2^10 W, [H][K]; column f of the output reads column perm[f] of the input (zero when
+// perm[f] < 0; perm may be null: identity)
+__global__ void split_weights_kernel(const double* __restrict__ W, int H, int K_in, int K, const int* __restrict__ perm,
                                      __half* __restrict__ Wh, __half* __restrict__ Wl) {
   const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= size_t(H) * K) return;
   const int h = int(i / K), f = int(i % K);
+  const int src = perm ? perm[f] : f;
   __half hi, lo;
-  split_f16(double(kWScale) * W[size_t(h) * K + (perm ? perm[f] : f)], hi, lo);
+  split_f16(src < 0 ? 0.0 : double(kWScale) * W[size_t(h) * K_in + src], hi, lo);
   Wh[i] = hi;
   Wl[i] = lo;
 }
@@ -305,8 +421,25 @@ siren_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
 
 namespace rangeb200 {
 
-cudaError_t launch_sh_rowmajor(const ShTable& t, const double* lonlat, int N, void* Yh, void* Yl, cudaStream_t s) {
+size_t sh_rounds_smem_bytes(int L, int rounds, int rtab_doubles) {
+  if (rounds <= 0) return 0;
+  const size_t table = (size_t(rtab_doubles) * 8 + size_t(rounds) * 128 + size_t(rounds + 1) * 4 + 15) & ~size_t(15);
+  return table + size_t(kRoundWarps) * round_scratch_doubles(L) * 8;
+}
+
+cudaError_t launch_sh_rowmajor(const ShTable& t, const double* lonlat, int N, void* Yh, void* Yl, int sm_count,
+                               cudaStream_t s) {
   if (N <= 0) return cudaSuccess;
+  if (t.rounds > 0) {
+    const size_t smem = sh_rounds_smem_bytes(t.L, t.rounds, t.rtab_doubles);
+    cudaError_t e = cudaFuncSetAttribute(sh_rounds_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    if (e != cudaSuccess) return e;
+    const int nb = (N + kRoundQ - 1) / kRoundQ;
+    const int grid = min(sm_count, (nb + kRoundWarps - 1) / kRoundWarps);
+    sh_rounds_kernel<<<grid, kRoundWarps * 32, smem, s>>>(lonlat, N, t.L, t.rounds, t.rtab, t.rtab_doubles, t.rmeta, t.rroff,
+                                                         t.K0, reinterpret_cast<uint32_t*>(Yh), reinterpret_cast<uint32_t*>(Yl));
+    return cudaGetLastError();
+  }
   const int per_block = kShWarps * 32;
   sh_rowmajor_kernel<<<(N + per_block - 1) / per_block, per_block, 0, s>>>(lonlat, N, t.L, t.pref, t.off, t.coef,
                                                                            t.par, t.closed_form, t.norm, reinterpret_cast<__half*>(Yh),
@@ -314,9 +447,10 @@ cudaError_t launch_sh_rowmajor(const ShTable& t, const double* lonlat, int N, vo
   return cudaGetLastError();
 }
 
-cudaError_t launch_split_weights(const double* W, int H, int K, const int* perm, void* Wh, void* Wl, cudaStream_t s) {
+cudaError_t launch_split_weights(const double* W, int H, int K_in, int K, const int* perm, void* Wh, void* Wl,
+                                 cudaStream_t s) {
   const size_t total = size_t(H) * K;
-  split_weights_kernel<<<unsigned((total + 255) / 256), 256, 0, s>>>(W, H, K, perm, reinterpret_cast<__half*>(Wh),
+  split_weights_kernel<<<unsigned((total + 255) / 256), 256, 0, s>>>(W, H, K_in, K, perm, reinterpret_cast<__half*>(Wh),
                                                                      reinterpret_cast<__half*>(Wl));
   return cudaGetLastError();
 }

@@ -20,7 +20,24 @@ struct ShTable {
   // normalisation factors (sqrt(2) *) SH_renormalization(l, |m|), |m|-major like the entries above
   int closed_form = 0;
   const double* norm = nullptr;   // [n_entries]
+  // ---- set by range_ctx_prepare_encoder (tensor-core encoder): the feature layout of the first layer's input ----
+  // K0 columns per query row (a multiple of 64); fmap[f] = entry | |m| << 16 | is_sin << 24, or kShZeroSlot for a
+  // column that is always zero.  Two layouts:
+  //   production order (closed-form harmonics, or a table too large for shared memory): K0 = L*L, for am: for l >= am:
+  //     cos, then sin (am > 0);
+  //   rounds (sh_rounds_kernel): the entries sorted by Horner-chain length, 32 per round; round r, lane i owns columns
+  //     64 r + 2 i (cos) and 64 r + 2 i + 1 (sin): K0 = 64 * ceil(n_entries / 32), one 128-byte k-block per round.
+  int K0 = 0;
+  const int* fmap = nullptr;      // [K0]
+  int rounds = 0;                 // > 0: rounds layout
+  const double* rtab = nullptr;   // per round: pref[32], then coef[nsteps][32] (leading zeros pad shorter chains)
+  int rtab_doubles = 0;
+  const int* rmeta = nullptr;     // [rounds][32]  |m| | parity << 8
+  const int* rroff = nullptr;     // [rounds + 1]  offsets into rtab (doubles)
 };
+constexpr int kShZeroSlot = 1 << 25;
+// dynamic shared memory sh_rounds_kernel needs for this table (0: no rounds layout)
+size_t sh_rounds_smem_bytes(int L, int rounds, int rtab_doubles);
 // Yt[f * ld + n] for f < L*L, n < N   (feature-major so a thread per query writes coalesced)
 cudaError_t launch_sh(const ShTable& t, const double* lonlat, int N, double* Yt, size_t ld, cudaStream_t s);
 
@@ -31,10 +48,13 @@ cudaError_t launch_siren_layer(const double* W, const double* b, const double* X
                                double act_w0, double* out, size_t ldo, int out_rowmajor, cudaStream_t s);
 
 // ---- K1/K1b on the tensor cores: split-precision (3 x fp16) tcgen05 GEMMs (encoder_tc.cu) ------------------
-// features as hi/lo fp16, row-major [N][L*L], in PRODUCTION order (|m|-major: for am: for l >= am: cos, sin)
-cudaError_t launch_sh_rowmajor(const ShTable& t, const double* lonlat, int N, void* Yh, void* Yl, cudaStream_t s);
-// W fp64 [H][K] -> hi/lo fp16 of 2^10 W, [H][K]; output column f = input column perm[f] (perm may be null)
-cudaError_t launch_split_weights(const double* W, int H, int K, const int* perm, void* Wh, void* Wl, cudaStream_t s);
+// features as hi/lo fp16, row-major [N][t.K0], in the layout t.fmap describes (rounds or production order)
+cudaError_t launch_sh_rowmajor(const ShTable& t, const double* lonlat, int N, void* Yh, void* Yl, int sm_count,
+                               cudaStream_t s);
+// W fp64 [H][K_in] -> hi/lo fp16 of 2^10 W, [H][K]; output column f = input column perm[f] (zero when perm[f] < 0;
+// perm == null: K == K_in, identity)
+cudaError_t launch_split_weights(const double* W, int H, int K_in, int K, const int* perm, void* Wh, void* Wl,
+                                 cudaStream_t s);
 // out = act(A . B^T + bias): A hi/lo [N][K], B hi/lo [H][K] (tensor maps: fp16, box [rows x 64], SWIZZLE_128B);
 // act_w0 > 0 -> sin(act_w0 x) written as hi/lo fp16 [N][H]; out_f64 != null -> plain fp64 [N][H]
 cudaError_t launch_siren_tc(const CUtensorMap& tmAh, const CUtensorMap& tmAl, const CUtensorMap& tmBh,
@@ -48,7 +68,6 @@ struct RasterTables {
   void* trig = nullptr;           // [W][L] double2  (cos |m| phi, sin |m| phi)
   double* lat = nullptr;          // [H] degrees
   double* lon = nullptr;          // [W] degrees
-  int* fmap = nullptr;            // [L*L] production-order feature -> entry | |m| << 16 | is_sin << 24
 };
 size_t raster_tables_bytes(int L, int H, int W);
 RasterTables raster_tables_layout(int L, int H, int W, void* buf);     // buf 256-byte aligned
@@ -57,7 +76,7 @@ cudaError_t launch_raster_tables(const ShTable& sh, const double* lat, const dou
 // raster points p0 + (perm ? perm[n] : n), n < N (point p = i * W + j): ij (N,2) and / or lonlat (N,2), either may be null
 cudaError_t launch_raster_points(const RasterTables& t, long long p0, int N, const int32_t* perm, int32_t* ij,
                                  double* lonlat, cudaStream_t s);
-// ij (N,2) int32 = (latitude index, longitude index) -> features hi/lo fp16 [N][L*L], lonlat (N,2) fp64
+// ij (N,2) int32 = (latitude index, longitude index) -> features hi/lo fp16 [N][sh.K0] (layout sh.fmap), lonlat (N,2) fp64
 cudaError_t launch_raster_combine(const ShTable& sh, const RasterTables& t, const int32_t* ij, int N, void* Yh, void* Yl,
                                   double* lonlat, cudaStream_t s);
 
