@@ -106,7 +106,8 @@ struct range_ctx {
   int enc_precision = RANGE_ENC_F64;
   bool enc_prepared = false;
   const int* perm = nullptr;
-  std::vector<CUtensorMap> tmWh, tmWl;
+  std::vector<CUtensorMap> tmWh, tmWl;         // weights hi / lo, box [256 rows x 64] (siren_tc_kernel)
+  std::vector<CUtensorMap> tmWh2, tmWl2;       // the same arrays, box [128 rows x 64] (siren_pair_kernel: half a tile per CTA)
   std::vector<int> sh_off, sh_par;     // host copies of the harmonics table's chain offsets / parities (layout planning)
 };
 
@@ -202,6 +203,16 @@ struct RetrievalPlan {
   bool stats_pc;                            // statistics with the CTA-pair / four-group kernel (retrieval_pc.cu)
   size_t off_part_sum, off_part_max, off_sums, off_maxs, off_rowc, off_mask, off_ring, off_flags, off_pc_part, off_pc_scratch, off_part_out, off_O, total;
 };
+
+// RANGE_SIREN_KERNEL=cta: the one-tile-per-CTA layer kernel (siren_tc_kernel) instead of the persistent CTA pairs
+int siren_kernel_override() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("RANGE_SIREN_KERNEL");
+    v = (e && !strcmp(e, "cta")) ? 1 : 0;
+  }
+  return v;
+}
 
 // 0 = choose by batch size, 1 = always the single-role CTA-pair kernel, 2 = producer/consumer whenever possible
 int apply_kernel_override() {
@@ -542,6 +553,7 @@ int range_ctx_prepare_encoder(range_ctx* c, void* buf, size_t bytes, void* strea
   CUDA_TRY(cudaStreamSynchronize(s));          // the sources above are stack-lifetime host vectors
   c->perm = dperm;
   c->tmWh.assign(c->n_layers, CUtensorMap{}); c->tmWl.assign(c->n_layers, CUtensorMap{});
+  c->tmWh2.assign(c->n_layers, CUtensorMap{}); c->tmWl2.assign(c->n_layers, CUtensorMap{});
   for (int i = 0; i < c->n_layers; ++i) {
     const int K_in = c->dims[i], K = i == 0 ? y.K0 : K_in, H = c->dims[i + 1];
     void* wh = p; p += align_up(size_t(K) * H * 2, 256);
@@ -551,6 +563,10 @@ int range_ctx_prepare_encoder(range_ctx* c, void* buf, size_t bytes, void* strea
     int r = make_tmap(&c->tmWh[i], wh, uint64_t(H), uint64_t(K), 256);
     if (r) return r;
     r = make_tmap(&c->tmWl[i], wl, uint64_t(H), uint64_t(K), 256);
+    if (r) return r;
+    r = make_tmap(&c->tmWh2[i], wh, uint64_t(H), uint64_t(K), 128);
+    if (r) return r;
+    r = make_tmap(&c->tmWl2[i], wl, uint64_t(H), uint64_t(K), 128);
     if (r) return r;
   }
   c->enc_prepared = true;
@@ -614,9 +630,14 @@ static int encode_tc(range_ctx* c, int64_t N, const double* lonlat, const Raster
       if (r) return r;
       r = make_tmap(&tmAl, al, uint64_t(n), uint64_t(K), 128);
       if (r) return r;
-      CUDA_TRY(launch_siren_tc(tmAh, tmAl, c->tmWh[i], c->tmWl[i], c->b[i], n, K, H,
-                               last ? 0.0 : (i == 0 ? c->w0_first : c->w0_hidden), last ? nullptr : hid[i & 1][0],
-                               last ? nullptr : hid[i & 1][1], last ? emb : nullptr, s));
+      const double w0 = last ? 0.0 : (i == 0 ? c->w0_first : c->w0_hidden);
+      void* oh = last ? nullptr : hid[i & 1][0];
+      void* ol = last ? nullptr : hid[i & 1][1];
+      if (siren_kernel_override() == 1)
+        CUDA_TRY(launch_siren_tc(tmAh, tmAl, c->tmWh[i], c->tmWl[i], c->b[i], n, K, H, w0, oh, ol, last ? emb : nullptr, s));
+      else
+        CUDA_TRY(launch_siren_pair(tmAh, tmAl, c->tmWh2[i], c->tmWl2[i], c->b[i], n, K, H, w0, oh, ol, last ? emb : nullptr,
+                                   c->sm_count, s));
       ah = hid[i & 1][0]; al = hid[i & 1][1];
     }
     CUDA_TRY(launch_normalize(emb, coords, n, kDimK, q64 + n0 * kDimK, kDimK,

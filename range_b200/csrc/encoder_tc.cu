@@ -417,6 +417,209 @@ siren_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant_
   if (warp == kTcEpiWarps + 1) ptx::tmem_dealloc<256>(tmem_base);
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// The same GEMM + epilogue on CTA pairs, persistent: out(256 x 256 per pair) = act(A . B^T + bias)
+// ---------------------------------------------------------------------------------------------------
+// siren_tc_kernel's CTAs each re-read their 256 weight rows for every 128 queries: 98 KB of operands per 12 MMAs, 4 GB
+// of L2 -> shared-memory traffic for the first layer (8.5 TB/s: the L2 is the bound, not the tensor core), and prologue,
+// pipeline fill and epilogue are exposed once per tile (layers 1-2 have 8 k-blocks per tile).  Here a CTA pair
+// (cta_group::2, M = 256) shares the weight tile - each CTA loads its own 128 query rows and HALF of the 256 weight rows,
+// 64 KB per 12 MMAs - and a cluster walks over its tiles with the accumulator double-buffered in TMEM (2 x 256 columns):
+// the epilogue warps of both CTAs drain tile i while the pair's tensor cores run tile i + 1, the TMA warp never stops.
+constexpr int kSpStages = 3;
+constexpr int kSpStageBytes = 4 * 16384;                 // A_hi | A_lo | B_hi | B_lo, 128 rows x 128 B each
+constexpr int kSpEpiWarps = 8;
+constexpr int kSpWarpTma = kSpEpiWarps, kSpWarpMma = kSpEpiWarps + 1;
+constexpr int kSpThreads = (kSpEpiWarps + 2) * 32;
+constexpr int kSpBiasBytes = kSpEpiWarps * 1024;         // per epilogue warp: its 128 columns' bias terms (fp32 w0 b, or fp64 b)
+constexpr int kSpSmem = kSpStages * kSpStageBytes + 256 + kSpBiasBytes + 1024;
+
+__global__ void __launch_bounds__(kSpThreads, 1)
+siren_pair_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
+                  const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
+                  const double* __restrict__ bias, int N, int K, int H, double act_w0, __half* __restrict__ out_hi,
+                  __half* __restrict__ out_lo, double* __restrict__ out_f64) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // full[S] | empty[S] | acc_full[2] | acc_empty[2]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSpStages * kSpStageBytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kSpStages;
+  uint64_t* acc_full = bars + 2 * kSpStages;
+  uint64_t* acc_empty = bars + 2 * kSpStages + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kSpStages + 4);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const bool leader = rank == 0;
+  const int cluster = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+  const int KB = K / 64, CB = H / 256;
+  const int tiles = ((N + 255) / 256) * CB;              // tile t: row pair t / CB, column block t % CB (neighbours share A)
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kSpStages; ++i) {
+      ptx::mbar_init(&full[i], 1);
+      ptx::mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&acc_full[i], 1);
+      ptx::mbar_init(&acc_empty[i], 2 * kSpEpiWarps);    // the epilogue warps of both CTAs
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == kSpWarpMma) ptx::tmem_alloc_2sm<512>(tmem_slot);
+  ptx::tc_fence_before();
+  ptx::cluster_sync();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  const uint32_t smem_u = __shfl_sync(0xffffffffu, ptx::smem_u32(smem), 0);
+  const uint32_t bars_u = smem_u + kSpStages * kSpStageBytes;
+
+  if (warp == kSpWarpTma) {
+    if (lane == 0) {
+      ptx::prefetch_tmap(&tmAh); ptx::prefetch_tmap(&tmAl); ptx::prefetch_tmap(&tmBh); ptx::prefetch_tmap(&tmBl);
+      int idx = 0; uint32_t phase = 0;
+      for (int t = cluster; t < tiles; t += n_clusters) {
+        const int row0 = (t / CB) * 256 + int(rank) * 128, col0 = (t % CB) * 256 + int(rank) * 128;
+        for (int kb = 0; kb < KB; ++kb) {
+          ptx::mbar_wait(&empty[idx], phase ^ 1);
+          uint8_t* st = smem + idx * kSpStageBytes;
+          if (leader) ptx::mbar_expect_tx(&full[idx], 2 * kSpStageBytes);     // both CTAs' bytes are credited to the leader
+          ptx::tma_load_2d_2sm(st, &tmAh, &full[idx], kb * 64, row0);
+          ptx::tma_load_2d_2sm(st + 16384, &tmAl, &full[idx], kb * 64, row0);
+          ptx::tma_load_2d_2sm(st + 32768, &tmBh, &full[idx], kb * 64, col0);
+          ptx::tma_load_2d_2sm(st + 49152, &tmBl, &full[idx], kb * 64, col0);
+          if (++idx == kSpStages) { idx = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == kSpWarpMma) {
+    if (leader) {
+      constexpr uint32_t idesc = ptx::umma_idesc_f16(256, 256);
+      int idx = 0; uint32_t phase = 0;
+      int i = 0;
+      for (int t = cluster; t < tiles; t += n_clusters, ++i) {
+        const int buf = i & 1;
+        ptx::mbar_wait_cluster(&acc_empty[buf], ((i >> 1) & 1) ^ 1);          // both CTAs drained this accumulator
+        ptx::tc_fence_after();
+        const uint32_t d = tmem_base + buf * 256;
+        for (int kb = 0; kb < KB; ++kb) {
+          ptx::mbar_wait(&full[idx], phase);
+          ptx::tc_fence_after();
+          if (ptx::elect_one()) {
+            const uint32_t st = smem_u + idx * kSpStageBytes;
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              const uint64_t ah = ptx::umma_desc_kmajor_sw128(st + kk * 32);
+              const uint64_t al = ptx::umma_desc_kmajor_sw128(st + 16384 + kk * 32);
+              const uint64_t bh = ptx::umma_desc_kmajor_sw128(st + 32768 + kk * 32);
+              const uint64_t bl = ptx::umma_desc_kmajor_sw128(st + 49152 + kk * 32);
+              ptx::umma_f16_ss_2sm(d, al, bh, idesc, (kb | kk) != 0);          // small terms first
+              ptx::umma_f16_ss_2sm(d, ah, bl, idesc, 1);
+              ptx::umma_f16_ss_2sm(d, ah, bh, idesc, 1);
+            }
+            ptx::umma_commit_2sm_u32(bars_u + 8 * (kSpStages + idx));
+            if (kb == KB - 1) ptx::umma_commit_2sm_u32(bars_u + 8 * (2 * kSpStages + buf));
+          }
+          __syncwarp();
+          if (++idx == kSpStages) { idx = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ===== epilogue: warp w -> TMEM lanes 32 (w%4).., columns 128 (w/4) .. +127 of the current accumulator =====
+    // Hidden layers: sin(w0 (acc + b)) entirely in fp32 - x = fma(acc, w0 / 2^10, w0 b) (half an ulp of |x| <= 64: 2e-6,
+    // the size of the accumulator's own rounding times w0), two-constant Cody-Waite reduction to [-pi, pi], MUFU.SIN.
+    // (siren_tc_kernel reduces in fp64: 5 fp64 + 3 conversion instructions per output, which left the 8 epilogue warps
+    // waiting on the fp64 / conversion pipes for longer than a K = 512 tile's MMAs take.)
+    const int quarter = warp & 3, half = warp >> 2;
+    const uint32_t acc_empty_leader = ptx::mapa(ptx::smem_u32(acc_empty), 0);
+    uint8_t* bias_w = smem + kSpStages * kSpStageBytes + 256 + warp * 1024;
+    float* bias_f = reinterpret_cast<float*>(bias_w);
+    double* bias_d = reinterpret_cast<double*>(bias_w);
+    const float xscale = float(act_w0) * (1.f / kWScale);
+    const uint32_t bias_u = smem_u + kSpStages * kSpStageBytes + 256 + warp * 1024;     // explicit LDS (generic loads -> LD.E)
+    int i = 0;
+    for (int t = cluster; t < tiles; t += n_clusters, ++i) {
+      const int buf = i & 1;
+      const int n = (t / CB) * 256 + int(rank) * 128 + quarter * 32 + lane;
+      const int col0 = (t % CB) * 256;
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const double b = __ldg(bias + col0 + half * 128 + j * 32 + lane);
+        if (out_f64) bias_d[j * 32 + lane] = b;
+        else bias_f[j * 32 + lane] = float(act_w0 * b);
+      }
+      __syncwarp();
+      ptx::mbar_wait(&acc_full[buf], (i >> 1) & 1);
+      ptx::tc_fence_after();
+#pragma unroll 1
+      for (int cc = 0; cc < 4; ++cc) {
+        uint32_t v[32];
+        const int c0 = half * 128 + cc * 32;
+        ptx::tmem_ld32(tmem_base + (uint32_t(quarter * 32) << 16) + buf * 256 + c0, v);
+        ptx::tmem_ld_wait();
+        if (cc == 3) {                   // this warp's part of the accumulator is in registers: hand the buffer back
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (leader) ptx::mbar_arrive(&acc_empty[buf]);
+            else ptx::mbar_arrive_cluster_relaxed(acc_empty_leader + 8 * buf);
+          }
+        }
+        if (n < N) {
+          if (out_f64) {
+            double* o = out_f64 + size_t(n) * H + col0 + c0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              const float4 braw = ptx::lds_f4(bias_u + (cc * 32 + j) * 8);
+              const double2 b = make_double2(__hiloint2double(__float_as_int(braw.y), __float_as_int(braw.x)),
+                                             __hiloint2double(__float_as_int(braw.w), __float_as_int(braw.z)));
+              *reinterpret_cast<double2*>(o + j) = make_double2(double(__uint_as_float(v[j]) * (1.f / kWScale)) + b.x,
+                                                                double(__uint_as_float(v[j + 1]) * (1.f / kWScale)) + b.y);
+            }
+          } else {
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b4 = ptx::lds_f4(bias_u + (cc * 32 + j) * 4);
+              const float bw[4] = {b4.x, b4.y, b4.z, b4.w};
+              float sv[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const float x = fmaf(__uint_as_float(v[j + u]), xscale, bw[u]);
+                // k = rint(x / 2 pi) by the 1.5 * 2^23 trick (|x / 2 pi| < 2^22), r = x - k 2 pi with 2 pi = hi + lo
+                const float k = __fadd_rn(__fadd_rn(__fmul_rn(x, 0.15915494309189535f), 12582912.f), -12582912.f);
+                const float r = fmaf(k, 1.7484555e-7f, fmaf(k, -6.2831855f, x));
+                sv[u] = __sinf(r);
+              }
+              const __half2 h = __floats2half2_rn(sv[0], sv[1]);
+              const __half2 l = __floats2half2_rn(sv[0] - __low2float(h), sv[1] - __high2float(h));
+              hi[j / 2] = *reinterpret_cast<const uint32_t*>(&h);
+              lo[j / 2] = *reinterpret_cast<const uint32_t*>(&l);
+              const __half2 h2 = __floats2half2_rn(sv[2], sv[3]);
+              const __half2 l2 = __floats2half2_rn(sv[2] - __low2float(h2), sv[3] - __high2float(h2));
+              hi[j / 2 + 1] = *reinterpret_cast<const uint32_t*>(&h2);
+              lo[j / 2 + 1] = *reinterpret_cast<const uint32_t*>(&l2);
+            }
+            uint4* oh = reinterpret_cast<uint4*>(out_hi + size_t(n) * H + col0 + c0);
+            uint4* ol = reinterpret_cast<uint4*>(out_lo + size_t(n) * H + col0 + c0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              oh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+              ol[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+            }
+          }
+        }
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  ptx::cluster_sync();
+  if (warp == kSpWarpMma) ptx::tmem_dealloc_2sm<512>(tmem_base);
+}
+
 }  // namespace
 
 namespace rangeb200 {
@@ -453,6 +656,29 @@ cudaError_t launch_split_weights(const double* W, int H, int K_in, int K, const 
   split_weights_kernel<<<unsigned((total + 255) / 256), 256, 0, s>>>(W, H, K_in, K, perm, reinterpret_cast<__half*>(Wh),
                                                                      reinterpret_cast<__half*>(Wl));
   return cudaGetLastError();
+}
+
+cudaError_t launch_siren_pair(const CUtensorMap& tmAh, const CUtensorMap& tmAl, const CUtensorMap& tmBh,
+                              const CUtensorMap& tmBl, const double* bias, int N, int K, int H, double act_w0,
+                              void* out_hi, void* out_lo, double* out_f64, int sm_count, cudaStream_t s) {
+  if (N <= 0) return cudaSuccess;
+  if (K % 64 || H % 256) return cudaErrorInvalidValue;
+  cudaError_t e = cudaFuncSetAttribute(siren_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSpSmem);
+  if (e != cudaSuccess) return e;
+  const int tiles = ((N + 255) / 256) * (H / 256);
+  const int clusters = tiles < sm_count / 2 ? tiles : sm_count / 2;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * clusters);
+  cfg.blockDim = dim3(kSpThreads);
+  cfg.dynamicSmemBytes = kSpSmem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, siren_pair_kernel, tmAh, tmAl, tmBh, tmBl, bias, N, K, H, act_w0,
+                            reinterpret_cast<__half*>(out_hi), reinterpret_cast<__half*>(out_lo), out_f64);
 }
 
 cudaError_t launch_siren_tc(const CUtensorMap& tmAh, const CUtensorMap& tmAl, const CUtensorMap& tmBh,

@@ -60,6 +60,10 @@ cudaError_t launch_split_weights(const double* W, int H, int K_in, int K, const 
 cudaError_t launch_siren_tc(const CUtensorMap& tmAh, const CUtensorMap& tmAl, const CUtensorMap& tmBh,
                             const CUtensorMap& tmBl, const double* bias, int N, int K, int H, double act_w0,
                             void* out_hi, void* out_lo, double* out_f64, cudaStream_t s);
+// the same layer on persistent CTA pairs (cta_group::2): B tensor maps with box [128 rows x 64], A as above
+cudaError_t launch_siren_pair(const CUtensorMap& tmAh, const CUtensorMap& tmAl, const CUtensorMap& tmBh,
+                              const CUtensorMap& tmBl, const double* bias, int N, int K, int H, double act_w0,
+                              void* out_hi, void* out_lo, double* out_f64, int sm_count, cudaStream_t s);
 
 // ---- K1 on a lat/lon raster: separable evaluation, bit-identical to launch_sh_rowmajor (encoder_raster.cu) ----
 struct RasterTables {
