@@ -68,9 +68,12 @@ int range_ctx_set_encoder(range_ctx* ctx, int n_layers, const int32_t* dims, con
 /* Optional tensor-core encoder: the SIREN layers as split-precision tcgen05 GEMMs - every operand as hi + lo fp16,
  * three kind::f16 products per term, fp32 accumulation (fp32-class accuracy; the reference's fp64 SIREN sits on
  * spherical-harmonic input that carries >= 1e-3 of its own rounding noise).
- * Needs every layer width % 256 == 0 and input width % 64 == 0.  The prepared (split / permuted) weights live in `buf`, a device
- * buffer of range_encoder_prepared_bytes() the caller keeps alive; after a successful prepare the ctx
- * encodes in RANGE_ENC_F16X3 until range_ctx_set_encoder_precision(ctx, RANGE_ENC_F64). */
+ * Needs every layer width % 256 == 0 and input width % 64 == 0; call after range_ctx_set_sh_table / _closed_form and
+ * range_ctx_set_encoder (setting either again requires a new prepare).  `buf`, a device buffer of
+ * range_encoder_prepared_bytes() the caller keeps alive, receives the split weights - the first layer's columns permuted
+ * and zero-padded to the order in which the harmonics kernel emits features (analytic tables: Horner chains sorted by
+ * length, 64 columns per round of 32 chains; closed form: |m|-major) - and that kernel's tables.  After a successful
+ * prepare the ctx encodes in RANGE_ENC_F16X3 until range_ctx_set_encoder_precision(ctx, RANGE_ENC_F64). */
 #define RANGE_ENC_F64 0
 #define RANGE_ENC_F16X3 1
 #define RANGE_ENC_TF32X3 RANGE_ENC_F16X3 /* earlier name of the same mode */

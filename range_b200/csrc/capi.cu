@@ -376,6 +376,7 @@ int range_ctx_set_sh_table(range_ctx* c, int L, int n_entries, const double* pre
       return fail(RANGE_ERR_INVALID, "spherical-harmonics table: entry %d has %d coefficients", e, c->sh_off[e + 1] - c->sh_off[e]);
     }
   c->enc_prepared = false;
+  c->enc_precision = RANGE_ENC_F64;    // the prepared feature layout belonged to the previous table
   return RANGE_OK;
 }
 
@@ -390,6 +391,7 @@ int range_ctx_set_sh_closed_form(range_ctx* c, int L, int n_entries, const doubl
   c->sh.norm = norm;
   c->sh_off.clear(); c->sh_par.clear();
   c->enc_prepared = false;
+  c->enc_precision = RANGE_ENC_F64;
   return RANGE_OK;
 }
 
