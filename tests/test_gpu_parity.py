@@ -112,7 +112,7 @@ def test_encoder_split_vs_fp64(sh_entries):
     e64 = RangeEngine(DEV, encoder=enc, encoder_precision="fp64")
     etc = RangeEngine(DEV, encoder=enc, encoder_precision="auto")
     assert e64.precision == "fp64" and etc.precision == "f16x3"
-    for N in (1, 129, 3000):
+    for N in (1, 3, 129, 255, 257, 3000):       # partial 4-query harmonics batches, partial 256-row CTA-pair tiles
         c = O.area_uniform(N, np.random.default_rng(N))
         c[0] = [0.0, 90.0]
         a, b = e64.encode(torch.tensor(c))[0], etc.encode(torch.tensor(c))[0]
