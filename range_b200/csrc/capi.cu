@@ -337,6 +337,21 @@ int range_version(void) { return 100; }
 int64_t range_launch_count(void) { return g_launches.load(); }
 // not in the public header: work decomposition of the producer/consumer apply kernel (tests/test_capi.py; host code only)
 void range_debug_apply_plan(int sm_count, int64_t N, int64_t M, int32_t* out7) { apply_pc_describe_plan(sm_count, N, M, out7); }
+// not in the public header: feature layout of the tensor-core encoder's first layer for a harmonics table with these
+// chain offsets (tests/test_capi.py; host code only).  off: n_entries + 1 host ints; perm / fmap: K0 ints each (cap >= K0).
+// Returns K0 (<= 0 on bad arguments or cap too small); *rounds = 0 for the production-order layout.
+int range_debug_sh_layout(int L, const int32_t* off, int want_rounds, int32_t* rounds, int32_t* round_table_doubles,
+                          int32_t* perm, int32_t* fmap, int cap) {
+  if (L <= 0 || !off || !rounds || !round_table_doubles || !perm || !fmap) return -1;
+  const int E = L * (L + 1) / 2;
+  const ShLayout y = plan_sh_layout(L, std::vector<int>(off, off + E + 1), want_rounds != 0);
+  if (y.K0 > cap) return -1;
+  *rounds = y.rounds;
+  *round_table_doubles = y.rounds ? y.roff.back() : 0;
+  std::copy(y.perm.begin(), y.perm.end(), perm);
+  std::copy(y.fmap.begin(), y.fmap.end(), fmap);
+  return y.K0;
+}
 // not in the public header: developer hook used by tools/time_apply.py
 void range_debug_set_profile_buffer(void* device_buffer) { set_profile_buffer(reinterpret_cast<long long*>(device_buffer)); }
 

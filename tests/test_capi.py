@@ -155,3 +155,50 @@ def test_host_unpack_widens_packed_rows_exactly():
                 assert lib.range_host_unpack(packed.ctypes.data if N else None, N, out.ctypes.data if N else None, threads) == 0
                 assert np.array_equal(out, want) and np.array_equal(np.signbit(out), np.signbit(want))
     assert lib.range_host_unpack(None, 5, None, 1) == -1
+
+
+def test_encoder_feature_layout_is_a_permutation_of_the_reference_features():
+    """host-side plan of the tensor-core encoder's first-layer input (csrc/capi.cu: plan_sh_layout): every reference feature
+    l*l + l +- |m| appears in exactly one column, the other columns are zero columns, the column -> entry map agrees with
+    it, and the rounds are ordered by Horner-chain length (what sh_rounds_kernel's table relies on)"""
+    import ctypes
+    import numpy as np
+    from range_b200 import _lib
+    from range_b200.sh_table import build_table
+    lib = _lib.load()
+    I32P = ctypes.POINTER(ctypes.c_int32)
+    lib.range_debug_sh_layout.argtypes = [ctypes.c_int, I32P, ctypes.c_int, I32P, I32P, I32P, I32P, ctypes.c_int]
+    lib.range_debug_sh_layout.restype = ctypes.c_int
+    ZERO = 1 << 25
+    for L in (8, 32, 40):
+        t = build_table(L)
+        off = np.ascontiguousarray(t["off"], np.int32)
+        E = L * (L + 1) // 2
+        assert off.shape == (E + 1,)
+        ent = [(l, am) for am in range(L) for l in range(am, L)]            # the table's |m|-major entry order
+        for want_rounds in (1, 0):
+            cap = L * (L + 1) + 64
+            perm, fmap = np.full(cap, -7, np.int32), np.full(cap, -7, np.int32)
+            rounds, tab = ctypes.c_int32(-1), ctypes.c_int32(-1)
+            K0 = lib.range_debug_sh_layout(L, off.ctypes.data_as(I32P), want_rounds, ctypes.byref(rounds), ctypes.byref(tab),
+                                           perm.ctypes.data_as(I32P), fmap.ctypes.data_as(I32P), cap)
+            assert K0 == (64 * -(-E // 32) if want_rounds else L * L) and K0 % 2 == 0
+            assert rounds.value == (-(-E // 32) if want_rounds else 0)
+            perm, fmap = perm[:K0], fmap[:K0]
+            real = perm[perm >= 0]
+            assert sorted(real.tolist()) == list(range(L * L))                # each reference feature exactly once
+            assert ((perm < 0) == (fmap == ZERO)).all() and (perm >= -1).all()
+            for f in np.nonzero(perm >= 0)[0]:
+                e, am, is_sin = fmap[f] & 0xffff, (fmap[f] >> 16) & 0xff, (fmap[f] >> 24) & 1
+                l, m = ent[e]
+                assert m == am and perm[f] == l * l + l + (-am if is_sin else am) and (am > 0 or not is_sin)
+            if want_rounds:
+                # column 64 r + 2 i (cos) and + 1 (sin) belong to the same chain; chain lengths never grow from round to round
+                cos, sin = fmap[0::2], fmap[1::2]
+                same = (cos != ZERO) & (sin != ZERO)
+                assert ((cos[same] & 0xffffff) == (sin[same] & 0xffffff)).all() and ((sin[same] >> 24) & 1).all()
+                assert ((cos == ZERO) <= (sin == ZERO)).all()                  # an unused slot has neither column
+                length = np.diff(off)
+                per_round = [[length[c & 0xffff] for c in cos[32 * r:32 * r + 32] if c != ZERO] for r in range(rounds.value)]
+                assert all(min(a) >= max(b) for a, b in zip(per_round, per_round[1:]) if a and b)
+                assert tab.value == 32 * sum(1 + max(p) for p in per_round)
