@@ -151,9 +151,15 @@ class LocationEncoder(nn.Module):
         takes the fraction `taper` of what is left (whole rounds of the producer/consumer apply kernel - 24 units x 256
         rows on 148 SMs - while it is at least one round, else whole 128-row tiles), down to a last piece of about
         `tail` rows.  taper <= 0.64 keeps a piece's copy (5.6 M rows/s over PCIe) shorter than the computation that
-        follows it (3.2 M rows/s)."""
+        follows it (3.2 M rows/s).  No piece is longer than chunk + ROUND_ROWS - 1 rows."""
         cuts, lo = [], 0
         tail = max(1, tail)
+        # The rows beyond whole rounds go into the FIRST piece: the apply kernel spreads such leftover tile pairs over
+        # database ranges wherever they are, but at the end they would lengthen the one copy nothing overlaps
+        # (100 000 rows: last piece 6 144 instead of 7 840 rows).
+        ragged = N % ROUND_ROWS
+        if ragged and chunk % ROUND_ROWS == 0 and tail % ROUND_ROWS == 0 and N - ragged >= chunk + tail:
+            cuts.append((0, chunk + ragged)); lo = chunk + ragged
         while N - lo > 2 * chunk:
             cuts.append((lo, lo + chunk)); lo += chunk
         while N - lo > tail + tail // 2:

@@ -113,8 +113,10 @@ def test_forward_chunking_covers_every_row():
         for taper in (0.5, 0.6):
             cuts = LocationEncoder._chunks(N, 24576, 6144, taper)
             assert cuts[0][0] == 0 and cuts[-1][1] == N and all(a[1] == b[0] for a, b in zip(cuts, cuts[1:]))
-            assert all(0 < hi - lo <= 24576 for lo, hi in cuts)
+            assert all(0 < hi - lo <= 24576 + 6143 for lo, hi in cuts) and all(hi - lo <= 24576 for lo, hi in cuts[1:])
             assert cuts[-1][1] - cuts[-1][0] <= 6144 + 3072          # the unoverlapped last copy stays short
+            if N >= 24576 + 6144:                                    # ragged rows travel with the first piece: whole rounds after it
+                assert all((hi - lo) % 6144 == 0 for lo, hi in cuts[1:])
             sizes = [hi - lo for lo, hi in cuts]
             assert all(a >= b or b <= 6144 + 3072 for a, b in zip(sizes, sizes[1:]))     # pieces shrink towards the end
     cuts = LocationEncoder._chunks(100_000, 49152, 2048)
