@@ -173,8 +173,16 @@ sh_rowmajor_kernel(const double* __restrict__ lonlat, int N, int L, const double
 // transposing stores around 5 950 DFMAs) and waits on the coefficient loads (L1 hit rate 57 %); here the round table sits
 // in shared memory, a coefficient load feeds kRoundQ DFMAs and nothing is transposed: 1 670 warp instructions per query
 // (676 -> 244 us per 100 000 queries; ncu: issue slots 68 % busy, conversion pipe 53 %, fp64 pipe 35 %).
-constexpr int kRoundWarps = 24;
-constexpr int kRoundQ = 4;
+#ifndef RANGE_SH_WARPS
+#define RANGE_SH_WARPS 24
+#endif
+#ifndef RANGE_SH_Q
+#define RANGE_SH_Q 4
+#endif
+// Measured, whole encoder per 100 000 queries (warps, queries per pass): (24, 4) 0.986 ms, (16, 8) 0.977, (32, 4) 0.979,
+// (16, 4) 0.982, (20, 6) 0.968, (24, 2) 1.026 - flat once a coefficient load feeds four DFMAs.
+constexpr int kRoundWarps = RANGE_SH_WARPS;      // warps per CTA (one CTA per SM: the round table is staged once per CTA)
+constexpr int kRoundQ = RANGE_SH_Q;              // queries per warp pass
 
 __host__ __device__ constexpr size_t round_scratch_doubles(int L) { return size_t(kRoundQ) * 4 + size_t(3) * kRoundQ * L; }
 
